@@ -1,0 +1,17 @@
+// Library-level entry points: version, build info, thread-local error text.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void crn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int crn_version(void) { return 100; }
+extern "C" const char* crn_build_arch(void) { return "sm_100a"; }
+extern "C" const char* crn_last_error(void) { return g_err; }

@@ -1,0 +1,197 @@
+// Small HBM-bound ops of the encoder + layout glue + fused Adam.
+// Replaces model/resnet50.py:134-140 (ZeroPad+MaxPool), :183 (mean), :189-204
+// (Caffe preprocessing) and state.py:65-66 / pipeline.py:230 (Adam step).
+#include "common.cuh"
+
+namespace {
+constexpr int NT = 256;
+
+__global__ void preprocess_kernel(const uint8_t* __restrict__ img, int N, int HW, float4* __restrict__ out) {
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    const int64_t n = i / HW, p = i - n * HW;
+    const uint8_t* b = img + n * 3 * HW + p;
+    const float r = (float)b[0], g = (float)b[HW], bl = (float)b[2 * (int64_t)HW];
+    // RGB -> BGR, then ADD the Caffe mean (resnet50.py:200-204, bug-for-bug)
+    out[i] = make_float4(bl + 103.939f, g + 116.779f, r + 123.68f, 0.f);
+  }
+}
+
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+                                   float* __restrict__ y, int8_t* __restrict__ idx) {
+  const int OH = H / 2, OW = W / 2, C4 = C / 4;
+  const int64_t total = (int64_t)N * OH * OW * C4;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    const int c4 = (int)(i % C4); int64_t q = i / C4;
+    const int ox = (int)(q % OW); q /= OW;
+    const int oy = (int)(q % OH); const int n = (int)(q / OH);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = 2 * oy - 1 + ky, ix = 2 * ox - 1 + kx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);   // zero padding takes part in the max
+        if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+          v = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)n * H + iy) * W + ix) * C) + c4);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (vv[e] > best[e]) { best[e] = vv[e]; bi[e] = ky * 3 + kx; }   // first max wins
+      }
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(best[0], best[1], best[2], best[3]);
+    reinterpret_cast<char4*>(idx)[i] = make_char4((char)bi[0], (char)bi[1], (char)bi[2], (char)bi[3]);
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const int8_t* __restrict__ idx, int N,
+                                   int H, int W, int C, float* __restrict__ dx) {
+  const int OH = H / 2, OW = W / 2, C4 = C / 4;
+  const int64_t total = (int64_t)N * H * W * C4;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    const int c4 = (int)(i % C4); int64_t q = i / C4;
+    const int ix = (int)(q % W); q /= W;
+    const int iy = (int)(q % H); const int n = (int)(q / H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // windows containing (iy, ix): oy in {ceil((iy-1)/2) .. floor((iy+1)/2)}
+    const int oy0 = iy >> 1, oy1 = (iy + 1) >> 1;
+    const int ox0 = ix >> 1, ox1 = (ix + 1) >> 1;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      if (oy >= OH) continue;
+      const int ky = iy - (2 * oy - 1);
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        if (ox >= OW) continue;
+        const int kx = ix - (2 * ox - 1);
+        const int64_t o = (((int64_t)n * OH + oy) * OW + ox) * C4 + c4;
+        const char4 t = reinterpret_cast<const char4*>(idx)[o];
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + o);
+        const int tap = ky * 3 + kx;
+        if (t.x == tap) acc[0] += g.x;
+        if (t.y == tap) acc[1] += g.y;
+        if (t.z == tap) acc[2] += g.z;
+        if (t.w == tap) acc[3] += g.w;
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+__global__ void spatial_mean_fwd_kernel(const float* __restrict__ x, int N, int HW, int C,
+                                        float* __restrict__ y) {
+  const int i = blockIdx.x * NT + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  const float* p = x + (int64_t)n * HW * C + c;
+  float s = 0.f;
+  for (int k = 0; k < HW; ++k) s += __ldg(p + (int64_t)k * C);
+  y[i] = s / (float)HW;
+}
+
+__global__ void spatial_mean_bwd_kernel(const float* __restrict__ dy, int N, int HW, int C,
+                                        float* __restrict__ dx, int accumulate) {
+  const int64_t total = (int64_t)N * HW * C;
+  const float inv = 1.0f / (float)HW;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    const int c = (int)(i % C);
+    const int n = (int)(i / ((int64_t)HW * C));
+    const float g = __ldg(dy + n * C + c) * inv;
+    dx[i] = accumulate ? dx[i] + g : g;
+  }
+}
+
+__global__ void planar_to_rows_kernel(const float* __restrict__ x, int N, int C, int64_t S, int CP,
+                                      float* __restrict__ out) {
+  const int64_t total = (int64_t)N * S;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    const int64_t n = i / S, s = i - n * S;
+    for (int c = 0; c < CP; ++c)
+      out[i * CP + c] = c < C ? __ldg(x + (n * C + c) * S + s) : 0.f;
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+inline unsigned grid_for(int64_t total) {
+  int64_t b = crn_ceil_div(total, NT);
+  if (b > 16LL * kNumSMs) b = 16LL * kNumSMs;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+}  // namespace
+
+extern "C" int crn_preprocess_image(const uint8_t* image, int32_t N, int32_t H, int32_t W, float* out,
+                                    void* stream) {
+  CRN_REQUIRE(image && out && N > 0 && H > 0 && W > 0, "crn_preprocess_image: bad args");
+  preprocess_kernel<<<grid_for((int64_t)N * H * W), NT, 0, crn_stream(stream)>>>(
+      image, N, H * W, reinterpret_cast<float4*>(out));
+  CRN_LAUNCH_CHECK("preprocess");
+  return CRN_OK;
+}
+
+extern "C" int crn_maxpool_fwd(const float* x, int32_t N, int32_t H, int32_t W, int32_t C, float* y,
+                               int8_t* idx, void* stream) {
+  CRN_REQUIRE(x && y && idx && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "crn_maxpool_fwd: bad args");
+  maxpool_fwd_kernel<<<grid_for((int64_t)N * (H / 2) * (W / 2) * (C / 4)), NT, 0, crn_stream(stream)>>>(
+      x, N, H, W, C, y, idx);
+  CRN_LAUNCH_CHECK("maxpool_fwd");
+  return CRN_OK;
+}
+
+extern "C" int crn_maxpool_bwd(const float* dy, const int8_t* idx, int32_t N, int32_t H, int32_t W,
+                               int32_t C, float* dx, void* stream) {
+  CRN_REQUIRE(dy && dx && idx && C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "crn_maxpool_bwd: bad args");
+  maxpool_bwd_kernel<<<grid_for((int64_t)N * H * W * (C / 4)), NT, 0, crn_stream(stream)>>>(dy, idx, N, H,
+                                                                                         W, C, dx);
+  CRN_LAUNCH_CHECK("maxpool_bwd");
+  return CRN_OK;
+}
+
+extern "C" int crn_spatial_mean_fwd(const float* x, int32_t N, int32_t HW, int32_t C, float* y,
+                                    void* stream) {
+  CRN_REQUIRE(x && y && N > 0 && HW > 0 && C > 0, "crn_spatial_mean_fwd: bad args");
+  spatial_mean_fwd_kernel<<<(N * C + NT - 1) / NT, NT, 0, crn_stream(stream)>>>(x, N, HW, C, y);
+  CRN_LAUNCH_CHECK("spatial_mean_fwd");
+  return CRN_OK;
+}
+
+extern "C" int crn_spatial_mean_bwd(const float* dy, int32_t N, int32_t HW, int32_t C, float* dx,
+                                    int32_t accumulate, void* stream) {
+  CRN_REQUIRE(dy && dx && N > 0 && HW > 0 && C > 0, "crn_spatial_mean_bwd: bad args");
+  spatial_mean_bwd_kernel<<<grid_for((int64_t)N * HW * C), NT, 0, crn_stream(stream)>>>(dy, N, HW, C, dx,
+                                                                                       accumulate);
+  CRN_LAUNCH_CHECK("spatial_mean_bwd");
+  return CRN_OK;
+}
+
+extern "C" int crn_planar_to_rows(const float* x, int32_t N, int32_t C, int64_t S, int32_t CP, float* out,
+                                  void* stream) {
+  CRN_REQUIRE(x && out && N > 0 && C > 0 && S > 0 && CP >= C, "crn_planar_to_rows: bad args");
+  planar_to_rows_kernel<<<grid_for((int64_t)N * S), NT, 0, crn_stream(stream)>>>(x, N, C, S, CP, out);
+  CRN_LAUNCH_CHECK("planar_to_rows");
+  return CRN_OK;
+}
+
+extern "C" int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                             float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                             void* stream) {
+  CRN_REQUIRE(p && g && m && v && n > 0 && step >= 1, "crn_adam_step: bad args");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n), NT, 0, crn_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1,
+                                                         sqrtf(bc2), grad_scale);
+  CRN_LAUNCH_CHECK("adam");
+  return CRN_OK;
+}

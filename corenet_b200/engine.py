@@ -1,0 +1,683 @@
+"""Execution engine: CoReNet forward/backward as a static plan of C-ABI kernel launches.
+
+This is the host side of the hot path.  It replaces the
+autograd graph of ATen ops the reference builds in
+src/corenet/model/core_net.py:36-43 -> resnet50.py:176-186 ->
+reconstruction_decoder.py:119-152.  Design (DESIGN.md "Engine"):
+
+  * activations are channels-last rows x C buffers allocated once per
+    (batch, mode) plan; concat buffers are written in place by their two
+    producers (transposed conv + ray-traced skip kernel);
+  * weights are re-packed tap-major into one arena by ONE kernel per step,
+    weight gradients land in a mirror arena and are un-packed by ONE kernel;
+  * every launch goes through the C-ABI in include/corenet_b200.h on the
+    current torch stream; torch is used for memory, streams and tiny 4x4 /
+    [B,C]-sized glue only;
+  * gradients reach autograd through ONE torch.autograd.Function whose inputs
+    are the model's parameters, so DDP hooks / optimisers see ordinary grads.
+"""
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch as t
+
+from corenet_b200 import _lib
+from corenet_b200._lib import ConvDesc, PackItem, UnpackItem
+
+BRN_EPS = 1e-3        # every BatchRenorm of the model is built with eps=0.001
+BRN_MOMENTUM = 0.01
+
+# (stage, cin is derived, conv k, convT k, convT pad, conv out, convT out, encoder channels of the skip)
+DECODER_PYRAMID = ((2, 3, 3, 1, 256, 128, 2048), (3, 5, 7, 3, 128, 64, 1024), (4, 5, 7, 3, 64, 32, 512),
+                   (5, 5, 7, 3, 32, 16, 256), (6, 5, 7, 3, 16, None, None))
+ENC_STAGE_OF = {2048: "stage5", 1024: "stage4", 512: "stage3", 256: "stage2"}
+
+
+def _r4(c: int) -> int:
+  return (c + 3) // 4 * 4
+
+
+def _call(name, *args):
+  _lib.call(name, *args)
+
+
+class Buf:
+  """rows x C activation, channels-last with channel stride cs; .g is its gradient."""
+
+  def __init__(self, dev, n, spatial, C_, cs=None, grad=True):
+    self.n, self.spatial, self.C = n, tuple(spatial), C_
+    self.cs = cs or _r4(C_)
+    self.rows = n
+    for s in spatial:
+      self.rows *= s
+    self.v = t.zeros(self.rows, self.cs, dtype=t.float32, device=dev)
+    self.g = t.zeros_like(self.v) if grad else None
+
+  @property
+  def p(self):
+    return self.v.data_ptr()
+
+  @property
+  def gp(self):
+    return self.g.data_ptr()
+
+
+class Slot:
+  """n doubles inside one of the plan's accumulator arenas."""
+
+  def __init__(self, plan, which, off, n):
+    self.plan, self.which, self.off, self.n = plan, which, off, n
+
+  def _arena(self):
+    return self.plan.arena_fwd if self.which == "fwd" else self.plan.arena_bwd
+
+  def data_ptr(self):
+    return self._arena().data_ptr() + 8 * self.off
+
+  def view(self):
+    return self._arena()[self.off:self.off + self.n]
+
+
+class ConvLayer:
+  """One (transposed) convolution / linear layer bound to a parameter."""
+
+  def __init__(self, eng, name, cin, cout, k, stride=1, pad=0, transposed=False, src_cin=None):
+    self.name, self.cin, self.cout = name, cin, cout
+    self.k = tuple(k)
+    self.taps = k[0] * k[1] * k[2]
+    self.stride, self.pad, self.transposed = stride, pad, transposed
+    self.src_cin = src_cin or cin          # channels of the parameter's input dim
+    self.cinp, self.coutp = _r4(max(self.src_cin, cin)), _r4(cout)
+    self.size = self.taps * self.cinp * self.coutp
+    self.off = eng._reserve(self)
+
+  def desc(self, x_cs, idims, y_cs, odims, n, planar=False, bias_n_stride=0, x_co=0, y_co=0) -> ConvDesc:
+    d = ConvDesc()
+    d.N, d.Cin, d.Cout = n, self.cin, self.cout
+    d.iD, d.iH, d.iW = idims
+    d.oD, d.oH, d.oW = odims
+    d.kD, d.kH, d.kW = self.k
+    d.stride, d.pad, d.transposed = self.stride, self.pad, int(self.transposed)
+    d.x_cs, d.x_co, d.y_cs, d.y_co = x_cs, x_co, y_cs, y_co
+    d.CinP, d.CoutP = self.cinp, self.coutp
+    d.y_planar, d.bias_n_stride = int(planar), bias_n_stride
+    return d
+
+
+class Engine:
+  """Per-model state: layer table, weight arenas, cached plans."""
+
+  def __init__(self, model):
+    self.model = model
+    self.layers: List[ConvLayer] = []
+    self.total = 0
+    self.dev = None
+    self.plans: Dict = {}
+    self._ptr_sig = None
+    self._ver_sig = None
+    self._pcache = None
+    self._build_layers()
+
+  # ------------------------------------------------------------------ layers
+  def _reserve(self, layer):
+    off = self.total
+    self.total += layer.size
+    self.layers.append(layer)
+    return off
+
+  def _build_layers(self):
+    from corenet_b200.model import resnet50
+    L = {}
+    mk = lambda *a, **k: ConvLayer(self, *a, **k)
+    L["stem"] = mk("encoder.stage1.conv", 4, 64, (1, 7, 7), stride=2, pad=3, src_cin=3)
+    cin = 64
+    for sname, letters, (f1, f2, f3), stride in resnet50.STAGES:
+      for i, letter in enumerate(letters):
+        p = f"encoder.{sname}.{letter}."
+        s = stride if i == 0 else 1
+        L[p + "op_a"] = mk(p + "op_a.conv", cin, f1, (1, 1, 1), stride=s)
+        L[p + "op_b"] = mk(p + "op_b.conv", f1, f2, (1, 3, 3), pad=1)
+        L[p + "op_c"] = mk(p + "op_c.conv", f2, f3, (1, 1, 1))
+        if i == 0:
+          L[p + "shortcut"] = mk(p + "shortcut.conv", cin, f3, (1, 1, 1), stride=s)
+        cin = f3
+    dc = self.model.config.decoder
+    lat = dc.latent_channels
+    self.lat = lat
+    L["stage_0"] = mk("decoder.stage_0", 2048, lat, (1, 1, 1))
+    L["stage_1.t1"] = mk("decoder.stage_1.t1", _r4(lat + 3), 256, (4, 4, 4), stride=4, transposed=True,
+                         src_cin=lat + 3)
+    self.dec_plan = []
+    cin, grid = 256, 4
+    for stage, k, kt, pt, mid, t_out, enc_c in DECODER_PYRAMID:
+      last = t_out is None
+      t_out = dc.num_output_channels if last else t_out
+      L[f"stage_{stage}.c1"] = mk(f"decoder.stage_{stage}.c1", cin, mid, (k, k, k), pad=k // 2)
+      L[f"stage_{stage}.t1"] = mk(f"decoder.stage_{stage}.t1", mid, t_out, (kt, kt, kt), stride=2, pad=pt,
+                                  transposed=True)
+      skip_c = 0
+      if not last:
+        skip_c = round(t_out * dc.skip_fraction)
+        if skip_c > 0:
+          L[f"rt_skip_{stage}"] = mk(f"decoder.rt_skip_{stage}.compress_channels", enc_c, skip_c, (1, 1, 1),
+                                     src_cin=enc_c + 3)
+      self.dec_plan.append((stage, cin, mid, t_out, skip_c, enc_c, grid))
+      grid *= 2
+      cin = t_out + skip_c
+    self.L = L
+
+  # ------------------------------------------------------------------ arenas
+  def _ensure_device(self, dev):
+    if self.dev == dev:
+      return
+    self.dev = dev
+    self.w_fwd = t.zeros(self.total, dtype=t.float32, device=dev)
+    self.w_dgrad = t.zeros(self.total, dtype=t.float32, device=dev)
+    self.dw = t.zeros(self.total, dtype=t.float32, device=dev)
+    self.plans = {}
+    self._ptr_sig = None
+    self._ver_sig = None
+
+  def tensors(self):
+    """(name -> parameter, name -> buffer), cached."""
+    if self._pcache is None:
+      self._pcache = dict(self.model.named_parameters())
+      self._bcache = dict(self.model.named_buffers())
+    return self._pcache, self._bcache
+
+  def invalidate(self):
+    self._pcache = None
+    self._ptr_sig = None
+
+  @staticmethod
+  def _to_dev(ctypes_array, dev):
+    return t.frombuffer(bytearray(bytes(ctypes_array)), dtype=t.uint8).to(dev)
+
+  def pack_weights(self):
+    """One launch: all parameters -> tap-major fwd + dgrad arenas (skipped when unchanged)."""
+    P, _ = self.tensors()
+    ws = [P[l.name + ".weight"] for l in self.layers]
+    ptr_sig = tuple(w.data_ptr() for w in ws)
+    ver_sig = tuple(w._version for w in ws)
+    if ptr_sig != self._ptr_sig:
+      items = (PackItem * len(self.layers))()
+      offs = (C.c_int64 * (len(self.layers) + 1))()
+      for i, (l, w) in enumerate(zip(self.layers, ws)):
+        assert w.is_contiguous() and w.dtype == t.float32 and w.device == self.dev
+        it = items[i]
+        it.src = w.data_ptr()
+        it.dst_fwd = self.w_fwd.data_ptr() + 4 * l.off
+        it.dst_dgrad = self.w_dgrad.data_ptr() + 4 * l.off
+        it.Cin, it.Cout, it.taps, it.CinP, it.CoutP = l.src_cin, l.cout, l.taps, l.cinp, l.coutp
+        it.src_is_transposed = int(l.transposed)
+        offs[i] = l.off
+      offs[len(self.layers)] = self.total
+      self._items_dev = self._to_dev(items, self.dev)
+      self._offs_dev = self._to_dev(offs, self.dev)
+      self._ptr_sig = ptr_sig
+      self._ver_sig = None
+    if ver_sig != self._ver_sig:
+      _call("crn_pack_weights", self._items_dev.data_ptr(), self._offs_dev.data_ptr(), len(self.layers),
+            self.total, _lib.stream_ptr())
+      self._ver_sig = ver_sig
+
+  def unpack_wgrads(self, grads: Dict[str, t.Tensor]):
+    items = (UnpackItem * len(self.layers))()
+    offs = (C.c_int64 * (len(self.layers) + 1))()
+    tot = 0
+    for i, l in enumerate(self.layers):
+      it = items[i]
+      it.src_packed = self.dw.data_ptr() + 4 * l.off
+      it.dst = grads[l.name + ".weight"].data_ptr()
+      it.Cin, it.Cout, it.taps, it.CinP, it.CoutP = l.src_cin, l.cout, l.taps, l.cinp, l.coutp
+      it.dst_is_transposed = int(l.transposed)
+      offs[i] = tot
+      tot += l.src_cin * l.cout * l.taps
+    offs[len(self.layers)] = tot
+    self._uitems_dev = self._to_dev(items, self.dev)
+    self._uoffs_dev = self._to_dev(offs, self.dev)
+    _call("crn_unpack_wgrads", self._uitems_dev.data_ptr(), self._uoffs_dev.data_ptr(), len(self.layers),
+          tot, _lib.stream_ptr())
+
+  def wf(self, l):
+    return self.w_fwd.data_ptr() + 4 * l.off
+
+  def wd(self, l):
+    return self.w_dgrad.data_ptr() + 4 * l.off
+
+  def dwp(self, l):
+    return self.dw.data_ptr() + 4 * l.off
+
+  def get_plan(self, batch: int, dev, need_grad: bool):
+    self._ensure_device(dev)
+    pool = self.plans.setdefault((batch, need_grad), [])
+    for p in pool:
+      if not p.busy:
+        return p
+    p = Plan(self, batch, need_grad)
+    pool.append(p)
+    return p
+
+
+# ====================================================================== plan
+class BRNOp:
+  """One BatchRenorm instance bound to buffers inside a plan."""
+
+  def __init__(self, plan, name, x: Buf, C_, relu_in, y: Buf, res: Optional[Buf] = None, relu_out=False,
+               y_pre: Optional[Buf] = None):
+    self.plan, self.name, self.x, self.C = plan, name, x, C_
+    self.relu_in, self.relu_out, self.y, self.res, self.y_pre = relu_in, relu_out, y, res, y_pre
+    self.coef = plan.f32(6 * C_)
+    self.acc = plan.slot("fwd", 3 * C_)
+    self.bacc = plan.slot("bwd", 2 * C_)
+    self.dxsum = plan.slot("bwd", C_)
+
+  def fwd(self, training):
+    P, Bf = self.plan.eng.tensors()
+    st = _lib.stream_ptr()
+    n, x = self.name, self.x
+    if training:
+      _call("crn_brn_stats", x.p, x.rows, self.C, x.cs, 0, int(self.relu_in), self.acc.data_ptr(), st)
+    _call("crn_brn_finalize", self.acc.data_ptr(), x.rows, self.C, P[n + ".weight"].data_ptr(),
+          P[n + ".bias"].data_ptr(), Bf[n + ".running_mean"].data_ptr(), Bf[n + ".running_var"].data_ptr(),
+          Bf[n + ".num_batches_tracked"].data_ptr(), BRN_EPS, BRN_MOMENTUM, int(training),
+          self.coef.data_ptr(), st)
+    _call("crn_brn_apply", x.p, x.rows, self.C, x.cs, 0, self.coef.data_ptr(),
+          self.res.p if self.res is not None else None, int(self.relu_in), int(self.relu_out), self.y.p,
+          self.y.cs, 0, self.y_pre.p if self.y_pre is not None else None, st)
+
+  def bwd(self, training, grads, dy_ptr, dy_cs, dx_ptr, dx_cs, g_extra_ptr=None, g_store_ptr=None):
+    """dy: gradient wrt this op's (activated) output.  The masked / combined
+    gradient is written to g_store (defaults to in-place over dy when a mask or
+    extra term exists).  dx: gradient wrt the op's input x.  Returns the Slot
+    holding column sums of dx (= bias gradient of the conv that produced x)."""
+    st = _lib.stream_ptr()
+    n, x = self.name, self.x
+    g_out = g_store_ptr
+    if g_out is None and (self.relu_out or g_extra_ptr is not None):
+      g_out = dy_ptr
+    _call("crn_brn_bwd_reduce", dy_ptr, dy_cs, 0, self.y.p if self.relu_out else None, g_extra_ptr, x.p,
+          x.cs, 0, x.rows, self.C, self.coef.data_ptr(), int(self.relu_in), int(self.relu_out), g_out,
+          self.bacc.data_ptr(), st)
+    g = g_out if g_out is not None else dy_ptr
+    _call("crn_brn_bwd_dx", g, dy_cs, 0, x.p, x.cs, 0, x.rows, self.C, self.coef.data_ptr(),
+          self.bacc.data_ptr(), None, int(self.relu_in), int(training), dx_ptr, dx_cs, 0, 0,
+          grads[n + ".weight"].data_ptr(), grads[n + ".bias"].data_ptr(), self.dxsum.data_ptr(), st)
+    return self.dxsum
+
+
+class Plan:
+  """All buffers + the launch sequence for one batch size."""
+
+  def __init__(self, eng: Engine, batch: int, need_grad: bool):
+    self.eng, self.B, self.need_grad = eng, batch, need_grad
+    self.dev = eng.dev
+    self.busy = False
+    self._n = {"fwd": 0, "bwd": 0}
+    self._build()
+    self.arena_fwd = t.zeros(max(self._n["fwd"], 1), dtype=t.float64, device=self.dev)
+    self.arena_bwd = t.zeros(max(self._n["bwd"], 1), dtype=t.float64, device=self.dev)
+    self.training = True
+    self.launches = 0
+
+  def f32(self, n):
+    return t.zeros(n, dtype=t.float32, device=self.dev)
+
+  def slot(self, which, n):
+    s = Slot(self, which, self._n[which], n)
+    self._n[which] += n
+    return s
+
+  def buf(self, spatial, C_, cs=None, grad=None):
+    return Buf(self.dev, self.B, spatial, C_, cs, self.need_grad if grad is None else grad)
+
+  # ------------------------------------------------------------------ build
+  def _build(self):
+    from corenet_b200.model import resnet50
+    eng, B, L = self.eng, self.B, self.eng.L
+    R = 256
+    self.img4 = self.buf((R, R), 4, grad=False)
+    self.s1 = self.buf((128, 128), 64)
+    self.s1a = self.buf((128, 128), 64)
+    self.brn_stem = BRNOp(self, "encoder.stage1_part2.bn", self.s1, 64, False, self.s1a, relu_out=True)
+    self.p1 = self.buf((64, 64), 64)
+    self.p1_idx = t.zeros(self.p1.rows * 64, dtype=t.int8, device=self.dev)
+    self.d_stem = L["stem"].desc(4, (1, R, R), 64, (1, 128, 128), B)
+    self.blocks = []
+    x, hw = self.p1, 64
+    self.enc_pre = {}
+    for sname, letters, (f1, f2, f3), stride in resnet50.STAGES:
+      pre = None
+      for i, letter in enumerate(letters):
+        p = f"encoder.{sname}.{letter}."
+        s = stride if i == 0 else 1
+        ohw = hw // s
+        blk = {"p": p, "x": x, "down": i == 0}
+        a_c, a_y = self.buf((ohw, ohw), f1), self.buf((ohw, ohw), f1)
+        b_c, b_y = self.buf((ohw, ohw), f2), self.buf((ohw, ohw), f2)
+        c_c, out = self.buf((ohw, ohw), f3), self.buf((ohw, ohw), f3)
+        pre = self.buf((ohw, ohw), f3) if i == len(letters) - 1 else None
+        blk.update(a_c=a_c, a_y=a_y, b_c=b_c, b_y=b_y, c_c=c_c, out=out, pre=pre)
+        blk["la"], blk["lb"], blk["lc"] = L[p + "op_a"], L[p + "op_b"], L[p + "op_c"]
+        blk["d_a"] = blk["la"].desc(x.cs, (1, hw, hw), a_c.cs, (1, ohw, ohw), B)
+        blk["d_b"] = blk["lb"].desc(a_y.cs, (1, ohw, ohw), b_c.cs, (1, ohw, ohw), B)
+        blk["d_c"] = blk["lc"].desc(b_y.cs, (1, ohw, ohw), c_c.cs, (1, ohw, ohw), B)
+        blk["bn_a"] = BRNOp(self, p + "op_a.bn", a_c, f1, False, a_y, relu_out=True)
+        blk["bn_b"] = BRNOp(self, p + "op_b.bn", b_c, f2, False, b_y, relu_out=True)
+        if i == 0:
+          s_c, s_y = self.buf((ohw, ohw), f3), self.buf((ohw, ohw), f3)
+          blk.update(s_c=s_c, s_y=s_y, ls=L[p + "shortcut"])
+          blk["d_s"] = blk["ls"].desc(x.cs, (1, hw, hw), s_c.cs, (1, ohw, ohw), B)
+          blk["bn_s"] = BRNOp(self, p + "shortcut.bn", s_c, f3, False, s_y)
+          res = s_y
+        else:
+          res = x
+        blk["bn_c"] = BRNOp(self, p + "op_c.bn", c_c, f3, False, out, res=res, relu_out=True, y_pre=pre)
+        self.blocks.append(blk)
+        x, hw = out, ohw
+      self.enc_pre[sname] = pre
+    self.enc_out = x                      # [B, 8, 8, 2048] post-ReLU
+    self.feat = Buf(self.dev, B, (), 2048, grad=self.need_grad)
+    # ---- decoder
+    lat = eng.lat
+    self.latb = Buf(self.dev, B, (), lat + 3, grad=self.need_grad)
+    self.z1 = Buf(self.dev, B, (), lat + 3, grad=self.need_grad)
+    self.d_s0 = L["stage_0"].desc(2048, (1, 1, 1), self.latb.cs, (1, 1, 1), B)
+    self.brn_s1 = BRNOp(self, "decoder.stage_1.b1", self.latb, lat + 3, True, self.z1)
+    self.x1 = self.buf((4, 4, 4), 256)
+    self.d_s1t = L["stage_1.t1"].desc(self.z1.cs, (1, 1, 1), 256, (4, 4, 4), B)
+    self.stages = []
+    cat = self.x1
+    for stage, cin, mid, t_out, skip_c, enc_c, g in eng.dec_plan:
+      st = {"stage": stage, "cat": cat, "g": g, "cin": cin, "mid": mid, "t_out": t_out, "skip_c": skip_c}
+      z, c, z2 = self.buf((g, g, g), cin), self.buf((g, g, g), mid), self.buf((g, g, g), mid)
+      st.update(z=z, c=c, z2=z2)
+      st["bn1"] = BRNOp(self, f"decoder.stage_{stage}.b1", cat, cin, True, z)
+      st["bn2"] = BRNOp(self, f"decoder.stage_{stage}.b2", c, mid, True, z2)
+      st["lc"], st["lt"] = L[f"stage_{stage}.c1"], L[f"stage_{stage}.t1"]
+      st["d_c"] = st["lc"].desc(z.cs, (g, g, g), c.cs, (g, g, g), B)
+      g2 = 2 * g
+      if stage < 6:
+        nxt = self.buf((g2, g2, g2), t_out + skip_c)
+        st["next"] = nxt
+        st["d_t"] = st["lt"].desc(z2.cs, (g, g, g), nxt.cs, (g2, g2, g2), B)
+        if skip_c:
+          ls = L[f"rt_skip_{stage}"]
+          src = self.enc_pre[ENC_STAGE_OF[enc_c]]
+          hw = src.spatial[0]
+          cmap = self.buf((hw, hw), skip_c)
+          st.update(ls=ls, src=src, cmap=cmap, hw=hw)
+          st["d_s"] = ls.desc(src.cs, (1, hw, hw), cmap.cs, (1, hw, hw), B, bias_n_stride=skip_c)
+        cat = nxt
+      else:
+        cp = _r4(t_out)
+        st["glog"] = t.zeros(B * g2 ** 3, cp, dtype=t.float32, device=self.dev) if self.need_grad else None
+        st["d_t"] = st["lt"].desc(z2.cs, (g, g, g), cp, (g2, g2, g2), B, planar=True)
+        st["d_t_bwd"] = st["lt"].desc(z2.cs, (g, g, g), cp, (g2, g2, g2), B, planar=False)
+      self.stages.append(st)
+    self.scratch64 = t.zeros(4096, dtype=t.float64, device=self.dev)
+
+  # ------------------------------------------------------------------ forward
+  def forward(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, training: bool,
+              want_features: bool = False) -> t.Tensor:
+    eng, B = self.eng, self.B
+    P, _ = eng.tensors()
+    st = _lib.stream_ptr()
+    self.training = training
+    bias = lambda l: P[l.name + ".bias"].data_ptr()
+    eng.pack_weights()
+    if training:
+      self.arena_fwd.zero_()
+    # ---- encoder
+    _call("crn_preprocess_image", image.data_ptr(), B, 256, 256, self.img4.p, st)
+    _call("crn_conv_fwd", C.byref(self.d_stem), self.img4.p, eng.wf(eng.L["stem"]), bias(eng.L["stem"]),
+          self.s1.p, 0, st)
+    self.brn_stem.fwd(training)
+    _call("crn_maxpool_fwd", self.s1a.p, B, 128, 128, 64, self.p1.p, self.p1_idx.data_ptr(), st)
+    for blk in self.blocks:
+      x = blk["x"]
+      if blk["down"]:
+        _call("crn_conv_fwd", C.byref(blk["d_s"]), x.p, eng.wf(blk["ls"]), bias(blk["ls"]), blk["s_c"].p, 0, st)
+        blk["bn_s"].fwd(training)
+      _call("crn_conv_fwd", C.byref(blk["d_a"]), x.p, eng.wf(blk["la"]), bias(blk["la"]), blk["a_c"].p, 0, st)
+      blk["bn_a"].fwd(training)
+      _call("crn_conv_fwd", C.byref(blk["d_b"]), blk["a_y"].p, eng.wf(blk["lb"]), bias(blk["lb"]),
+            blk["b_c"].p, 0, st)
+      blk["bn_b"].fwd(training)
+      _call("crn_conv_fwd", C.byref(blk["d_c"]), blk["b_y"].p, eng.wf(blk["lc"]), bias(blk["lc"]),
+            blk["c_c"].p, 0, st)
+      blk["bn_c"].fwd(training)
+    _call("crn_spatial_mean_fwd", self.enc_out.p, B, 64, 2048, self.feat.p, st)
+    if want_features:
+      return None
+    # ---- decoder
+    L = eng.L
+    lat = eng.lat
+    _call("crn_conv_fwd", C.byref(self.d_s0), self.feat.p, eng.wf(L["stage_0"]), bias(L["stage_0"]),
+          self.latb.p, 0, st)
+    self.latb.v[:, lat:lat + 3].copy_(offsets)
+    self.brn_s1.fwd(training)
+    _call("crn_conv_fwd", C.byref(self.d_s1t), self.z1.p, eng.wf(L["stage_1.t1"]), bias(L["stage_1.t1"]),
+          self.x1.p, 0, st)
+    # per-scale layer matrices (reconstruction_decoder.py:111-115) and offsets
+    self.offs = offsets.contiguous()
+    res = eng.model.config.decoder.resolution
+    logits = None
+    for sd in self.stages:
+      g = sd["g"]
+      sd["bn1"].fwd(training)
+      _call("crn_conv_fwd", C.byref(sd["d_c"]), sd["z"].p, eng.wf(sd["lc"]), bias(sd["lc"]), sd["c"].p, 0, st)
+      sd["bn2"].fwd(training)
+      if sd["stage"] < 6:
+        nxt = sd["next"]
+        _call("crn_conv_fwd", C.byref(sd["d_t"]), sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]), nxt.p, 0, st)
+        if sd["skip_c"]:
+          ls, src, cmap, hw = sd["ls"], sd["src"], sd["cmap"], sd["hw"]
+          w = P[ls.name + ".weight"]
+          # the 3 offset channels are constant per scene -> exact per-scene bias
+          sbias = (P[ls.name + ".bias"][None, :] + offsets @ w[:, ls.cin:, 0, 0].t()).contiguous()
+          sd["sbias"] = sbias
+          _call("crn_conv_fwd", C.byref(sd["d_s"]), src.p, eng.wf(ls), sbias.data_ptr(), cmap.p, 0, st)
+          g2 = 2 * g
+          scale = t.diag(t.tensor([res[0] / g2, res[1] / g2, res[2] / g2, 1.0], dtype=t.float32, device=self.dev))
+          mat = v2s.matmul(scale).contiguous()
+          sd["mat"] = mat
+          _call("crn_skip_sample_fwd", cmap.p, B, hw, hw, sd["skip_c"], cmap.cs, mat.data_ptr(),
+                self.offs.data_ptr(), g2, g2, g2, nxt.p, nxt.cs, sd["t_out"], st)
+      else:
+        g2 = 2 * g
+        logits = t.empty(B, sd["t_out"], g2, g2, g2, dtype=t.float32, device=self.dev)
+        _call("crn_conv_fwd", C.byref(sd["d_t"]), sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]),
+              logits.data_ptr(), 0, st)
+    return logits
+
+  # ------------------------------------------------------------------ backward
+  def backward(self, grad_logits: t.Tensor, grads: Dict[str, t.Tensor], encoder_only_grads=None):
+    """grads: name -> zero/empty tensor per parameter (filled here)."""
+    eng, B = self.eng, self.B
+    P, _ = eng.tensors()
+    st = _lib.stream_ptr()
+    L = eng.L
+    tr = self.training
+    self.arena_bwd.zero_()
+    eng.dw.zero_()
+
+    def bias_from(slot: Slot, name, lo=0, n=None):
+      v = slot.view()
+      n = n if n is not None else grads[name].numel()
+      grads[name].copy_(v[lo:lo + n])
+
+    def wgrad(l, d, x_ptr, dy_ptr):
+      _call("crn_conv_wgrad", C.byref(d), x_ptr, dy_ptr, eng.dwp(l), st)
+
+    def dgrad(l, d, dy_ptr, dx_ptr, acc=0):
+      _call("crn_conv_dgrad", C.byref(d), dy_ptr, eng.wd(l), dx_ptr, acc, st)
+
+    # ---- decoder, last stage first
+    grad_logits = grad_logits.contiguous()
+    for sd in reversed(self.stages):
+      g, stage = sd["g"], sd["stage"]
+      lt, lc = sd["lt"], sd["lc"]
+      if stage == 6:
+        g2 = 2 * g
+        S = g2 ** 3
+        cp = sd["glog"].shape[1]
+        _call("crn_planar_to_rows", grad_logits.data_ptr(), B, sd["t_out"], S, cp, sd["glog"].data_ptr(), st)
+        _call("crn_colsum_planar", grad_logits.data_ptr(), B, sd["t_out"], S,
+              grads[lt.name + ".bias"].data_ptr(), self.scratch64.data_ptr(), st)
+        dy_ptr, d_t = sd["glog"].data_ptr(), sd["d_t_bwd"]
+      else:
+        nxt = sd["next"]
+        dy_ptr, d_t = nxt.gp, sd["d_t"]
+        if sd["skip_c"]:
+          ls, src, cmap, hw = sd["ls"], sd["src"], sd["cmap"], sd["hw"]
+          cmap.g.zero_()
+          g2 = 2 * g
+          _call("crn_skip_sample_bwd", nxt.gp, nxt.cs, sd["t_out"], B, hw, hw, sd["skip_c"], cmap.cs,
+                sd["mat"].data_ptr(), self.offs.data_ptr(), g2, g2, g2, cmap.gp, st)
+          wgrad(ls, sd["d_s"], src.p, cmap.gp)
+          dgrad(ls, sd["d_s"], cmap.gp, src.gp, 0)
+          # per-scene sums of d(cmap) -> bias and offset-channel weight grads (tiny glue)
+          ssum = t.empty(B, sd["skip_c"], dtype=t.float32, device=self.dev)
+          _call("crn_spatial_mean_fwd", cmap.gp, B, hw * hw, cmap.cs, ssum.data_ptr(), st)
+          ssum = ssum * float(hw * hw)
+          sd["ssum"] = ssum
+      wgrad(lt, d_t, sd["z2"].p, dy_ptr)
+      dgrad(lt, d_t, dy_ptr, sd["z2"].gp, 0)
+      dxs = sd["bn2"].bwd(tr, grads, sd["z2"].gp, sd["z2"].cs, sd["c"].gp, sd["c"].cs)
+      bias_from(dxs, lc.name + ".bias")
+      wgrad(lc, sd["d_c"], sd["z"].p, sd["c"].gp)
+      dgrad(lc, sd["d_c"], sd["c"].gp, sd["z"].gp, 0)
+      cat = sd["cat"]
+      dxs = sd["bn1"].bwd(tr, grads, sd["z"].gp, sd["z"].cs, cat.gp, cat.cs)
+      sd["dxs_cat"] = dxs
+    # bias grads of the transposed convs = column sums of the next stage's cat gradient
+    for i, sd in enumerate(self.stages):
+      if sd["stage"] < 6:
+        nxt_sd = self.stages[i + 1]
+        bias_from(nxt_sd["dxs_cat"], sd["lt"].name + ".bias", 0, sd["t_out"])
+        if sd["skip_c"]:
+          ls = sd["ls"]
+          ssum = sd["ssum"]
+          grads[ls.name + ".bias"].copy_(ssum.sum(0))
+    bias_from(self.stages[0]["dxs_cat"], L["stage_1.t1"].name + ".bias")
+    # ---- stage_1 / stage_0
+    l1 = L["stage_1.t1"]
+    wgrad(l1, self.d_s1t, self.z1.p, self.x1.gp)
+    dgrad(l1, self.d_s1t, self.x1.gp, self.z1.gp, 0)
+    dxs = self.brn_s1.bwd(tr, grads, self.z1.gp, self.z1.cs, self.latb.gp, self.latb.cs)
+    l0 = L["stage_0"]
+    bias_from(dxs, l0.name + ".bias", 0, eng.lat)
+    wgrad(l0, self.d_s0, self.feat.p, self.latb.gp)
+    dgrad(l0, self.d_s0, self.latb.gp, self.feat.gp, 0)
+    _call("crn_spatial_mean_bwd", self.feat.gp, B, 64, 2048, self.enc_out.gp, 0, st)
+    # ---- encoder, last block first
+    for blk in reversed(self.blocks):
+      x = blk["x"]
+      out, pre = blk["out"], blk["pre"]
+      la, lb, lc = blk["la"], blk["lb"], blk["lc"]
+      res_g = blk["s_y"].gp if blk["down"] else x.gp
+      # masked (and skip-combined) gradient doubles as the residual branch's gradient
+      dxs = blk["bn_c"].bwd(tr, grads, out.gp, out.cs, blk["c_c"].gp, blk["c_c"].cs,
+                            g_extra_ptr=pre.gp if pre is not None else None, g_store_ptr=res_g)
+      bias_from(dxs, lc.name + ".bias")
+      wgrad(lc, blk["d_c"], blk["b_y"].p, blk["c_c"].gp)
+      dgrad(lc, blk["d_c"], blk["c_c"].gp, blk["b_y"].gp, 0)
+      dxs = blk["bn_b"].bwd(tr, grads, blk["b_y"].gp, blk["b_y"].cs, blk["b_c"].gp, blk["b_c"].cs)
+      bias_from(dxs, lb.name + ".bias")
+      wgrad(lb, blk["d_b"], blk["a_y"].p, blk["b_c"].gp)
+      dgrad(lb, blk["d_b"], blk["b_c"].gp, blk["a_y"].gp, 0)
+      dxs = blk["bn_a"].bwd(tr, grads, blk["a_y"].gp, blk["a_y"].cs, blk["a_c"].gp, blk["a_c"].cs)
+      bias_from(dxs, la.name + ".bias")
+      wgrad(la, blk["d_a"], x.p, blk["a_c"].gp)
+      if blk["down"]:
+        ls = blk["ls"]
+        dxs = blk["bn_s"].bwd(tr, grads, blk["s_y"].gp, blk["s_y"].cs, blk["s_c"].gp, blk["s_c"].cs)
+        bias_from(dxs, ls.name + ".bias")
+        wgrad(ls, blk["d_s"], x.p, blk["s_c"].gp)
+        dgrad(ls, blk["d_s"], blk["s_c"].gp, x.gp, 0)
+        dgrad(la, blk["d_a"], blk["a_c"].gp, x.gp, 1)
+      else:
+        dgrad(la, blk["d_a"], blk["a_c"].gp, x.gp, 1)
+    # ---- stem
+    _call("crn_maxpool_bwd", self.p1.gp, self.p1_idx.data_ptr(), B, 128, 128, 64, self.s1a.gp, st)
+    dxs = self.brn_stem.bwd(tr, grads, self.s1a.gp, self.s1a.cs, self.s1.gp, self.s1.cs)
+    stem = L["stem"]
+    bias_from(dxs, stem.name + ".bias")
+    wgrad(stem, self.d_stem, self.img4.p, self.s1.gp)
+    # ---- weight gradients back to the parameters' layout (one launch)
+    eng.unpack_wgrads(grads)
+    # offset-channel columns of the skip compress convs (the GEMM ran without them)
+    for sd in self.stages:
+      if sd["stage"] < 6 and sd["skip_c"]:
+        ls = sd["ls"]
+        grads[ls.name + ".weight"][:, ls.cin:, 0, 0] = sd["ssum"].t() @ self.offs
+
+  # ------------------------------------------------------------------ features (NCHW copies)
+  def features_nchw(self):
+    B = self.B
+    def nchw(b: Buf):
+      hw = b.spatial[0]
+      return b.v.view(B, hw, hw, b.cs)[..., :b.C].permute(0, 3, 1, 2).contiguous()
+    return (nchw(self.s1), nchw(self.enc_pre["stage2"]), nchw(self.enc_pre["stage3"]),
+            nchw(self.enc_pre["stage4"]), nchw(self.enc_pre["stage5"]), self.feat.v[:, :2048].clone())
+
+
+# ====================================================================== autograd bridge
+class _CoreNetFn(t.autograd.Function):
+  @staticmethod
+  def forward(ctx, model, need_grad, image, v2s, offsets, *params):
+    eng = get_engine(model)
+    plan = eng.get_plan(image.shape[0], image.device, need_grad)
+    logits = plan.forward(image, v2s, offsets, model.training)
+    if need_grad:
+      plan.busy = True
+      ctx.plan = plan
+      ctx.model = model
+    ctx.nparams = len(params)
+    return logits
+
+  @staticmethod
+  def backward(ctx, grad_logits):
+    plan, model = ctx.plan, ctx.model
+    eng = plan.eng
+    names = [n for n, _ in model.named_parameters()]
+    P, _ = eng.tensors()
+    grads = {n: t.zeros_like(P[n]) for n in names}
+    try:
+      plan.backward(grad_logits, grads)
+    finally:
+      plan.busy = False
+    return (None, None, None, None, None) + tuple(grads[n] for n in names)
+
+
+def get_engine(model) -> Engine:
+  eng = model.__dict__.get("_crn_engine")
+  if eng is None:
+    eng = Engine(model)
+    model.__dict__["_crn_engine"] = eng
+  return eng
+
+
+def corenet_forward(model, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor) -> t.Tensor:
+  if not image.is_cuda:
+    raise RuntimeError("corenet_b200.CoreNet runs on CUDA only (no CPU fallback); move the module and "
+                       "its inputs to a B200")
+  if image.dtype != t.uint8 or image.dim() != 4 or image.shape[1] != 3:
+    raise AssertionError("image must be uint8[B,3,H,W]")
+  if tuple(image.shape[2:]) != (256, 256):
+    raise ValueError("the encoder feature pyramid (256 -> 8) is fixed: image must be 256x256")
+  b = image.shape[0]
+  v2s = v2s.to(dtype=t.float32)
+  offsets = offsets.to(dtype=t.float32)
+  assert v2s.shape == (b, 4, 4) and offsets.shape == (b, 3)
+  params = list(model.parameters())
+  need_grad = t.is_grad_enabled() and any(p.requires_grad for p in params)
+  return _CoreNetFn.apply(model, need_grad, image.contiguous(), v2s.contiguous(), offsets.contiguous(),
+                          *params)
+
+
+def encoder_forward(encoder, image_f32: t.Tensor):
+  raise NotImplementedError(
+      "standalone encoder forward: use CoreNet.forward / CoreNet.encode_features (the engine fuses the "
+      "Caffe preprocessing into its staging kernel and takes the uint8 image)")

@@ -1,0 +1,252 @@
+/* corenet_b200 — C-ABI of the B200 (sm_100a) CoReNet hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a
+ * `cudaStream_t` (passed as void*), launches asynchronously on that stream and
+ * returns 0 on success or a negative `crn_status`.  No entry point allocates
+ * device memory, synchronises the device, or owns any of its arguments.
+ *
+ * Activation layout inside the path is channels-last ("rows x channels"):
+ *   2-D maps  [N, H, W, Cs]      3-D grids [N, D, H, W, Cs]
+ * with an explicit channel stride Cs (floats) and channel offset so that a
+ * producer can write straight into a slice of a wider (concat) buffer.
+ * Weights are consumed in a packed, tap-major layout produced by
+ * crn_pack_weights (see there).
+ *
+ * Each group cites the reference interface it replaces (paths relative to
+ * /root/reference/src/corenet).
+ */
+#ifndef CORENET_B200_H_
+#define CORENET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CRN_OK = 0,
+  CRN_ERR_BAD_ARG = -1,     /* shape / alignment / null pointer */
+  CRN_ERR_UNSUPPORTED = -2, /* valid request this build has no kernel for */
+  CRN_ERR_LAUNCH = -3       /* cudaGetLastError() after the launch was not cudaSuccess */
+} crn_status;
+
+/* Version + build info (arch string the kernels were compiled for). */
+int crn_version(void);
+const char* crn_build_arch(void);
+/* Text of the last error on this thread ("" if none). */
+const char* crn_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Convolutions.  Replaces the ATen/cuDNN calls behind nn.Conv2d / nn.Conv3d /
+ * nn.ConvTranspose3d / nn.Linear at model/resnet50.py:61-70,94-108,122-131,
+ * model/reconstruction_decoder.py:47-95 and
+ * model/ray_traced_skip_connection.py:38,85.
+ *
+ * One descriptor covers 2-D (D = 1, kD = 1) and 3-D, plain and transposed.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t N;               /* batch */
+  int32_t Cin, Cout;       /* logical channels of the conv (x has Cin, y has Cout) */
+  int32_t iD, iH, iW;      /* spatial dims of x */
+  int32_t oD, oH, oW;      /* spatial dims of y */
+  int32_t kD, kH, kW;      /* kernel */
+  int32_t stride;          /* same on every spatial axis with extent > 1 */
+  int32_t pad;             /* same on every axis with k > 1 */
+  int32_t transposed;      /* 0: y = conv(x)   1: y = conv_transpose(x) */
+  int32_t x_cs, x_co;      /* channel stride / offset of x rows (floats) */
+  int32_t y_cs, y_co;      /* channel stride / offset of y rows (floats) */
+  int32_t CinP, CoutP;     /* padded channel counts of the packed weights (multiples of 4) */
+  int32_t y_planar;        /* 1: y is NC(D)HW planar (only for fwd; used for the logits) */
+  int32_t bias_n_stride;   /* 0: bias[Cout]; else bias[n*bias_n_stride + co] (per-scene bias) */
+} crn_conv_desc;
+
+/* Packed weight layouts (floats):
+ *   fwd  : Wf[tap][CinP][CoutP]   tap = (kz*kH + ky)*kW + kx
+ *   dgrad: Wd[tap][CoutP][CinP]
+ * Source is the PyTorch parameter: conv [Cout][Cin][taps], transposed conv
+ * [Cin][Cout][taps], linear [Cout][Cin] (taps = 1). Padding entries are zero. */
+typedef struct {
+  const float* src;        /* parameter tensor */
+  float* dst_fwd;          /* may be NULL */
+  float* dst_dgrad;        /* may be NULL */
+  int32_t Cin, Cout, taps, CinP, CoutP;
+  int32_t src_is_transposed; /* 1: src is [Cin][Cout][taps] */
+} crn_pack_item;
+/* `items` is a DEVICE array of n items; total = sum(taps*CinP*CoutP) elements and
+ * `offsets` a DEVICE int64 array [n+1] of exclusive prefix sums of those sizes. */
+int crn_pack_weights(const crn_pack_item* items, const int64_t* offsets, int32_t n,
+                     int64_t total, void* stream);
+/* Inverse for gradients: grad_packed is Wf layout [tap][CinP][CoutP] (what
+ * crn_conv_wgrad writes); dst is the PyTorch layout of the parameter's .grad.
+ * Here offsets/total count DESTINATION elements (taps*Cin*Cout per item). */
+typedef struct {
+  const float* src_packed;
+  float* dst;
+  int32_t Cin, Cout, taps, CinP, CoutP;
+  int32_t dst_is_transposed;
+} crn_unpack_item;
+int crn_unpack_wgrads(const crn_unpack_item* items, const int64_t* offsets, int32_t n,
+                      int64_t total, void* stream);
+
+/* y = conv(x, Wf) + bias.           accumulate != 0: y += ... (bias ignored). */
+int crn_conv_fwd(const crn_conv_desc* d, const float* x, const float* w_fwd, const float* bias,
+                 float* y, int32_t accumulate, void* stream);
+/* dx = conv^T(dy, Wd) (the gradient wrt x of crn_conv_fwd with the same desc). */
+int crn_conv_dgrad(const crn_conv_desc* d, const float* dy, const float* w_dgrad, float* dx,
+                   int32_t accumulate, void* stream);
+/* dWf[tap][ci][co] += sum_rows x * dy.  dw must be zeroed by the caller
+ * before the first call (split-K partial sums are added atomically). */
+int crn_conv_wgrad(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed,
+                   void* stream);
+
+/* ------------------------------------------------------------------------
+ * Batch renormalisation.  Replaces model/batch_renorm.py:33-62.
+ * x is rows x C channels-last with channel stride x_cs.  `relu_in` applies
+ * ReLU to x before the statistics / normalisation (decoder order
+ * ReLU -> BRN -> conv, reconstruction_decoder.py:51-60).
+ * ---------------------------------------------------------------------- */
+/* acc: double[3*C]; [0,2C) zeroed by caller, receives sum(x-k), sum((x-k)^2); [2C,3C) receives the shift k
+ * (the channel's value in row 0). */
+int crn_brn_stats(const float* x, int64_t rows, int32_t C, int32_t x_cs, int32_t x_co,
+                  int32_t relu_in, double* acc, void* stream);
+/* Turns the sums into per-channel coefficients and updates the running
+ * statistics exactly like the reference (including the channel-count Bessel
+ * quirk and num_batches_tracked += 1).  coef: float[6*C] =
+ *   a (scale), b (shift), mean, invstd, r, d.   training==0: uses running stats only. */
+int crn_brn_finalize(const double* acc, int64_t rows, int32_t C, const float* weight,
+                     const float* bias, float* running_mean, float* running_var,
+                     int64_t* num_batches_tracked, float eps, float momentum, int32_t training,
+                     float* coef, void* stream);
+/* y = act( a*f(x) + b [+ res] ),  f = relu if relu_in.  If y_pre != NULL the
+ * pre-activation value is stored there too (encoder skip taps,
+ * resnet50.py:76-80).  relu_out: apply ReLU to y. */
+int crn_brn_apply(const float* x, int64_t rows, int32_t C, int32_t x_cs, int32_t x_co,
+                  const float* coef, const float* res, int32_t relu_in, int32_t relu_out,
+                  float* y, int32_t y_cs, int32_t y_co, float* y_pre, void* stream);
+/* Backward, pass 1: g = dy * (relu_out ? y>0 : 1) [+ g_extra]; accumulates
+ * sum(g) and sum(g*xhat) per channel into acc (double[2*C], zeroed by caller).
+ * If g_out != NULL the masked/combined g is stored (it is the residual
+ * branch's gradient). */
+int crn_brn_bwd_reduce(const float* dy, int32_t dy_cs, int32_t dy_co, const float* y_act,
+                       const float* g_extra, const float* x, int32_t x_cs, int32_t x_co,
+                       int64_t rows, int32_t C, const float* coef, int32_t relu_in,
+                       int32_t relu_out, float* g_out, double* acc, void* stream);
+/* Backward, pass 2: dx = (relu_in ? x>0 : 1) * a' * (g - S1/R - xhat*S2/R)  (training)
+ *                   dx = (relu_in ? x>0 : 1) * a * g                       (eval)
+ * Also writes dweight, dbias (float[C]) and accumulates column sums of dx into
+ * dxsum (double[C], zeroed by caller; it is the preceding conv's bias gradient)
+ * when dxsum != NULL.  g is the masked gradient (g_out of pass 1, or dy when no mask). */
+int crn_brn_bwd_dx(const float* g, int32_t g_cs, int32_t g_co, const float* x, int32_t x_cs,
+                   int32_t x_co, int64_t rows, int32_t C, const float* coef, const double* acc,
+                   const float* weight, int32_t relu_in, int32_t training, float* dx,
+                   int32_t dx_cs, int32_t dx_co, int32_t dx_accumulate, float* dweight,
+                   float* dbias, double* dxsum, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Small encoder ops (model/resnet50.py:134-140,176-204).
+ * ---------------------------------------------------------------------- */
+/* u8 NCHW RGB -> f32 NHWC4 BGR + Caffe mean (added, bug-for-bug), 4th channel 0. */
+int crn_preprocess_image(const uint8_t* image, int32_t N, int32_t H, int32_t W, float* out,
+                         void* stream);
+/* ZeroPad2d(1) + MaxPool2d(3, stride 2) on NHWC (input is post-ReLU). idx: int8 argmax tap. */
+int crn_maxpool_fwd(const float* x, int32_t N, int32_t H, int32_t W, int32_t C, float* y,
+                    int8_t* idx, void* stream);
+int crn_maxpool_bwd(const float* dy, const int8_t* idx, int32_t N, int32_t H, int32_t W,
+                    int32_t C, float* dx, void* stream);
+/* y[n][c] = mean over HW of x[n][hw][c];  bwd: dx[n][hw][c] (+)= dy[n][c]/HW */
+int crn_spatial_mean_fwd(const float* x, int32_t N, int32_t HW, int32_t C, float* y, void* stream);
+int crn_spatial_mean_bwd(const float* dy, int32_t N, int32_t HW, int32_t C, float* dx,
+                         int32_t accumulate, void* stream);
+/* out[c] = sum over rows of x[row][c] (double accumulators, out is float[C]). */
+int crn_colsum(const float* x, int64_t rows, int32_t C, int32_t x_cs, int32_t x_co, float* out,
+               double* scratch, void* stream);
+/* planar variant: x is [N][C][S]; out[c] = sum_n sum_s */
+int crn_colsum_planar(const float* x, int32_t N, int32_t C, int64_t S, float* out, double* scratch,
+                      void* stream);
+/* planar [N][C][S] -> channels-last rows [N*S][CP] (zero padded), for the logits gradient. */
+int crn_planar_to_rows(const float* x, int32_t N, int32_t C, int64_t S, int32_t CP, float* out,
+                       void* stream);
+
+/* ------------------------------------------------------------------------
+ * Ray-traced skip connection.  Replaces the index/gather part of
+ * SampleGrid2d.forward, model/ray_traced_skip_connection.py:91-142, and the
+ * torch.cat at model/reconstruction_decoder.py:117.
+ *   map   : compressed 2-D map, channels-last [N, h, w, map_cs]
+ *   m     : float[N*16] row-major layer matrix (v2s @ scale(res/g))
+ *   offs  : float[N*3] voxel sample offsets
+ *   out   : 3-D grid [N, g, g, g, out_cs]; writes channels [out_co, out_co+C)
+ * Nearest-pixel with truncation toward zero, clamp into the 1-px border
+ * (= outside_value 0), zero behind the camera: bit-exact data movement.
+ * ---------------------------------------------------------------------- */
+int crn_skip_sample_fwd(const float* map, int32_t N, int32_t h, int32_t w, int32_t C,
+                        int32_t map_cs, const float* m, const float* offs, int32_t gD, int32_t gH,
+                        int32_t gW, float* out, int32_t out_cs, int32_t out_co, void* stream);
+/* dmap (zeroed by caller) += scatter of dout channels [out_co, out_co+C). */
+int crn_skip_sample_bwd(const float* dout, int32_t out_cs, int32_t out_co, int32_t N, int32_t h,
+                        int32_t w, int32_t C, int32_t map_cs, const float* m, const float* offs,
+                        int32_t gD, int32_t gH, int32_t gW, float* dmap, void* stream);
+/* The int32 pixel index (iy*(w+2)+ix into the padded map, or -1 behind the
+ * camera) for every voxel: test/debug hook for bit-exact index parity. */
+int crn_skip_indices(int32_t N, int32_t h, int32_t w, const float* m, const float* offs,
+                     int32_t gD, int32_t gH, int32_t gW, int32_t* idx, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Losses on planar logits [N, C, S].  Replaces model/losses.py:64-114
+ * (iou_fgbg) and :144-160 (xent_times_iou_agnostic).  gt: int32 or int64 [N,S].
+ * Pass 1 accumulates per-scene sums (double[N*4]: inter, union, xent, -);
+ * the scalar combination is done by the host wrapper; pass 2 writes dlogits.
+ * ---------------------------------------------------------------------- */
+int crn_loss_sums(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N, int32_t C,
+                  int64_t S, int32_t mode /*0 fgbg, 1 agnostic+xent*/, double* sums, void* stream);
+/* loss[0] and coef float[2N+1] = (dL/dI_n, dL/dU_n)..., dL/d(sum xent) from the per-scene sums. */
+int crn_loss_finalize(const double* sums, int32_t N, int32_t C, int64_t S, int32_t mode, float* loss,
+                      float* coef, void* stream);
+/* dlogits = gscale * (coef-weighted derivative); gscale: device float (upstream grad) or NULL = 1. */
+int crn_loss_bwd(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N, int32_t C,
+                 int64_t S, int32_t mode, const float* coef, const float* gscale, float* dlogits,
+                 void* stream);
+/* Eval: softmax over C (planar) and argmax -> confusion matrix counts
+ * (evaluation_results.py:249-254, voxel_metrics.py:33-58).  cm: int64[C*C] zeroed by caller. */
+int crn_softmax_planar(const float* logits, int32_t N, int32_t C, int64_t S, float* pmf,
+                       void* stream);
+int crn_argmax_confusion(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N,
+                         int32_t C, int64_t S, int64_t* cm, void* stream);
+
+/* ------------------------------------------------------------------------
+ * fill_inside_voxels.  Replaces cc/fill_voxels_gpu.cu:136-171 (kernels
+ * :96-132) / cc/fill_voxels_cpu.cc:158-183.  grid: [N, D, H, W] of `elem_size`
+ * byte elements of kind `dtype_kind` (0 = signed int, 1 = float, 2 = unsigned int);
+ * any value > 0 is occupied.  Every voxel is overwritten with 0/1 in the
+ * element type.  Empty voxels connected (6-neighbourhood) to the x=0, y=0 or
+ * z=0 faces stay 0 (near-face rule, bug-for-bug); all others become 1.
+ * workspace: crn_fill_workspace_bytes(N,D,H,W) bytes.
+ * ---------------------------------------------------------------------- */
+int64_t crn_fill_workspace_bytes(int32_t N, int32_t D, int32_t H, int32_t W);
+int crn_fill_inside(const void* grid_in, void* grid_out, int32_t elem_size, int32_t dtype_kind,
+                    int32_t N, int32_t D, int32_t H, int32_t W, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------
+ * voxelize_mesh.  Replaces geometry/voxelization.py:32-164 +
+ * geometry/shaders/voxelize.geom:37-60 + voxelize.frag:29-58 (the EGL/GLSL
+ * rasteriser).  triangles: float[T*9] view space; tri_mesh: int32[T] mesh id;
+ * view2voxel: float[M*16] row-major.  grid: float[M, gD, gH, gW] ZEROED by the
+ * caller, where (gD,gH,gW) = (D,H,W) or (2D+1,2H+1,2W+1) with sub_grid != 0.
+ * ---------------------------------------------------------------------- */
+int crn_voxelize_mesh(const float* triangles, const int32_t* tri_mesh, int32_t T,
+                      const float* view2voxel, int32_t M, int32_t D, int32_t H, int32_t W,
+                      int32_t image_resolution, int32_t depth_mult, int32_t sub_grid_side,
+                      int32_t conservative, float* grid, void* stream);
+/* grid[b] = max_m(label_m * occ_m) as int32 (data/batched_example.py:186-196).
+ * mesh_scene: int32[M] scene index per mesh; labels: float[M]. out zeroed by caller. */
+int crn_merge_mesh_grids(const float* mesh_grids, const int32_t* mesh_scene, const float* labels,
+                         int32_t M, int64_t voxels, int32_t* out, void* stream);
+
+/* Fused Adam step over a flat list (state.py:65-66) — next-row (f2) op. */
+int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORENET_B200_H_ */
