@@ -3,7 +3,11 @@
 #include <string.h>
 #include "common.cuh"
 
+#include <atomic>
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void crn_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" int64_t crn_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 void crn_set_error(const char* fmt, ...) {
   va_list ap;

@@ -423,7 +423,7 @@ extern "C" int crn_brn_finalize(const double* acc, int64_t rows, int32_t C, cons
   brn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, rows, C, weight, bias, running_mean,
                                                        running_var, num_batches_tracked, eps, momentum,
                                                        training, coef);
-  if (training) brn_bump_counter<<<1, 1, 0, st>>>(num_batches_tracked);
+  if (training) { brn_bump_counter<<<1, 1, 0, st>>>(num_batches_tracked); crn_count_launches(1); }
   CRN_LAUNCH_CHECK("brn_finalize");
   return CRN_OK;
 }
@@ -504,6 +504,7 @@ extern "C" int crn_colsum(const float* x, int64_t rows, int32_t C, int32_t x_cs,
     colsum_kernel<1><<<g.grid, NT, 0, st>>>(x, rows, C, x_cs, x_co, scratch, g.txc);
   }
   f64_to_f32_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, out, C);
+  crn_count_launches(1);
   CRN_LAUNCH_CHECK("colsum");
   return CRN_OK;
 }
@@ -517,6 +518,7 @@ extern "C" int crn_colsum_planar(const float* x, int32_t N, int32_t C, int64_t S
   if (chunks > 64) chunks = 64;
   colsum_planar_kernel<<<dim3((unsigned)chunks, C, N), NT, 0, st>>>(x, N, C, S, scratch);
   f64_to_f32_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, out, C);
+  crn_count_launches(1);
   CRN_LAUNCH_CHECK("colsum_planar");
   return CRN_OK;
 }

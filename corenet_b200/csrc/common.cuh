@@ -6,6 +6,7 @@
 #include "corenet_b200.h"
 
 void crn_set_error(const char* fmt, ...);
+void crn_count_launches(int n);   // bumps the process-wide kernel launch counter
 
 #define CRN_REQUIRE(cond, ...)            \
   do {                                    \
@@ -22,6 +23,7 @@ void crn_set_error(const char* fmt, ...);
       crn_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
       return CRN_ERR_LAUNCH;                                                \
     }                                                                       \
+    crn_count_launches(1);                                                  \
   } while (0)
 
 static inline cudaStream_t crn_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

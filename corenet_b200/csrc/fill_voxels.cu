@@ -221,6 +221,7 @@ extern "C" int crn_fill_inside(const void* grid_in, void* grid_out, int32_t elem
     default: fill_flood_kernel<8><<<N, threads, 0, st>>>(E, R, D, H); break;
   }
   fill_unpack_kernel<<<grid_for(rows * W), NT, 0, st>>>(R, elem_size, dtype_kind, rows, W, nw, grid_out);
+  crn_count_launches(2);
   CRN_LAUNCH_CHECK("fill_inside");
   return CRN_OK;
 }

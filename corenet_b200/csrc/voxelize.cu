@@ -39,9 +39,9 @@ __device__ __forceinline__ void setup_triangle(const float* __restrict__ tri, co
     const float x = tri[k * 3 + 0], y = tri[k * 3 + 1], z = tri[k * 3 + 2];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      float t = __fmul_rn(M[r * 4 + 0], x);
-      t = __fmaf_rn(M[r * 4 + 1], y, t);
-      t = __fmaf_rn(M[r * 4 + 2], z, t);
+      // ((m0*x + m1*y) + m2*z) + m3, every step rounded to fp32 (no FMA contraction)
+      float t = __fadd_rn(__fmul_rn(M[r * 4 + 0], x), __fmul_rn(M[r * 4 + 1], y));
+      t = __fadd_rn(t, __fmul_rn(M[r * 4 + 2], z));
       s.v[k][r] = __fadd_rn(t, M[r * 4 + 3]);
     }
   }
@@ -50,15 +50,15 @@ __device__ __forceinline__ void setup_triangle(const float* __restrict__ tri, co
   float n1 = 0.f, n2 = 0.f;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    e1[r] = s.v[1][r] - s.v[0][r]; e2[r] = s.v[2][r] - s.v[0][r];
-    n1 += e1[r] * e1[r]; n2 += e2[r] * e2[r];
+    e1[r] = __fsub_rn(s.v[1][r], s.v[0][r]); e2[r] = __fsub_rn(s.v[2][r], s.v[0][r]);
+    n1 = __fadd_rn(n1, __fmul_rn(e1[r], e1[r])); n2 = __fadd_rn(n2, __fmul_rn(e2[r], e2[r]));
   }
-  n1 = sqrtf(n1); n2 = sqrtf(n2);
+  n1 = __fsqrt_rn(n1); n2 = __fsqrt_rn(n2);
 #pragma unroll
-  for (int r = 0; r < 3; ++r) { e1[r] /= n1; e2[r] /= n2; }
-  const float nx = fabsf(e1[1] * e2[2] - e1[2] * e2[1]);
-  const float ny = fabsf(e1[2] * e2[0] - e1[0] * e2[2]);
-  const float nz = fabsf(e1[0] * e2[1] - e1[1] * e2[0]);
+  for (int r = 0; r < 3; ++r) { e1[r] = __fdiv_rn(e1[r], n1); e2[r] = __fdiv_rn(e2[r], n2); }
+  const float nx = fabsf(__fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1])));
+  const float ny = fabsf(__fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2])));
+  const float nz = fabsf(__fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0])));
   int axA = 0, axB = 1;                                  // screen = (X, Y), depth Z
   if (nx > ny && nx > nz) { axA = 1; axB = 2; }          // .yzxw: screen = (Y, Z), depth X
   else if (ny > nx && ny > nz) { axA = 2; axB = 0; }     // .zxyw: screen = (Z, X), depth Y
@@ -67,11 +67,11 @@ __device__ __forceinline__ void setup_triangle(const float* __restrict__ tri, co
   long long mnU = LLONG_MAX, mxU = LLONG_MIN, mnV = LLONG_MAX, mxV = LLONG_MIN;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    s.u[k] = (double)s.v[k][axA] * (double)R / ext[axA];
-    s.w[k] = (double)s.v[k][axB] * (double)R / ext[axB];
+    s.u[k] = __ddiv_rn(__dmul_rn((double)s.v[k][axA], (double)R), ext[axA]);
+    s.w[k] = __ddiv_rn(__dmul_rn((double)s.v[k][axB], (double)R), ext[axB]);
     if (!(fabs(s.u[k]) < 1e9) || !(fabs(s.w[k]) < 1e9)) return;   // NaN / absurd
-    s.U[k] = llrint(s.u[k] * 256.0);
-    s.V[k] = llrint(s.w[k] * 256.0);
+    s.U[k] = llrint(__dmul_rn(s.u[k], 256.0));
+    s.V[k] = llrint(__dmul_rn(s.w[k], 256.0));
     mnU = min(mnU, s.U[k]); mxU = max(mxU, s.U[k]);
     mnV = min(mnV, s.V[k]); mxV = max(mxV, s.V[k]);
   }
@@ -87,9 +87,10 @@ __device__ __forceinline__ void setup_triangle(const float* __restrict__ tri, co
     s.C[k] = -(s.A[k] * s.U[a] + s.B[k] * s.V[a]);
     s.tl[k] = s.A[k] > 0 || (s.A[k] == 0 && s.B[k] > 0);
   }
-  const double area_d = (s.u[1] - s.u[0]) * (s.w[2] - s.w[0]) - (s.w[1] - s.w[0]) * (s.u[2] - s.u[0]);
+  const double area_d = __dsub_rn(__dmul_rn(s.u[1] - s.u[0], s.w[2] - s.w[0]),
+                                  __dmul_rn(s.w[1] - s.w[0], s.u[2] - s.u[0]));
   if (area_d == 0.0) return;
-  s.inv_area = 1.0 / area_d;
+  s.inv_area = area_d;   // (kept as the area; the barycentrics divide by it)
   long long i0, i1, j0, j1;
   auto fdiv = [](long long a, long long b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); };  // floor
   auto cdiv = [&](long long a, long long b) { return -fdiv(-a, b); };                            // ceil
@@ -111,13 +112,16 @@ __device__ __forceinline__ void shade_fragment(const TriSetup& s, int i, int j, 
                                                int side, float* __restrict__ grid) {
   // attribute interpolation at the pixel centre
   const double su = i + 0.5, sv = j + 0.5;
-  const double l1 = ((su - s.u[0]) * (s.w[2] - s.w[0]) - (sv - s.w[0]) * (s.u[2] - s.u[0])) * s.inv_area;
-  const double l2 = ((s.u[1] - s.u[0]) * (sv - s.w[0]) - (s.w[1] - s.w[0]) * (su - s.u[0])) * s.inv_area;
-  const double l0 = 1.0 - l1 - l2;
+  const double l1 = __ddiv_rn(__dsub_rn(__dmul_rn(su - s.u[0], s.w[2] - s.w[0]),
+                                        __dmul_rn(sv - s.w[0], s.u[2] - s.u[0])), s.inv_area);
+  const double l2 = __ddiv_rn(__dsub_rn(__dmul_rn(s.u[1] - s.u[0], sv - s.w[0]),
+                                        __dmul_rn(s.w[1] - s.w[0], su - s.u[0])), s.inv_area);
+  const double l0 = (1.0 - l1) - l2;
   float p[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
-    p[r] = (float)(l0 * (double)s.v[0][r] + l1 * (double)s.v[1][r] + l2 * (double)s.v[2][r]);
+    p[r] = (float)__dadd_rn(__dadd_rn(__dmul_rn(l0, (double)s.v[0][r]), __dmul_rn(l1, (double)s.v[1][r])),
+                            __dmul_rn(l2, (double)s.v[2][r]));
   // voxelize.frag:36-38
   if (p[0] < 0 || p[1] < 0 || p[2] < 0 || p[0] >= (float)W || p[1] >= (float)H || p[2] >= (float)D) return;
   if (side <= 0) {
@@ -127,7 +131,7 @@ __device__ __forceinline__ void shade_fragment(const TriSetup& s, int i, int j, 
     int c[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int v = (int)floorf(p[r] * (float)side) + side / 2;
+      const int v = (int)floorf(__fmul_rn(p[r], (float)side)) + side / 2;
       c[r] = 2 * (v / side) + ((v % side) == side - 1 ? 1 : 0);
     }
     grid[(((int64_t)mesh * (2 * D + 1) + c[2]) * (2 * H + 1) + c[1]) * (2 * W + 1) + c[0]] = 1.0f;

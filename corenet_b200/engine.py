@@ -41,6 +41,30 @@ def _call(name, *args):
   _lib.call(name, *args)
 
 
+# bench.py sets this to a list to time every convolution launch with CUDA events:
+# entries are (kind, layer name, MACs, start event, end event).
+PROFILE = None
+_CONV_FN = {"fwd": "crn_conv_fwd", "dgrad": "crn_conv_dgrad", "wgrad": "crn_conv_wgrad"}
+
+
+def conv_macs(d: ConvDesc) -> int:
+  """Algorithmic multiply-accumulates of one conv launch (same for fwd, dgrad and wgrad)."""
+  taps = d.kD * d.kH * d.kW
+  pos = d.iD * d.iH * d.iW if d.transposed else d.oD * d.oH * d.oW
+  return d.N * pos * taps * d.Cin * d.Cout
+
+
+def conv_call(kind, layer, d, *args):
+  if PROFILE is None:
+    _lib.call(_CONV_FN[kind], C.byref(d), *args)
+    return
+  e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+  e0.record()
+  _lib.call(_CONV_FN[kind], C.byref(d), *args)
+  e1.record()
+  PROFILE.append((kind, layer.name, conv_macs(d), e0, e1))
+
+
 class Buf:
   """rows x C activation, channels-last with channel stride cs; .g is its gradient."""
 
@@ -430,22 +454,22 @@ class Plan:
       self.arena_fwd.zero_()
     # ---- encoder
     _call("crn_preprocess_image", image.data_ptr(), B, 256, 256, self.img4.p, st)
-    _call("crn_conv_fwd", C.byref(self.d_stem), self.img4.p, eng.wf(eng.L["stem"]), bias(eng.L["stem"]),
-          self.s1.p, 0, st)
+    conv_call("fwd", eng.L["stem"], self.d_stem, self.img4.p, eng.wf(eng.L["stem"]), bias(eng.L["stem"]),
+              self.s1.p, 0, st)
     self.brn_stem.fwd(training)
     _call("crn_maxpool_fwd", self.s1a.p, B, 128, 128, 64, self.p1.p, self.p1_idx.data_ptr(), st)
     for blk in self.blocks:
       x = blk["x"]
       if blk["down"]:
-        _call("crn_conv_fwd", C.byref(blk["d_s"]), x.p, eng.wf(blk["ls"]), bias(blk["ls"]), blk["s_c"].p, 0, st)
+        conv_call("fwd", blk["ls"], blk["d_s"], x.p, eng.wf(blk["ls"]), bias(blk["ls"]), blk["s_c"].p, 0, st)
         blk["bn_s"].fwd(training)
-      _call("crn_conv_fwd", C.byref(blk["d_a"]), x.p, eng.wf(blk["la"]), bias(blk["la"]), blk["a_c"].p, 0, st)
+      conv_call("fwd", blk["la"], blk["d_a"], x.p, eng.wf(blk["la"]), bias(blk["la"]), blk["a_c"].p, 0, st)
       blk["bn_a"].fwd(training)
-      _call("crn_conv_fwd", C.byref(blk["d_b"]), blk["a_y"].p, eng.wf(blk["lb"]), bias(blk["lb"]),
-            blk["b_c"].p, 0, st)
+      conv_call("fwd", blk["lb"], blk["d_b"], blk["a_y"].p, eng.wf(blk["lb"]), bias(blk["lb"]),
+                blk["b_c"].p, 0, st)
       blk["bn_b"].fwd(training)
-      _call("crn_conv_fwd", C.byref(blk["d_c"]), blk["b_y"].p, eng.wf(blk["lc"]), bias(blk["lc"]),
-            blk["c_c"].p, 0, st)
+      conv_call("fwd", blk["lc"], blk["d_c"], blk["b_y"].p, eng.wf(blk["lc"]), bias(blk["lc"]),
+                blk["c_c"].p, 0, st)
       blk["bn_c"].fwd(training)
     _call("crn_spatial_mean_fwd", self.enc_out.p, B, 64, 2048, self.feat.p, st)
     if want_features:
@@ -453,12 +477,12 @@ class Plan:
     # ---- decoder
     L = eng.L
     lat = eng.lat
-    _call("crn_conv_fwd", C.byref(self.d_s0), self.feat.p, eng.wf(L["stage_0"]), bias(L["stage_0"]),
-          self.latb.p, 0, st)
+    conv_call("fwd", L["stage_0"], self.d_s0, self.feat.p, eng.wf(L["stage_0"]), bias(L["stage_0"]),
+              self.latb.p, 0, st)
     self.latb.v[:, lat:lat + 3].copy_(offsets)
     self.brn_s1.fwd(training)
-    _call("crn_conv_fwd", C.byref(self.d_s1t), self.z1.p, eng.wf(L["stage_1.t1"]), bias(L["stage_1.t1"]),
-          self.x1.p, 0, st)
+    conv_call("fwd", L["stage_1.t1"], self.d_s1t, self.z1.p, eng.wf(L["stage_1.t1"]), bias(L["stage_1.t1"]),
+              self.x1.p, 0, st)
     # per-scale layer matrices (reconstruction_decoder.py:111-115) and offsets
     self.offs = offsets.contiguous()
     res = eng.model.config.decoder.resolution
@@ -466,18 +490,18 @@ class Plan:
     for sd in self.stages:
       g = sd["g"]
       sd["bn1"].fwd(training)
-      _call("crn_conv_fwd", C.byref(sd["d_c"]), sd["z"].p, eng.wf(sd["lc"]), bias(sd["lc"]), sd["c"].p, 0, st)
+      conv_call("fwd", sd["lc"], sd["d_c"], sd["z"].p, eng.wf(sd["lc"]), bias(sd["lc"]), sd["c"].p, 0, st)
       sd["bn2"].fwd(training)
       if sd["stage"] < 6:
         nxt = sd["next"]
-        _call("crn_conv_fwd", C.byref(sd["d_t"]), sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]), nxt.p, 0, st)
+        conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]), nxt.p, 0, st)
         if sd["skip_c"]:
           ls, src, cmap, hw = sd["ls"], sd["src"], sd["cmap"], sd["hw"]
           w = P[ls.name + ".weight"]
           # the 3 offset channels are constant per scene -> exact per-scene bias
           sbias = (P[ls.name + ".bias"][None, :] + offsets @ w[:, ls.cin:, 0, 0].t()).contiguous()
           sd["sbias"] = sbias
-          _call("crn_conv_fwd", C.byref(sd["d_s"]), src.p, eng.wf(ls), sbias.data_ptr(), cmap.p, 0, st)
+          conv_call("fwd", ls, sd["d_s"], src.p, eng.wf(ls), sbias.data_ptr(), cmap.p, 0, st)
           g2 = 2 * g
           scale = t.diag(t.tensor([res[0] / g2, res[1] / g2, res[2] / g2, 1.0], dtype=t.float32, device=self.dev))
           mat = v2s.matmul(scale).contiguous()
@@ -487,8 +511,8 @@ class Plan:
       else:
         g2 = 2 * g
         logits = t.empty(B, sd["t_out"], g2, g2, g2, dtype=t.float32, device=self.dev)
-        _call("crn_conv_fwd", C.byref(sd["d_t"]), sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]),
-              logits.data_ptr(), 0, st)
+        conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]),
+                  logits.data_ptr(), 0, st)
     return logits
 
   # ------------------------------------------------------------------ backward
@@ -508,10 +532,10 @@ class Plan:
       grads[name].copy_(v[lo:lo + n])
 
     def wgrad(l, d, x_ptr, dy_ptr):
-      _call("crn_conv_wgrad", C.byref(d), x_ptr, dy_ptr, eng.dwp(l), st)
+      conv_call("wgrad", l, d, x_ptr, dy_ptr, eng.dwp(l), st)
 
     def dgrad(l, d, dy_ptr, dx_ptr, acc=0):
-      _call("crn_conv_dgrad", C.byref(d), dy_ptr, eng.wd(l), dx_ptr, acc, st)
+      conv_call("dgrad", l, d, dy_ptr, eng.wd(l), dx_ptr, acc, st)
 
     # ---- decoder, last stage first
     grad_logits = grad_logits.contiguous()

@@ -1,0 +1,102 @@
+"""Data-parallel training step (SURVEY §8 rows e, f2): one process per GPU, scenes sharded by rank,
+ONE NCCL all-reduce over a flat fp32 gradient buffer, one fused Adam launch.
+
+Host-side mirror of TrainPipeline._process_batch (src/corenet/pipeline.py:215-240 of the reference:
+zero_grad -> model -> loss -> backward [DDP all-reduce] -> Adam step) and of the fixed-seed index
+shard of distributed.DistributedSampler (src/corenet/distributed.py:204-230).
+"""
+from typing import Optional
+
+import torch as t
+
+from corenet_b200 import _lib
+from corenet_b200 import engine as engine_lib
+
+_call = _lib.call
+
+
+def shard_indices(num_items: int, rank: int, world: int, pad: bool = True):
+  """Rank-strided shard of range(num_items) (distributed.py:204-224): rank r gets r, r+world, ...;
+  with pad=True the tail is padded by wrapping so that every rank gets the same count."""
+  idx = list(range(num_items))
+  if pad and num_items % world:
+    idx += idx[:world - num_items % world]
+  return idx[rank::world]
+
+
+def flatten_parameters(model: t.nn.Module):
+  """Re-points every parameter at a view of ONE flat fp32 buffer (names/shapes/state_dict unchanged)."""
+  params = list(model.parameters())
+  total = sum(p.numel() for p in params)
+  flat = t.empty(total, dtype=t.float32, device=params[0].device)
+  off = 0
+  views = []
+  for p in params:
+    n = p.numel()
+    v = flat[off:off + n].view(p.shape)
+    v.copy_(p.data)
+    p.data = v
+    views.append((off, n))
+    off += n
+  return flat, views
+
+
+class Trainer:
+  """Owns the flat parameter / gradient / Adam-moment buffers of a CoreNet and runs train steps."""
+
+  def __init__(self, model, lr: float = 4e-4, eps: float = 1e-4, betas=(0.9, 0.999),
+               loss: str = "iou_fgbg", process_group=None):
+    self.model = model
+    self.lr, self.eps, self.betas = lr, eps, betas
+    self.mode = {"iou_fgbg": 0, "xent_times_iou_agnostic": 1}[loss]
+    self.pg = process_group
+    self.world = t.distributed.get_world_size(process_group) if t.distributed.is_initialized() else 1
+    self.flat, self.views = flatten_parameters(model)
+    eng = engine_lib.get_engine(model)
+    eng.invalidate()
+    self.eng = eng
+    self.grad = t.zeros_like(self.flat)
+    self.m = t.zeros_like(self.flat)
+    self.v = t.zeros_like(self.flat)
+    self.step_count = 0
+    self.names = [n for n, _ in model.named_parameters()]
+    self.grads = {}
+    for (off, n), (name, p) in zip(self.views, model.named_parameters()):
+      self.grads[name] = self.grad[off:off + n].view(p.shape)
+    self._loss_bufs = {}
+
+  def _bufs(self, b, c, dev):
+    key = (b, c)
+    if key not in self._loss_bufs:
+      self._loss_bufs[key] = dict(
+          sums=t.empty(4 * b, dtype=t.float64, device=dev), loss=t.empty(1, dtype=t.float32, device=dev),
+          coef=t.empty(2 * b + 1, dtype=t.float32, device=dev),
+          dlogits=t.empty(b, c, 128, 128, 128, dtype=t.float32, device=dev))
+    return self._loss_bufs[key]
+
+  def step(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, gt: t.Tensor) -> t.Tensor:
+    """One optimisation step on this rank's scenes; returns the (device) loss scalar."""
+    model, eng = self.model, self.eng
+    st = _lib.stream_ptr()
+    b = image.shape[0]
+    plan = eng.get_plan(b, image.device, True)
+    logits = plan.forward(image, v2s, offsets, model.training)
+    c = logits.shape[1]
+    s = logits[0, 0].numel()
+    lb = self._bufs(b, c, image.device)
+    is64 = int(gt.dtype == t.int64)
+    _call("crn_loss_sums", logits.data_ptr(), gt.data_ptr(), is64, b, c, s, self.mode, lb["sums"].data_ptr(), st)
+    _call("crn_loss_finalize", lb["sums"].data_ptr(), b, c, s, self.mode, lb["loss"].data_ptr(),
+          lb["coef"].data_ptr(), st)
+    _call("crn_loss_bwd", logits.data_ptr(), gt.data_ptr(), is64, b, c, s, self.mode, lb["coef"].data_ptr(),
+          None, lb["dlogits"].data_ptr(), st)
+    plan.backward(lb["dlogits"], self.grads)
+    if self.world > 1:
+      # the path's single exchange step: sum-all-reduce of the flat gradient (DDP averages -> 1/world below)
+      t.distributed.all_reduce(self.grad, op=t.distributed.ReduceOp.SUM, group=self.pg)
+    self.step_count += 1
+    _call("crn_adam_step", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+          self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
+          1.0 / self.world, st)
+    eng._ver_sig = None        # the fused Adam kernel changed the weights: re-pack on the next forward
+    return lb["loss"]

@@ -36,6 +36,8 @@ int crn_version(void);
 const char* crn_build_arch(void);
 /* Text of the last error on this thread ("" if none). */
 const char* crn_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py gpu_launches). */
+int64_t crn_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * Convolutions.  Replaces the ATen/cuDNN calls behind nn.Conv2d / nn.Conv3d /

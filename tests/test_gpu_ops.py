@@ -1,0 +1,418 @@
+"""Per-kernel parity on a real B200: every C-ABI op against the CPU oracle.
+
+Integer / index / data-movement ops: bit-exact.  fp32 arithmetic ops: relative
+tolerances written next to each assert (the kernels use fp32 FFMA; only the
+summation order differs from the oracle).
+"""
+import zlib
+
+import numpy as np
+import pytest
+import torch as t
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import corenet_oracle as O
+from oracle import fill_voxels_oracle as FO
+from oracle import voxelize_oracle as VO
+from tests.conftest import cube_mesh, fill_test_grids
+from tests.test_oracle_losses import GT, LOGITS
+
+
+def dev():
+  return t.device("cuda", 0)
+
+
+def rel_err(a: t.Tensor, b: t.Tensor) -> float:
+  """max|a-b| / max|b| (SURVEY 8d parity metric)."""
+  a, b = a.detach().double().cpu(), b.detach().double().cpu()
+  return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+# ---------------------------------------------------------------------------- convolutions
+CONV_CASES = [
+    # (name, x shape NC.., weight shape, stride, pad, transposed, output_padding)
+    ("1x1", (2, 64, 16, 16), (96, 64, 1, 1), 1, 0, False, 0),
+    ("1x1_s2", (2, 64, 16, 16), (128, 64, 1, 1), 2, 0, False, 0),
+    ("3x3", (2, 32, 14, 14), (48, 32, 3, 3), 1, 1, False, 0),
+    ("stem7x7_s2_cin3", (2, 3, 40, 40), (64, 3, 7, 7), 2, 3, False, 0),
+    ("small_cout", (1, 28, 12, 12, 12), (16, 28, 5, 5, 5), 1, 2, False, 0),
+    ("3d_k3", (2, 16, 6, 6, 6), (24, 16, 3, 3, 3), 1, 1, False, 0),
+    ("3d_k5_wide", (1, 56, 8, 8, 8), (132, 56, 5, 5, 5), 1, 2, False, 0),
+    ("convT_k7_s2", (1, 16, 6, 6, 6), (16, 12, 7, 7, 7), 2, 3, True, 1),
+    ("convT_k3_s2", (2, 32, 4, 4, 4), (32, 20, 3, 3, 3), 2, 1, True, 1),
+    ("convT_k4_s4_latent", (3, 67, 1, 1, 1), (67, 40, 4, 4, 4), 4, 0, True, 0),
+    ("convT_cout2", (1, 16, 8, 8, 8), (16, 2, 7, 7, 7), 2, 3, True, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_fwd_bwd(case):
+  from corenet_b200 import ops
+  name, xs, ws, stride, pad, transposed, opad = case
+  g = t.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+  x = t.randn(xs, generator=g)
+  w = t.randn(ws, generator=g) * 0.1
+  cout = ws[1] if transposed else ws[0]
+  b = t.randn(cout, generator=g)
+  nd = len(xs) - 2
+  x_o, w_o, b_o = [v.clone().requires_grad_(True) for v in (x, w, b)]
+  if transposed:
+    y_o = F.conv_transpose3d(x_o, w_o, b_o, stride=stride, padding=pad, output_padding=opad)
+  else:
+    y_o = (F.conv2d if nd == 2 else F.conv3d)(x_o, w_o, b_o, stride=stride, padding=pad)
+  gy = t.randn(y_o.shape, generator=g)
+  y_o.backward(gy)
+  x_c, w_c, b_c = [v.clone().to(dev()).requires_grad_(True) for v in (x, w, b)]
+  if transposed:
+    y_c = ops.conv_transpose(x_c, w_c, b_c, stride=stride, padding=pad, output_padding=opad)
+  else:
+    y_c = ops.conv(x_c, w_c, b_c, stride=stride, padding=pad)
+  assert tuple(y_c.shape) == tuple(y_o.shape)
+  y_c.backward(gy.to(dev()))
+  # fp32 FFMA vs fp32 oneDNN: only the summation order differs -> 2e-5 of the tensor's max
+  assert rel_err(y_c, y_o) < 2e-5, "fwd"
+  assert rel_err(x_c.grad, x_o.grad) < 2e-5, "dgrad"
+  assert rel_err(w_c.grad, w_o.grad) < 5e-5, "wgrad"
+  assert rel_err(b_c.grad, b_o.grad) < 2e-5, "bias grad"
+
+
+def test_linear():
+  from corenet_b200 import ops
+  g = t.Generator().manual_seed(5)
+  x, w, b = t.randn(4, 2048, generator=g), t.randn(64, 2048, generator=g) * 0.02, t.randn(64, generator=g)
+  y = ops.conv(x.to(dev()), w.to(dev()), b.to(dev()))
+  assert rel_err(y, F.linear(x, w, b)) < 2e-5
+
+
+# ---------------------------------------------------------------------------- BatchRenorm
+@pytest.mark.parametrize("shape", [(4, 64, 9, 9), (2, 28, 6, 6, 6), (4, 67, 1, 1, 1), (3, 2048, 2, 2)],
+                         ids=["2d", "3d_c28", "latent_c67", "wide"])
+@pytest.mark.parametrize("training,nbt", [(True, 0), (True, 50000), (False, 123)])
+def test_batch_renorm(shape, training, nbt):
+  from corenet_b200.model.batch_renorm import BatchRenorm
+  c = shape[1]
+  g = t.Generator().manual_seed(c + nbt)
+  x = t.randn(shape, generator=g) * 2 + 0.7
+  st = {"weight": t.rand(c, generator=g) + 0.5, "bias": t.randn(c, generator=g),
+        "running_mean": t.randn(c, generator=g) * 0.3, "running_var": t.rand(c, generator=g) + 0.4,
+        "num_batches_tracked": t.tensor(nbt, dtype=t.int64)}
+  gy = t.randn(shape, generator=g)
+  so = {k: v.clone().requires_grad_(k in ("weight", "bias")) for k, v in st.items()}
+  xo = x.clone().requires_grad_(True)
+  nb = {}
+  yo = O.batch_renorm(xo, so, "", training, nb)
+  yo.backward(gy)
+  m = BatchRenorm(c, eps=0.001).to(dev())
+  m.load_state_dict(st)
+  m.train(training)
+  xc = x.clone().to(dev()).requires_grad_(True)
+  yc = m(xc)
+  yc.backward(gy.to(dev()))
+  tol = 1e-4 if shape[0] * int(np.prod(shape[2:])) > 8 else 2e-3   # tiny batches: 1/sigma amplifies rounding
+  assert rel_err(yc, yo) < tol
+  assert rel_err(xc.grad, xo.grad) < 5 * tol
+  assert rel_err(m.weight.grad, so["weight"].grad) < 5 * tol
+  assert rel_err(m.bias.grad, so["bias"].grad) < 1e-4
+  if training:
+    assert int(m.num_batches_tracked) == nbt + 1
+    assert rel_err(m.running_mean, nb["running_mean"]) < 1e-5
+    assert rel_err(m.running_var, nb["running_var"]) < 1e-5
+  else:
+    assert int(m.num_batches_tracked) == nbt
+
+
+# ---------------------------------------------------------------------------- small encoder ops
+def test_preprocess_and_maxpool_and_mean():
+  from corenet_b200 import _lib
+  g = t.Generator().manual_seed(0)
+  img = t.randint(0, 256, (2, 3, 256, 256), dtype=t.uint8, generator=g)
+  out = t.empty(2, 256, 256, 4, device=dev())
+  _lib.call("crn_preprocess_image", img.to(dev()).data_ptr(), 2, 256, 256, out.data_ptr(), _lib.stream_ptr())
+  ref = O.preprocess_image_caffe(img).permute(0, 2, 3, 1)
+  assert t.equal(out[..., :3].cpu(), ref) and float(out[..., 3].abs().max()) == 0.0   # exact
+  # ZeroPad2d(1) + MaxPool2d(3, 2) on post-ReLU data, forward values exact, gradient exact
+  x = t.randn(2, 8, 12, 12, generator=g).relu()
+  xo = x.clone().requires_grad_(True)
+  yo = F.max_pool2d(F.pad(xo, [1, 1, 1, 1]), 3, 2)
+  gy = t.randn(yo.shape, generator=g)
+  yo.backward(gy)
+  xr = x.permute(0, 2, 3, 1).contiguous().to(dev())
+  y = t.empty(2, 6, 6, 8, device=dev())
+  idx = t.empty(2 * 6 * 6 * 8, dtype=t.int8, device=dev())
+  _lib.call("crn_maxpool_fwd", xr.data_ptr(), 2, 12, 12, 8, y.data_ptr(), idx.data_ptr(), _lib.stream_ptr())
+  assert t.equal(y.cpu().permute(0, 3, 1, 2), yo.detach())
+  dx = t.empty_like(xr)
+  gyr = gy.permute(0, 2, 3, 1).contiguous().to(dev())
+  _lib.call("crn_maxpool_bwd", gyr.data_ptr(), idx.data_ptr(), 2, 12, 12, 8, dx.data_ptr(), _lib.stream_ptr())
+  # ties can only happen at 0 (post-ReLU) where the ReLU mask kills the gradient anyway
+  mask = (x > 0).permute(0, 2, 3, 1)
+  assert t.allclose((dx.cpu() * mask), (xo.grad.permute(0, 2, 3, 1) * mask), rtol=0, atol=1e-6)
+  # spatial mean
+  f = t.randn(3, 64, 2048, generator=g)
+  m = t.empty(3, 2048, device=dev())
+  _lib.call("crn_spatial_mean_fwd", f.to(dev()).data_ptr(), 3, 64, 2048, m.data_ptr(), _lib.stream_ptr())
+  assert rel_err(m, f.mean(1)) < 1e-6
+
+
+# ---------------------------------------------------------------------------- ray-traced skip
+def _skip_inputs(b, seed, dense=False):
+  g = t.Generator().manual_seed(seed)
+  v2s = O.default_v2s(b).clone()
+  offs = t.rand(b, 3, generator=g)
+  offs[0] = 0.5
+  if b > 1:   # one camera translated so a chunk of the grid falls outside the image / behind it
+    v2s[1] = O.dataset_camera() @ O.translate([0.35, -0.2, -1.1]) @ O.scale([128.0] * 3).inverse()
+  if dense and b > 2:
+    v2s[2] = v2s[2] + 0.01 * t.randn(4, 4, generator=g)
+  return v2s, offs
+
+
+@pytest.mark.parametrize("g3,hw", [(8, 8), (16, 16), (32, 32), (64, 64), (16, 8)])
+def test_skip_indices_bit_exact(g3, hw):
+  """Index parity with the reference's projection arithmetic: bit-exact."""
+  from corenet_b200 import ops
+  b = 3
+  v2s, offs = _skip_inputs(b, g3, dense=True)
+  mat = v2s.matmul(O.scale([128.0 / g3] * 3))
+  ix, iy, front = O.sample_grid2d_indices(b, (g3, g3, g3), (hw, hw), mat, offs)
+  exp = t.where(front, iy * (hw + 2) + ix, t.full_like(ix, -1)).to(t.int32)
+  got = ops.skip_indices(b, (hw, hw), (g3, g3, g3), mat.to(dev()), offs.to(dev())).cpu()
+  assert (front.float().mean() < 1.0) and (front.float().mean() > 0.3)   # the edge cases are exercised
+  assert t.equal(got, exp)
+
+
+@pytest.mark.parametrize("g3,c_in,c_out", [(8, 40, 96), (16, 36, 48), (32, 20, 24), (64, 8, 12)])
+def test_sample_grid2d_module(g3, c_in, c_out):
+  from corenet_b200.model.ray_traced_skip_connection import SampleGrid2d
+  b, hw = 2, g3
+  g = t.Generator().manual_seed(g3)
+  v2s, offs = _skip_inputs(b, g3)
+  mat = v2s.matmul(O.scale([128.0 / g3] * 3))
+  x = t.randn(b, c_in, hw, hw, generator=g)
+  m = SampleGrid2d(c_in, c_out, (g3, g3, g3))
+  w, bias = m.compress_channels.weight.detach().clone(), m.compress_channels.bias.detach().clone()
+  xo, wo, bo = x.clone().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+  yo = O.sample_grid2d(xo, wo, bo, (g3, g3, g3), mat, offs)
+  gy = t.randn(yo.shape, generator=g)
+  yo.backward(gy)
+  m = m.to(dev())
+  xc = x.clone().to(dev()).requires_grad_(True)
+  yc = m(xc, mat.to(dev()), offs.to(dev()))
+  yc.backward(gy.to(dev()))
+  assert rel_err(yc, yo) < 2e-5
+  # the gather itself is pure data movement: exact zero pattern (outside / behind camera)
+  assert t.equal(yc.cpu() == 0, yo == 0)
+  assert rel_err(xc.grad, xo.grad) < 5e-5
+  assert rel_err(m.compress_channels.weight.grad, wo.grad) < 5e-5
+  assert rel_err(m.compress_channels.bias.grad, bo.grad) < 5e-5
+
+
+def test_skip_gather_bit_exact():
+  """With the compress conv factored out the kernel's output must equal the reference gather bit for bit."""
+  from corenet_b200.ops import _SkipGatherFn
+  b, g3, hw, c = 2, 16, 16, 48
+  v2s, offs = _skip_inputs(b, 7)
+  mat = v2s.matmul(O.scale([128.0 / g3] * 3))
+  cmap = t.randn(b, c, hw, hw, generator=t.Generator().manual_seed(3))
+  ix, iy, front = O.sample_grid2d_indices(b, (g3,) * 3, (hw, hw), mat, offs)
+  padded = F.pad(cmap, [1, 1, 1, 1])
+  bb = t.arange(b)[:, None, None, None].expand_as(ix)
+  exp = padded[bb, :, iy, ix].permute(0, 4, 1, 2, 3) * front[:, None]
+  got = _SkipGatherFn.apply(cmap.to(dev()), (g3,) * 3, mat.to(dev()), offs.to(dev())).cpu()
+  assert t.equal(got, exp)
+
+
+# ---------------------------------------------------------------------------- losses
+def test_losses_known_answers():
+  """src/corenet/test/losses_test.py:72-88 through the CUDA kernels."""
+  from corenet_b200.model import losses
+  lg, gt = LOGITS.contiguous().to(dev()), GT.to(dev())
+  np.testing.assert_allclose(losses.iou_fgbg(gt, lg).item(), 0.3579613, rtol=1e-5, atol=1e-6)
+  want = (1 + 0.8060565) * (1 + 1.4547757)
+  np.testing.assert_allclose(losses.xent_times_iou_agnostic(gt, lg).item(), want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("c,loss", [(2, "iou_fgbg"), (5, "iou_fgbg"), (5, "xent_times_iou_agnostic"),
+                                    (15, "xent_times_iou_agnostic")])
+def test_losses_random(c, loss):
+  from corenet_b200.model import losses
+  g = t.Generator().manual_seed(c)
+  lg = t.randn(3, c, 12, 10, 14, generator=g) * 3
+  gt = t.randint(0, c, (3, 12, 10, 14), generator=g)
+  gt[2] = 0     # a scene without foreground
+  lo = lg.clone().requires_grad_(True)
+  vo = getattr(O, loss)(gt, lo)
+  (vo * 1.7).backward()
+  lc = lg.clone().to(dev()).requires_grad_(True)
+  vc = getattr(losses, loss)(gt.to(dev()), lc)
+  (vc * 1.7).backward()
+  np.testing.assert_allclose(vc.item(), vo.item(), rtol=2e-6, atol=1e-6)
+  assert rel_err(lc.grad, lo.grad) < 1e-4
+  vc32 = getattr(losses, loss)(gt.to(dev()).to(t.int32), lc.detach())
+  assert vc32.item() == vc.item()
+
+
+def test_softmax_and_confusion():
+  from corenet_b200 import ops
+  g = t.Generator().manual_seed(1)
+  lg = t.randn(2, 6, 9, 9, 9, generator=g)
+  gt = t.randint(0, 6, (2, 9, 9, 9), generator=g)
+  assert rel_err(ops.softmax_channels(lg.to(dev())), lg.softmax(1)) < 1e-6
+  cm = ops.argmax_confusion(lg.to(dev()), gt.to(dev())).cpu()
+  assert t.equal(cm, O.confusion_matrix(lg.argmax(1), gt, 6))      # integer: exact
+
+
+# ---------------------------------------------------------------------------- fill_inside_voxels
+@pytest.mark.parametrize("dtype", [t.float32, t.uint8, t.int32, t.float64, t.int64, t.int8])
+def test_fill_known_answers(dtype):
+  """EmptyRegionFillTests (src/corenet/test/voxelization_test.py:197-244)."""
+  from corenet_b200.cc import fill_voxels
+  grids, expected = fill_test_grids()
+  gi = t.from_numpy(grids).to(dtype)
+  out = fill_voxels.fill_inside_voxels_gpu(gi.to(dev()), inplace=False)
+  assert out.dtype == dtype
+  np.testing.assert_array_equal(out.cpu().numpy(), expected.astype(out.cpu().numpy().dtype))
+  np.testing.assert_array_equal(fill_voxels.fill_inside_voxels_cpu(gi).numpy(),
+                                expected.astype(out.cpu().numpy().dtype))
+  x = gi.to(dev())
+  assert fill_voxels.fill_inside_voxels_gpu(x, inplace=True) is x
+  np.testing.assert_array_equal(x.cpu().numpy(), expected.astype(out.cpu().numpy().dtype))
+
+
+@pytest.mark.parametrize("shape,p", [((3, 16, 16, 16), 0.3), ((2, 9, 20, 45), 0.45), ((2, 7, 7, 7), 0.5),
+                                     ((1, 40, 33, 70), 0.38), ((1, 1, 1, 1), 0.5), ((2, 1, 8, 3), 0.4),
+                                     ((2, 64, 64, 64), 0.34), ((1, 33, 65, 129), 0.36), ((1, 5, 5, 256), 0.3)])
+def test_fill_random_bit_exact(shape, p):
+  from corenet_b200.cc import fill_voxels
+  rng = np.random.default_rng(sum(shape))
+  g = (rng.random(shape) < p).astype(np.float32)
+  out = fill_voxels.fill_inside_voxels_gpu(t.from_numpy(g).to(dev())).cpu().numpy()
+  np.testing.assert_array_equal(out, FO.fill_inside_voxels_oracle(g))
+
+
+def test_fill_maze_and_shells_128():
+  """Worst-case-ish connectivity at the full 128^3 size: a serpentine corridor (many sweeps) plus
+  closed shells; checked against the oracle bit for bit."""
+  from corenet_b200.cc import fill_voxels
+  g = np.zeros((2, 128, 128, 128), np.float32)
+  # scene 0: walls every 4 voxels along y with alternating gaps -> serpentine empty corridor
+  for i, y in enumerate(range(3, 128, 4)):
+    g[0, :, y, :] = 1
+    if i % 2 == 0:
+      g[0, :, y, 120:] = 0
+    else:
+      g[0, :, y, :8] = 0
+  g[0, :, :, 127] = 0
+  # scene 1: nested closed shells + one shell with a hole towards the far face
+  for lo, hi in ((10, 60), (20, 50), (70, 120)):
+    g[1, lo:hi, lo:hi, lo:hi] = 1
+    g[1, lo + 1:hi - 1, lo + 1:hi - 1, lo + 1:hi - 1] = 0
+  g[1, 95, 95, 119:] = 0
+  out = fill_voxels.fill_inside_voxels_gpu(t.from_numpy(g).to(dev())).cpu().numpy()
+  np.testing.assert_array_equal(out, FO.fill_inside_voxels_oracle(g))
+  # size-independent properties: idempotent, monotone, occupied voxels stay occupied
+  again = fill_voxels.fill_inside_voxels_gpu(t.from_numpy(out).to(dev())).cpu().numpy()
+  np.testing.assert_array_equal(again, out)
+  assert (out >= g).all()
+
+
+def test_fill_errors():
+  from corenet_b200.cc import fill_voxels
+  with pytest.raises(ValueError):
+    fill_voxels.fill_inside_voxels_gpu(t.zeros(4, 4, 4, device=dev()))
+  with pytest.raises(ValueError):
+    fill_voxels.fill_inside_voxels_gpu(t.zeros(1, 4, 4, 4))
+  assert fill_voxels.fill_inside_voxels_gpu(t.zeros(0, 4, 4, 4, device=dev())).shape == (0, 4, 4, 4)
+
+
+# ---------------------------------------------------------------------------- voxelize_mesh
+def test_voxelize_reference_vectors():
+  """VoxelizationTests (src/corenet/test/voxelization_test.py:53-147) end to end on the GPU."""
+  from corenet_b200.cc import fill_voxels
+  from corenet_b200.geometry import transformations, voxelization
+  quad = t.tensor([[[0, 0, 0], [1, 0, 1], [0, 1, 0]], [[1, 0, 1], [0, 1, 0], [1, 1, 1]]], dtype=t.float32)
+  vg = voxelization.voxelize_mesh(quad, [2], (4, 4, 4), transformations.scale([4, 4, 4]),
+                                  image_resolution_multiplier=16)
+  fill_voxels.fill_inside_voxels_gpu(vg, inplace=True)
+  exp = np.zeros((4, 4, 4), np.float32)
+  for z in range(4):
+    exp[z, :, z] = 1
+  np.testing.assert_array_equal(vg.cpu().numpy(), exp[None])
+  cube = t.from_numpy(cube_mesh(0.99))
+  eye = transformations.scale([1, 1, 1])
+  grid = voxelization.voxelize_mesh(cube, [12], (3, 3, 3), eye, image_resolution_multiplier=1)
+  e = np.zeros((3, 3, 3)); e[1, 1, [0, 2]] = e[1, [0, 2], 1] = e[[0, 2], 1, 1] = 1
+  np.testing.assert_array_equal(grid.cpu().numpy(), e[None])
+  grid = voxelization.voxelize_mesh(cube, [12], (3, 3, 3), eye, image_resolution_multiplier=1,
+                                    conservative_rasterization=True)
+  e = np.ones((3, 3, 3)); e[1, 1, 1] = 0
+  np.testing.assert_array_equal(grid.cpu().numpy(), e[None])
+  grid = voxelization.voxelize_mesh(cube, [12], (3, 3, 3), eye, sub_grid_sampling=True,
+                                    image_resolution_multiplier=9, conservative_rasterization=True)
+  grid = fill_voxels.fill_inside_voxels_gpu(grid, inplace=False)
+  e = np.zeros((1, 7, 7, 7)); e[0, 2:5, 2:5, 2:5] = 1
+  np.testing.assert_array_equal(grid.cpu().numpy(), e)
+  e = np.zeros((1, 3, 3, 3)); e[0, 1, 1, 1] = 1
+  np.testing.assert_array_equal(voxelization.get_sub_grid_centers(grid).cpu().numpy(), e)
+  cubes = t.cat([cube, cube - 0.5])
+  transf = t.stack([transformations.translate([-0.5, 0, 0]), transformations.translate([0.5, 1, 1])])
+  grid = voxelization.voxelize_mesh(cubes, [12, 12], (3, 3, 3), transf, sub_grid_sampling=True,
+                                    image_resolution_multiplier=9, conservative_rasterization=True)
+  grid = voxelization.get_sub_grid_centers(fill_voxels.fill_inside_voxels_gpu(grid)).cpu().numpy()
+  e1 = np.zeros((3, 3, 3)); e1[1, 1, [0, 1]] = 1
+  e2 = np.zeros((3, 3, 3)); e2[1, [1, 2], 1] = e2[2, [1, 2], 1] = 1
+  np.testing.assert_array_equal(grid[0], e1)
+  np.testing.assert_array_equal(grid[1], e2)
+  with pytest.raises(ValueError):
+    voxelization.voxelize_mesh(cube, [12], (3, 3, 3), eye, sub_grid_sampling=True, image_resolution_multiplier=8)
+
+
+@pytest.mark.parametrize("cons,sub,mult,pdm", [(False, False, 4, 1), (True, False, 3, 1), (False, False, 4, 2),
+                                               (True, True, 5, 1), (False, True, 3, 1)])
+def test_voxelize_random_meshes_bit_exact(cons, sub, mult, pdm):
+  """Random triangle soups (incl. slivers and out-of-bounds parts) vs the numpy oracle: bit-exact."""
+  from corenet_b200.geometry import voxelization
+  rng = np.random.default_rng(mult * 10 + pdm + cons)
+  res = (6, 7, 8)
+  ntri = [25, 17]
+  tris = rng.uniform(-0.2, 1.2, size=(sum(ntri), 3, 3)).astype(np.float32)
+  tris[5] = tris[5, 0][None] + rng.normal(0, 0.01, (3, 3)).astype(np.float32)      # sliver
+  v2x = np.stack([np.diag([8, 7, 6, 1]).astype(np.float32), np.diag([8, 7, 6, 1]).astype(np.float32)])
+  v2x[1, :3, 3] = [0.3, -0.4, 0.25]
+  exp = VO.voxelize_mesh_oracle(tris, ntri, res, v2x, sub_grid_sampling=sub, image_resolution_multiplier=mult,
+                                conservative_rasterization=cons, projection_depth_multiplier=pdm)
+  got = voxelization.voxelize_mesh(t.from_numpy(tris), ntri, res, t.from_numpy(v2x), sub_grid_sampling=sub,
+                                   image_resolution_multiplier=mult, conservative_rasterization=cons,
+                                   projection_depth_multiplier=pdm).cpu().numpy()
+  assert exp.sum() > 20
+  np.testing.assert_array_equal(got, exp)
+
+
+def test_voxelize_fill_roundtrip_128():
+  """Full size (128^3, mult 8): a closed icosphere-ish mesh voxelised + filled must be solid:
+  every voxel whose centre is well inside the sphere is 1, everything well outside is 0."""
+  from corenet_b200.cc import fill_voxels
+  from corenet_b200.geometry import transformations, voxelization
+  # UV sphere, radius 0.3 at (0.5, 0.5, 0.5) in the unit cube
+  nu, nv = 48, 24
+  th = np.linspace(0, 2 * np.pi, nu + 1)
+  ph = np.linspace(0, np.pi, nv + 1)
+  P = lambda i, j: np.array([0.5 + 0.3 * np.sin(ph[j]) * np.cos(th[i]), 0.5 + 0.3 * np.sin(ph[j]) * np.sin(th[i]),
+                             0.5 + 0.3 * np.cos(ph[j])], np.float32)
+  tris = []
+  for i in range(nu):
+    for j in range(nv):
+      a, b, c, d = P(i, j), P(i + 1, j), P(i + 1, j + 1), P(i, j + 1)
+      tris += [[a, b, c], [a, c, d]]
+  tris = t.from_numpy(np.array(tris, np.float32))
+  grid = voxelization.voxelize_mesh(tris, [tris.shape[0]], (128, 128, 128), transformations.scale([128.0] * 3),
+                                    image_resolution_multiplier=8)
+  shell = grid.clone()
+  fill_voxels.fill_inside_voxels_gpu(grid, inplace=True)
+  g = grid[0].cpu().numpy()
+  zz, yy, xx = np.meshgrid(*[np.arange(128) + 0.5] * 3, indexing="ij")
+  r = np.sqrt((zz - 64) ** 2 + (yy - 64) ** 2 + (xx - 64) ** 2) / 128
+  assert g[r < 0.28].min() == 1 and g[r > 0.32].max() == 0
+  assert shell[0].cpu().numpy()[r < 0.25].max() == 0        # surface only before the fill
