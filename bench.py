@@ -242,6 +242,15 @@ def run_native(args):
       k = "wgrad_kernel" if kind == "wgrad" else "gather_gemm_kernel"
       f = fam.setdefault(k, [0.0, 0.0, 0])
       f[0] += e0.elapsed_time(e1); f[1] += 2.0 * macs; f[2] += 1
+    if args.layers:
+      per = {}
+      for kind, name, macs, e0, e1 in prof:
+        q = per.setdefault((name, kind), [0.0, 0.0])
+        q[0] += e0.elapsed_time(e1) / args.steps; q[1] += 2.0 * macs / args.steps
+      rows_ = sorted(((v[0], k[0], k[1], v[1] / (v[0] * 1e-3) / 1e12) for k, v in per.items()), reverse=True)
+      with open(args.layers, "w") as f:
+        for ms_, n_, k_, tf_ in rows_:
+          f.write(f"{ms_:9.3f} ms  {tf_:7.2f} TFLOP/s  {k_:6s} {n_}\n")
     dom = max(fam.items(), key=lambda kv: kv[1][0])
     conv_ms = sum(v[0] for v in fam.values())
     achieved = dom[1][1] / (dom[1][0] * 1e-3) / 1e12
@@ -308,6 +317,7 @@ def main():
   ap.add_argument("--batch", type=int, default=4, help="scenes per GPU")
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--layers", default=None, help="write a per-layer conv timing table to this file")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

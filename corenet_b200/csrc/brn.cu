@@ -153,7 +153,7 @@ __global__ void brn_finalize_kernel(const double* __restrict__ acc, int64_t rows
     d = fminf(fmaxf((mean - rm) / rstd, -dmax), dmax);
     invstd = 1.0f / std;
     a = w * r / std;
-    b = w * (d - mean / std * r) + bz;
+    b = fmaf(w, d, bz);          // y = a * (x - mean) + b, mean subtracted first like the reference
     // running statistics (batch_renorm.py:54-57; "Bessel" uses the channel count)
     const float unbiased = var * (float)C / (float)(C - 1);
     running_var[c] = rv + momentum * (unbiased - rv);
@@ -161,7 +161,7 @@ __global__ void brn_finalize_kernel(const double* __restrict__ acc, int64_t rows
   } else {
     mean = rm; invstd = 1.0f / rstd; r = 1.f; d = 0.f;
     a = w / rstd;
-    b = bz - w * (rm / rstd);
+    b = bz;
   }
   coef[c] = a; coef[C + c] = b; coef[2 * C + c] = mean; coef[3 * C + c] = invstd;
   coef[4 * C + c] = r; coef[5 * C + c] = d;
@@ -180,14 +180,15 @@ __global__ void __launch_bounds__(NT) brn_apply_kernel(const float* __restrict__
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
     const int64_t r = i / cg;
     const int c = (int)(i - r * cg) * VEC;
-    float v[VEC], a[VEC], b[VEC], o[VEC];
+    float v[VEC], a[VEC], b[VEC], mu[VEC], o[VEC];
     Vec<VEC>::load(x + r * x_cs + x_co + c, v);
     Vec<VEC>::load(coef + c, a);
     Vec<VEC>::load(coef + C + c, b);
+    Vec<VEC>::load(coef + 2 * C + c, mu);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const float u = relu_in ? fmaxf(v[e], 0.f) : v[e];
-      o[e] = fmaf(a[e], u, b[e]);
+      o[e] = fmaf(a[e], u - mu[e], b[e]);
     }
     if (res) {
       float rr[VEC];

@@ -543,11 +543,17 @@ extern "C" int crn_conv_dgrad(const crn_conv_desc* d, const float* dy, const flo
   return launch_gather(p, crn_stream(stream));
 }
 
+int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st);
+
 extern "C" int crn_conv_wgrad(const crn_conv_desc* d, const float* x, const float* dy,
                               float* dw_packed, void* stream) {
   CRN_REQUIRE(check_desc(d), "crn_conv_wgrad: bad descriptor");
   CRN_REQUIRE(x && dy && dw_packed, "crn_conv_wgrad: null pointer");
   CRN_REQUIRE(!d->y_planar, "crn_conv_wgrad: planar dy unsupported");
+  {   // small-channel 3-D decoder layers: tap-row kernel (conv_wgrad_row.cu)
+    const int rc = crn_wgrad_row_try(d, x, dy, dw_packed, crn_stream(stream));
+    if (rc != CRN_ERR_UNSUPPORTED) return rc;
+  }
   WgradParams p{};
   p.P = x; p.Q = dy; p.dw = dw_packed; p.N = d->N;
   int s[3], pad[3], K[3], iD[3], oD[3];

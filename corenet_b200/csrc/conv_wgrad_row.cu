@@ -1,0 +1,246 @@
+// Weight gradient of the 3-D decoder convolutions with small channel counts
+// (Conv3d k=5 and ConvTranspose3d k=7 s=2; model/reconstruction_decoder.py:57-95).
+//
+//   conv  (SS=1): dW[kz,ky,kx][ci][co] = sum_pos  X[pos + k - pad][ci]      * dY[pos][co]
+//   convT (SS=2): dW[kz,ky,kx][ci][co] = sum_pos  X[pos][ci]                * dY[2*pos + k - pad][co]
+//
+// The output (taps x Cin x Cout) is tiny and the reduction (all voxels) is huge, so the
+// generic split-K GEMM tile is mostly padding.  Here a thread owns a "tap row":
+// all KX taps along x for one (kz,ky), 4 channels of the centre operand and SW channels
+// of the shifted operand = KX*4*SW accumulators in registers, and walks along x with a
+// sliding register window over the shifted operand, so each position costs SS+1 shared
+// loads for KX*4*SW FMAs (FFMA-bound, fp32).  Blocks are persistent over (n, z, y-block)
+// tiles; operands are staged once per tile in shared memory in their global
+// channels-last layout (no transpose); partial sums are flushed with one atomicAdd
+// per accumulator per block.
+#include "common.cuh"
+
+namespace {
+
+struct WRowParams {
+  const float* C;     // centre operand  [N, cD, cH, cW, c_cs] (+ c_co)
+  const float* S;     // shifted operand [N, sD, sH, sW, s_cs] (+ s_co)
+  float* dw;          // [tap][wK][wN]
+  int N, cD, cH, cW, sD, sH, sW;
+  int c_cs, c_co, s_cs, s_co;
+  int CQ, SQ;         // quads of the centre operand (4 wide), groups of the shifted operand (SW wide)
+  int pad, KZ, KY;
+  int wK, wN;
+  int gM, gN;         // logical Cin, Cout (for the flush bounds)
+  int TY, nstream, CQb, NCQG;   // rows per tile, position streams, centre quads per block, centre-quad groups
+  int SR, SWd;        // shifted tile rows / width (voxels)
+  int center_floats;  // floats of the centre tile
+  long long ntiles;
+};
+
+template <int SW>
+__device__ __forceinline__ void load_group(const float* p, float (&v)[SW]) {
+  if constexpr (SW == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+}
+
+template <int KX, int SS, int SW, bool SHIFT_IS_CI>
+__global__ void __launch_bounds__(320) wgrad_row_kernel(const WRowParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* cS = smem;
+  float* sS = smem + p.center_floats;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int roles = p.KY * p.SQ * p.CQb;
+  const int rho = tid % roles, sigma = tid / roles;
+  const bool active = sigma < p.nstream;
+  const int cq = rho % p.CQb, sq = (rho / p.CQb) % p.SQ, ky = rho / (p.CQb * p.SQ);
+  const int cqg = blockIdx.y % p.NCQG, kz = blockIdx.y / p.NCQG;
+  const int cstride = p.CQb * 4;        // floats per voxel in the centre tile
+  const int sstride = p.SQ * SW;        // floats per voxel in the shifted tile
+
+  float acc[KX][4][SW];
+#pragma unroll
+  for (int k = 0; k < KX; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < SW; ++j) acc[k][i][j] = 0.f;
+
+  const int yblocks = (p.cH + p.TY - 1) / p.TY;
+  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int yb = (int)(tile % yblocks);
+    long long q = tile / yblocks;
+    const int z = (int)(q % p.cD);
+    const int n = (int)(q / p.cD);
+    const int y0 = yb * p.TY;
+    const int sz = z * SS - p.pad + kz;
+    if (sz < 0 || sz >= p.sD) continue;            // block-uniform
+    __syncthreads();
+    // ---- stage the centre tile: [TY][cW][CQb*4]
+    {
+      const int units = p.TY * p.cW * p.CQb;       // float4 units
+      for (int u = tid; u < units; u += nthr) {
+        const int qq = u % p.CQb; int r = u / p.CQb;
+        const int x = r % p.cW; const int yy = r / p.cW;
+        const int y = y0 + yy;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y < p.cH) {
+          const long long off = ((((long long)n * p.cD + z) * p.cH + y) * p.cW + x) * p.c_cs + p.c_co +
+                                (cqg * p.CQb + qq) * 4;
+          v = __ldg(reinterpret_cast<const float4*>(p.C + off));
+        }
+        *reinterpret_cast<float4*>(cS + (size_t)u * 4) = v;
+      }
+    }
+    // ---- stage the shifted tile: [SR][SWd][SQ*SW], zero outside the grid (conv padding)
+    {
+      constexpr int V = 2;                          // float2 units (channel counts are even)
+      const int upv = sstride / V;                  // units per voxel
+      const int units = p.SR * p.SWd * upv;
+      const int sy0 = y0 * SS - p.pad, sx0 = -p.pad;
+      for (int u = tid; u < units; u += nthr) {
+        const int qq = u % upv; int r = u / upv;
+        const int c = r % p.SWd; const int rr = r / p.SWd;
+        const int sy = sy0 + rr, sx = sx0 + c;
+        float2 v = make_float2(0.f, 0.f);
+        if ((unsigned)sy < (unsigned)p.sH && (unsigned)sx < (unsigned)p.sW) {
+          const long long off = ((((long long)n * p.sD + sz) * p.sH + sy) * p.sW + sx) * p.s_cs + p.s_co + qq * V;
+          v = __ldg(reinterpret_cast<const float2*>(p.S + off));
+        }
+        *reinterpret_cast<float2*>(sS + (size_t)u * V) = v;
+      }
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int yy = sigma; yy < p.TY && y0 + yy < p.cH; yy += p.nstream) {
+      const float* crow = cS + (size_t)(yy * p.cW) * cstride + cq * 4;
+      const float* srow = sS + (size_t)((yy * SS + ky) * p.SWd) * sstride + sq * SW;
+      float w[KX][SW];
+#pragma unroll
+      for (int k = 0; k < KX; ++k) load_group<SW>(srow + (size_t)k * sstride, w[k]);
+      for (int x0 = 0; x0 < p.cW; x0 += KX) {
+#pragma unroll
+        for (int jj = 0; jj < KX; ++jj) {
+          const int x = x0 + jj;
+          if (x < p.cW) {
+            const float4 c4 = *reinterpret_cast<const float4*>(crow + (size_t)x * cstride);
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int k = 0; k < KX; ++k) {
+              const int slot = (SS * jj + k) % KX;      // compile-time after unrolling
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < SW; ++j) acc[k][i][j] = fmaf(cv[i], w[slot][j], acc[k][i][j]);
+            }
+            if (x + 1 < p.cW) {
+#pragma unroll
+              for (int e = 0; e < SS; ++e) {
+                const int slot = (SS * jj + e) % KX;
+                load_group<SW>(srow + (size_t)(SS * x + KX + e) * sstride, w[slot]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- flush
+  if (active && ky < p.KY) {
+#pragma unroll
+    for (int k = 0; k < KX; ++k) {
+      const int tap = (kz * p.KY + ky) * KX + k;
+      float* dwt = p.dw + (long long)tap * p.wK * p.wN;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < SW; ++j) {
+          const int cc = (cqg * p.CQb + cq) * 4 + i;     // centre channel
+          const int sc = sq * SW + j;                    // shifted channel
+          const int ci = SHIFT_IS_CI ? sc : cc;
+          const int co = SHIFT_IS_CI ? cc : sc;
+          if (ci < p.gM && co < p.gN) atomicAdd(dwt + (long long)ci * p.wN + co, acc[k][i][j]);
+        }
+    }
+  }
+}
+
+template <int KX, int SS, int SW, bool SHIFT_IS_CI>
+int launch(const WRowParams& p, int threads, size_t smem_bytes, int groups, cudaStream_t st) {
+  auto kern = wgrad_row_kernel<KX, SS, SW, SHIFT_IS_CI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    configured = true;
+  }
+  int per_sm = (int)((200 * 1024) / (smem_bytes + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  long long gx = ((long long)per_sm * kNumSMs + groups - 1) / groups;
+  if (gx > p.ntiles) gx = p.ntiles;
+  if (gx < 1) gx = 1;
+  kern<<<dim3((unsigned)gx, (unsigned)groups), threads, smem_bytes, st>>>(p);
+  CRN_LAUNCH_CHECK("wgrad_row");
+  return CRN_OK;
+}
+
+}  // namespace
+
+// Returns CRN_ERR_UNSUPPORTED when the shape is outside this kernel's envelope (the caller falls
+// back to the generic split-K kernel).
+int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st) {
+  const bool conv5 = !d->transposed && d->kD == 5 && d->kH == 5 && d->kW == 5 && d->stride == 1 && d->pad == 2;
+  const bool convT7 = d->transposed && d->kD == 7 && d->kH == 7 && d->kW == 7 && d->stride == 2 && d->pad == 3;
+  if (!conv5 && !convT7) return CRN_ERR_UNSUPPORTED;
+  if (d->y_planar) return CRN_ERR_UNSUPPORTED;
+  WRowParams p{};
+  p.dw = dw; p.N = d->N; p.pad = d->pad; p.KZ = d->kD; p.KY = d->kH;
+  p.wK = d->CinP; p.wN = d->CoutP; p.gM = d->Cin; p.gN = d->Cout;
+  int SW, Cc, Cs;
+  if (conv5) {            // centre = dY (positions of y), shifted = X
+    p.C = dy; p.c_cs = d->y_cs; p.c_co = d->y_co; p.cD = d->oD; p.cH = d->oH; p.cW = d->oW; Cc = d->Cout;
+    p.S = x; p.s_cs = d->x_cs; p.s_co = d->x_co; p.sD = d->iD; p.sH = d->iH; p.sW = d->iW; Cs = d->Cin;
+    SW = 4;
+  } else {                // centre = X (positions of x), shifted = dY
+    p.C = x; p.c_cs = d->x_cs; p.c_co = d->x_co; p.cD = d->iD; p.cH = d->iH; p.cW = d->iW; Cc = d->Cin;
+    p.S = dy; p.s_cs = d->y_cs; p.s_co = d->y_co; p.sD = d->oD; p.sH = d->oH; p.sW = d->oW; Cs = d->Cout;
+    SW = 2;
+  }
+  // reads are done in whole groups: the buffers must hold the rounded-up channel counts
+  const int Cc4 = (Cc + 3) / 4 * 4, CsG = (Cs + SW - 1) / SW * SW;
+  if (p.c_co + Cc4 > p.c_cs || p.s_co + CsG > p.s_cs) return CRN_ERR_UNSUPPORTED;
+  if (p.c_cs % 4 || p.c_co % 4 || p.s_cs % 2 || p.s_co % 2) return CRN_ERR_UNSUPPORTED;
+  p.CQ = Cc4 / 4; p.SQ = CsG / SW;
+  const int KX = d->kW, SS = conv5 ? 1 : 2;
+  // centre quads per block: keep roles = KY*SQ*CQb <= 160
+  int CQb = p.CQ;
+  while (CQb > 1 && p.KY * p.SQ * CQb > 160) CQb = (CQb + 1) / 2;
+  while (p.CQ % CQb) --CQb;
+  const int roles = p.KY * p.SQ * CQb;
+  if (roles > 320 || p.cW < KX) return CRN_ERR_UNSUPPORTED;
+  p.CQb = CQb; p.NCQG = p.CQ / CQb;
+  int nstream = 224 / roles;
+  if (nstream < 1) nstream = 1;
+  if (nstream > 8) nstream = 8;
+  int TY = nstream > 2 ? nstream : 2;
+  if (TY > p.cH) TY = p.cH;
+  if (nstream > TY) nstream = TY;
+  size_t smem_bytes = 0;
+  for (;;) {
+    p.TY = TY; p.nstream = nstream;
+    p.SR = (TY - 1) * SS + p.KY;
+    p.SWd = (p.cW - 1) * SS + KX;
+    p.center_floats = TY * p.cW * CQb * 4;
+    smem_bytes = sizeof(float) * ((size_t)p.center_floats + (size_t)p.SR * p.SWd * p.SQ * SW);
+    if (smem_bytes <= 100 * 1024 || TY == 1) break;
+    TY = TY > 2 ? TY / 2 : 1;
+    if (nstream > TY) nstream = TY;
+  }
+  if (smem_bytes > 150 * 1024) return CRN_ERR_UNSUPPORTED;
+  p.ntiles = (long long)p.N * p.cD * ((p.cH + TY - 1) / TY);
+  int threads = ((nstream * roles + 31) / 32) * 32;
+  if (threads > 320) return CRN_ERR_UNSUPPORTED;
+  const int groups = p.KZ * p.NCQG;
+  if (conv5) return launch<5, 1, 4, true>(p, threads, smem_bytes, groups, st);
+  return launch<7, 2, 2, false>(p, threads, smem_bytes, groups, st);
+}

@@ -115,12 +115,12 @@ int crn_brn_stats(const float* x, int64_t rows, int32_t C, int32_t x_cs, int32_t
 /* Turns the sums into per-channel coefficients and updates the running
  * statistics exactly like the reference (including the channel-count Bessel
  * quirk and num_batches_tracked += 1).  coef: float[6*C] =
- *   a (scale), b (shift), mean, invstd, r, d.   training==0: uses running stats only. */
+ *   a (scale), b (shift), mean, invstd, r, d with y = a*(x - mean) + b.   training==0: running stats only. */
 int crn_brn_finalize(const double* acc, int64_t rows, int32_t C, const float* weight,
                      const float* bias, float* running_mean, float* running_var,
                      int64_t* num_batches_tracked, float eps, float momentum, int32_t training,
                      float* coef, void* stream);
-/* y = act( a*f(x) + b [+ res] ),  f = relu if relu_in.  If y_pre != NULL the
+/* y = act( a*(f(x) - mean) + b [+ res] ),  f = relu if relu_in.  If y_pre != NULL the
  * pre-activation value is stored there too (encoder skip taps,
  * resnet50.py:76-80).  relu_out: apply ReLU to y. */
 int crn_brn_apply(const float* x, int64_t rows, int32_t C, int32_t x_cs, int32_t x_co,

@@ -164,22 +164,28 @@ def _conv_bn(x, st, p, training, nb, stride=1, padding=0):
   return batch_renorm(x, st, p + "bn.", training, nb)
 
 
-def _identity_block(x, st, p, training, nb):
+def _rec(taps, key, v):
+  if taps is not None:
+    taps[key] = v
+  return v
+
+
+def _identity_block(x, st, p, training, nb, taps=None):
   """resnet50.py:72-83."""
   inp = x
-  x = _conv_bn(x, st, p + "op_a.", training, nb).relu()
-  x = _conv_bn(x, st, p + "op_b.", training, nb, padding=1).relu()
+  x = _rec(taps, p + "a_y", _conv_bn(x, st, p + "op_a.", training, nb).relu())
+  x = _rec(taps, p + "b_y", _conv_bn(x, st, p + "op_b.", training, nb, padding=1).relu())
   x = _conv_bn(x, st, p + "op_c.", training, nb) + inp
-  return x.relu(), x
+  return _rec(taps, p + "out", x.relu()), x
 
 
-def _downscale_block(x, st, p, training, nb, stride):
+def _downscale_block(x, st, p, training, nb, stride, taps=None):
   """resnet50.py:110-115."""
   s = _conv_bn(x, st, p + "shortcut.", training, nb, stride=stride)
-  x = _conv_bn(x, st, p + "op_a.", training, nb, stride=stride).relu()
-  x = _conv_bn(x, st, p + "op_b.", training, nb, padding=1).relu()
+  x = _rec(taps, p + "a_y", _conv_bn(x, st, p + "op_a.", training, nb, stride=stride).relu())
+  x = _rec(taps, p + "b_y", _conv_bn(x, st, p + "op_b.", training, nb, padding=1).relu())
   x = (_conv_bn(x, st, p + "op_c.", training, nb) + s).relu()
-  return x
+  return _rec(taps, p + "out", x)
 
 
 ENCODER_STAGES = (("stage2", "abc", 1), ("stage3", "abcd", 2),
@@ -187,7 +193,7 @@ ENCODER_STAGES = (("stage2", "abc", 1), ("stage3", "abcd", 2),
 
 
 def resnet50_features(st: State, image_f32: t.Tensor, training: bool,
-                      nb: Optional[State] = None, prefix: str = "encoder.") -> Features:
+                      nb: Optional[State] = None, prefix: str = "encoder.", taps=None) -> Features:
   """resnet50.py:176-186."""
   p = prefix
   x = F.pad(image_f32, [3, 3, 3, 3])
@@ -196,10 +202,10 @@ def resnet50_features(st: State, image_f32: t.Tensor, training: bool,
   x = F.max_pool2d(F.pad(x, [1, 1, 1, 1]), kernel_size=3, stride=2)
   outs = []
   for name, blocks, stride in ENCODER_STAGES:
-    x = _downscale_block(x, st, f"{p}{name}.a.", training, nb, stride)
+    x = _downscale_block(x, st, f"{p}{name}.a.", training, nb, stride, taps)
     pre = None
     for b in blocks[1:]:
-      x, pre = _identity_block(x, st, f"{p}{name}.{b}.", training, nb)
+      x, pre = _identity_block(x, st, f"{p}{name}.{b}.", training, nb, taps)
     outs.append(pre)
   return Features(stage1, outs[0], outs[1], outs[2], outs[3], x.mean(dim=(2, 3)))
 
@@ -235,7 +241,8 @@ def sample_grid2d(grid2d: t.Tensor, weight: t.Tensor, bias: t.Tensor, res3d, mat
                   offsets: t.Tensor, outside_value: float = 0.0) -> t.Tensor:
   compressed = F.conv2d(grid2d, weight, bias)
   b, c, h, w = compressed.shape
-  ix, iy, front = sample_grid2d_indices(b, tuple(res3d), (h, w), matrix, offsets)
+  # the index arithmetic is fp32 in the reference whatever the dtype of the features
+  ix, iy, front = sample_grid2d_indices(b, tuple(res3d), (h, w), matrix.float(), offsets.float())
   padded = t.constant_pad_nd(compressed, [1, 1, 1, 1], value=outside_value)
   bb = t.arange(b, dtype=t.int64)[:, None, None, None].expand_as(ix)
   result = padded[bb, :, iy, ix].permute([0, 4, 1, 2, 3])
@@ -251,11 +258,11 @@ def _apply_skip(st, p, x3d, src2d, stage, v2s, offsets, resolution):
   key = f"{p}rt_skip_{stage}.compress_channels.weight"
   if key not in st:
     return x3d
-  o = offsets[:, :, None, None].expand(src2d.shape[0], 3, *src2d.shape[2:])
+  o = offsets.to(src2d.dtype)[:, :, None, None].expand(src2d.shape[0], 3, *src2d.shape[2:])
   src2d = t.cat([src2d, o], 1)
   r1 = t.tensor(x3d.shape[2:], dtype=t.float32)
   r2 = t.tensor(resolution, dtype=t.float32)
-  layer_matrix = v2s.matmul(scale(r2 / r1))
+  layer_matrix = v2s.matmul(scale(r2 / r1).to(v2s.dtype))
   skip = sample_grid2d(src2d, st[key], st[f"{p}rt_skip_{stage}.compress_channels.bias"],
                        x3d.shape[2:], layer_matrix, offsets)
   return t.cat([x3d, skip], dim=1)
@@ -274,7 +281,7 @@ def decoder_forward(st: State, f: Features, v2s: t.Tensor, offsets: t.Tensor, tr
 
   x = F.linear(f.global_average_2048, W("stage_0"), Bz("stage_0"))
   rec("stage_0", x)
-  x = t.cat([x, offsets], 1)[:, :, None, None, None]
+  x = t.cat([x, offsets.to(x.dtype)], 1)[:, :, None, None, None]
   ir = tuple(r // 32 for r in resolution)
   x = F.conv_transpose3d(bn(x.relu(), "stage_1.b1"), W("stage_1.t1"), Bz("stage_1.t1"), stride=ir)
   rec("stage_1", x)
@@ -298,10 +305,14 @@ def decoder_forward(st: State, f: Features, v2s: t.Tensor, offsets: t.Tensor, tr
 
 
 def corenet_forward(st: State, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, training: bool,
-                    new_buffers: Optional[State] = None, taps: Optional[dict] = None) -> t.Tensor:
-  """model/core_net.py:36-43."""
+                    new_buffers: Optional[State] = None, taps: Optional[dict] = None,
+                    dtype: Optional[t.dtype] = None) -> t.Tensor:
+  """model/core_net.py:36-43.  dtype=float64 (with a float64 state) gives the "exact" answer used to
+  calibrate how much of a mismatch is fp32 rounding noise of the reference itself."""
   x = preprocess_image_caffe(image)
-  f = resnet50_features(st, x, training, new_buffers)
+  if dtype is not None:
+    x = x.to(dtype)
+  f = resnet50_features(st, x, training, new_buffers, taps=taps)
   if taps is not None:
     for k, v in f._asdict().items():
       taps[k] = v

@@ -44,6 +44,9 @@ CONV_CASES = [
     ("convT_k3_s2", (2, 32, 4, 4, 4), (32, 20, 3, 3, 3), 2, 1, True, 1),
     ("convT_k4_s4_latent", (3, 67, 1, 1, 1), (67, 40, 4, 4, 4), 4, 0, True, 0),
     ("convT_cout2", (1, 16, 8, 8, 8), (16, 2, 7, 7, 7), 2, 3, True, 1),
+    ("convT_k7_s2_rowkernel", (2, 32, 9, 8, 10), (32, 16, 7, 7, 7), 2, 3, True, 1),
+    ("conv_k5_rowkernel_56_32", (2, 56, 7, 9, 11), (32, 56, 5, 5, 5), 1, 2, False, 0),
+    ("conv_k5_rowkernel_112_64", (1, 112, 6, 6, 16), (64, 112, 5, 5, 5), 1, 2, False, 0),
 ]
 
 
