@@ -43,6 +43,7 @@ _SIGS = {
     "crn_build_arch": ([], C.c_char_p),
     "crn_last_error": ([], C.c_char_p),
     "crn_launch_count": ([], i64),
+    "crn_set_flags": ([i32], None),
     "crn_pack_weights": ([vp, vp, i32, i64, vp], i32),
     "crn_unpack_wgrads": ([vp, vp, i32, i64, vp], i32),
     "crn_conv_fwd": ([_P(ConvDesc), vp, vp, vp, vp, i32, vp], i32),

@@ -19,3 +19,7 @@ void crn_set_error(const char* fmt, ...) {
 extern "C" int crn_version(void) { return 100; }
 extern "C" const char* crn_build_arch(void) { return "sm_100a"; }
 extern "C" const char* crn_last_error(void) { return g_err; }
+
+static std::atomic<int> g_flags{0};
+int crn_get_flags() { return g_flags.load(std::memory_order_relaxed); }
+extern "C" void crn_set_flags(int flags) { g_flags.store(flags, std::memory_order_relaxed); }

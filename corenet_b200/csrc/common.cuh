@@ -6,7 +6,8 @@
 #include "corenet_b200.h"
 
 void crn_set_error(const char* fmt, ...);
-void crn_count_launches(int n);   // bumps the process-wide kernel launch counter
+void crn_count_launches(int n);
+int crn_get_flags();              // debug switches, see crn_set_flags   // bumps the process-wide kernel launch counter
 
 #define CRN_REQUIRE(cond, ...)            \
   do {                                    \

@@ -510,10 +510,17 @@ int launch_gather(const GatherParams& p, cudaStream_t st) {
 
 }  // namespace
 
+int crn_rowdirect_try(const crn_conv_desc* d, int kind, const float* in, const float* w, const float* bias,
+                      float* out, int accumulate, cudaStream_t st);
+
 extern "C" int crn_conv_fwd(const crn_conv_desc* d, const float* x, const float* w_fwd,
                             const float* bias, float* y, int32_t accumulate, void* stream) {
   CRN_REQUIRE(check_desc(d), "crn_conv_fwd: bad descriptor");
   CRN_REQUIRE(x && w_fwd && y, "crn_conv_fwd: null pointer");
+  {   // small-channel 3-D decoder layers: row-direct kernel (conv_rowdirect.cu)
+    const int rc = crn_rowdirect_try(d, 0, x, w_fwd, bias, y, accumulate, crn_stream(stream));
+    if (rc != CRN_ERR_UNSUPPORTED) return rc;
+  }
   GatherParams p{};
   p.in = x; p.w = w_fwd; p.bias = accumulate ? nullptr : bias; p.out = y;
   p.N = d->N;
@@ -530,6 +537,10 @@ extern "C" int crn_conv_dgrad(const crn_conv_desc* d, const float* dy, const flo
   CRN_REQUIRE(check_desc(d), "crn_conv_dgrad: bad descriptor");
   CRN_REQUIRE(dy && w_dgrad && dx, "crn_conv_dgrad: null pointer");
   CRN_REQUIRE(!d->y_planar, "crn_conv_dgrad: planar dy unsupported");
+  {
+    const int rc = crn_rowdirect_try(d, 1, dy, w_dgrad, nullptr, dx, accumulate, crn_stream(stream));
+    if (rc != CRN_ERR_UNSUPPORTED) return rc;
+  }
   GatherParams p{};
   p.in = dy; p.w = w_dgrad; p.bias = nullptr; p.out = dx;
   p.N = d->N;

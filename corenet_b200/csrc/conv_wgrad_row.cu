@@ -173,10 +173,11 @@ int launch(const WRowParams& p, int threads, size_t smem_bytes, int groups, cuda
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     configured = true;
   }
-  int per_sm = (int)((200 * 1024) / (smem_bytes + 1024));
-  if (per_sm > 4) per_sm = 4;
-  if (per_sm < 1) per_sm = 1;
-  long long gx = ((long long)per_sm * kNumSMs + groups - 1) / groups;
+  // persistent grid: exactly what is co-resident (one extra block would serialise a whole second wave)
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_bytes) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  long long gx = ((long long)per_sm * kNumSMs) / groups;
   if (gx > p.ntiles) gx = p.ntiles;
   if (gx < 1) gx = 1;
   kern<<<dim3((unsigned)gx, (unsigned)groups), threads, smem_bytes, st>>>(p);
@@ -189,6 +190,9 @@ int launch(const WRowParams& p, int threads, size_t smem_bytes, int groups, cuda
 // Returns CRN_ERR_UNSUPPORTED when the shape is outside this kernel's envelope (the caller falls
 // back to the generic split-K kernel).
 int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st) {
+  if (crn_get_flags() & 2) return CRN_ERR_UNSUPPORTED;
+  // the generic split-K GEMM wins once the Cin x Cout tile is large enough to fill its 64x64 tile
+  if (d->Cin * d->Cout >= 2048) return CRN_ERR_UNSUPPORTED;
   const bool conv5 = !d->transposed && d->kD == 5 && d->kH == 5 && d->kW == 5 && d->stride == 1 && d->pad == 2;
   const bool convT7 = d->transposed && d->kD == 7 && d->kH == 7 && d->kW == 7 && d->stride == 2 && d->pad == 3;
   if (!conv5 && !convT7) return CRN_ERR_UNSUPPORTED;

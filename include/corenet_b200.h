@@ -38,6 +38,9 @@ const char* crn_build_arch(void);
 const char* crn_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py gpu_launches). */
 int64_t crn_launch_count(void);
+/* Debug / A-B switches: bit0 = disable the row-direct conv kernels, bit1 = disable the tap-row wgrad
+ * kernel (both fall back to the generic implicit-GEMM kernels). */
+void crn_set_flags(int32_t flags);
 
 /* ------------------------------------------------------------------------
  * Convolutions.  Replaces the ATen/cuDNN calls behind nn.Conv2d / nn.Conv3d /

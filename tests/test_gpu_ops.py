@@ -47,6 +47,14 @@ CONV_CASES = [
     ("convT_k7_s2_rowkernel", (2, 32, 9, 8, 10), (32, 16, 7, 7, 7), 2, 3, True, 1),
     ("conv_k5_rowkernel_56_32", (2, 56, 7, 9, 11), (32, 56, 5, 5, 5), 1, 2, False, 0),
     ("conv_k5_rowkernel_112_64", (1, 112, 6, 6, 16), (64, 112, 5, 5, 5), 1, 2, False, 0),
+    # shapes inside the row-direct envelope (x extent a multiple of 8, <= 64 channels)
+    ("rd_conv_k5_28_16", (1, 28, 6, 9, 16), (16, 28, 5, 5, 5), 1, 2, False, 0),
+    ("rd_conv_k5_56_32", (2, 56, 5, 7, 32), (32, 56, 5, 5, 5), 1, 2, False, 0),
+    ("rd_conv_k5_16_3", (1, 16, 5, 6, 8), (3, 16, 5, 5, 5), 1, 2, False, 0),
+    ("rd_convT_k7_32_16", (2, 32, 5, 6, 8), (32, 16, 7, 7, 7), 2, 3, True, 1),
+    ("rd_convT_k7_16_2", (1, 16, 6, 9, 32), (16, 2, 7, 7, 7), 2, 3, True, 1),
+    ("rd_convT_k7_16_15", (1, 16, 4, 5, 8), (16, 15, 7, 7, 7), 2, 3, True, 1),
+    ("rd_convT_k7_64_32", (1, 64, 4, 4, 16), (64, 32, 7, 7, 7), 2, 3, True, 1),
 ]
 
 
