@@ -239,7 +239,7 @@ def run_native(args):
     # roofline of the dominant kernel family (conv launches timed live with CUDA events)
     fam = {}
     for kind, name, macs, e0, e1 in prof:
-      k = "wgrad_kernel" if kind == "wgrad" else "gather_gemm_kernel"
+      k = "wgrad_kernels(ffma)" if kind == "wgrad" else ("conv_tc5_kernel(tcgen05)" if kind.endswith("_tc") else "conv_fwd_dgrad_kernels(ffma)")
       f = fam.setdefault(k, [0.0, 0.0, 0])
       f[0] += e0.elapsed_time(e1); f[1] += 2.0 * macs; f[2] += 1
     if args.layers:

@@ -1,0 +1,397 @@
+// Conv3d k=5, stride 1, pad 2 (forward and dgrad) on the 5th-gen tensor cores: tcgen05.mma with the
+// accumulators in TMEM, 3xTF32 operand splitting for fp32-class accuracy.
+// Replaces the cuDNN calls behind nn.Conv3d(k=5) at model/reconstruction_decoder.py:66,74,82,91.
+//
+// Implicit GEMM without im2col copies:
+//   * one CTA owns an (8 x 16) xy tile (M = 128 voxels) and ZT = 8 output z-planes: 8 accumulators of
+//     128 x N fp32 live in TMEM (double buffered across work items);
+//   * each input z-plane of the tile (+2 halo) is staged ONCE per K-pass (8 channels) in shared memory as
+//     [hi|lo][k-chunk][y 20][x 12][4 ch]: that is the canonical no-swizzle K-major UMMA layout in which
+//     the 8 x-neighbours of a row group are one 128 B core matrix, so a filter tap (ky, kx) is just a
+//     +(ky*12+kx)*16 B shift of the descriptor start address -- every tap reads the same bytes;
+//   * loop order kz -> ky -> z-plane: for a fixed kz the 8 output planes need 8 consecutive input planes,
+//     so the plane ring slides by one per kz (9 slots) and a weight row (5 taps) is reused for 8 planes;
+//   * weights are pre-split/pre-packed per (pass, tap) in the UMMA layout and streamed by cp.async.bulk
+//     (TMA bulk copy) into a 3-stage ring with mbarrier transaction counts;
+//   * warp roles: 4 epilogue warps (TMEM -> registers -> +bias -> global), 4 producer warps (halo gather,
+//     hi/lo split, st.shared, fence.proxy.async), 1 MMA warp (single elected thread issues tcgen05.mma and
+//     tcgen05.commit), 1 weight-copy warp.  All waits are bounded (a protocol bug cannot hang the GPU).
+//
+// a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b with hi = rna_tf32(a), lo = a - hi: relative error ~4e-7
+// (measured by crn_tc_probe), i.e. the parity budget of the fp32 path, at 3 MMAs per product.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TX = 8, TY = 16;                   // tile: 8 x 16 voxels per plane (ZT planes, template)
+constexpr int XS = TX + 4, YS = TY + 4;          // staged plane with halo
+constexpr int CHUNK_BYTES = YS * XS * 16;        // one 4-channel chunk of a plane  (3840)
+constexpr int PART_BYTES = 2 * CHUNK_BYTES;      // 8 channels                       (7680)
+constexpr int PLANE_BYTES = 2 * PART_BYTES;      // hi + lo                          (15360)
+constexpr int MAXSLOT = 9;                       // plane ring capacity (ZT + 1 slots used)
+constexpr int WSTAGES = 3;
+constexpr int NTHREADS = 320;                    // 4 epilogue + 4 producer + MMA + weight warps
+
+struct TC5Params {
+  const float* in;      // [N, D, H, W, in_cs] (+ in_co)
+  const float* wtc;     // packed weights [P][125][hi|lo][2][NPAD][4]
+  const float* bias;    // [gN] or null
+  float* out;           // [N, D, H, W, out_cs] (+ out_co)
+  int* status;          // set to 1 on a barrier timeout
+  int N, D, H, W;
+  int gK, gN;           // logical channels in / out
+  int in_cs, in_co, out_cs, out_co;
+  int P;                // K passes of 8 channels
+  int tiles_x, tiles_y, tiles_z;
+  int nitems;
+};
+
+struct __align__(8) Barriers {
+  uint64_t plane_full[MAXSLOT], plane_empty[MAXSLOT];
+  uint64_t w_full[WSTAGES], w_empty[WSTAGES];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  int abort_flag;
+};
+
+template <int ZT>
+__device__ __forceinline__ void decode_item(const TC5Params& p, int item, int& n, int& z0, int& y0, int& x0) {
+  int t = item;
+  x0 = (t % p.tiles_x) * TX; t /= p.tiles_x;
+  y0 = (t % p.tiles_y) * TY; t /= p.tiles_y;
+  z0 = (t % p.tiles_z) * ZT; n = t / p.tiles_z;
+}
+
+template <int NPAD, int ZT>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NSLOT = ZT + 1;                            // plane ring
+  constexpr int NPLANE = ZT + 4;                           // planes loaded per pass
+  constexpr int WTAP_BYTES = 2 * 2 * NPAD * 16;            // one tap: hi|lo x 2 k-chunks x NPAD x 16 B
+  constexpr int WROW_BYTES = 5 * WTAP_BYTES;               // one (kz, ky) row of 5 taps
+  constexpr int ASTG = (2 * ZT * NPAD <= 512) ? 2 : 1;    // accumulator stages (epilogue overlap when 2)
+  constexpr int TMEM_COLS = (ASTG * ZT * NPAD <= 256) ? 256 : 512;
+  static_assert(ASTG * ZT * NPAD <= 512, "TMEM budget");
+  uint8_t* ring = smem;
+  uint8_t* wring = smem + NSLOT * PLANE_BYTES;
+  Barriers* B = reinterpret_cast<Barriers*>(wring + WSTAGES * WROW_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&B->plane_full[i], 128); tc::mbar_init(&B->plane_empty[i], 1); }
+    for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&B->w_full[i], 1); tc::mbar_init(&B->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&B->acc_full[i], 1); tc::mbar_init(&B->acc_empty[i], 128); }
+    B->abort_flag = 0;
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&B->tmem_base, TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = B->tmem_base;
+  const uint32_t ring_u32 = tc::smem_u32(ring), wring_u32 = tc::smem_u32(wring);
+
+  auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
+  volatile int* ab = &B->abort_flag;
+
+  if (warp < 4) {
+    // ============================ EPILOGUE: one flush per (pass, kz) group.
+    // The tensor core's fp32 accumulate truncates, so a 375-MMA chain drifts by ~3e-5; flushing every
+    // 75 MMAs and summing the groups in fp32 registers / global (round-to-nearest) keeps the result at
+    // fp32-FFMA accuracy.  out (+)= acc with the same thread owning the same addresses across groups.
+    long long G = 0;
+    bool dead = false;
+    for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
+      int n, z0, y0, x0;
+      decode_item<ZT>(p, item, n, z0, y0, x0);
+      const int m = warp * 32 + lane;              // row of the tile = TMEM lane
+      const int y = y0 + (m >> 3), x = x0 + (m & 7);
+      for (int pass = 0; pass < p.P && !dead; ++pass) {
+        for (int kz = 0; kz < 5; ++kz, ++G) {
+          const int st = (int)(G % ASTG);
+          if (!tc::mbar_wait(&B->acc_full[st], (uint32_t)(G / ASTG) & 1, ab)) { fail(); dead = true; break; }
+          tc::fence_after_sync();
+          const bool first = pass == 0 && kz == 0;
+          for (int zz = 0; zz < ZT; ++zz) {
+            const int q = z0 + zz + kz - 2;
+            const bool valid = q >= 0 && q < p.D;
+            if (!valid && !first) continue;
+            const long long pos = (((long long)n * p.D + (z0 + zz)) * p.H + y) * p.W + x;
+            float* dst = p.out + pos * p.out_cs + p.out_co;
+#pragma unroll
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+              float v[16];
+              if (valid) {
+                tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + st * (ZT * NPAD) + zz * NPAD + c0, v);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0.f;
+              }
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                const int c = c0 + qd * 4;
+                if (c < p.gN) {                          // gN is a multiple of 4
+                  float4 o = make_float4(v[qd * 4], v[qd * 4 + 1], v[qd * 4 + 2], v[qd * 4 + 3]);
+                  if (first) {
+                    if (p.bias) {
+                      o.x += __ldg(p.bias + c); o.y += __ldg(p.bias + c + 1);
+                      o.z += __ldg(p.bias + c + 2); o.w += __ldg(p.bias + c + 3);
+                    }
+                  } else {
+                    const float4 old = *reinterpret_cast<const float4*>(dst + c);
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + c) = o;
+                }
+              }
+            }
+          }
+          tc::fence_before_sync();
+          tc::mbar_arrive(&B->acc_empty[st]);
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ============================ PRODUCERS: halo gather + hi/lo split into the plane ring
+    const int pt = tid - 128;                      // 0..127
+    long long L = 0;                               // running plane-load index (slot = L % NSLOT)
+    bool dead = false;
+    for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
+      int n, z0, y0, x0;
+      decode_item<ZT>(p, item, n, z0, y0, x0);
+      for (int pass = 0; pass < p.P && !dead; ++pass) {
+        for (int r = 0; r < NPLANE; ++r, ++L) {
+          const int slot = (int)(L % NSLOT);
+          const uint32_t use = (uint32_t)(L / NSLOT);
+          if (use > 0 && !tc::mbar_wait(&B->plane_empty[slot], (use - 1) & 1, ab)) { fail(); dead = true; break; }
+          const int q = z0 - 2 + r;
+          if (q >= 0 && q < p.D) {
+            uint8_t* dst = ring + slot * PLANE_BYTES;
+            for (int u = pt; u < YS * XS * 2; u += 128) {
+              const int kc = u & 1; const int v = u >> 1;
+              const int xs = v % XS, ys = v / XS;
+              const int y = y0 - 2 + ys, x = x0 - 2 + xs;
+              const int k = pass * 8 + kc * 4;
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
+                const long long off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
+                a = __ldg(reinterpret_cast<const float4*>(p.in + off));
+              }
+              float4 hi, lo;
+              tc::split_tf32(a.x, hi.x, lo.x); tc::split_tf32(a.y, hi.y, lo.y);
+              tc::split_tf32(a.z, hi.z, lo.z); tc::split_tf32(a.w, hi.w, lo.w);
+              const int o = kc * CHUNK_BYTES + v * 16;
+              *reinterpret_cast<float4*>(dst + o) = hi;
+              *reinterpret_cast<float4*>(dst + PART_BYTES + o) = lo;
+            }
+            tc::fence_async_smem();
+          }
+          tc::mbar_arrive(&B->plane_full[slot]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ============================ MMA ISSUER (one elected thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(128, NPAD, 0, 0);
+      constexpr uint32_t A_DESC_HI = (uint32_t)((XS * 16) >> 4) | (1u << 14);   // SBO field | version 1 (bit 46)
+      long long L0 = 0;                             // plane-load index of r = 0 of the current pass
+      long long Wn = 0;                             // running weight-row index
+      long long G = 0;                              // running (pass, kz) group index -> accumulator stage
+      bool dead = false;
+      for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
+        int n, z0, y0, x0;
+        decode_item<ZT>(p, item, n, z0, y0, x0);
+        for (int pass = 0; pass < p.P && !dead; ++pass, L0 += NPLANE) {
+          for (int kz = 0; kz < 5 && !dead; ++kz, ++G) {
+            const int st = (int)(G % ASTG);
+            if (G >= ASTG && !tc::mbar_wait(&B->acc_empty[st], (uint32_t)((G / ASTG) - 1) & 1, ab)) { fail(); dead = true; break; }
+            tc::fence_after_sync();
+            uint32_t started = 0;                   // bit zz: accumulator zz already written in this group
+            // planes r = kz .. kz+7 must be resident: r <= 7 are awaited at kz = 0, then one new per kz
+            const int rlo = kz == 0 ? 0 : kz + ZT - 1, rhi = kz + ZT - 1;
+            for (int r = rlo; r <= rhi; ++r) {
+              const long long L = L0 + r;
+              if (!tc::mbar_wait(&B->plane_full[L % NSLOT], (uint32_t)(L / NSLOT) & 1, ab)) { fail(); dead = true; break; }
+            }
+            if (dead) break;
+            tc::fence_after_sync();
+            uint32_t abase[ZT];
+            uint32_t valid = 0;
+#pragma unroll
+            for (int zz = 0; zz < ZT; ++zz) {
+              const int q = z0 + zz + kz - 2;
+              if (q >= 0 && q < p.D) valid |= 1u << zz;     // zero planes contribute nothing
+              // low descriptor word of the plane: (addr >> 4) | LBO field; taps/parts add a constant to it
+              abase[zz] = ((ring_u32 + (uint32_t)((L0 + zz + kz) % NSLOT) * PLANE_BYTES) >> 4) |
+                          ((uint32_t)(CHUNK_BYTES >> 4) << 16);
+            }
+            for (int ky = 0; ky < 5; ++ky, ++Wn) {
+              const int ws = (int)(Wn % WSTAGES);
+              if (!tc::mbar_wait(&B->w_full[ws], (uint32_t)(Wn / WSTAGES) & 1, ab)) { fail(); dead = true; break; }
+              tc::fence_after_sync();
+              const uint32_t wbase = wring_u32 + ws * WROW_BYTES;
+              // Interleave the 8 output planes: consecutive tcgen05.mma go to DIFFERENT accumulators, so the
+              // tensor pipe never waits on a read-after-write of the same TMEM tile.
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) {
+                const uint32_t b_hi = wbase + kx * WTAP_BYTES, b_lo = b_hi + 2 * NPAD * 16;
+                const uint64_t dbh = tc::make_desc(b_hi, NPAD * 16, 128);
+                const uint64_t dbl = tc::make_desc(b_lo, NPAD * 16, 128);
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+#pragma unroll
+                  for (int zz = 0; zz < ZT; ++zz) {
+                    if (!((valid >> zz) & 1u)) continue;
+                    const uint32_t alo = abase[zz] + (ky * XS + kx) + (part == 1 ? (PART_BYTES >> 4) : 0);
+                    const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
+                    const uint32_t acc = (kx | part) ? 1u : ((started >> zz) & 1u);
+                    tc::mma_tf32(tmem + st * (ZT * NPAD) + zz * NPAD, da, part == 2 ? dbl : dbh, idesc, acc);
+                  }
+                }
+              }
+              started |= valid;
+              tc::commit(&B->w_empty[ws]);          // weight row free once these MMAs have completed
+            }
+            if (dead) break;
+            tc::commit(&B->plane_empty[(L0 + kz) % NSLOT]);      // plane r = kz is done
+            tc::commit(&B->acc_full[st]);                        // this group's partial sums are complete
+          }
+          if (dead) break;
+          for (int r = 5; r < NPLANE; ++r) tc::commit(&B->plane_empty[(L0 + r) % NSLOT]);
+        }
+      }
+    }
+  } else {
+    // ============================ WEIGHT COPIES: one cp.async.bulk per (pass, kz, ky) row
+    if (lane == 0) {
+      long long Wn = 0;
+      bool dead = false;
+      for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
+        for (int pass = 0; pass < p.P && !dead; ++pass) {
+          for (int row = 0; row < 25; ++row, ++Wn) {
+            const int ws = (int)(Wn % WSTAGES);
+            const uint32_t use = (uint32_t)(Wn / WSTAGES);
+            if (use > 0 && !tc::mbar_wait(&B->w_empty[ws], (use - 1) & 1, ab)) { fail(); dead = true; break; }
+            const float* src = p.wtc + ((size_t)pass * 25 + row) * (WROW_BYTES / 4);
+            const uint32_t bar = tc::smem_u32(&B->w_full[ws]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WROW_BYTES)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    wring_u32 + ws * WROW_BYTES),
+                "l"(src), "r"((uint32_t)WROW_BYTES), "r"(bar)
+                : "memory");
+          }
+        }
+      }
+    }
+  }
+  // ---- teardown
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// pack kernel: PyTorch conv weight [Cout][Cin][125] -> wtc[P][125][hi|lo][2][NPAD][4]
+//   fwd  : k = ci, n = co, tap t
+//   dgrad: k = co, n = ci, tap 124 - t   (the gradient wrt x is a conv with the flipped kernel)
+__global__ void tc5_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, int NPAD, int P,
+                                float* __restrict__ out) {
+  const long long total = (long long)P * 125 * 2 * NPAD * 4;     // (pass, tap, kc, n, e)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 3); long long r = i >> 2;
+    const int n = (int)(r % NPAD); r /= NPAD;
+    const int kc = (int)(r & 1); r >>= 1;
+    const int t = (int)(r % 125); const int pass = (int)(r / 125);
+    const int k = pass * 8 + kc * 4 + e;
+    const int K = dgrad ? Cout : Cin, Nn = dgrad ? Cin : Cout;
+    float v = 0.f;
+    if (k < K && n < Nn) {
+      const int co = dgrad ? k : n, ci = dgrad ? n : k;
+      const int ts = dgrad ? 124 - t : t;
+      v = w[((long long)co * Cin + ci) * 125 + ts];
+    }
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hi = __uint_as_float(h), lo = v - hi;
+    const long long base = (((long long)pass * 125 + t) * 2) * 2 * NPAD * 4;      // start of this tap (hi part)
+    const long long off = ((long long)kc * NPAD + n) * 4 + e;
+    out[base + off] = hi;
+    out[base + 2LL * NPAD * 4 + off] = lo;
+  }
+}
+
+template <int NPAD, int ZT>
+int launch_tc5(TC5Params p, cudaStream_t st) {
+  constexpr int WROW_BYTES = 5 * 2 * 2 * NPAD * 16;
+  const size_t smem = (size_t)(ZT + 1) * PLANE_BYTES + (size_t)WSTAGES * WROW_BYTES + sizeof(Barriers) + 64;
+  p.tiles_z = p.D / ZT;
+  p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
+  auto kern = conv_tc5_kernel<NPAD, ZT>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      crn_set_error("conv_tc5: cannot set %zu bytes of dynamic shared memory", smem);
+      return CRN_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  int grid = p.nitems < kNumSMs ? p.nitems : kNumSMs;
+  kern<<<grid, NTHREADS, smem, st>>>(p);
+  CRN_LAUNCH_CHECK("conv_tc5");
+  return CRN_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t crn_tc5_packed_floats(int32_t K, int32_t N) {
+  const int P = (K + 7) / 8;
+  const int NPAD = N <= 16 ? 16 : (N <= 32 ? 32 : 64);
+  return (int64_t)P * 125 * 2 * 2 * NPAD * 4;
+}
+
+extern "C" int crn_tc5_pack(const float* w, int32_t Cout, int32_t Cin, int32_t dgrad, float* out, void* stream) {
+  CRN_REQUIRE(w && out && Cout > 0 && Cin > 0, "crn_tc5_pack: bad args");
+  const int K = dgrad ? Cout : Cin, N = dgrad ? Cin : Cout;
+  CRN_REQUIRE(N <= 64, "crn_tc5_pack: N > 64 unsupported");
+  const int P = (K + 7) / 8;
+  const int NPAD = N <= 16 ? 16 : (N <= 32 ? 32 : 64);
+  const long long total = (long long)P * 125 * 2 * NPAD * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  tc5_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cout, Cin, dgrad, NPAD, P, out);
+  CRN_LAUNCH_CHECK("tc5_pack");
+  return CRN_OK;
+}
+
+// kind 0: y = conv5(x) + bias (in = x, gK = Cin, gN = Cout); kind 1: dx = conv5^T(dy) (in = dy, gK = Cout, gN = Cin).
+extern "C" int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc,
+                            const float* bias, float* out, int32_t* status, void* stream) {
+  CRN_REQUIRE(d && in && wtc && out && status, "crn_conv5_tc: null pointer");
+  CRN_REQUIRE(!d->transposed && d->kD == 5 && d->kH == 5 && d->kW == 5 && d->stride == 1 && d->pad == 2,
+              "crn_conv5_tc: only Conv3d k=5 s=1 p=2");
+  CRN_REQUIRE(d->iD == d->oD && d->iH == d->oH && d->iW == d->oW, "crn_conv5_tc: shape mismatch");
+  CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % 8 == 0, "crn_conv5_tc: grid must tile by 8x16x8");
+  CRN_REQUIRE(!d->y_planar && !d->bias_n_stride, "crn_conv5_tc: planar / per-scene bias unsupported");
+  TC5Params p{};
+  p.in = in; p.wtc = wtc; p.bias = kind == 0 ? bias : nullptr; p.out = out; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  if (kind == 0) {
+    p.gK = d->Cin; p.gN = d->Cout; p.in_cs = d->x_cs; p.in_co = d->x_co; p.out_cs = d->y_cs; p.out_co = d->y_co;
+  } else {
+    p.gK = d->Cout; p.gN = d->Cin; p.in_cs = d->y_cs; p.in_co = d->y_co; p.out_cs = d->x_cs; p.out_co = d->x_co;
+  }
+  CRN_REQUIRE(p.gN % 4 == 0 && p.gK % 4 == 0 && p.gN <= 64, "crn_conv5_tc: channels must be multiples of 4, N <= 64");
+  CRN_REQUIRE(p.in_cs % 4 == 0 && p.in_co % 4 == 0 && p.out_cs % 4 == 0 && p.out_co % 4 == 0,
+              "crn_conv5_tc: channel strides/offsets must be multiples of 4");
+  p.P = (p.gK + 7) / 8;
+  p.tiles_x = p.W / TX; p.tiles_y = p.H / TY;
+  cudaStream_t st = crn_stream(stream);
+  // 8 output planes per item while two accumulator stages fit in TMEM (2*ZT*NPAD <= 512 columns), else 4
+  if (p.gN <= 16) return launch_tc5<16, 8>(p, st);
+  if (p.gN <= 32) return launch_tc5<32, 8>(p, st);
+  return launch_tc5<64, 4>(p, st);
+}

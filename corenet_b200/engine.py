@@ -65,6 +65,23 @@ def conv_call(kind, layer, d, *args):
   PROFILE.append((kind, layer.name, conv_macs(d), e0, e1))
 
 
+# Conv3d k=5 layers at >= 32^3 run forward/dgrad on the tcgen05 tensor cores (3xTF32, csrc/conv_tc5.cu).
+USE_TC = True
+
+
+def conv5_tc_call(kind, layer, d, inp, wtc, bias, out, status, st):
+  """kind: 'fwd' | 'dgrad' through crn_conv5_tc."""
+  k = 0 if kind == "fwd" else 1
+  if PROFILE is None:
+    _lib.call("crn_conv5_tc", C.byref(d), k, inp, wtc, bias, out, status, st)
+    return
+  e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+  e0.record()
+  _lib.call("crn_conv5_tc", C.byref(d), k, inp, wtc, bias, out, status, st)
+  e1.record()
+  PROFILE.append((kind + "_tc", layer.name, conv_macs(d), e0, e1))
+
+
 class Buf:
   """rows x C activation, channels-last with channel stride cs; .g is its gradient."""
 
@@ -198,6 +215,15 @@ class Engine:
     self.w_fwd = t.zeros(self.total, dtype=t.float32, device=dev)
     self.w_dgrad = t.zeros(self.total, dtype=t.float32, device=dev)
     self.dw = t.zeros(self.total, dtype=t.float32, device=dev)
+    # tcgen05 path: per eligible Conv3d(k=5) layer a pre-split (hi/lo) packed copy for fwd and for dgrad
+    self.tc_status = t.zeros(1, dtype=t.int32, device=dev)
+    self.tc_w = {}
+    lib = _lib.lib()
+    for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
+      l = self.L[f"stage_{stage}.c1"]
+      if l.k == (5, 5, 5) and g >= 32 and g % 16 == 0 and cin <= 64 and mid <= 64:
+        self.tc_w[l.name] = (t.zeros(lib.crn_tc5_packed_floats(cin, mid), dtype=t.float32, device=dev),
+                             t.zeros(lib.crn_tc5_packed_floats(mid, cin), dtype=t.float32, device=dev))
     self.plans = {}
     self._ptr_sig = None
     self._ver_sig = None
@@ -243,6 +269,12 @@ class Engine:
     if ver_sig != self._ver_sig:
       _call("crn_pack_weights", self._items_dev.data_ptr(), self._offs_dev.data_ptr(), len(self.layers),
             self.total, _lib.stream_ptr())
+      for l in self.layers:
+        if l.name in self.tc_w:
+          w = P[l.name + ".weight"]
+          wf, wd = self.tc_w[l.name]
+          _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 0, wf.data_ptr(), _lib.stream_ptr())
+          _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 1, wd.data_ptr(), _lib.stream_ptr())
       self._ver_sig = ver_sig
 
   def unpack_wgrads(self, grads: Dict[str, t.Tensor]):
@@ -490,7 +522,11 @@ class Plan:
     for sd in self.stages:
       g = sd["g"]
       sd["bn1"].fwd(training)
-      conv_call("fwd", sd["lc"], sd["d_c"], sd["z"].p, eng.wf(sd["lc"]), bias(sd["lc"]), sd["c"].p, 0, st)
+      if USE_TC and sd["lc"].name in eng.tc_w:
+        conv5_tc_call("fwd", sd["lc"], sd["d_c"], sd["z"].p, eng.tc_w[sd["lc"].name][0].data_ptr(), bias(sd["lc"]),
+                      sd["c"].p, eng.tc_status.data_ptr(), st)
+      else:
+        conv_call("fwd", sd["lc"], sd["d_c"], sd["z"].p, eng.wf(sd["lc"]), bias(sd["lc"]), sd["c"].p, 0, st)
       sd["bn2"].fwd(training)
       if sd["stage"] < 6:
         nxt = sd["next"]
@@ -571,7 +607,11 @@ class Plan:
       dxs = sd["bn2"].bwd(tr, grads, sd["z2"].gp, sd["z2"].cs, sd["c"].gp, sd["c"].cs)
       bias_from(dxs, lc.name + ".bias")
       wgrad(lc, sd["d_c"], sd["z"].p, sd["c"].gp)
-      dgrad(lc, sd["d_c"], sd["c"].gp, sd["z"].gp, 0)
+      if USE_TC and lc.name in eng.tc_w:
+        conv5_tc_call("dgrad", lc, sd["d_c"], sd["c"].gp, eng.tc_w[lc.name][1].data_ptr(), None, sd["z"].gp,
+                      eng.tc_status.data_ptr(), st)
+      else:
+        dgrad(lc, sd["d_c"], sd["c"].gp, sd["z"].gp, 0)
       cat = sd["cat"]
       dxs = sd["bn1"].bwd(tr, grads, sd["z"].gp, sd["z"].cs, cat.gp, cat.cs)
       sd["dxs_cat"] = dxs

@@ -247,6 +247,24 @@ int crn_voxelize_mesh(const float* triangles, const int32_t* tri_mesh, int32_t T
 int crn_merge_mesh_grids(const float* mesh_grids, const int32_t* mesh_scene, const float* labels,
                          int32_t M, int64_t voxels, int32_t* out, void* stream);
 
+/* Bring-up / self-test of the tcgen05 (5th-gen tensor core) path: D[128,N] = A[128,K] * B[N,K]^T with
+ * tf32 operands and an fp32 TMEM accumulator; mode 0 = single-pass TF32, 1 = 3xTF32 split.
+ * status (device int) is set to 1 if the mbarrier wait timed out. */
+int crn_tc_probe(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode,
+                 int32_t* status, void* stream);
+
+/* Conv3d k=5 s=1 p=2 forward / dgrad on tcgen05 tensor cores (3xTF32, fp32 TMEM accumulators):
+ * replaces the cuDNN call behind nn.Conv3d(k=5) at model/reconstruction_decoder.py:66,74,82,91.
+ * Weights are pre-split (hi/lo) and packed per 8-channel pass by crn_tc5_pack (w is the PyTorch
+ * parameter [Cout][Cin][5][5][5]; dgrad != 0 packs the flipped/transposed operator); out must hold
+ * crn_tc5_packed_floats(K, N) floats.  kind 0: y = conv(x)+bias, kind 1: dx = conv^T(dy).
+ * The grid must tile by 8 (x) x 16 (y) x 8 (z); N <= 64.  *status (device int) is set to 1 if an
+ * internal barrier wait timed out (the result is then invalid). */
+int64_t crn_tc5_packed_floats(int32_t K, int32_t N);
+int crn_tc5_pack(const float* w, int32_t Cout, int32_t Cin, int32_t dgrad, float* out, void* stream);
+int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc, const float* bias,
+                 float* out, int32_t* status, void* stream);
+
 /* Fused Adam step over a flat list (state.py:65-66) — next-row (f2) op. */
 int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream);

@@ -84,6 +84,8 @@ def test_forward_backward_parity(golden, case, mode):
   loss = losses.iou_fgbg(gt.to(dev), logits)
   loss.backward()
   e = rel_err(logits, lo)
+  from corenet_b200 import engine as engine_lib
+  assert int(engine_lib.get_engine(m).tc_status) == 0, "tcgen05 conv kernel reported a barrier timeout"
   print(f"\n[{case}/{mode}] logits rel err {e:.3e}  loss {loss.item():.7f} vs {loss_o:.7f}")
   assert e <= FWD_TOL
   assert abs(loss.item() - loss_o) <= 1e-4

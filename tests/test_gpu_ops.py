@@ -89,6 +89,45 @@ def test_conv_fwd_bwd(case):
   assert rel_err(b_c.grad, b_o.grad) < 2e-5, "bias grad"
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw", [(1, 8, 16, (8, 16, 8)), (2, 28, 16, (16, 32, 16)), (1, 56, 32, (8, 16, 16)),
+                                              (1, 16, 12, (8, 16, 24))])
+@pytest.mark.parametrize("kind", [0, 1], ids=["fwd", "dgrad"])
+def test_conv5_tcgen05(n, cin, cout, dhw, kind):
+  """Conv3d k=5 on the tcgen05 tensor cores (3xTF32 + fp32 TMEM accumulation) against the fp64 oracle.
+  Tolerance 2e-4 of the tensor max: the tensor core's fp32 accumulator truncates (measured ~3e-5 over 375
+  accumulations), operands are exact to ~2^-21."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 7 + cout + kind)
+  wt = t.randn(cout, cin, 5, 5, 5, generator=g) * 0.05
+  bias = t.randn(cout, generator=g)
+  r4 = lambda c: (c + 3) // 4 * 4
+  if kind == 0:
+    x = t.randn(n, cin, d, h, w, generator=g)
+    ref = F.conv3d(x.double(), wt.double(), bias.double(), padding=2)
+    K, N = cin, cout
+  else:
+    x = t.randn(n, cout, d, h, w, generator=g)
+    ref = F.conv_transpose3d(x.double(), wt.double(), None, padding=2)
+    K, N = cout, cin
+  xin = t.zeros(n * d * h * w, r4(K), device=dev())
+  xin[:, :K] = x.permute(0, 2, 3, 4, 1).reshape(-1, K).to(dev())
+  out = t.full((n * d * h * w, r4(N)), float("nan"), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tc5_packed_floats(K, N), device=dev())
+  st = _lib.stream_ptr()
+  _lib.call("crn_tc5_pack", wt.to(dev()).contiguous().data_ptr(), cout, cin, kind, wtc.data_ptr(), st)
+  desc = ops.make_desc(n, cin, cout, (d, h, w), (d, h, w), (5, 5, 5), 1, 2, False, r4(cin), r4(cout))
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  b = bias.to(dev())
+  _lib.call("crn_conv5_tc", C.byref(desc), kind, xin.data_ptr(), wtc.data_ptr(), b.data_ptr(), out.data_ptr(),
+            status.data_ptr(), st)
+  t.cuda.synchronize()
+  assert int(status) == 0
+  got = out[:, :N].reshape(n, d, h, w, N).permute(0, 4, 1, 2, 3)
+  assert rel_err(got, ref) < 2e-4
+
+
 def test_linear():
   from corenet_b200 import ops
   g = t.Generator().manual_seed(5)
