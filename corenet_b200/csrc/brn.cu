@@ -25,7 +25,9 @@ static ColGrid col_grid(int64_t rows, int cgroups) {
   const int tyc = NT / txc;
   const int gy = (int)crn_ceil_div(cgroups, txc);
   int64_t gx = crn_ceil_div(rows, tyc);
-  int64_t target = crn_ceil_div(8LL * kNumSMs, gy);
+  // few, fat blocks: every block ends with one double atomicAdd per channel, and >1000 blocks hammering
+  // the same 2*C addresses cost more than the whole streaming pass (profiles/r01_launch_list_step_summary.txt)
+  int64_t target = crn_ceil_div(2LL * kNumSMs, gy);
   if (gx > target) gx = target;
   if (gx < 1) gx = 1;
   g.grid = dim3((unsigned)gx, (unsigned)gy, 1);

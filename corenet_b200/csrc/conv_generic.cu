@@ -42,6 +42,7 @@ struct GatherParams {
   int in_cs, in_co, out_cs, out_co;
   int class_mode;   // 0 DIRECT, 1 CLASS
   int accumulate, planar, bias_n_stride;
+  int ksplit;       // >1: the (tap, K-chunk) loop is split over blockIdx.z and partial sums are added atomically
 };
 
 struct AxisPlan {
@@ -83,8 +84,9 @@ __global__ void __launch_bounds__(NT) gather_gemm_kernel(const GatherParams p) {
   const int tid = threadIdx.x;
   // ---- per-class axis plans
   int cz = 0, cy = 0, cx = 0;
+  const int split = blockIdx.z % p.ksplit;
   if (p.class_mode) {
-    int c = blockIdx.z;
+    int c = blockIdx.z / p.ksplit;
     cx = c % p.s[2]; c /= p.s[2];
     cy = c % p.s[1]; c /= p.s[1];
     cz = c;
@@ -97,7 +99,10 @@ __global__ void __launch_bounds__(NT) gather_gemm_kernel(const GatherParams p) {
 
   const int ntaps = az.nk * ay.nk * ax.nk;
   const int nchunks = (p.gK + KC - 1) / KC;
-  const int niter = ntaps * nchunks;
+  const int niter_all = ntaps * nchunks;
+  const int it_begin = (int)((long long)niter_all * split / p.ksplit);
+  const int niter = (int)((long long)niter_all * (split + 1) / p.ksplit);   // loop runs [it_begin, niter)
+  const bool atomic_out = p.ksplit > 1;
 
   // ---- A-load slots: this thread loads float4 (row a_row0 + s*64, chans a_kq*4..+3)
   constexpr int LA = (TM * KC / 4) / NT;
@@ -187,12 +192,12 @@ __global__ void __launch_bounds__(NT) gather_gemm_kernel(const GatherParams p) {
 #pragma unroll
     for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
 
-  if (niter > 0) {
-    load_global(0);
+  if (niter > it_begin) {
+    load_global(it_begin);
     store_smem();
   }
   __syncthreads();
-  for (int it = 0; it < niter; ++it) {
+  for (int it = it_begin; it < niter; ++it) {
     if (it + 1 < niter) load_global(it + 1);
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
@@ -244,7 +249,14 @@ __global__ void __launch_bounds__(NT) gather_gemm_kernel(const GatherParams p) {
           if (c >= p.gN) continue;
           float* dst = p.out + pos * p.out_cs + p.out_co + c;
           float v[4] = {acc[i][j4 * 4 + 0], acc[i][j4 * 4 + 1], acc[i][j4 * 4 + 2], acc[i][j4 * 4 + 3]};
-          if (c + 3 < p.gN) {
+          if (atomic_out) {
+            // split-K: partial sums meet in memory (out was zeroed, or holds the value to accumulate onto)
+            for (int e = 0; e < 4 && c + e < p.gN; ++e) {
+              float u = v[e];
+              if (split == 0 && !p.accumulate && p.bias) u += p.bias[(long long)n * p.bias_n_stride + c + e];
+              atomicAdd(dst + e, u);
+            }
+          } else if (c + 3 < p.gN) {
             if (p.accumulate) {
               const float4 o = *reinterpret_cast<const float4*>(dst);
               v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
@@ -279,6 +291,11 @@ __global__ void __launch_bounds__(NT) gather_gemm_kernel(const GatherParams p) {
         o = ((long long)n * p.gN + c) * S + (((long long)oz * p.oD[1] + oy) * p.oD[2] + ox);
       } else {
         o = pos * p.out_cs + p.out_co + c;
+      }
+      if (atomic_out) {
+        if (split == 0 && !p.accumulate && p.bias) v += p.bias[(long long)n * p.bias_n_stride + c];
+        atomicAdd(p.out + o, v);
+        continue;
       }
       if (p.accumulate) {
         v += p.out[o];
@@ -477,35 +494,55 @@ void axis_setup(const crn_conv_desc* d, int s[3], int pad[3], int K[3], int iD[3
 }
 
 template <int TM, int TN, int RM, int RN>
-int launch_gather_cfg(const GatherParams& p, long long max_rows, int nclasses, cudaStream_t st) {
-  dim3 grid((unsigned)crn_ceil_div(max_rows, TM), (unsigned)crn_ceil_div(p.gN, TN), (unsigned)nclasses);
+int launch_gather_cfg(GatherParams p, long long max_rows, int nclasses, int taps, cudaStream_t st) {
+  const long long blocks = crn_ceil_div(max_rows, TM) * crn_ceil_div(p.gN, TN) * nclasses;
+  // split-K when the output tile grid cannot fill the machine (small grids with a huge tap x channel
+  // reduction: encoder stages 4-5 at small batch, decoder stages 1-3).  Needs a dense, exclusively owned
+  // output so that it can be zeroed first.
+  p.ksplit = 1;
+  const long long niter = (long long)taps * crn_ceil_div(p.gK, KC);
+  const bool dense_out = !p.planar && p.out_co == 0 && p.out_cs == (p.gN + 3) / 4 * 4;
+  if (blocks < kNumSMs && niter >= 8 && dense_out && !(crn_get_flags() & 16)) {
+    long long ks = crn_ceil_div(2LL * kNumSMs, blocks);
+    if (ks > niter / 4) ks = niter / 4;
+    if (ks > 64) ks = 64;
+    if (ks > 1) {
+      p.ksplit = (int)ks;
+      if (!p.accumulate) {
+        long long out_rows = p.N;
+        for (int a = 0; a < 3; ++a) out_rows *= p.oD[a];
+        cudaMemsetAsync(p.out, 0, sizeof(float) * out_rows * p.out_cs, st);
+      }
+    }
+  }
+  dim3 grid((unsigned)crn_ceil_div(max_rows, TM), (unsigned)crn_ceil_div(p.gN, TN), (unsigned)(nclasses * p.ksplit));
   gather_gemm_kernel<TM, TN, RM, RN><<<grid, NT, 0, st>>>(p);
   CRN_LAUNCH_CHECK("gather_gemm");
   return CRN_OK;
 }
 
 int launch_gather(const GatherParams& p, cudaStream_t st) {
-  // rows of the largest class
+  // rows of the largest class, taps of the largest class
   long long max_rows = p.N;
-  int nclasses = 1;
+  int nclasses = 1, taps = 1;
   for (int a = 0; a < 3; ++a) {
     if (p.class_mode) {
       max_rows *= (p.oD[a] + p.s[a] - 1) / p.s[a];
       nclasses *= p.s[a];
+      taps *= (p.Kd[a] + p.s[a] - 1) / p.s[a];
     } else {
       max_rows *= p.oD[a];
+      taps *= p.Kd[a];
     }
   }
   if (max_rows <= 0) return CRN_OK;
   const int n = p.gN;
-  if (n <= 16) return launch_gather_cfg<256, 16, 8, 2>(p, max_rows, nclasses, st);
-  if (n <= 32) return launch_gather_cfg<256, 32, 8, 4>(p, max_rows, nclasses, st);
-  // pick the largest tile that still fills the machine
-  const long long b128 = crn_ceil_div(max_rows, 128) * crn_ceil_div(n, 128) * nclasses;
-  if (n > 64 && b128 >= 2 * kNumSMs) return launch_gather_cfg<128, 128, 8, 8>(p, max_rows, nclasses, st);
-  const long long b64 = crn_ceil_div(max_rows, 128) * crn_ceil_div(n, 64) * nclasses;
-  if (b64 >= kNumSMs) return launch_gather_cfg<128, 64, 8, 4>(p, max_rows, nclasses, st);
-  return launch_gather_cfg<64, 64, 4, 4>(p, max_rows, nclasses, st);
+  if (n <= 16) return launch_gather_cfg<256, 16, 8, 2>(p, max_rows, nclasses, taps, st);
+  if (n <= 32) return launch_gather_cfg<256, 32, 8, 4>(p, max_rows, nclasses, taps, st);
+  // the largest register tile the problem can use; split-K restores the parallelism on small grids
+  if (max_rows <= 64) return launch_gather_cfg<64, 64, 4, 4>(p, max_rows, nclasses, taps, st);
+  if (n > 64 && max_rows >= 256) return launch_gather_cfg<128, 128, 8, 8>(p, max_rows, nclasses, taps, st);
+  return launch_gather_cfg<128, 64, 8, 4>(p, max_rows, nclasses, taps, st);
 }
 
 }  // namespace

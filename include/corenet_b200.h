@@ -39,7 +39,7 @@ const char* crn_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py gpu_launches). */
 int64_t crn_launch_count(void);
 /* Debug / A-B switches: bit0 = disable the row-direct conv kernels, bit1 = disable the tap-row wgrad
- * kernel (both fall back to the generic implicit-GEMM kernels). */
+ * kernel (both fall back to the generic implicit-GEMM kernels), bit4 = disable split-K in the generic kernel. */
 void crn_set_flags(int32_t flags);
 
 /* ------------------------------------------------------------------------
