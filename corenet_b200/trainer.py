@@ -24,6 +24,15 @@ def shard_indices(num_items: int, rank: int, world: int, pad: bool = True):
   return idx[rank::world]
 
 
+def allreduce_flat_grad(flat_grad: t.Tensor, world: int, group=None) -> float:
+  """The path's single exchange step: in-place sum-all-reduce of the flat gradient buffer (NCCL on the
+  GPU box, gloo in the CPU tests).  Returns the scale (1/world) the optimiser kernel must apply to get
+  DDP's rank average."""
+  if world > 1:
+    t.distributed.all_reduce(flat_grad, op=t.distributed.ReduceOp.SUM, group=group)
+  return 1.0 / world
+
+
 def flatten_parameters(model: t.nn.Module):
   """Re-points every parameter at a view of ONE flat fp32 buffer (names/shapes/state_dict unchanged)."""
   params = list(model.parameters())
@@ -91,12 +100,9 @@ class Trainer:
     _call("crn_loss_bwd", logits.data_ptr(), gt.data_ptr(), is64, b, c, s, self.mode, lb["coef"].data_ptr(),
           None, lb["dlogits"].data_ptr(), st)
     plan.backward(lb["dlogits"], self.grads)
-    if self.world > 1:
-      # the path's single exchange step: sum-all-reduce of the flat gradient (DDP averages -> 1/world below)
-      t.distributed.all_reduce(self.grad, op=t.distributed.ReduceOp.SUM, group=self.pg)
+    scale = allreduce_flat_grad(self.grad, self.world, self.pg)
     self.step_count += 1
     _call("crn_adam_step", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-          self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
-          1.0 / self.world, st)
+          self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, scale, st)
     eng._ver_sig = None        # the fused Adam kernel changed the weights: re-pack on the next forward
     return lb["loss"]
