@@ -214,3 +214,56 @@ def test_trainer_step_matches_reference_adam():
   # docstring); bound the distribution: median tight, worst loose
   med = sorted(e for e, _ in errs)[len(errs) // 2]
   assert med < 1e-2 and errs[0][0] < 0.25, (med, errs[:3])
+
+
+def test_mean_iou_parity_and_inference_plug():
+  """h7-style eval (B=2, C=2): forward -> softmax -> argmax -> confusion matrix -> mean IoU through the CUDA
+  kernels vs the oracle (voxel_metrics.py:33-58, evaluation_results.py:262-266): |delta mIoU| <= 0.1 pt."""
+  from corenet_b200 import ops
+  from corenet_b200.super_resolution import super_resolution_from_model
+  dev = t.device("cuda", 0)
+  inp = MG.case_inputs("B")
+  m = build_model()
+  sd = {k: v.clone() for k, v in m.state_dict().items()}
+  gt = MG.synthetic_gt(2, 2)
+  lo = O.corenet_forward(dict(sd), inp["image"], inp["v2s"], inp["offsets"], False)
+  cm_o = O.confusion_matrix(lo.argmax(1), gt, 2)
+  m = m.to(dev).eval()
+  with t.no_grad():
+    logits = m(inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev))
+  cm = ops.argmax_confusion(logits, gt.to(dev)).cpu()
+  assert int(cm.sum()) == gt.numel()
+  assert abs(O.mean_iou(cm) - O.mean_iou(cm_o)) <= 1e-3           # 0.1 pt
+  assert (cm - cm_o).abs().sum().item() <= 1e-5 * gt.numel()      # only near-tie voxels may differ
+  # inference plug point at the native resolution = softmax of the model output
+  sr = super_resolution_from_model(m)
+  cam = t.eye(4, device=dev)[None].expand(2, 4, 4)
+  pmf = sr(inp["image"].to(dev), inp["v2s"].to(dev), cam, inp["offsets"].to(dev), (128, 128, 128))
+  assert rel_err(pmf, lo.softmax(1)) <= 1e-3
+
+
+def test_device_resident_gt_pipeline():
+  """batched_example.voxelize on the GPU (rasterise -> fill -> label merge) vs the oracles, two scenes with
+  1 and 2 meshes (cubes), semantic labels."""
+  from corenet_b200.data import batched_example as be
+  from oracle import fill_voxels_oracle as FO
+  from oracle import voxelize_oracle as VO
+  from tests.conftest import cube_mesh
+  res = (12, 12, 12)
+  c1 = cube_mesh(0.99) / 3.0 * 0.5 + 0.1          # cubes inside the unit cube
+  c2 = cube_mesh(0.99) / 3.0 * 0.4 + 0.45
+  c3 = cube_mesh(0.99) / 3.0 * 0.3 + 0.05
+  verts = t.from_numpy(np.concatenate([c1, c2, c3]))
+  ntri = [t.tensor([12], dtype=t.int32), t.tensor([12, 12], dtype=t.int32)]
+  offs = t.tensor([[0.5, 0.5, 0.5], [0.25, 0.5, 0.75]])
+  labels = [[3], [2, 5]]
+  v2x, grid = be.voxelize(verts, ntri, offs, res, be.VoxelContentSemanticLabel(labels), image_resolution_multiplier=8)
+  assert grid.dtype == t.int32 and tuple(grid.shape) == (2, 12, 12, 12) and grid.is_cuda
+  # oracle chain
+  w2x = [O.translate(offs[b] - 0.5) @ O.scale([12.0] * 3) for b in range(2)]
+  mesh_v2x = np.stack([w2x[0].numpy(), w2x[1].numpy(), w2x[1].numpy()])
+  occ = VO.voxelize_mesh_oracle(verts.numpy(), [12, 12, 12], res, mesh_v2x, image_resolution_multiplier=8)
+  occ = FO.fill_inside_voxels_oracle(occ)
+  exp = np.stack([3 * occ[0], np.maximum(2 * occ[1], 5 * occ[2])]).astype(np.int32)
+  np.testing.assert_array_equal(grid.cpu().numpy(), exp)
+  assert exp[0].sum() > 0 and (exp[1] == 5).sum() > 0
