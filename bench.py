@@ -230,6 +230,9 @@ def run_native(args):
   for _ in range(2):
     e2e_step()
   ms_e2e = timed(e2e_step, args.steps)
+  tc_status = int(engine.get_engine(model).tc_status)
+  if tc_status != 0:
+    raise RuntimeError("tcgen05 conv kernel reported a barrier timeout: results are invalid")
   total_vox = world * b * VOX * args.steps
   value = total_vox / (ms * 1e-3)
   e2e_value = total_vox / (ms_e2e * 1e-3)

@@ -72,7 +72,7 @@ __device__ __forceinline__ AxisPlan make_axis(const GatherParams& p, int a, int 
 }
 
 template <int TM, int TN, int RM, int RN>
-__global__ void __launch_bounds__(NT) gather_gemm_kernel(const GatherParams p) {
+__global__ void __launch_bounds__(NT, (RM * RN <= 32) ? 2 : 1) gather_gemm_kernel(const GatherParams p) {
   constexpr int TX = TN / RN;
   constexpr int TY = TM / RM;
   static_assert(TX * TY == NT, "thread layout");

@@ -45,7 +45,7 @@ __device__ __forceinline__ void load_group(const float* p, float (&v)[SW]) {
 }
 
 template <int KX, int SS, int SW, bool SHIFT_IS_CI>
-__global__ void __launch_bounds__(320) wgrad_row_kernel(const WRowParams p) {
+__global__ void __launch_bounds__(KX == 5 ? 160 : 256, KX == 5 ? 3 : 2) wgrad_row_kernel(const WRowParams p) {
   extern __shared__ __align__(16) float smem[];
   float* cS = smem;
   float* sS = smem + p.center_floats;
@@ -113,33 +113,52 @@ __global__ void __launch_bounds__(320) wgrad_row_kernel(const WRowParams p) {
     __syncthreads();
     if (!active) continue;
     for (int yy = sigma; yy < p.TY && y0 + yy < p.cH; yy += p.nstream) {
-      const float* crow = cS + (size_t)(yy * p.cW) * cstride + cq * 4;
-      const float* srow = sS + (size_t)((yy * SS + ky) * p.SWd) * sstride + sq * SW;
+      // running pointers (in floats): the unrolled body below only uses compile-time offsets from them
+      const float* cptr = cS + (yy * p.cW) * cstride + cq * 4;
+      const float* sptr = sS + ((yy * SS + ky) * p.SWd) * sstride + sq * SW;
       float w[KX][SW];
 #pragma unroll
-      for (int k = 0; k < KX; ++k) load_group<SW>(srow + (size_t)k * sstride, w[k]);
-      for (int x0 = 0; x0 < p.cW; x0 += KX) {
+      for (int k = 0; k < KX; ++k) load_group<SW>(sptr + k * sstride, w[k]);
+      sptr += KX * sstride;                       // next shifted element to load
+      const int nfull = p.cW / KX;                // full groups of KX positions (no bounds checks inside)
+      for (int gi = 0; gi < nfull; ++gi) {
 #pragma unroll
         for (int jj = 0; jj < KX; ++jj) {
-          const int x = x0 + jj;
-          if (x < p.cW) {
-            const float4 c4 = *reinterpret_cast<const float4*>(crow + (size_t)x * cstride);
-            const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+          const float4 c4 = *reinterpret_cast<const float4*>(cptr + jj * cstride);
+          const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-            for (int k = 0; k < KX; ++k) {
-              const int slot = (SS * jj + k) % KX;      // compile-time after unrolling
+          for (int k = 0; k < KX; ++k) {
+            const int slot = (SS * jj + k) % KX;      // compile-time after unrolling
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < SW; ++j) acc[k][i][j] = fmaf(cv[i], w[slot][j], acc[k][i][j]);
-            }
-            if (x + 1 < p.cW) {
+              for (int j = 0; j < SW; ++j) acc[k][i][j] = fmaf(cv[i], w[slot][j], acc[k][i][j]);
+          }
+          // slide the window by SS elements; the staged row holds SS*(cW-1)+KX elements, so only the load
+          // after the very last position could run past it (guarded by the host-side +SS padding columns)
 #pragma unroll
-              for (int e = 0; e < SS; ++e) {
-                const int slot = (SS * jj + e) % KX;
-                load_group<SW>(srow + (size_t)(SS * x + KX + e) * sstride, w[slot]);
-              }
-            }
+          for (int e = 0; e < SS; ++e) load_group<SW>(sptr + (SS * jj + e) * sstride, w[(SS * jj + e) % KX]);
+        }
+        cptr += KX * cstride;
+        sptr += SS * KX * sstride;
+      }
+      const int rem = p.cW - nfull * KX;          // tail positions (< KX), same code with guards
+#pragma unroll
+      for (int jj = 0; jj < KX; ++jj) {
+        if (jj < rem) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cptr + jj * cstride);
+          const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int k = 0; k < KX; ++k) {
+            const int slot = (SS * jj + k) % KX;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < SW; ++j) acc[k][i][j] = fmaf(cv[i], w[slot][j], acc[k][i][j]);
+          }
+          if (jj + 1 < rem) {
+#pragma unroll
+            for (int e = 0; e < SS; ++e) load_group<SW>(sptr + (SS * jj + e) * sstride, w[(SS * jj + e) % KX]);
           }
         }
       }
@@ -223,7 +242,9 @@ int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, f
   const int roles = p.KY * p.SQ * CQb;
   if (roles > 320 || p.cW < KX) return CRN_ERR_UNSUPPORTED;
   p.CQb = CQb; p.NCQG = p.CQ / CQb;
-  int nstream = 224 / roles;
+  const int max_threads = conv5 ? 160 : 256;     // = the kernel's __launch_bounds__
+  if (roles > max_threads) return CRN_ERR_UNSUPPORTED;
+  int nstream = (conv5 ? 160 : 224) / roles;
   if (nstream < 1) nstream = 1;
   if (nstream > 8) nstream = 8;
   int TY = nstream > 2 ? nstream : 2;
@@ -233,7 +254,7 @@ int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, f
   for (;;) {
     p.TY = TY; p.nstream = nstream;
     p.SR = (TY - 1) * SS + p.KY;
-    p.SWd = (p.cW - 1) * SS + KX;
+    p.SWd = (p.cW - 1) * SS + KX + SS;       // + SS look-ahead columns read (never used) by the window slide
     p.center_floats = TY * p.cW * CQb * 4;
     smem_bytes = sizeof(float) * ((size_t)p.center_floats + (size_t)p.SR * p.SWd * p.SQ * SW);
     if (smem_bytes <= 100 * 1024 || TY == 1) break;
@@ -243,7 +264,7 @@ int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, f
   if (smem_bytes > 150 * 1024) return CRN_ERR_UNSUPPORTED;
   p.ntiles = (long long)p.N * p.cD * ((p.cH + TY - 1) / TY);
   int threads = ((nstream * roles + 31) / 32) * 32;
-  if (threads > 320) return CRN_ERR_UNSUPPORTED;
+  if (threads > max_threads) return CRN_ERR_UNSUPPORTED;
   const int groups = p.KZ * p.NCQG;
   if (conv5) return launch<5, 1, 4, true>(p, threads, smem_bytes, groups, st);
   return launch<7, 2, 2, false>(p, threads, smem_bytes, groups, st);
