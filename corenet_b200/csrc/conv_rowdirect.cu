@@ -29,6 +29,7 @@ struct RDParams {
   int class_mode, accumulate, planar, bias_n_stride;
   int TY, XG, NCG;     // lattice rows per tile, thread groups along x, cout groups per block
   int KCH;             // K channels staged per step (multiple of KW)
+  int g_shift;         // log2(KCH / KW) or -1
   int SR, SWd, SWs;    // staged rows, staged width (voxels), skewed width
 };
 
@@ -67,6 +68,18 @@ __device__ __forceinline__ void lds_group(const float* p, float (&v)[KW]) {
   } else {
     const float2 t = *reinterpret_cast<const float2*>(p);
     v[0] = t.x; v[1] = t.y;
+  }
+}
+
+template <int KW>
+__device__ __forceinline__ void cp_async_group(float* dst, const float* src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  if constexpr (KW == 4) {
+    const int sz = ok ? 16 : 0;                    // src-size 0 => zeros, nothing read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
+  } else {
+    const int sz = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
   }
 }
 
@@ -118,52 +131,49 @@ __global__ void __launch_bounds__(256) rowdirect_kernel(const RDParams p) {
     const int kz = az.k0 + az.kstep * jz;
     for (int kc0 = 0; kc0 < p.gK; kc0 += p.KCH) {
       __syncthreads();
-      // ---- stage the input slab (zero outside the grid = conv padding / missing taps)
+      // ---- stage the input slab with cp.async (zero-fill outside the grid = conv padding / missing taps);
+      // (row, unit) advance incrementally per thread: no per-element divisions
       {
-        const int units = p.SR * p.SWd * groups;
-        for (int u = tid; u < units; u += blockDim.x) {
-          const int g = u % groups; int r = u / groups;
-          const int c = r % p.SWd; const int rr = r / p.SWd;
-          const int py = y0 * ISTEP + ymin + rr, px = xmin + c;
+        const int upr = p.SWd * groups;               // K-group units per staged row
+        int rr = tid / upr, cu = tid - rr * upr;
+        const long long plane = ((long long)n * p.iD[0] + pz) * p.iD[1];
+        const int py0 = y0 * ISTEP + ymin;
+        while (rr < p.SR) {
+          int c, g;
+          if (p.g_shift >= 0) { c = cu >> p.g_shift; g = cu & (groups - 1); } else { c = cu / groups; g = cu - c * groups; }
+          const int py = py0 + rr, px = xmin + c;
           const int k = kc0 + g * KW;
-          float v[KW];
-#pragma unroll
-          for (int e = 0; e < KW; ++e) v[e] = 0.f;
-          if ((unsigned)py < (unsigned)p.iD[1] && (unsigned)px < (unsigned)p.iD[2] && k < p.gK) {
-            const long long off = ((((long long)n * p.iD[0] + pz) * p.iD[1] + py) * p.iD[2] + px) * p.in_cs +
-                                  p.in_co + k;
-            if constexpr (KW == 4) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(p.in + off));
-              v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-            } else {
-              const float2 q = __ldg(reinterpret_cast<const float2*>(p.in + off));
-              v[0] = q.x; v[1] = q.y;
-            }
-          }
+          const bool ok = (unsigned)py < (unsigned)p.iD[1] && (unsigned)px < (unsigned)p.iD[2] && k < p.gK;
+          const long long off = ok ? ((plane + py) * p.iD[2] + px) * p.in_cs + p.in_co + k : 0;
           float* dst = inS + ((size_t)rr * p.SWs + skew(c)) * p.KCH + g * KW;
-#pragma unroll
-          for (int e = 0; e < KW; ++e) dst[e] = v[e];
+          cp_async_group<KW>(dst, p.in + off, ok);
+          cu += blockDim.x;
+          while (cu >= upr) { cu -= upr; ++rr; }
         }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
       }
-      // ---- stage this step's weights in window order: wS[ryc][dxc][k][co]
+      // ---- stage this step's weights in window order: wS[ryc][dxc][k][co]; a warp per (ryc, dxc) tap
       {
-        const int units = ay.nk * NKX * p.KCH * ncols;
-        for (int u = tid; u < units; u += blockDim.x) {
-          const int c = u % ncols; int r = u / ncols;
-          const int k = r % p.KCH; r /= p.KCH;
-          const int dxc = r % NKX; const int ryc = r / NKX;
-          float v = 0.f;
-          const int co = co_blk + c;
-          if (dxc < ax.nk && kc0 + k < p.wK && co < p.wN) {
-            const int jy = ay.offstep > 0 ? ryc : ay.nk - 1 - ryc;
-            const int jx = ax.offstep > 0 ? dxc : ax.nk - 1 - dxc;
-            const int ky = ay.k0 + ay.kstep * jy, kx = ax.k0 + ax.kstep * jx;
-            const long long tap = ((long long)kz * p.Kd[1] + ky) * p.Kd[2] + kx;
-            v = __ldg(p.w + (tap * p.wK + kc0 + k) * p.wN + co);
+        const int per_tap = p.KCH * ncols;
+        const int ntap = ay.nk * NKX;
+        for (int tp = tid >> 5; tp < ntap; tp += (int)(blockDim.x >> 5)) {
+          const int ryc = tp / NKX, dxc = tp - ryc * NKX;
+          const int jy = ay.offstep > 0 ? ryc : ay.nk - 1 - ryc;
+          const int jx = ax.offstep > 0 ? dxc : ax.nk - 1 - dxc;
+          const int ky = ay.k0 + ay.kstep * jy, kx = ax.k0 + ax.kstep * jx;
+          const long long tap = ((long long)kz * p.Kd[1] + ky) * p.Kd[2] + kx;
+          const float* wsrc = p.w + (tap * p.wK + kc0) * p.wN + co_blk;
+          float* wdst = wS + (size_t)tp * per_tap;
+          const bool tap_ok = dxc < ax.nk;
+          for (int e = (int)(tid & 31); e < per_tap; e += 32) {
+            const int k = e / ncols, c = e - k * ncols;
+            float v = 0.f;
+            if (tap_ok && kc0 + k < p.wK && co_blk + c < p.wN) v = __ldg(wsrc + (long long)k * p.wN + c);
+            wdst[e] = v;
           }
-          wS[u] = v;
         }
       }
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
       __syncthreads();
       if (!active) continue;
       for (int ryc = 0; ryc < ay.nk; ++ryc) {
@@ -256,6 +266,12 @@ int launch(RDParams p, int lext_x, int lext_y, int lext_z, int nclasses, int max
     if (kch > KW && kch > 4) kch = (kch / 2 + KW - 1) / KW * KW;
     else if (ty > 1) ty = (ty + 1) / 2;
     else return CRN_ERR_UNSUPPORTED;
+  }
+  {
+    const int g = p.KCH / KW;
+    int sh = 0;
+    while ((1 << sh) < g) ++sh;
+    p.g_shift = (1 << sh) == g ? sh : -1;
   }
   const int threads = ((p.XG * ty * ncg + 31) / 32) * 32;
   if (threads > 256) return CRN_ERR_UNSUPPORTED;

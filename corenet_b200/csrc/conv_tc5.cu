@@ -35,7 +35,7 @@ constexpr int NTHREADS = 320;                    // 4 epilogue + 4 producer + MM
 
 struct TC5Params {
   const float* in;      // [N, D, H, W, in_cs] (+ in_co)
-  const float* wtc;     // packed weights [P][125][hi|lo][2][NPAD][4]
+  const float* wtc;     // packed weights [P][125] x ([2][hi|lo][NPAD][4] (ND) or [hi|lo][2][NPAD][4])
   const float* bias;    // [gN] or null
   float* out;           // [N, D, H, W, out_cs] (+ out_co)
   int* status;          // set to 1 on a barrier timeout
@@ -63,16 +63,21 @@ __device__ __forceinline__ void decode_item(const TC5Params& p, int item, int& n
   z0 = (t % p.tiles_z) * ZT; n = t / p.tiles_z;
 }
 
-template <int NPAD, int ZT>
+// ND ("N doubling"): the hi*hi and hi*lo products share their A operand, so they are issued as ONE MMA
+// against the concatenated B = [hi rows | lo rows] (N = 2*NPAD) into 2*NPAD accumulator columns that the
+// epilogue adds; with the narrow N of these layers the MMA cost is set by the A fetch, so 2 MMAs per
+// (tap, plane) instead of 3.
+template <int NPAD, int ZT, bool ND>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NSLOT = ZT + 1;                            // plane ring
   constexpr int NPLANE = ZT + 4;                           // planes loaded per pass
   constexpr int WTAP_BYTES = 2 * 2 * NPAD * 16;            // one tap: hi|lo x 2 k-chunks x NPAD x 16 B
   constexpr int WROW_BYTES = 5 * WTAP_BYTES;               // one (kz, ky) row of 5 taps
-  constexpr int ASTG = (2 * ZT * NPAD <= 512) ? 2 : 1;    // accumulator stages (epilogue overlap when 2)
-  constexpr int TMEM_COLS = (ASTG * ZT * NPAD <= 256) ? 256 : 512;
-  static_assert(ASTG * ZT * NPAD <= 512, "TMEM budget");
+  constexpr int ACOLS = ND ? 2 * NPAD : NPAD;              // accumulator columns per output plane
+  constexpr int ASTG = (2 * ZT * ACOLS <= 512) ? 2 : 1;    // accumulator stages (epilogue overlap when 2)
+  constexpr int TMEM_COLS = (ASTG * ZT * ACOLS <= 256) ? 256 : 512;
+  static_assert(ASTG * ZT * ACOLS <= 512, "TMEM budget");
   uint8_t* ring = smem;
   uint8_t* wring = smem + NSLOT * PLANE_BYTES;
   Barriers* B = reinterpret_cast<Barriers*>(wring + WSTAGES * WROW_BYTES);
@@ -123,7 +128,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
             for (int c0 = 0; c0 < NPAD; c0 += 16) {
               float v[16];
               if (valid) {
-                tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + st * (ZT * NPAD) + zz * NPAD + c0, v);
+                const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + st * (ZT * ACOLS) + zz * ACOLS + c0;
+                tc::tmem_ld16(ta, v);
+                if constexpr (ND) {
+                  float v2[16];
+                  tc::tmem_ld16(ta + NPAD, v2);
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) v[e] += v2[e];
+                }
               } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = 0.f;
@@ -195,6 +207,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
     // ============================ MMA ISSUER (one elected thread)
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, NPAD, 0, 0);
+      constexpr uint32_t idesc2 = tc::make_idesc_tf32(128, 2 * NPAD, 0, 0);
       constexpr uint32_t A_DESC_HI = (uint32_t)((XS * 16) >> 4) | (1u << 14);   // SBO field | version 1 (bit 46)
       long long L0 = 0;                             // plane-load index of r = 0 of the current pass
       long long Wn = 0;                             // running weight-row index
@@ -236,18 +249,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
               // tensor pipe never waits on a read-after-write of the same TMEM tile.
 #pragma unroll
               for (int kx = 0; kx < 5; ++kx) {
-                const uint32_t b_hi = wbase + kx * WTAP_BYTES, b_lo = b_hi + 2 * NPAD * 16;
-                const uint64_t dbh = tc::make_desc(b_hi, NPAD * 16, 128);
-                const uint64_t dbl = tc::make_desc(b_lo, NPAD * 16, 128);
+                if constexpr (ND) {
+                  // tap layout [kc][hi rows | lo rows][16 B]: one descriptor, N = 2*NPAD or the first NPAD rows
+                  const uint64_t db = tc::make_desc(wbase + kx * WTAP_BYTES, 2 * NPAD * 16, 128);
 #pragma unroll
-                for (int part = 0; part < 3; ++part) {
+                  for (int part = 0; part < 2; ++part) {
 #pragma unroll
-                  for (int zz = 0; zz < ZT; ++zz) {
-                    if (!((valid >> zz) & 1u)) continue;
-                    const uint32_t alo = abase[zz] + (ky * XS + kx) + (part == 1 ? (PART_BYTES >> 4) : 0);
-                    const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
-                    const uint32_t acc = (kx | part) ? 1u : ((started >> zz) & 1u);
-                    tc::mma_tf32(tmem + st * (ZT * NPAD) + zz * NPAD, da, part == 2 ? dbl : dbh, idesc, acc);
+                    for (int zz = 0; zz < ZT; ++zz) {
+                      if (!((valid >> zz) & 1u)) continue;
+                      const uint32_t alo = abase[zz] + (ky * XS + kx) + (part == 1 ? (PART_BYTES >> 4) : 0);
+                      const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
+                      const uint32_t acc = (kx | part) ? 1u : ((started >> zz) & 1u);
+                      tc::mma_tf32(tmem + st * (ZT * ACOLS) + zz * ACOLS, da, db, part == 0 ? idesc2 : idesc, acc);
+                    }
+                  }
+                } else {
+                  const uint32_t b_hi = wbase + kx * WTAP_BYTES, b_lo = b_hi + 2 * NPAD * 16;
+                  const uint64_t dbh = tc::make_desc(b_hi, NPAD * 16, 128);
+                  const uint64_t dbl = tc::make_desc(b_lo, NPAD * 16, 128);
+#pragma unroll
+                  for (int part = 0; part < 3; ++part) {
+#pragma unroll
+                    for (int zz = 0; zz < ZT; ++zz) {
+                      if (!((valid >> zz) & 1u)) continue;
+                      const uint32_t alo = abase[zz] + (ky * XS + kx) + (part == 1 ? (PART_BYTES >> 4) : 0);
+                      const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
+                      const uint32_t acc = (kx | part) ? 1u : ((started >> zz) & 1u);
+                      tc::mma_tf32(tmem + st * (ZT * ACOLS) + zz * ACOLS, da, part == 2 ? dbl : dbh, idesc, acc);
+                    }
                   }
                 }
               }
@@ -294,11 +323,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
   if (warp == 8) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// pack kernel: PyTorch conv weight [Cout][Cin][125] -> wtc[P][125][hi|lo][2][NPAD][4]
+// pack kernel: PyTorch conv weight [Cout][Cin][125] -> wtc[P][125][tap block] (see TC5Params::wtc)
 //   fwd  : k = ci, n = co, tap t
 //   dgrad: k = co, n = ci, tap 124 - t   (the gradient wrt x is a conv with the flipped kernel)
 __global__ void tc5_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, int NPAD, int P,
-                                float* __restrict__ out) {
+                                int nd, float* __restrict__ out) {
   const long long total = (long long)P * 125 * 2 * NPAD * 4;     // (pass, tap, kc, n, e)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -318,19 +347,25 @@ __global__ void tc5_pack_kernel(const float* __restrict__ w, int Cout, int Cin, 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
     const float hi = __uint_as_float(h), lo = v - hi;
     const long long base = (((long long)pass * 125 + t) * 2) * 2 * NPAD * 4;      // start of this tap (hi part)
-    const long long off = ((long long)kc * NPAD + n) * 4 + e;
-    out[base + off] = hi;
-    out[base + 2LL * NPAD * 4 + off] = lo;
+    if (nd) {            // [kc][hi rows | lo rows][4]
+      const long long off = ((long long)kc * 2 * NPAD + n) * 4 + e;
+      out[base + off] = hi;
+      out[base + off + (long long)NPAD * 4] = lo;
+    } else {             // [hi: [kc][NPAD][4]] [lo: [kc][NPAD][4]]
+      const long long off = ((long long)kc * NPAD + n) * 4 + e;
+      out[base + off] = hi;
+      out[base + 2LL * NPAD * 4 + off] = lo;
+    }
   }
 }
 
-template <int NPAD, int ZT>
+template <int NPAD, int ZT, bool ND>
 int launch_tc5(TC5Params p, cudaStream_t st) {
   constexpr int WROW_BYTES = 5 * 2 * 2 * NPAD * 16;
   const size_t smem = (size_t)(ZT + 1) * PLANE_BYTES + (size_t)WSTAGES * WROW_BYTES + sizeof(Barriers) + 64;
   p.tiles_z = p.D / ZT;
   p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
-  auto kern = conv_tc5_kernel<NPAD, ZT>;
+  auto kern = conv_tc5_kernel<NPAD, ZT, ND>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -347,6 +382,12 @@ int launch_tc5(TC5Params p, cudaStream_t st) {
 
 }  // namespace
 
+// the packed-weight layout and the kernel variant must agree: both follow this switch (flag 64 = 3 narrow MMAs)
+static bool tc5_use_nd(int N) {
+  if (crn_get_flags() & 64) return false;
+  return N <= 16;
+}
+
 extern "C" int64_t crn_tc5_packed_floats(int32_t K, int32_t N) {
   const int P = (K + 7) / 8;
   const int NPAD = N <= 16 ? 16 : (N <= 32 ? 32 : 64);
@@ -362,7 +403,7 @@ extern "C" int crn_tc5_pack(const float* w, int32_t Cout, int32_t Cin, int32_t d
   const long long total = (long long)P * 125 * 2 * NPAD * 4;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  tc5_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cout, Cin, dgrad, NPAD, P, out);
+  tc5_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cout, Cin, dgrad, NPAD, P, tc5_use_nd(N) ? 1 : 0, out);
   CRN_LAUNCH_CHECK("tc5_pack");
   return CRN_OK;
 }
@@ -391,7 +432,12 @@ extern "C" int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* i
   p.tiles_x = p.W / TX; p.tiles_y = p.H / TY;
   cudaStream_t st = crn_stream(stream);
   // 8 output planes per item while two accumulator stages fit in TMEM (2*ZT*NPAD <= 512 columns), else 4
-  if (p.gN <= 16) return launch_tc5<16, 8>(p, st);
-  if (p.gN <= 32) return launch_tc5<32, 8>(p, st);
-  return launch_tc5<64, 4>(p, st);
+  // N doubling pays where it keeps two accumulator stages (measured on a B200, scripts/tc5_test.py):
+  //   N<=16: 3.09 -> 2.25 ms (stage-6 forward); N<=32 (ZT=8 or 4) and N<=64 do not gain.
+  if (tc5_use_nd(p.gN)) {
+    return launch_tc5<16, 8, true>(p, st);
+  }
+  if (p.gN <= 16) return launch_tc5<16, 8, false>(p, st);
+  if (p.gN <= 32) return launch_tc5<32, 8, false>(p, st);
+  return launch_tc5<64, 4, false>(p, st);
 }

@@ -30,8 +30,20 @@ struct WRowParams {
   int TY, nstream, CQb, NCQG;   // rows per tile, position streams, centre quads per block, centre-quad groups
   int SR, SWd;        // shifted tile rows / width (voxels)
   int center_floats;  // floats of the centre tile
+  int cq_shift, sv_shift, s_vec4;   // log2(CQb) / log2(float4 units per shifted voxel) or -1; shifted tile copied in 16-B units
   long long ntiles;
 };
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = ok ? 16 : 0;                      // src-size 0 => 16 B of zeros, nothing read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8(float* dst, const float* src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
 
 template <int SW>
 __device__ __forceinline__ void load_group(const float* p, float (&v)[SW]) {
@@ -76,40 +88,61 @@ __global__ void __launch_bounds__(KX == 5 ? 160 : 256, KX == 5 ? 3 : 2) wgrad_ro
     const int sz = z * SS - p.pad + kz;
     if (sz < 0 || sz >= p.sD) continue;            // block-uniform
     __syncthreads();
-    // ---- stage the centre tile: [TY][cW][CQb*4]
+    // Both tiles are staged with cp.async (zero-fill for the conv padding / rows past the grid):
+    // no registers, no per-element divisions -- (row, unit) advance incrementally per thread.
+    // ---- centre tile: [TY][cW][CQb*4]
     {
-      const int units = p.TY * p.cW * p.CQb;       // float4 units
-      for (int u = tid; u < units; u += nthr) {
-        const int qq = u % p.CQb; int r = u / p.CQb;
-        const int x = r % p.cW; const int yy = r / p.cW;
+      const int upr = p.cW * p.CQb;                // float4 units per row
+      int yy = tid / upr, c = tid - yy * upr;
+      const long long plane = ((long long)n * p.cD + z) * p.cH;
+      while (yy < p.TY) {
         const int y = y0 + yy;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y < p.cH) {
-          const long long off = ((((long long)n * p.cD + z) * p.cH + y) * p.cW + x) * p.c_cs + p.c_co +
-                                (cqg * p.CQb + qq) * 4;
-          v = __ldg(reinterpret_cast<const float4*>(p.C + off));
-        }
-        *reinterpret_cast<float4*>(cS + (size_t)u * 4) = v;
+        const bool ok = y < p.cH;
+        int x, qq;
+        if (p.cq_shift >= 0) { x = c >> p.cq_shift; qq = c & (p.CQb - 1); } else { x = c / p.CQb; qq = c - x * p.CQb; }
+        const long long off = ((plane + (ok ? y : 0)) * p.cW + x) * p.c_cs + p.c_co + (cqg * p.CQb + qq) * 4;
+        cp_async16(cS + ((size_t)yy * upr + c) * 4, p.C + off, ok);
+        c += nthr;
+        while (c >= upr) { c -= upr; ++yy; }
       }
     }
-    // ---- stage the shifted tile: [SR][SWd][SQ*SW], zero outside the grid (conv padding)
+    // ---- shifted tile: [SR][SWd][SQ*SW]
     {
-      constexpr int V = 2;                          // float2 units (channel counts are even)
-      const int upv = sstride / V;                  // units per voxel
-      const int units = p.SR * p.SWd * upv;
-      const int sy0 = y0 * SS - p.pad, sx0 = -p.pad;
-      for (int u = tid; u < units; u += nthr) {
-        const int qq = u % upv; int r = u / upv;
-        const int c = r % p.SWd; const int rr = r / p.SWd;
-        const int sy = sy0 + rr, sx = sx0 + c;
-        float2 v = make_float2(0.f, 0.f);
-        if ((unsigned)sy < (unsigned)p.sH && (unsigned)sx < (unsigned)p.sW) {
-          const long long off = ((((long long)n * p.sD + sz) * p.sH + sy) * p.sW + sx) * p.s_cs + p.s_co + qq * V;
-          v = __ldg(reinterpret_cast<const float2*>(p.S + off));
+      const int sy0 = y0 * SS - p.pad;
+      const long long plane = ((long long)n * p.sD + sz) * p.sH;
+      if (p.s_vec4) {
+        const int upv = sstride >> 2;
+        const int upr = p.SWd * upv;
+        int rr = tid / upr, c = tid - rr * upr;
+        while (rr < p.SR) {
+          const int sy = sy0 + rr;
+          int xx, qq;
+          if (p.sv_shift >= 0) { xx = c >> p.sv_shift; qq = c & (upv - 1); } else { xx = c / upv; qq = c - xx * upv; }
+          const int sx = xx - p.pad;
+          const bool ok = (unsigned)sy < (unsigned)p.sH && (unsigned)sx < (unsigned)p.sW;
+          const long long off = ok ? ((plane + sy) * p.sW + sx) * p.s_cs + p.s_co + qq * 4 : 0;
+          cp_async16(sS + ((size_t)rr * upr + c) * 4, p.S + off, ok);
+          c += nthr;
+          while (c >= upr) { c -= upr; ++rr; }
         }
-        *reinterpret_cast<float2*>(sS + (size_t)u * V) = v;
+      } else {
+        const int upv = sstride >> 1;
+        const int upr = p.SWd * upv;
+        int rr = tid / upr, c = tid - rr * upr;
+        while (rr < p.SR) {
+          const int sy = sy0 + rr;
+          const int xx = c / upv, qq = c - xx * upv;
+          const int sx = xx - p.pad;
+          const bool ok = (unsigned)sy < (unsigned)p.sH && (unsigned)sx < (unsigned)p.sW;
+          const long long off = ok ? ((plane + sy) * p.sW + sx) * p.s_cs + p.s_co + qq * 2 : 0;
+          cp_async8(sS + ((size_t)rr * upr + c) * 2, p.S + off, ok);
+          c += nthr;
+          while (c >= upr) { c -= upr; ++rr; }
+        }
       }
     }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
     if (!active) continue;
     for (int yy = sigma; yy < p.TY && y0 + yy < p.cH; yy += p.nstream) {
@@ -211,10 +244,11 @@ int launch(const WRowParams& p, int threads, size_t smem_bytes, int groups, cuda
 int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st) {
   if (crn_get_flags() & 2) return CRN_ERR_UNSUPPORTED;
   // the generic split-K GEMM wins once the Cin x Cout tile is large enough to fill its 64x64 tile
-  if (d->Cin * d->Cout >= 2048) return CRN_ERR_UNSUPPORTED;
   const bool conv5 = !d->transposed && d->kD == 5 && d->kH == 5 && d->kW == 5 && d->stride == 1 && d->pad == 2;
   const bool convT7 = d->transposed && d->kD == 7 && d->kH == 7 && d->kW == 7 && d->stride == 2 && d->pad == 3;
   if (!conv5 && !convT7) return CRN_ERR_UNSUPPORTED;
+  // measured crossover on a B200 (profiles/r01_layers_conv_per_step.txt): conv5 up to 56x32, convT7 up to 64x32
+  if (d->Cin * d->Cout >= (convT7 ? 2049 : 2048) && !(crn_get_flags() & 32)) return CRN_ERR_UNSUPPORTED;
   if (d->y_planar) return CRN_ERR_UNSUPPORTED;
   WRowParams p{};
   p.dw = dw; p.N = d->N; p.pad = d->pad; p.KZ = d->kD; p.KY = d->kH;
@@ -263,6 +297,10 @@ int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, f
   }
   if (smem_bytes > 150 * 1024) return CRN_ERR_UNSUPPORTED;
   p.ntiles = (long long)p.N * p.cD * ((p.cH + TY - 1) / TY);
+  auto log2_or_neg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
+  p.cq_shift = log2_or_neg(p.CQb);
+  p.s_vec4 = ((p.SQ * SW) % 4 == 0 && p.s_cs % 4 == 0 && p.s_co % 4 == 0) ? 1 : 0;
+  p.sv_shift = p.s_vec4 ? log2_or_neg(p.SQ * SW / 4) : -1;
   int threads = ((nstream * roles + 31) / 32) * 32;
   if (threads > max_threads) return CRN_ERR_UNSUPPORTED;
   const int groups = p.KZ * p.NCQG;

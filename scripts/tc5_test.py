@@ -4,6 +4,7 @@ import torch as t
 import torch.nn.functional as F
 from corenet_b200 import _lib, ops
 dev = t.device("cuda", 0)
+_lib.lib().crn_set_flags(int(os.environ.get("CRN_FLAGS", "0")))
 r4 = lambda c: (c + 3) // 4 * 4
 
 def run(n, cin, cout, d, h, w, kind, time_it=False):
