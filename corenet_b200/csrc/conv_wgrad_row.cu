@@ -27,11 +27,12 @@ struct WRowParams {
   int pad, KZ, KY;
   int wK, wN;
   int gM, gN;         // logical Cin, Cout (for the flush bounds)
-  int TY, nstream, CQb, NCQG;   // rows per tile, position streams, centre quads per block, centre-quad groups
-  int SR, SWd;        // shifted tile rows / width (voxels)
-  int center_floats;  // floats of the centre tile
+  int TY, nstream, CQb, NCQG;   // centre rows per step (= position streams), centre quads per block, centre-quad groups
+  int SR, SWd, RING;  // shifted rows one step reads, staged width (voxels), rows in the ring (SR + TY*SS)
+  int nseg, rows_per_seg;       // y segments per plane (load balance) and their height
+  int center_floats;  // floats of ONE centre buffer
   int cq_shift, sv_shift, s_vec4;   // log2(CQb) / log2(float4 units per shifted voxel) or -1; shifted tile copied in 16-B units
-  long long ntiles;
+  long long nitems;
 };
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool ok) {
@@ -59,8 +60,8 @@ __device__ __forceinline__ void load_group(const float* p, float (&v)[SW]) {
 template <int KX, int SS, int SW, bool SHIFT_IS_CI>
 __global__ void __launch_bounds__(KX == 5 ? 160 : 256, KX == 5 ? 3 : 2) wgrad_row_kernel(const WRowParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* cS = smem;
-  float* sS = smem + p.center_floats;
+  float* cS = smem;                              // 2 x [TY][cW][CQb*4]   (double buffer)
+  float* sS = smem + 2 * p.center_floats;        // [RING][SWd][SQ*SW]    (ring of shifted rows)
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int roles = p.KY * p.SQ * p.CQb;
   const int rho = tid % roles, sigma = tid / roles;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(KX == 5 ? 160 : 256, KX == 5 ? 3 : 2) wgrad_ro
   const int cqg = blockIdx.y % p.NCQG, kz = blockIdx.y / p.NCQG;
   const int cstride = p.CQb * 4;        // floats per voxel in the centre tile
   const int sstride = p.SQ * SW;        // floats per voxel in the shifted tile
+  const int row_floats = p.SWd * sstride;
 
   float acc[KX][4][SW];
 #pragma unroll
@@ -78,50 +80,56 @@ __global__ void __launch_bounds__(KX == 5 ? 160 : 256, KX == 5 ? 3 : 2) wgrad_ro
 #pragma unroll
       for (int j = 0; j < SW; ++j) acc[k][i][j] = 0.f;
 
-  const int yblocks = (p.cH + p.TY - 1) / p.TY;
-  for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    const int yb = (int)(tile % yblocks);
-    long long q = tile / yblocks;
-    const int z = (int)(q % p.cD);
-    const int n = (int)(q / p.cD);
-    const int y0 = yb * p.TY;
+  // Work item = (scene, z plane, y segment).  The block walks down y: every step computes TY centre rows
+  // (one per position stream) and meanwhile cp.async-prefetches the TY*SS shifted rows + TY centre rows of the
+  // next step into the ring, so each shifted row is fetched once per (item, kz) and the copy latency hides
+  // behind a row of FMAs.  One __syncthreads per step.
+  for (long long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+    const int seg = (int)(item % p.nseg);
+    const long long pl = item / p.nseg;
+    const int z = (int)(pl % p.cD);
+    const int n = (int)(pl / p.cD);
     const int sz = z * SS - p.pad + kz;
     if (sz < 0 || sz >= p.sD) continue;            // block-uniform
-    __syncthreads();
-    // Both tiles are staged with cp.async (zero-fill for the conv padding / rows past the grid):
-    // no registers, no per-element divisions -- (row, unit) advance incrementally per thread.
-    // ---- centre tile: [TY][cW][CQb*4]
-    {
+    const int ybeg = seg * p.rows_per_seg;
+    const int yend = min(p.cH, ybeg + p.rows_per_seg);
+    if (ybeg >= yend) continue;
+    const int nsteps = (yend - ybeg + p.TY - 1) / p.TY;
+    const int sy_origin = ybeg * SS - p.pad;       // ring row g holds shifted row sy_origin + g
+    const long long cplane = ((long long)n * p.cD + z) * p.cH;
+    const long long splane = ((long long)n * p.sD + sz) * p.sH;
+
+    // centre rows y0 .. y0+TY-1 -> buffer buf (zero-fill past the grid)
+    auto stage_centre = [&](int buf, int y0) {
       const int upr = p.cW * p.CQb;                // float4 units per row
+      float* dst = cS + (size_t)buf * p.center_floats;
       int yy = tid / upr, c = tid - yy * upr;
-      const long long plane = ((long long)n * p.cD + z) * p.cH;
       while (yy < p.TY) {
         const int y = y0 + yy;
         const bool ok = y < p.cH;
         int x, qq;
         if (p.cq_shift >= 0) { x = c >> p.cq_shift; qq = c & (p.CQb - 1); } else { x = c / p.CQb; qq = c - x * p.CQb; }
-        const long long off = ((plane + (ok ? y : 0)) * p.cW + x) * p.c_cs + p.c_co + (cqg * p.CQb + qq) * 4;
-        cp_async16(cS + ((size_t)yy * upr + c) * 4, p.C + off, ok);
+        const long long off = ((cplane + (ok ? y : 0)) * p.cW + x) * p.c_cs + p.c_co + (cqg * p.CQb + qq) * 4;
+        cp_async16(dst + ((size_t)yy * upr + c) * 4, p.C + off, ok);
         c += nthr;
         while (c >= upr) { c -= upr; ++yy; }
       }
-    }
-    // ---- shifted tile: [SR][SWd][SQ*SW]
-    {
-      const int sy0 = y0 * SS - p.pad;
-      const long long plane = ((long long)n * p.sD + sz) * p.sH;
+    };
+    // ring rows g0 .. g0+cnt-1 (zero-fill outside the grid = conv padding)
+    auto stage_shifted = [&](int g0, int cnt) {
       if (p.s_vec4) {
         const int upv = sstride >> 2;
         const int upr = p.SWd * upv;
         int rr = tid / upr, c = tid - rr * upr;
-        while (rr < p.SR) {
-          const int sy = sy0 + rr;
+        while (rr < cnt) {
+          const int g = g0 + rr;
+          const int sy = sy_origin + g;
           int xx, qq;
           if (p.sv_shift >= 0) { xx = c >> p.sv_shift; qq = c & (upv - 1); } else { xx = c / upv; qq = c - xx * upv; }
           const int sx = xx - p.pad;
           const bool ok = (unsigned)sy < (unsigned)p.sH && (unsigned)sx < (unsigned)p.sW;
-          const long long off = ok ? ((plane + sy) * p.sW + sx) * p.s_cs + p.s_co + qq * 4 : 0;
-          cp_async16(sS + ((size_t)rr * upr + c) * 4, p.S + off, ok);
+          const long long off = ok ? ((splane + sy) * p.sW + sx) * p.s_cs + p.s_co + qq * 4 : 0;
+          cp_async16(sS + (size_t)(g % p.RING) * row_floats + (size_t)c * 4, p.S + off, ok);
           c += nthr;
           while (c >= upr) { c -= upr; ++rr; }
         }
@@ -129,26 +137,38 @@ __global__ void __launch_bounds__(KX == 5 ? 160 : 256, KX == 5 ? 3 : 2) wgrad_ro
         const int upv = sstride >> 1;
         const int upr = p.SWd * upv;
         int rr = tid / upr, c = tid - rr * upr;
-        while (rr < p.SR) {
-          const int sy = sy0 + rr;
+        while (rr < cnt) {
+          const int g = g0 + rr;
+          const int sy = sy_origin + g;
           const int xx = c / upv, qq = c - xx * upv;
           const int sx = xx - p.pad;
           const bool ok = (unsigned)sy < (unsigned)p.sH && (unsigned)sx < (unsigned)p.sW;
-          const long long off = ok ? ((plane + sy) * p.sW + sx) * p.s_cs + p.s_co + qq * 2 : 0;
-          cp_async8(sS + ((size_t)rr * upr + c) * 2, p.S + off, ok);
+          const long long off = ok ? ((splane + sy) * p.sW + sx) * p.s_cs + p.s_co + qq * 2 : 0;
+          cp_async8(sS + (size_t)(g % p.RING) * row_floats + (size_t)c * 2, p.S + off, ok);
           c += nthr;
           while (c >= upr) { c -= upr; ++rr; }
         }
       }
-    }
+    };
+
+    __syncthreads();                               // the previous item's last step is fully consumed
+    stage_shifted(0, p.SR);
+    stage_centre(0, ybeg);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
-    if (!active) continue;
-    for (int yy = sigma; yy < p.TY && y0 + yy < p.cH; yy += p.nstream) {
+    for (int s = 0; s < nsteps; ++s) {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      __syncthreads();                             // step s landed; step s-1 consumed -> its ring rows are free
+      if (s + 1 < nsteps) {
+        stage_shifted(p.SR + s * p.TY * SS, p.TY * SS);
+        stage_centre((s + 1) & 1, ybeg + (s + 1) * p.TY);
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      const int yy = sigma;                        // TY == nstream: one centre row per stream and step
+      const int y = ybeg + s * p.TY + yy;
+      if (!active || y >= yend) continue;
       // running pointers (in floats): the unrolled body below only uses compile-time offsets from them
-      const float* cptr = cS + (yy * p.cW) * cstride + cq * 4;
-      const float* sptr = sS + ((yy * SS + ky) * p.SWd) * sstride + sq * SW;
+      const float* cptr = cS + (size_t)(s & 1) * p.center_floats + (yy * p.cW) * cstride + cq * 4;
+      const float* sptr = sS + (size_t)(((s * p.TY + yy) * SS + ky) % p.RING) * row_floats + sq * SW;
       float w[KX][SW];
 #pragma unroll
       for (int k = 0; k < KX; ++k) load_group<SW>(sptr + k * sstride, w[k]);
@@ -197,6 +217,7 @@ __global__ void __launch_bounds__(KX == 5 ? 160 : 256, KX == 5 ? 3 : 2) wgrad_ro
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   // ---- flush
   if (active && ky < p.KY) {
 #pragma unroll
@@ -229,10 +250,18 @@ int launch(const WRowParams& p, int threads, size_t smem_bytes, int groups, cuda
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_bytes) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  long long gx = ((long long)per_sm * kNumSMs) / groups;
-  if (gx > p.ntiles) gx = p.ntiles;
-  if (gx < 1) gx = 1;
-  kern<<<dim3((unsigned)gx, (unsigned)groups), threads, smem_bytes, st>>>(p);
+  const long long slots = ((long long)per_sm * kNumSMs) / groups > 0 ? ((long long)per_sm * kNumSMs) / groups : 1;
+  // split planes into y segments while the persistent blocks would otherwise run < 8 rounds of uneven length
+  // (each segment re-reads KY-SS halo rows, so keep segments >= 8 steps)
+  const long long planes = (long long)p.N * p.cD;
+  int nseg = 1;
+  while (planes * nseg < 8 * slots && (p.cH / (nseg * 2)) >= 8 * p.TY) nseg *= 2;
+  WRowParams q = p;
+  q.nseg = nseg;
+  q.rows_per_seg = ((p.cH + nseg - 1) / nseg + p.TY - 1) / p.TY * p.TY;
+  q.nitems = planes * nseg;
+  long long gx = slots < q.nitems ? slots : q.nitems;
+  kern<<<dim3((unsigned)gx, (unsigned)groups), threads, smem_bytes, st>>>(q);
   CRN_LAUNCH_CHECK("wgrad_row");
   return CRN_OK;
 }
@@ -281,22 +310,19 @@ int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, f
   int nstream = (conv5 ? 160 : 224) / roles;
   if (nstream < 1) nstream = 1;
   if (nstream > 8) nstream = 8;
-  int TY = nstream > 2 ? nstream : 2;
-  if (TY > p.cH) TY = p.cH;
-  if (nstream > TY) nstream = TY;
+  if (nstream > p.cH) nstream = p.cH;
   size_t smem_bytes = 0;
   for (;;) {
-    p.TY = TY; p.nstream = nstream;
-    p.SR = (TY - 1) * SS + p.KY;
+    p.TY = nstream; p.nstream = nstream;
+    p.SR = (p.TY - 1) * SS + p.KY;
+    p.RING = p.SR + p.TY * SS;
     p.SWd = (p.cW - 1) * SS + KX + SS;       // + SS look-ahead columns read (never used) by the window slide
-    p.center_floats = TY * p.cW * CQb * 4;
-    smem_bytes = sizeof(float) * ((size_t)p.center_floats + (size_t)p.SR * p.SWd * p.SQ * SW);
-    if (smem_bytes <= 100 * 1024 || TY == 1) break;
-    TY = TY > 2 ? TY / 2 : 1;
-    if (nstream > TY) nstream = TY;
+    p.center_floats = p.TY * p.cW * CQb * 4;
+    smem_bytes = sizeof(float) * (2 * (size_t)p.center_floats + (size_t)p.RING * p.SWd * p.SQ * SW);
+    if (smem_bytes <= 100 * 1024 || nstream == 1) break;
+    nstream = nstream / 2;
   }
   if (smem_bytes > 150 * 1024) return CRN_ERR_UNSUPPORTED;
-  p.ntiles = (long long)p.N * p.cD * ((p.cH + TY - 1) / TY);
   auto log2_or_neg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
   p.cq_shift = log2_or_neg(p.CQb);
   p.s_vec4 = ((p.SQ * SW) % 4 == 0 && p.s_cs % 4 == 0 && p.s_co % 4 == 0) ? 1 : 0;
@@ -304,6 +330,7 @@ int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, f
   int threads = ((nstream * roles + 31) / 32) * 32;
   if (threads > max_threads) return CRN_ERR_UNSUPPORTED;
   const int groups = p.KZ * p.NCQG;
+  p.nseg = 1; p.rows_per_seg = p.cH;           // launch() may split planes into y segments
   if (conv5) return launch<5, 1, 4, true>(p, threads, smem_bytes, groups, st);
   return launch<7, 2, 2, false>(p, threads, smem_bytes, groups, st);
 }
