@@ -43,6 +43,8 @@ struct TC5Params {
   int gK, gN;           // logical channels in / out
   int in_cs, in_co, out_cs, out_co;
   int P;                // K passes of 8 channels
+  int cout_cls;         // scatter mode (ConvTranspose3d k7 s2): output channels per parity class (gN = 8 * cout_cls)
+  int planar;           // scatter mode: out is [N, Cout, 2D, 2H, 2W] instead of channels-last
   int tiles_x, tiles_y, tiles_z;
   int nitems;
 };
@@ -67,13 +69,21 @@ __device__ __forceinline__ void decode_item(const TC5Params& p, int item, int& n
 // against the concatenated B = [hi rows | lo rows] (N = 2*NPAD) into 2*NPAD accumulator columns that the
 // epilogue adds; with the narrow N of these layers the MMA cost is set by the A fetch, so 2 MMAs per
 // (tap, plane) instead of 3.
-template <int NPAD, int ZT, bool ND>
+//
+// KT = taps per axis: 5 (Conv3d k=5, offsets -2..2) or 4 (ConvTranspose3d k=7 s=2 p=3 seen from the INPUT grid:
+// output voxel 2i+c gathers inputs i-1..i+2 with tap k = c+3-2o, so all 8 parity classes are one stride-1
+// 4x4x4-tap convolution with N = 8*Cout "class channels" -- the A tiles are shared by every class).
+// SCAT: epilogue scatters column (class, co) of voxel i to output voxel 2i+class.
+template <int NPAD, int ZT, bool ND, int KT, bool SCAT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p) {
+  constexpr int HLO = (KT == 5) ? 2 : 1;                   // most negative tap offset
+  constexpr int KZG = (KT == 4) ? 2 : 1;                   // kz planes per flush group (chain <= 96 MMAs)
+  constexpr bool RACC = SCAT && NPAD == 16;                // epilogue keeps the running sums in registers
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NSLOT = ZT + 1;                            // plane ring
-  constexpr int NPLANE = ZT + 4;                           // planes loaded per pass
+  constexpr int NPLANE = ZT + KT - 1;                      // planes loaded per pass
   constexpr int WTAP_BYTES = 2 * 2 * NPAD * 16;            // one tap: hi|lo x 2 k-chunks x NPAD x 16 B
-  constexpr int WROW_BYTES = 5 * WTAP_BYTES;               // one (kz, ky) row of 5 taps
+  constexpr int WROW_BYTES = KT * WTAP_BYTES;              // one (kz, ky) row of KT taps
   constexpr int ACOLS = ND ? 2 * NPAD : NPAD;              // accumulator columns per output plane
   constexpr int ASTG = (2 * ZT * ACOLS <= 512) ? 2 : 1;    // accumulator stages (epilogue overlap when 2)
   constexpr int TMEM_COLS = (ASTG * ZT * ACOLS <= 256) ? 256 : 512;
@@ -112,16 +122,116 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
       decode_item<ZT>(p, item, n, z0, y0, x0);
       const int m = warp * 32 + lane;              // row of the tile = TMEM lane
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
+      // scatter one 16-column chunk of plane zz (SCAT): all loads are issued before the stores (the compiler
+      // cannot reorder them itself: the scattered addresses may alias), one global round trip per chunk
+      auto scatter_chunk = [&](int zz, int c0, const float (&v)[16], bool first) {
+        const int OH = 2 * p.H, OW = 2 * p.W;
+        const long long oS = (long long)(2 * p.D) * OH * OW;
+        if (!p.planar && (p.cout_cls & 3) == 0) {             // a column quad stays inside one class
+          float* dst[4];
+          float4 old[4];
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const int cc = c0 + qd * 4;
+            dst[qd] = nullptr;
+            if (cc >= p.gN) continue;
+            const int cls = cc / p.cout_cls, co = cc - cls * p.cout_cls;
+            const int oz = 2 * (z0 + zz) + (cls >> 2), oy = 2 * y + ((cls >> 1) & 1), ox = 2 * x + (cls & 1);
+            const long long sp = ((long long)oz * OH + oy) * OW + ox;
+            dst[qd] = p.out + ((long long)n * oS + sp) * p.out_cs + p.out_co + co;
+            if (first) {
+              old[qd] = p.bias ? make_float4(__ldg(p.bias + co), __ldg(p.bias + co + 1), __ldg(p.bias + co + 2),
+                                             __ldg(p.bias + co + 3))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              old[qd] = *reinterpret_cast<const float4*>(dst[qd]);
+            }
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            if (!dst[qd]) continue;
+            float4 o = old[qd];
+            o.x += v[qd * 4]; o.y += v[qd * 4 + 1]; o.z += v[qd * 4 + 2]; o.w += v[qd * 4 + 3];
+            *reinterpret_cast<float4*>(dst[qd]) = o;
+          }
+        } else if (first) {                                     // nothing to read: plain stores, no batching
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int cc = c0 + e;
+            if (cc >= p.gN) continue;
+            const int cls = cc / p.cout_cls, co = cc - cls * p.cout_cls;
+            const int oz = 2 * (z0 + zz) + (cls >> 2), oy = 2 * y + ((cls >> 1) & 1), ox = 2 * x + (cls & 1);
+            const long long sp = ((long long)oz * OH + oy) * OW + ox;
+            float* dst = p.planar ? p.out + ((long long)n * p.cout_cls + co) * oS + sp
+                                  : p.out + ((long long)n * oS + sp) * p.out_cs + p.out_co + co;
+            *dst = v[e] + (p.bias ? __ldg(p.bias + co) : 0.f);
+          }
+        } else {
+          float* dst[16];
+          float old[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int cc = c0 + e;
+            dst[e] = nullptr;
+            if (cc >= p.gN) continue;
+            const int cls = cc / p.cout_cls, co = cc - cls * p.cout_cls;
+            const int oz = 2 * (z0 + zz) + (cls >> 2), oy = 2 * y + ((cls >> 1) & 1), ox = 2 * x + (cls & 1);
+            const long long sp = ((long long)oz * OH + oy) * OW + ox;
+            dst[e] = p.planar ? p.out + ((long long)n * p.cout_cls + co) * oS + sp
+                              : p.out + ((long long)n * oS + sp) * p.out_cs + p.out_co + co;
+            old[e] = *dst[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (dst[e]) *dst[e] = old[e] + v[e];
+        }
+      };
+      // RACC: with 16 columns the running sums of all ZT planes fit in registers -> no global read-modify-write,
+      // one store per item
+      float sum[RACC ? ZT : 1][16];
+      if constexpr (RACC) {
+#pragma unroll
+        for (int zz = 0; zz < ZT; ++zz)
+#pragma unroll
+          for (int e = 0; e < 16; ++e) sum[zz][e] = 0.f;
+      }
       for (int pass = 0; pass < p.P && !dead; ++pass) {
-        for (int kz = 0; kz < 5; ++kz, ++G) {
+        for (int kg = 0; kg < KT; kg += KZG, ++G) {
           const int st = (int)(G % ASTG);
           if (!tc::mbar_wait(&B->acc_full[st], (uint32_t)(G / ASTG) & 1, ab)) { fail(); dead = true; break; }
           tc::fence_after_sync();
-          const bool first = pass == 0 && kz == 0;
+          const bool first = pass == 0 && kg == 0;
+          const bool last = pass == p.P - 1 && kg + KZG >= KT;
+#pragma unroll
           for (int zz = 0; zz < ZT; ++zz) {
-            const int q = z0 + zz + kz - 2;
-            const bool valid = q >= 0 && q < p.D;
+            bool valid = false;                      // did any kz of this group write accumulator zz?
+#pragma unroll
+            for (int kz = kg; kz < kg + KZG; ++kz) {
+              const int q = z0 + zz + kz - HLO;
+              valid = valid || (kz < KT && q >= 0 && q < p.D);
+            }
+            if constexpr (RACC) {
+              if (valid) {
+                const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + st * (ZT * ACOLS) + zz * ACOLS;
+                float v[16];
+                tc::tmem_ld16(ta, v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) sum[zz][e] += v[e];
+                if constexpr (ND) {
+                  tc::tmem_ld16(ta + NPAD, v);
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) sum[zz][e] += v[e];
+                }
+              }
+              if (last) {
+                scatter_chunk(zz, 0, sum[zz], true);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) sum[zz][e] = 0.f;
+              }
+              continue;
+            }
             if (!valid && !first) continue;
+            if constexpr (!SCAT) {
             const long long pos = (((long long)n * p.D + (z0 + zz)) * p.H + y) * p.W + x;
             float* dst = p.out + pos * p.out_cs + p.out_co;
 #pragma unroll
@@ -158,6 +268,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
                 }
               }
             }
+            } else {
+            // scatter: column cc = class * cout_cls + co of voxel (z, y, x) -> output voxel (2z+cz, 2y+cy, 2x+cx)
+#pragma unroll 1
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+              if (c0 >= p.gN) break;
+              float v[16];
+              if (valid) {
+                const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + st * (ZT * ACOLS) + zz * ACOLS + c0;
+                tc::tmem_ld16(ta, v);
+                if constexpr (ND) {
+                  float v2[16];
+                  tc::tmem_ld16(ta + NPAD, v2);
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) v[e] += v2[e];
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0.f;
+              }
+              scatter_chunk(zz, c0, v, first);
+            }
+            }
           }
           tc::fence_before_sync();
           tc::mbar_arrive(&B->acc_empty[st]);
@@ -177,13 +309,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
           const int slot = (int)(L % NSLOT);
           const uint32_t use = (uint32_t)(L / NSLOT);
           if (use > 0 && !tc::mbar_wait(&B->plane_empty[slot], (use - 1) & 1, ab)) { fail(); dead = true; break; }
-          const int q = z0 - 2 + r;
+          const int q = z0 - HLO + r;
           if (q >= 0 && q < p.D) {
             uint8_t* dst = ring + slot * PLANE_BYTES;
             for (int u = pt; u < YS * XS * 2; u += 128) {
               const int kc = u & 1; const int v = u >> 1;
               const int xs = v % XS, ys = v / XS;
-              const int y = y0 - 2 + ys, x = x0 - 2 + xs;
+              const int y = y0 - HLO + ys, x = x0 - HLO + xs;
               const int k = pass * 8 + kc * 4;
               float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
               if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
@@ -217,11 +349,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
         int n, z0, y0, x0;
         decode_item<ZT>(p, item, n, z0, y0, x0);
         for (int pass = 0; pass < p.P && !dead; ++pass, L0 += NPLANE) {
-          for (int kz = 0; kz < 5 && !dead; ++kz, ++G) {
-            const int st = (int)(G % ASTG);
-            if (G >= ASTG && !tc::mbar_wait(&B->acc_empty[st], (uint32_t)((G / ASTG) - 1) & 1, ab)) { fail(); dead = true; break; }
-            tc::fence_after_sync();
-            uint32_t started = 0;                   // bit zz: accumulator zz already written in this group
+          int st = 0;
+          uint32_t started = 0;                     // bit zz: accumulator zz already written in this group
+          for (int kz = 0; kz < KT && !dead; ++kz) {
+            if (kz % KZG == 0) {                    // a new flush group starts
+              st = (int)(G % ASTG);
+              if (G >= ASTG && !tc::mbar_wait(&B->acc_empty[st], (uint32_t)((G / ASTG) - 1) & 1, ab)) { fail(); dead = true; break; }
+              tc::fence_after_sync();
+              started = 0;
+            }
             // planes r = kz .. kz+7 must be resident: r <= 7 are awaited at kz = 0, then one new per kz
             const int rlo = kz == 0 ? 0 : kz + ZT - 1, rhi = kz + ZT - 1;
             for (int r = rlo; r <= rhi; ++r) {
@@ -234,13 +370,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
             uint32_t valid = 0;
 #pragma unroll
             for (int zz = 0; zz < ZT; ++zz) {
-              const int q = z0 + zz + kz - 2;
+              const int q = z0 + zz + kz - HLO;
               if (q >= 0 && q < p.D) valid |= 1u << zz;     // zero planes contribute nothing
               // low descriptor word of the plane: (addr >> 4) | LBO field; taps/parts add a constant to it
               abase[zz] = ((ring_u32 + (uint32_t)((L0 + zz + kz) % NSLOT) * PLANE_BYTES) >> 4) |
                           ((uint32_t)(CHUNK_BYTES >> 4) << 16);
             }
-            for (int ky = 0; ky < 5; ++ky, ++Wn) {
+            for (int ky = 0; ky < KT; ++ky, ++Wn) {
               const int ws = (int)(Wn % WSTAGES);
               if (!tc::mbar_wait(&B->w_full[ws], (uint32_t)(Wn / WSTAGES) & 1, ab)) { fail(); dead = true; break; }
               tc::fence_after_sync();
@@ -248,7 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
               // Interleave the 8 output planes: consecutive tcgen05.mma go to DIFFERENT accumulators, so the
               // tensor pipe never waits on a read-after-write of the same TMEM tile.
 #pragma unroll
-              for (int kx = 0; kx < 5; ++kx) {
+              for (int kx = 0; kx < KT; ++kx) {
                 if constexpr (ND) {
                   // tap layout [kc][hi rows | lo rows][16 B]: one descriptor, N = 2*NPAD or the first NPAD rows
                   const uint64_t db = tc::make_desc(wbase + kx * WTAP_BYTES, 2 * NPAD * 16, 128);
@@ -285,10 +421,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
             }
             if (dead) break;
             tc::commit(&B->plane_empty[(L0 + kz) % NSLOT]);      // plane r = kz is done
-            tc::commit(&B->acc_full[st]);                        // this group's partial sums are complete
+            if (kz % KZG == KZG - 1 || kz == KT - 1) {
+              tc::commit(&B->acc_full[st]);                      // this group's partial sums are complete
+              ++G;
+            }
           }
           if (dead) break;
-          for (int r = 5; r < NPLANE; ++r) tc::commit(&B->plane_empty[(L0 + r) % NSLOT]);
+          for (int r = KT; r < NPLANE; ++r) tc::commit(&B->plane_empty[(L0 + r) % NSLOT]);
         }
       }
     }
@@ -299,11 +438,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
       bool dead = false;
       for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
         for (int pass = 0; pass < p.P && !dead; ++pass) {
-          for (int row = 0; row < 25; ++row, ++Wn) {
+          for (int row = 0; row < KT * KT; ++row, ++Wn) {
             const int ws = (int)(Wn % WSTAGES);
             const uint32_t use = (uint32_t)(Wn / WSTAGES);
             if (use > 0 && !tc::mbar_wait(&B->w_empty[ws], (use - 1) & 1, ab)) { fail(); dead = true; break; }
-            const float* src = p.wtc + ((size_t)pass * 25 + row) * (WROW_BYTES / 4);
+            const float* src = p.wtc + ((size_t)pass * (KT * KT) + row) * (WROW_BYTES / 4);
             const uint32_t bar = tc::smem_u32(&B->w_full[ws]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WROW_BYTES)
                          : "memory");
@@ -359,13 +498,50 @@ __global__ void tc5_pack_kernel(const float* __restrict__ w, int Cout, int Cin, 
   }
 }
 
-template <int NPAD, int ZT, bool ND>
+// pack kernel: PyTorch ConvTranspose3d weight [Cin][Cout][7][7][7] -> wtc[P][64 taps][tap block], column
+// n = class * Cout + co (class = cz*4 + cy*2 + cx), tap j = (jz*4 + jy)*4 + jx <-> input offset j - 1 per axis,
+// filter index k = c + 3 - 2*(j - 1) (zero weight where k falls outside 0..6: class 0 has 3 taps per axis).
+__global__ void tct_pack_kernel(const float* __restrict__ w, int Cin, int Cout, int NPAD, int P, int nd,
+                                float* __restrict__ out) {
+  const long long total = (long long)P * 64 * 2 * NPAD * 4;      // (pass, tap, kc, n, e)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 3); long long r = i >> 2;
+    const int n = (int)(r % NPAD); r /= NPAD;
+    const int kc = (int)(r & 1); r >>= 1;
+    const int t = (int)(r & 63); const int pass = (int)(r >> 6);
+    const int ci = pass * 8 + kc * 4 + e;
+    float v = 0.f;
+    if (ci < Cin && n < 8 * Cout) {
+      const int cls = n / Cout, co = n - cls * Cout;
+      const int kz = (cls >> 2) + 5 - 2 * (t >> 4), ky = ((cls >> 1) & 1) + 5 - 2 * ((t >> 2) & 3),
+                kx = (cls & 1) + 5 - 2 * (t & 3);
+      if ((unsigned)kz < 7u && (unsigned)ky < 7u && (unsigned)kx < 7u)
+        v = w[(((long long)ci * Cout + co) * 7 + kz) * 49 + ky * 7 + kx];
+    }
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hi = __uint_as_float(h), lo = v - hi;
+    const long long base = (((long long)pass * 64 + t) * 2) * 2 * NPAD * 4;
+    if (nd) {
+      const long long off = ((long long)kc * 2 * NPAD + n) * 4 + e;
+      out[base + off] = hi;
+      out[base + off + (long long)NPAD * 4] = lo;
+    } else {
+      const long long off = ((long long)kc * NPAD + n) * 4 + e;
+      out[base + off] = hi;
+      out[base + 2LL * NPAD * 4 + off] = lo;
+    }
+  }
+}
+
+template <int NPAD, int ZT, bool ND, int KT = 5, bool SCAT = false>
 int launch_tc5(TC5Params p, cudaStream_t st) {
-  constexpr int WROW_BYTES = 5 * 2 * 2 * NPAD * 16;
+  constexpr int WROW_BYTES = KT * 2 * 2 * NPAD * 16;
   const size_t smem = (size_t)(ZT + 1) * PLANE_BYTES + (size_t)WSTAGES * WROW_BYTES + sizeof(Barriers) + 64;
   p.tiles_z = p.D / ZT;
   p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
-  auto kern = conv_tc5_kernel<NPAD, ZT, ND>;
+  auto kern = conv_tc5_kernel<NPAD, ZT, ND, KT, SCAT>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -440,4 +616,62 @@ extern "C" int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* i
   if (p.gN <= 16) return launch_tc5<16, 8, false>(p, st);
   if (p.gN <= 32) return launch_tc5<32, 8, false>(p, st);
   return launch_tc5<64, 4, false>(p, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvTranspose3d k=7 s=2 p=3 op=1 forward on the same kernel (KT = 4, scatter epilogue).
+// Replaces the cuDNN call behind nn.ConvTranspose3d at model/reconstruction_decoder.py:69,77,85,95.
+static int tct_npad(int Cout) {
+  const int n = 8 * Cout;
+  return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128));
+}
+
+extern "C" int64_t crn_tct_packed_floats(int32_t Cin, int32_t Cout) {
+  const int P = (Cin + 7) / 8;
+  return (int64_t)P * 64 * 2 * 2 * tct_npad(Cout) * 4;
+}
+
+extern "C" int crn_tct_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream) {
+  CRN_REQUIRE(w && out && Cout > 0 && Cin > 0, "crn_tct_pack: bad args");
+  CRN_REQUIRE(8 * Cout <= 128, "crn_tct_pack: Cout > 16 unsupported");
+  const int P = (Cin + 7) / 8;
+  const int NPAD = tct_npad(Cout);
+  const long long total = (long long)P * 64 * 2 * NPAD * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  tct_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cin, Cout, NPAD, P, tc5_use_nd(8 * Cout) ? 1 : 0, out);
+  CRN_LAUNCH_CHECK("tct_pack");
+  return CRN_OK;
+}
+
+extern "C" int crn_convt7_tc(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
+                             int32_t* status, void* stream) {
+  CRN_REQUIRE(d && x && wtc && y && status, "crn_convt7_tc: null pointer");
+  CRN_REQUIRE(d->transposed && d->kD == 7 && d->kH == 7 && d->kW == 7 && d->stride == 2 && d->pad == 3,
+              "crn_convt7_tc: only ConvTranspose3d k=7 s=2 p=3");
+  CRN_REQUIRE(d->oD == 2 * d->iD && d->oH == 2 * d->iH && d->oW == 2 * d->iW, "crn_convt7_tc: output must be 2x input");
+  CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % 8 == 0, "crn_convt7_tc: input grid must tile by 8x16x8");
+  CRN_REQUIRE(!d->bias_n_stride, "crn_convt7_tc: per-scene bias unsupported");
+  CRN_REQUIRE(d->Cin % 4 == 0 && d->x_cs % 4 == 0 && d->x_co % 4 == 0 && 8 * d->Cout <= 128,
+              "crn_convt7_tc: Cin, x strides must be multiples of 4 and Cout <= 16");
+  TC5Params p{};
+  p.in = x; p.wtc = wtc; p.bias = bias; p.out = y; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  p.gK = d->Cin; p.gN = 8 * d->Cout; p.cout_cls = d->Cout; p.planar = d->y_planar;
+  p.in_cs = d->x_cs; p.in_co = d->x_co; p.out_cs = d->y_cs; p.out_co = d->y_co;
+  if (!d->y_planar && d->Cout % 4 == 0)
+    CRN_REQUIRE(d->y_cs % 4 == 0 && d->y_co % 4 == 0, "crn_convt7_tc: y strides must be multiples of 4");
+  p.P = (p.gK + 7) / 8;
+  p.tiles_x = p.W / TX; p.tiles_y = p.H / TY;
+  cudaStream_t st = crn_stream(stream);
+  if (p.gN <= 16) {
+    // ZT = 4: the epilogue keeps 4 x 16 running sums per thread in registers (8 planes would spill)
+    if (tc5_use_nd(p.gN)) return launch_tc5<16, 4, true, 4, true>(p, st);
+    return launch_tc5<16, 4, false, 4, true>(p, st);
+  }
+  if (p.gN <= 32) return launch_tc5<32, 8, false, 4, true>(p, st);
+  if (p.gN <= 64) return launch_tc5<64, 4, false, 4, true>(p, st);
+  // two planes per item keep two accumulator stages in TMEM (2*2*128 columns): 0.55 ms vs 0.74 ms with ZT = 4
+  // on the stage-5 layer (scripts/tct_test.py)
+  return launch_tc5<128, 2, false, 4, true>(p, st);
 }

@@ -69,6 +69,18 @@ def conv_call(kind, layer, d, *args):
 USE_TC = True
 
 
+def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
+  """ConvTranspose3d k=7 s=2 forward through crn_convt7_tc."""
+  if PROFILE is None:
+    _lib.call("crn_convt7_tc", C.byref(d), inp, wtc, bias, out, status, st)
+    return
+  e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+  e0.record()
+  _lib.call("crn_convt7_tc", C.byref(d), inp, wtc, bias, out, status, st)
+  e1.record()
+  PROFILE.append(("fwd_tc", layer.name, conv_macs(d), e0, e1))
+
+
 def conv5_tc_call(kind, layer, d, inp, wtc, bias, out, status, st):
   """kind: 'fwd' | 'dgrad' through crn_conv5_tc."""
   k = 0 if kind == "fwd" else 1
@@ -224,6 +236,12 @@ class Engine:
       if l.k == (5, 5, 5) and g >= 32 and g % 16 == 0 and cin <= 64 and mid <= 64:
         self.tc_w[l.name] = (t.zeros(lib.crn_tc5_packed_floats(cin, mid), dtype=t.float32, device=dev),
                              t.zeros(lib.crn_tc5_packed_floats(mid, cin), dtype=t.float32, device=dev))
+    # ... and per eligible ConvTranspose3d(k=7, s=2) layer a packed copy for the forward (csrc/conv_tc5.cu, KT=4)
+    self.tct_w = {}
+    for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
+      l = self.L[f"stage_{stage}.t1"]
+      if l.k == (7, 7, 7) and g >= 16 and g % 16 == 0 and mid % 4 == 0 and t_out <= 16:
+        self.tct_w[l.name] = t.zeros(lib.crn_tct_packed_floats(mid, t_out), dtype=t.float32, device=dev)
     self.plans = {}
     self._ptr_sig = None
     self._ver_sig = None
@@ -275,6 +293,9 @@ class Engine:
           wf, wd = self.tc_w[l.name]
           _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 0, wf.data_ptr(), _lib.stream_ptr())
           _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 1, wd.data_ptr(), _lib.stream_ptr())
+        if l.name in self.tct_w:
+          _call("crn_tct_pack", P[l.name + ".weight"].data_ptr(), l.cin, l.cout, self.tct_w[l.name].data_ptr(),
+                _lib.stream_ptr())
       self._ver_sig = ver_sig
 
   def unpack_wgrads(self, grads: Dict[str, t.Tensor]):
@@ -530,7 +551,11 @@ class Plan:
       sd["bn2"].fwd(training)
       if sd["stage"] < 6:
         nxt = sd["next"]
-        conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]), nxt.p, 0, st)
+        if USE_TC and sd["lt"].name in eng.tct_w:
+          convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name].data_ptr(), bias(sd["lt"]), nxt.p,
+                         eng.tc_status.data_ptr(), st)
+        else:
+          conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]), nxt.p, 0, st)
         if sd["skip_c"]:
           ls, src, cmap, hw = sd["ls"], sd["src"], sd["cmap"], sd["hw"]
           w = P[ls.name + ".weight"]
@@ -547,8 +572,12 @@ class Plan:
       else:
         g2 = 2 * g
         logits = t.empty(B, sd["t_out"], g2, g2, g2, dtype=t.float32, device=self.dev)
-        conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]),
-                  logits.data_ptr(), 0, st)
+        if USE_TC and sd["lt"].name in eng.tct_w:
+          convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name].data_ptr(), bias(sd["lt"]),
+                         logits.data_ptr(), eng.tc_status.data_ptr(), st)
+        else:
+          conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]),
+                    logits.data_ptr(), 0, st)
     return logits
 
   # ------------------------------------------------------------------ backward

@@ -265,6 +265,17 @@ int crn_tc5_pack(const float* w, int32_t Cout, int32_t Cin, int32_t dgrad, float
 int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc, const float* bias,
                  float* out, int32_t* status, void* stream);
 
+/* ConvTranspose3d k=7 s=2 p=3 output_padding=1 forward on the same tcgen05 kernel: seen from the input
+ * grid all 8 output parity classes form one stride-1 4x4x4-tap convolution with 8*Cout columns, whose
+ * epilogue scatters column (class, co) of input voxel i to output voxel 2i+class.  Replaces the cuDNN
+ * call behind nn.ConvTranspose3d at model/reconstruction_decoder.py:69,77,85,95.  w is the PyTorch
+ * parameter [Cin][Cout][7][7][7]; out of crn_tct_pack holds crn_tct_packed_floats(Cin, Cout) floats.
+ * Input grid must tile by 8 (x) x 16 (y) x 8 (z); Cout <= 16; y may be channels-last or planar (desc). */
+int64_t crn_tct_packed_floats(int32_t Cin, int32_t Cout);
+int crn_tct_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream);
+int crn_convt7_tc(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
+                  int32_t* status, void* stream);
+
 /* Fused Adam step over a flat list (state.py:65-66) — next-row (f2) op. */
 int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream);

@@ -128,6 +128,47 @@ def test_conv5_tcgen05(n, cin, cout, dhw, kind):
   assert rel_err(got, ref) < 2e-4
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw,planar", [(1, 8, 2, (8, 16, 8), True), (2, 16, 2, (8, 32, 16), True),
+                                                     (1, 12, 3, (8, 16, 8), True), (1, 8, 2, (8, 16, 8), False),
+                                                     (1, 32, 16, (8, 16, 16), False), (1, 16, 8, (8, 16, 8), False),
+                                                     (1, 20, 4, (16, 16, 8), False)])
+def test_conv_transpose7_tcgen05(n, cin, cout, dhw, planar):
+  """ConvTranspose3d k=7 s=2 p=3 op=1 forward on the tcgen05 kernel (8 parity classes as one 4^3-tap conv with a
+  scatter epilogue) against torch fp64; channels-last output inside a wider (concat) row, or planar logits.
+  Tolerance 2e-5 of the tensor max (3xTF32, accumulation chains of <= 96 MMAs, measured ~2e-6)."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 7 + cout)
+  wt = t.randn(cin, cout, 7, 7, 7, generator=g) * 0.05
+  bias = t.randn(cout, generator=g)
+  x = t.randn(n, cin, d, h, w, generator=g)
+  ref = F.conv_transpose3d(x.double(), wt.double(), bias.double(), stride=2, padding=3, output_padding=1)
+  r4 = lambda c: (c + 3) // 4 * 4
+  xin = t.zeros(n * d * h * w, r4(cin), device=dev())
+  xin[:, :cin] = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).to(dev())
+  S = 8 * d * h * w
+  ycs = r4(cout) + 4
+  out = t.full((n * cout * S,) if planar else (n * S, ycs), float("nan"), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tct_packed_floats(cin, cout), device=dev())
+  st = _lib.stream_ptr()
+  _lib.call("crn_tct_pack", wt.to(dev()).contiguous().data_ptr(), cin, cout, wtc.data_ptr(), st)
+  desc = ops.make_desc(n, cin, cout, (d, h, w), (2 * d, 2 * h, 2 * w), (7, 7, 7), 2, 3, True, r4(cin), ycs)
+  desc.y_planar = int(planar)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  b = bias.to(dev())
+  _lib.call("crn_convt7_tc", C.byref(desc), xin.data_ptr(), wtc.data_ptr(), b.data_ptr(), out.data_ptr(),
+            status.data_ptr(), st)
+  t.cuda.synchronize()
+  assert int(status) == 0
+  if planar:
+    got = out.reshape(n, cout, 2 * d, 2 * h, 2 * w)
+  else:
+    got = out[:, :cout].reshape(n, 2 * d, 2 * h, 2 * w, cout).permute(0, 4, 1, 2, 3)
+    assert bool(t.isnan(out[:, cout:]).all()), "columns outside the layer's slice must stay untouched"
+  assert rel_err(got, ref) < 2e-5
+
+
 def test_linear():
   from corenet_b200 import ops
   g = t.Generator().manual_seed(5)
