@@ -331,16 +331,20 @@ struct WgradParams {
 constexpr int WT = 64;   // wgrad tile (both M and N)
 constexpr int WR = 16;   // rows per chunk
 
+// TM = M (Cin) extent of the tile: 64, or 16 for the RGB stem (Cin = 3) where a 64-wide tile is 95% padding.
+template <int TM>
 __global__ void __launch_bounds__(NT) wgrad_kernel(const WgradParams p) {
-  __shared__ __align__(16) float Ps[WR][WT];
+  constexpr int RM = TM / 16;              // m values per thread
+  __shared__ __align__(16) float Ps[WR][TM];
   __shared__ __align__(16) float Qs[WR][WT];
   const int tid = threadIdx.x;
   const int tap = blockIdx.z;
   const int mt = blockIdx.y / p.ntiles, nt = blockIdx.y - mt * p.ntiles;
-  const int m0 = mt * WT, n0 = nt * WT;
-  const long long rbeg = (long long)blockIdx.x * p.rows_per_split;
-  long long rend = rbeg + p.rows_per_split;
-  if (rend > p.rows) rend = p.rows;
+  const int m0 = mt * TM, n0 = nt * WT;
+  const int rows = (int)p.rows;            // host guarantees rows < 2^31
+  const int rbeg = (int)(blockIdx.x * p.rows_per_split);
+  int rend = rbeg + (int)p.rows_per_split;
+  if (rend > rows) rend = rows;
   if (rbeg >= rend) return;
 
   int kx = tap % p.Kd[2]; int q = tap / p.Kd[2];
@@ -353,21 +357,21 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const WgradParams p) {
   const int lrow = tid >> 4;        // 0..15
   const int lc4 = (tid & 15) * 4;   // 0..60
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  float acc[RM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   float4 rp, rq;
-  auto load_global = [&](long long rchunk) {
-    const long long r = rchunk + lrow;
+  auto load_global = [&](int rchunk) {
+    const int r = rchunk + lrow;
     rp = make_float4(0.f, 0.f, 0.f, 0.f);
     rq = rp;
     if (r < rend) {
-      int ix = (int)(r % p.lext[2]); long long t = r / p.lext[2];
-      int iy = (int)(t % p.lext[1]); t /= p.lext[1];
-      int iz = (int)(t % p.lext[0]); const int n = (int)(t / p.lext[0]);
+      int ix = r % p.lext[2]; int t = r / p.lext[2];
+      int iy = t % p.lext[1]; t /= p.lext[1];
+      int iz = t % p.lext[0]; const int n = t / p.lext[0];
       const int pz = iz * p.pstep[0] + pdz, py = iy * p.pstep[1] + pdy, px = ix * p.pstep[2] + pdx;
       const int qz = iz * p.qstep[0] + qdz, qy = iy * p.qstep[1] + qdy, qx = ix * p.qstep[2] + qdx;
       const bool okp = (unsigned)pz < (unsigned)p.pD[0] && (unsigned)py < (unsigned)p.pD[1] &&
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const WgradParams p) {
       const bool okq = (unsigned)qz < (unsigned)p.qD[0] && (unsigned)qy < (unsigned)p.qD[1] &&
                        (unsigned)qx < (unsigned)p.qD[2];
       if (okp && okq) {
-        if (m0 + lc4 < p.gM) {
+        if (lc4 < TM && m0 + lc4 < p.gM) {
           const long long off = ((((long long)n * p.pD[0] + pz) * p.pD[1] + py) * p.pD[2] + px) * p.p_cs +
                                 p.p_co + m0 + lc4;
           rp = __ldg(reinterpret_cast<const float4*>(p.P + off));
@@ -390,19 +394,24 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const WgradParams p) {
   };
 
   load_global(rbeg);
-  for (long long rc = rbeg; rc < rend; rc += WR) {
-    *reinterpret_cast<float4*>(&Ps[lrow][lc4]) = rp;
+  for (int rc = rbeg; rc < rend; rc += WR) {
+    if (lc4 < TM) *reinterpret_cast<float4*>(&Ps[lrow][lc4]) = rp;
     *reinterpret_cast<float4*>(&Qs[lrow][lc4]) = rq;
     __syncthreads();
     if (rc + WR < rend) load_global(rc + WR);
 #pragma unroll
     for (int k = 0; k < WR; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&Ps[k][ty * 4]);
+      float av[RM];
+      if constexpr (RM == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&Ps[k][ty * 4]);
+        av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+      } else {
+        av[0] = Ps[k][ty];
+      }
       const float4 b = *reinterpret_cast<const float4*>(&Qs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
       const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -410,8 +419,8 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const WgradParams p) {
   }
   float* dwt = p.dw + (long long)tap * p.wK * p.wN;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
     if (m >= p.gM) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -622,7 +631,9 @@ extern "C" int crn_conv_wgrad(const crn_conv_desc* d, const float* x, const floa
   p.p_cs = d->x_cs; p.p_co = d->x_co; p.q_cs = d->y_cs; p.q_co = d->y_co;
   p.rows = (long long)p.N * p.lext[0] * p.lext[1] * p.lext[2];
   if (p.rows <= 0) return CRN_OK;
-  p.mtiles = (int)crn_ceil_div(p.gM, WT);
+  CRN_REQUIRE(p.rows < 0x7fffffffLL, "crn_conv_wgrad: too many rows");
+  const bool narrow = p.gM <= 16;            // RGB stem: a 16-wide M tile
+  p.mtiles = narrow ? 1 : (int)crn_ceil_div(p.gM, WT);
   p.ntiles = (int)crn_ceil_div(p.gN, WT);
   const int taps = K[0] * K[1] * K[2];
   const long long tiles = (long long)p.mtiles * p.ntiles * taps;
@@ -634,7 +645,8 @@ extern "C" int crn_conv_wgrad(const crn_conv_desc* d, const float* x, const floa
   nsplit = crn_ceil_div(p.rows, p.rows_per_split);
   CRN_REQUIRE(taps <= 65535 && (long long)p.mtiles * p.ntiles <= 65535, "crn_conv_wgrad: grid too large");
   dim3 grid((unsigned)nsplit, (unsigned)(p.mtiles * p.ntiles), (unsigned)taps);
-  wgrad_kernel<<<grid, NT, 0, crn_stream(stream)>>>(p);
+  if (narrow) wgrad_kernel<16><<<grid, NT, 0, crn_stream(stream)>>>(p);
+  else wgrad_kernel<64><<<grid, NT, 0, crn_stream(stream)>>>(p);
   CRN_LAUNCH_CHECK("wgrad");
   return CRN_OK;
 }

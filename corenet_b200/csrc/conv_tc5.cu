@@ -74,9 +74,11 @@ __device__ __forceinline__ void decode_item(const TC5Params& p, int item, int& n
 // output voxel 2i+c gathers inputs i-1..i+2 with tap k = c+3-2o, so all 8 parity classes are one stride-1
 // 4x4x4-tap convolution with N = 8*Cout "class channels" -- the A tiles are shared by every class).
 // SCAT: epilogue scatters column (class, co) of voxel i to output voxel 2i+class.
-template <int NPAD, int ZT, bool ND, int KT, bool SCAT>
+// GATH: the dgrad of that layer -- the same 4^3-tap convolution run backwards: K = 8*Cout class channels gathered
+// from dY (class channel (c, co) of coarse voxel i is dY[2i+c][co]), taps at offsets -2..1, N = Cin.
+template <int NPAD, int ZT, bool ND, int KT, bool SCAT, bool GATH>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p) {
-  constexpr int HLO = (KT == 5) ? 2 : 1;                   // most negative tap offset
+  constexpr int HLO = (KT == 5 || GATH) ? 2 : 1;           // most negative tap offset
   constexpr int KZG = (KT == 4) ? 2 : 1;                   // kz planes per flush group (chain <= 96 MMAs)
   constexpr bool RACC = SCAT && NPAD == 16;                // epilogue keeps the running sums in registers
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -319,7 +321,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
               const int k = pass * 8 + kc * 4;
               float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
               if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
-                const long long off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
+                long long off;
+                if constexpr (GATH) {                // class channel k = (cls, co) lives at fine voxel 2i + cls
+                  const int cls = k / p.cout_cls, co = k - cls * p.cout_cls;
+                  off = ((((long long)n * (2 * p.D) + 2 * q + (cls >> 2)) * (2 * p.H) + 2 * y + ((cls >> 1) & 1)) *
+                             (2 * p.W) + 2 * x + (cls & 1)) * p.in_cs + p.in_co + co;
+                } else {
+                  off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
+                }
                 a = __ldg(reinterpret_cast<const float4*>(p.in + off));
               }
               float4 hi, lo;
@@ -501,7 +510,8 @@ __global__ void tc5_pack_kernel(const float* __restrict__ w, int Cout, int Cin, 
 // pack kernel: PyTorch ConvTranspose3d weight [Cin][Cout][7][7][7] -> wtc[P][64 taps][tap block], column
 // n = class * Cout + co (class = cz*4 + cy*2 + cx), tap j = (jz*4 + jy)*4 + jx <-> input offset j - 1 per axis,
 // filter index k = c + 3 - 2*(j - 1) (zero weight where k falls outside 0..6: class 0 has 3 taps per axis).
-__global__ void tct_pack_kernel(const float* __restrict__ w, int Cin, int Cout, int NPAD, int P, int nd,
+// dgrad != 0: the transposed operator, K = (class, co), N = ci, tap j <-> offset j - 2, k = c - 1 + 2*j.
+__global__ void tct_pack_kernel(const float* __restrict__ w, int Cin, int Cout, int NPAD, int P, int nd, int dgrad,
                                 float* __restrict__ out) {
   const long long total = (long long)P * 64 * 2 * NPAD * 4;      // (pass, tap, kc, n, e)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -510,14 +520,26 @@ __global__ void tct_pack_kernel(const float* __restrict__ w, int Cin, int Cout, 
     const int n = (int)(r % NPAD); r /= NPAD;
     const int kc = (int)(r & 1); r >>= 1;
     const int t = (int)(r & 63); const int pass = (int)(r >> 6);
-    const int ci = pass * 8 + kc * 4 + e;
+    const int kk = pass * 8 + kc * 4 + e;
     float v = 0.f;
-    if (ci < Cin && n < 8 * Cout) {
-      const int cls = n / Cout, co = n - cls * Cout;
-      const int kz = (cls >> 2) + 5 - 2 * (t >> 4), ky = ((cls >> 1) & 1) + 5 - 2 * ((t >> 2) & 3),
-                kx = (cls & 1) + 5 - 2 * (t & 3);
-      if ((unsigned)kz < 7u && (unsigned)ky < 7u && (unsigned)kx < 7u)
-        v = w[(((long long)ci * Cout + co) * 7 + kz) * 49 + ky * 7 + kx];
+    if (!dgrad) {
+      const int ci = kk;
+      if (ci < Cin && n < 8 * Cout) {
+        const int cls = n / Cout, co = n - cls * Cout;
+        const int kz = (cls >> 2) + 5 - 2 * (t >> 4), ky = ((cls >> 1) & 1) + 5 - 2 * ((t >> 2) & 3),
+                  kx = (cls & 1) + 5 - 2 * (t & 3);
+        if ((unsigned)kz < 7u && (unsigned)ky < 7u && (unsigned)kx < 7u)
+          v = w[(((long long)ci * Cout + co) * 7 + kz) * 49 + ky * 7 + kx];
+      }
+    } else {
+      const int ci = n;
+      if (ci < Cin && kk < 8 * Cout) {
+        const int cls = kk / Cout, co = kk - cls * Cout;
+        const int kz = (cls >> 2) - 1 + 2 * (t >> 4), ky = ((cls >> 1) & 1) - 1 + 2 * ((t >> 2) & 3),
+                  kx = (cls & 1) - 1 + 2 * (t & 3);
+        if ((unsigned)kz < 7u && (unsigned)ky < 7u && (unsigned)kx < 7u)
+          v = w[(((long long)ci * Cout + co) * 7 + kz) * 49 + ky * 7 + kx];
+      }
     }
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
@@ -535,13 +557,13 @@ __global__ void tct_pack_kernel(const float* __restrict__ w, int Cin, int Cout, 
   }
 }
 
-template <int NPAD, int ZT, bool ND, int KT = 5, bool SCAT = false>
+template <int NPAD, int ZT, bool ND, int KT = 5, bool SCAT = false, bool GATH = false>
 int launch_tc5(TC5Params p, cudaStream_t st) {
   constexpr int WROW_BYTES = KT * 2 * 2 * NPAD * 16;
   const size_t smem = (size_t)(ZT + 1) * PLANE_BYTES + (size_t)WSTAGES * WROW_BYTES + sizeof(Barriers) + 64;
   p.tiles_z = p.D / ZT;
   p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
-  auto kern = conv_tc5_kernel<NPAD, ZT, ND, KT, SCAT>;
+  auto kern = conv_tc5_kernel<NPAD, ZT, ND, KT, SCAT, GATH>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -626,20 +648,26 @@ static int tct_npad(int Cout) {
   return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128));
 }
 
-extern "C" int64_t crn_tct_packed_floats(int32_t Cin, int32_t Cout) {
-  const int P = (Cin + 7) / 8;
-  return (int64_t)P * 64 * 2 * 2 * tct_npad(Cout) * 4;
+static int tc_npad64(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : 64); }
+
+extern "C" int64_t crn_tct_packed_floats(int32_t Cin, int32_t Cout, int32_t dgrad) {
+  const int P = ((dgrad ? 8 * Cout : Cin) + 7) / 8;
+  const int NPAD = dgrad ? tc_npad64(Cin) : tct_npad(Cout);
+  return (int64_t)P * 64 * 2 * 2 * NPAD * 4;
 }
 
-extern "C" int crn_tct_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream) {
+extern "C" int crn_tct_pack(const float* w, int32_t Cin, int32_t Cout, int32_t dgrad, float* out, void* stream) {
   CRN_REQUIRE(w && out && Cout > 0 && Cin > 0, "crn_tct_pack: bad args");
-  CRN_REQUIRE(8 * Cout <= 128, "crn_tct_pack: Cout > 16 unsupported");
-  const int P = (Cin + 7) / 8;
-  const int NPAD = tct_npad(Cout);
+  if (dgrad) CRN_REQUIRE(Cin <= 64 && Cout % 4 == 0, "crn_tct_pack: dgrad needs Cin <= 64 and Cout % 4 == 0");
+  else CRN_REQUIRE(8 * Cout <= 128, "crn_tct_pack: Cout > 16 unsupported");
+  const int K = dgrad ? 8 * Cout : Cin, N = dgrad ? Cin : 8 * Cout;
+  const int P = (K + 7) / 8;
+  const int NPAD = dgrad ? tc_npad64(Cin) : tct_npad(Cout);
   const long long total = (long long)P * 64 * 2 * NPAD * 4;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  tct_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cin, Cout, NPAD, P, tc5_use_nd(8 * Cout) ? 1 : 0, out);
+  tct_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cin, Cout, NPAD, P, tc5_use_nd(N) ? 1 : 0, dgrad ? 1 : 0,
+                                                          out);
   CRN_LAUNCH_CHECK("tct_pack");
   return CRN_OK;
 }
@@ -674,4 +702,34 @@ extern "C" int crn_convt7_tc(const crn_conv_desc* d, const float* x, const float
   // two planes per item keep two accumulator stages in TMEM (2*2*128 columns): 0.55 ms vs 0.74 ms with ZT = 4
   // on the stage-5 layer (scripts/tct_test.py)
   return launch_tc5<128, 2, false, 4, true>(p, st);
+}
+
+// dx = ConvTranspose3d^T(dy): the dgrad of the layer above (dy channels-last [N, 2D, 2H, 2W, y_cs]).
+extern "C" int crn_convt7_tc_dgrad(const crn_conv_desc* d, const float* dy, const float* wtc, float* dx,
+                                   int32_t* status, void* stream) {
+  CRN_REQUIRE(d && dy && wtc && dx && status, "crn_convt7_tc_dgrad: null pointer");
+  CRN_REQUIRE(d->transposed && d->kD == 7 && d->kH == 7 && d->kW == 7 && d->stride == 2 && d->pad == 3,
+              "crn_convt7_tc_dgrad: only ConvTranspose3d k=7 s=2 p=3");
+  CRN_REQUIRE(d->oD == 2 * d->iD && d->oH == 2 * d->iH && d->oW == 2 * d->iW,
+              "crn_convt7_tc_dgrad: output must be 2x input");
+  CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % 8 == 0,
+              "crn_convt7_tc_dgrad: input grid must tile by 8x16x8");
+  CRN_REQUIRE(!d->y_planar, "crn_convt7_tc_dgrad: planar dy unsupported");
+  CRN_REQUIRE(d->Cout % 4 == 0 && d->Cin % 4 == 0 && d->Cin <= 64, "crn_convt7_tc_dgrad: Cout % 4, Cin % 4, Cin <= 64");
+  CRN_REQUIRE(d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
+              "crn_convt7_tc_dgrad: channel strides/offsets must be multiples of 4");
+  TC5Params p{};
+  p.in = dy; p.wtc = wtc; p.bias = nullptr; p.out = dx; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  p.gK = 8 * d->Cout; p.gN = d->Cin; p.cout_cls = d->Cout;
+  p.in_cs = d->y_cs; p.in_co = d->y_co; p.out_cs = d->x_cs; p.out_co = d->x_co;
+  p.P = (p.gK + 7) / 8;
+  p.tiles_x = p.W / TX; p.tiles_y = p.H / TY;
+  cudaStream_t st = crn_stream(stream);
+  if (p.gN <= 16) {
+    if (tc5_use_nd(p.gN)) return launch_tc5<16, 8, true, 4, false, true>(p, st);
+    return launch_tc5<16, 8, false, 4, false, true>(p, st);
+  }
+  if (p.gN <= 32) return launch_tc5<32, 8, false, 4, false, true>(p, st);
+  return launch_tc5<64, 4, false, 4, false, true>(p, st);
 }

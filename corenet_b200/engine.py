@@ -81,6 +81,18 @@ def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
   PROFILE.append(("fwd_tc", layer.name, conv_macs(d), e0, e1))
 
 
+def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st):
+  """ConvTranspose3d k=7 s=2 dgrad through crn_convt7_tc_dgrad."""
+  if PROFILE is None:
+    _lib.call("crn_convt7_tc_dgrad", C.byref(d), dy, wtc, dx, status, st)
+    return
+  e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+  e0.record()
+  _lib.call("crn_convt7_tc_dgrad", C.byref(d), dy, wtc, dx, status, st)
+  e1.record()
+  PROFILE.append(("dgrad_tc", layer.name, conv_macs(d), e0, e1))
+
+
 def conv5_tc_call(kind, layer, d, inp, wtc, bias, out, status, st):
   """kind: 'fwd' | 'dgrad' through crn_conv5_tc."""
   k = 0 if kind == "fwd" else 1
@@ -240,8 +252,13 @@ class Engine:
     self.tct_w = {}
     for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
       l = self.L[f"stage_{stage}.t1"]
-      if l.k == (7, 7, 7) and g >= 16 and g % 16 == 0 and mid % 4 == 0 and t_out <= 16:
-        self.tct_w[l.name] = t.zeros(lib.crn_tct_packed_floats(mid, t_out), dtype=t.float32, device=dev)
+      if l.k == (7, 7, 7) and g >= 16 and g % 16 == 0 and mid % 4 == 0:
+        fwd_ok = t_out <= 16                          # 8 * Cout accumulator columns <= 128
+        # float4 class-channel gathers, N = Cin <= 64; at 16^3 the 32 work items leave most SMs idle (FFMA wins)
+        dgrad_ok = t_out % 4 == 0 and mid <= 64 and g >= 32
+        mk = lambda dg: t.zeros(lib.crn_tct_packed_floats(mid, t_out, dg), dtype=t.float32, device=dev)
+        if fwd_ok or dgrad_ok:
+          self.tct_w[l.name] = (mk(0) if fwd_ok else None, mk(1) if dgrad_ok else None)
     self.plans = {}
     self._ptr_sig = None
     self._ver_sig = None
@@ -294,8 +311,10 @@ class Engine:
           _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 0, wf.data_ptr(), _lib.stream_ptr())
           _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 1, wd.data_ptr(), _lib.stream_ptr())
         if l.name in self.tct_w:
-          _call("crn_tct_pack", P[l.name + ".weight"].data_ptr(), l.cin, l.cout, self.tct_w[l.name].data_ptr(),
-                _lib.stream_ptr())
+          for dg, wt in enumerate(self.tct_w[l.name]):
+            if wt is not None:
+              _call("crn_tct_pack", P[l.name + ".weight"].data_ptr(), l.cin, l.cout, dg, wt.data_ptr(),
+                    _lib.stream_ptr())
       self._ver_sig = ver_sig
 
   def unpack_wgrads(self, grads: Dict[str, t.Tensor]):
@@ -551,8 +570,8 @@ class Plan:
       sd["bn2"].fwd(training)
       if sd["stage"] < 6:
         nxt = sd["next"]
-        if USE_TC and sd["lt"].name in eng.tct_w:
-          convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name].data_ptr(), bias(sd["lt"]), nxt.p,
+        if USE_TC and eng.tct_w.get(sd["lt"].name, (None, None))[0] is not None:
+          convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name][0].data_ptr(), bias(sd["lt"]), nxt.p,
                          eng.tc_status.data_ptr(), st)
         else:
           conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]), nxt.p, 0, st)
@@ -572,8 +591,8 @@ class Plan:
       else:
         g2 = 2 * g
         logits = t.empty(B, sd["t_out"], g2, g2, g2, dtype=t.float32, device=self.dev)
-        if USE_TC and sd["lt"].name in eng.tct_w:
-          convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name].data_ptr(), bias(sd["lt"]),
+        if USE_TC and eng.tct_w.get(sd["lt"].name, (None, None))[0] is not None:
+          convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name][0].data_ptr(), bias(sd["lt"]),
                          logits.data_ptr(), eng.tc_status.data_ptr(), st)
         else:
           conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]),
@@ -632,7 +651,10 @@ class Plan:
           ssum = ssum * float(hw * hw)
           sd["ssum"] = ssum
       wgrad(lt, d_t, sd["z2"].p, dy_ptr)
-      dgrad(lt, d_t, dy_ptr, sd["z2"].gp, 0)
+      if USE_TC and eng.tct_w.get(lt.name, (None, None))[1] is not None:
+        convt7_tc_dgrad_call(lt, d_t, dy_ptr, eng.tct_w[lt.name][1].data_ptr(), sd["z2"].gp, eng.tc_status.data_ptr(), st)
+      else:
+        dgrad(lt, d_t, dy_ptr, sd["z2"].gp, 0)
       dxs = sd["bn2"].bwd(tr, grads, sd["z2"].gp, sd["z2"].cs, sd["c"].gp, sd["c"].cs)
       bias_from(dxs, lc.name + ".bias")
       wgrad(lc, sd["d_c"], sd["z"].p, sd["c"].gp)

@@ -271,10 +271,14 @@ int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* in, const fl
  * call behind nn.ConvTranspose3d at model/reconstruction_decoder.py:69,77,85,95.  w is the PyTorch
  * parameter [Cin][Cout][7][7][7]; out of crn_tct_pack holds crn_tct_packed_floats(Cin, Cout) floats.
  * Input grid must tile by 8 (x) x 16 (y) x 8 (z); Cout <= 16; y may be channels-last or planar (desc). */
-int64_t crn_tct_packed_floats(int32_t Cin, int32_t Cout);
-int crn_tct_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream);
+int64_t crn_tct_packed_floats(int32_t Cin, int32_t Cout, int32_t dgrad);
+int crn_tct_pack(const float* w, int32_t Cin, int32_t Cout, int32_t dgrad, float* out, void* stream);
 int crn_convt7_tc(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
                   int32_t* status, void* stream);
+/* ... and its dgrad, dx = convT^T(dy): the same kernel with K = 8*Cout class channels gathered from dy
+ * (channels-last) and the taps mirrored (crn_tct_pack with dgrad != 0).  Cout % 4 == 0, Cin <= 64. */
+int crn_convt7_tc_dgrad(const crn_conv_desc* d, const float* dy, const float* wtc, float* dx,
+                        int32_t* status, void* stream);
 
 /* Fused Adam step over a flat list (state.py:65-66) — next-row (f2) op. */
 int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

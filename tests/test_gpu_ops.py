@@ -150,9 +150,9 @@ def test_conv_transpose7_tcgen05(n, cin, cout, dhw, planar):
   S = 8 * d * h * w
   ycs = r4(cout) + 4
   out = t.full((n * cout * S,) if planar else (n * S, ycs), float("nan"), device=dev())
-  wtc = t.zeros(_lib.lib().crn_tct_packed_floats(cin, cout), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tct_packed_floats(cin, cout, 0), device=dev())
   st = _lib.stream_ptr()
-  _lib.call("crn_tct_pack", wt.to(dev()).contiguous().data_ptr(), cin, cout, wtc.data_ptr(), st)
+  _lib.call("crn_tct_pack", wt.to(dev()).contiguous().data_ptr(), cin, cout, 0, wtc.data_ptr(), st)
   desc = ops.make_desc(n, cin, cout, (d, h, w), (2 * d, 2 * h, 2 * w), (7, 7, 7), 2, 3, True, r4(cin), ycs)
   desc.y_planar = int(planar)
   status = t.zeros(1, dtype=t.int32, device=dev())
@@ -166,6 +166,35 @@ def test_conv_transpose7_tcgen05(n, cin, cout, dhw, planar):
   else:
     got = out[:, :cout].reshape(n, 2 * d, 2 * h, 2 * w, cout).permute(0, 4, 1, 2, 3)
     assert bool(t.isnan(out[:, cout:]).all()), "columns outside the layer's slice must stay untouched"
+  assert rel_err(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize("n,cin,cout,dhw", [(1, 8, 4, (8, 16, 8)), (1, 32, 16, (8, 16, 16)), (2, 20, 8, (8, 16, 8)),
+                                              (1, 64, 32, (8, 16, 8))])
+def test_conv_transpose7_dgrad_tcgen05(n, cin, cout, dhw):
+  """dgrad of ConvTranspose3d k=7 s=2 on the tcgen05 kernel (class-channel gather from dy) against torch fp64:
+  the adjoint of a transposed conv is the strided conv with the same weight tensor."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 7 + cout + 1)
+  wt = t.randn(cin, cout, 7, 7, 7, generator=g) * 0.05
+  dy = t.randn(n, cout, 2 * d, 2 * h, 2 * w, generator=g)
+  ref = F.conv3d(dy.double(), wt.double(), None, stride=2, padding=3)
+  r4 = lambda c: (c + 3) // 4 * 4
+  ycs = r4(cout) + 4
+  dyin = t.zeros(n * 8 * d * h * w, ycs, device=dev())
+  dyin[:, :cout] = dy.permute(0, 2, 3, 4, 1).reshape(-1, cout).to(dev())
+  out = t.full((n * d * h * w, r4(cin)), float("nan"), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tct_packed_floats(cin, cout, 1), device=dev())
+  st = _lib.stream_ptr()
+  _lib.call("crn_tct_pack", wt.to(dev()).contiguous().data_ptr(), cin, cout, 1, wtc.data_ptr(), st)
+  desc = ops.make_desc(n, cin, cout, (d, h, w), (2 * d, 2 * h, 2 * w), (7, 7, 7), 2, 3, True, r4(cin), ycs)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  _lib.call("crn_convt7_tc_dgrad", C.byref(desc), dyin.data_ptr(), wtc.data_ptr(), out.data_ptr(), status.data_ptr(), st)
+  t.cuda.synchronize()
+  assert int(status) == 0
+  got = out[:, :cin].reshape(n, d, h, w, cin).permute(0, 4, 1, 2, 3)
   assert rel_err(got, ref) < 2e-5
 
 
