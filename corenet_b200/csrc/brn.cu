@@ -5,31 +5,41 @@
 //
 // "Column-owner" mapping: a thread owns VEC consecutive channels and strides
 // over rows, so every per-channel reduction stays in registers; partial sums
-// are combined in double precision (smem, then one atomicAdd per block/channel).
+// are combined in double precision: shared memory inside a block, distributed shared memory
+// inside a thread-block cluster of 8, then ONE atomicAdd per cluster and channel -- same-address
+// double atomics serialise in L2 (~50 ns each), and with one per block they were a ~15 us floor
+// under every pass (scripts/brn_bench.py).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int NT = 256;
 
 struct ColGrid {
-  int txc;      // threads across channel groups (power of two <= 256)
+  int txc;      // threads across channel groups (power of two <= 8)
+  int cluster;  // blocks per cluster along x (8, or 1 for tiny grids)
   dim3 grid;
 };
 
 static ColGrid col_grid(int64_t rows, int cgroups) {
   ColGrid g;
+  // narrow blocks (<= 8 channel groups = 128 B per row) put the parallelism on gridDim.y, where blocks do
+  // not share accumulator addresses; gridDim.x (blocks that do share them) is grouped into clusters of 8
   int txc = 1;
-  while (txc < cgroups && txc < NT) txc <<= 1;
+  while (txc < cgroups && txc < 8) txc <<= 1;
   g.txc = txc;
   const int tyc = NT / txc;
   const int gy = (int)crn_ceil_div(cgroups, txc);
-  int64_t gx = crn_ceil_div(rows, tyc);
-  // few, fat blocks: every block ends with one double atomicAdd per channel, and >1000 blocks hammering
-  // the same 2*C addresses cost more than the whole streaming pass (profiles/r01_launch_list_step_summary.txt)
+  int64_t gx = crn_ceil_div(rows, (int64_t)tyc * 4);      // >= 4 rows per thread
   int64_t target = crn_ceil_div(2LL * kNumSMs, gy);
   if (gx > target) gx = target;
   if (gx < 1) gx = 1;
+  g.cluster = 1;
+  if (gx >= 8) { gx = gx / 8 * 8; g.cluster = 8; }
   g.grid = dim3((unsigned)gx, (unsigned)gy, 1);
   return g;
 }
@@ -52,11 +62,26 @@ struct Vec<1> {
   static __device__ __forceinline__ void store(float* p, const float v[1]) { p[0] = v[0]; }
 };
 
+constexpr int UNR = 4;   // independent row loads in flight per thread in the column-owner passes
+
+// plain (coherent) load: dx may have been written earlier in this kernel's lifetime by other kernels, but never
+// by this one before the read -- kept off the read-only path only because dx is not const/restrict-read-only
+template <int VEC>
+__device__ __forceinline__ void load_plain(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = p[0];
+  }
+}
+
 // Block-level combine of NV per-thread double partials per owned channel.
 template <int VEC, int NV>
 __device__ __forceinline__ void block_col_reduce(double (&part)[NV][VEC], int txc, int tx, int ty,
                                                  int c_first, int C, double* const (&dst)[NV]) {
   __shared__ double red[NT * 4];
+  __shared__ double blk[NV][8 * 4];          // this block's per-channel sums (txc <= 8), read by cluster rank 0
   const int tyc = NT / txc;
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
@@ -69,11 +94,45 @@ __device__ __forceinline__ void block_col_reduce(double (&part)[NV][VEC], int tx
       for (int e = 0; e < VEC; ++e) {
         double s = 0.0;
         for (int y = 0; y < tyc; ++y) s += red[(y * txc + tx) * VEC + e];
-        const int c = c_first + e;
-        if (c < C && dst[q]) atomic_add_f64(dst[q] + c, s);
+        blk[q][tx * VEC + e] = s;
       }
     }
   }
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();                            // every block's blk[][] is written
+  if (cluster.block_rank() == 0 && ty == 0) {
+    const unsigned nb = cluster.num_blocks();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const int c = c_first + e;
+        if (c >= C || !dst[q]) continue;
+        double s = 0.0;
+        for (unsigned rk = 0; rk < nb; ++rk) s += *cluster.map_shared_rank(&blk[q][tx * VEC + e], rk);
+        atomic_add_f64(dst[q] + c, s);
+      }
+    }
+  }
+  cluster.sync();                            // keep every block's shared memory alive until rank 0 has read it
+}
+
+// launch with a thread-block cluster of `cluster` blocks along x (grid.x is a multiple of it)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_clustered(void (*kern)(KArgs...), dim3 grid, int cluster, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ---------------------------------------------------------------- stats
@@ -97,9 +156,9 @@ __global__ void __launch_bounds__(NT) brn_stats_kernel(const float* __restrict__
 #pragma unroll
     for (int e = 0; e < VEC; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
     int cnt = 0;
-    for (int64_t r = (int64_t)blockIdx.x * tyc + ty; r < rows; r += (int64_t)gridDim.x * tyc) {
-      float v[VEC];
-      Vec<VEC>::load(x + r * x_cs + x_co + c_first, v);
+    const int64_t stride = (int64_t)gridDim.x * tyc;
+    int64_t r = (int64_t)blockIdx.x * tyc + ty;
+    auto accum = [&](const float (&v)[VEC]) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         float u = relu_in ? fmaxf(v[e], 0.f) : v[e];
@@ -107,13 +166,26 @@ __global__ void __launch_bounds__(NT) brn_stats_kernel(const float* __restrict__
         s1[e] += u;
         s2[e] = fmaf(u, u, s2[e]);
       }
-      if (++cnt == 256) {   // flush fp32 partials into double to bound the error
+    };
+    // UNR independent row loads in flight per thread: these passes are latency-bound, not bandwidth-bound
+    for (; r + (UNR - 1) * stride < rows; r += UNR * stride) {
+      float v[UNR][VEC];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) Vec<VEC>::load(x + (r + u * stride) * x_cs + x_co + c_first, v[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) accum(v[u]);
+      if (++cnt == 256 / UNR) {   // flush fp32 partials into double to bound the error
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           part[0][e] += s1[e]; part[1][e] += s2[e]; s1[e] = 0.f; s2[e] = 0.f;
         }
         cnt = 0;
       }
+    }
+    for (; r < rows; r += stride) {
+      float v[VEC];
+      Vec<VEC>::load(x + r * x_cs + x_co + c_first, v);
+      accum(v);
     }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) { part[0][e] += s1[e]; part[1][e] += s2[e]; }
@@ -168,6 +240,7 @@ __global__ void brn_finalize_kernel(const double* __restrict__ acc, int64_t rows
   coef[c] = a; coef[C + c] = b; coef[2 * C + c] = mean; coef[3 * C + c] = invstd;
   coef[4 * C + c] = r; coef[5 * C + c] = d;
 }
+// separate launch: every thread of finalize reads *nbt, so the increment must happen after that grid
 __global__ void brn_bump_counter(int64_t* nbt) { *nbt += 1; }
 
 // ---------------------------------------------------------------- apply
@@ -227,24 +300,19 @@ __global__ void __launch_bounds__(NT) brn_bwd_reduce_kernel(
 #pragma unroll
     for (int e = 0; e < VEC; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
     int cnt = 0;
-    for (int64_t r = (int64_t)blockIdx.x * tyc + ty; r < rows; r += (int64_t)gridDim.x * tyc) {
-      float g[VEC], v[VEC];
-      const int64_t go = r * dy_cs + dy_co + c_first;
-      Vec<VEC>::load(dy + go, g);
+    const int64_t stride = (int64_t)gridDim.x * tyc;
+    int64_t r = (int64_t)blockIdx.x * tyc + ty;
+    auto process = [&](int64_t go, float (&g)[VEC], const float (&ya)[VEC], const float (&ge)[VEC],
+                       const float (&v)[VEC]) {
       if (relu_out) {
-        float ya[VEC];
-        Vec<VEC>::load(y_act + go, ya);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) g[e] = ya[e] > 0.f ? g[e] : 0.f;
       }
       if (g_extra) {
-        float ge[VEC];
-        Vec<VEC>::load(g_extra + go, ge);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) g[e] += ge[e];
       }
       if (g_out) Vec<VEC>::store(g_out + go, g);
-      Vec<VEC>::load(x + r * x_cs + x_co + c_first, v);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const float u = relu_in ? fmaxf(v[e], 0.f) : v[e];
@@ -252,13 +320,35 @@ __global__ void __launch_bounds__(NT) brn_bwd_reduce_kernel(
         s1[e] += g[e];
         s2[e] = fmaf(g[e], xh, s2[e]);
       }
-      if (++cnt == 256) {
+    };
+    for (; r + (UNR - 1) * stride < rows; r += UNR * stride) {
+      float g[UNR][VEC], ya[UNR][VEC], ge[UNR][VEC], v[UNR][VEC];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t go = (r + u * stride) * dy_cs + dy_co + c_first;
+        Vec<VEC>::load(dy + go, g[u]);
+        if (relu_out) Vec<VEC>::load(y_act + go, ya[u]);
+        if (g_extra) Vec<VEC>::load(g_extra + go, ge[u]);
+        Vec<VEC>::load(x + (r + u * stride) * x_cs + x_co + c_first, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) process((r + u * stride) * dy_cs + dy_co + c_first, g[u], ya[u], ge[u], v[u]);
+      if (++cnt == 256 / UNR) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           part[0][e] += s1[e]; part[1][e] += s2[e]; s1[e] = 0.f; s2[e] = 0.f;
         }
         cnt = 0;
       }
+    }
+    for (; r < rows; r += stride) {
+      float g[VEC], ya[VEC], ge[VEC], v[VEC];
+      const int64_t go = r * dy_cs + dy_co + c_first;
+      Vec<VEC>::load(dy + go, g);
+      if (relu_out) Vec<VEC>::load(y_act + go, ya);
+      if (g_extra) Vec<VEC>::load(g_extra + go, ge);
+      Vec<VEC>::load(x + r * x_cs + x_co + c_first, v);
+      process(go, g, ya, ge, v);
     }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) { part[0][e] += s1[e]; part[1][e] += s2[e]; }
@@ -301,10 +391,10 @@ __global__ void __launch_bounds__(NT) brn_bwd_dx_kernel(
 #pragma unroll
     for (int e = 0; e < VEC; ++e) sdx[e] = 0.f;
     int cnt = 0;
-    for (int64_t r = (int64_t)blockIdx.x * tyc + ty; r < rows; r += (int64_t)gridDim.x * tyc) {
-      float gv[VEC], v[VEC], o[VEC];
-      Vec<VEC>::load(g + r * g_cs + g_co + c_first, gv);
-      Vec<VEC>::load(x + r * x_cs + x_co + c_first, v);
+    const int64_t stride = (int64_t)gridDim.x * tyc;
+    int64_t r = (int64_t)blockIdx.x * tyc + ty;
+    auto process = [&](int64_t rr, const float (&gv)[VEC], const float (&v)[VEC], const float (&old)[VEC]) {
+      float o[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
         const float u = relu_in ? fmaxf(v[e], 0.f) : v[e];
@@ -314,19 +404,35 @@ __global__ void __launch_bounds__(NT) brn_bwd_dx_kernel(
         o[e] = t;
         sdx[e] += t;
       }
-      float* dp = dx + r * dx_cs + dx_co + c_first;
       if (dx_accumulate) {
-        float old[VEC];
-        Vec<VEC>::load(dp, old);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) o[e] += old[e];
       }
-      Vec<VEC>::store(dp, o);
-      if (++cnt == 256) {
+      Vec<VEC>::store(dx + rr * dx_cs + dx_co + c_first, o);
+    };
+    for (; r + (UNR - 1) * stride < rows; r += UNR * stride) {
+      float gv[UNR][VEC], v[UNR][VEC], old[UNR][VEC];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t rr = r + u * stride;
+        Vec<VEC>::load(g + rr * g_cs + g_co + c_first, gv[u]);
+        Vec<VEC>::load(x + rr * x_cs + x_co + c_first, v[u]);
+        if (dx_accumulate) load_plain<VEC>(dx + rr * dx_cs + dx_co + c_first, old[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) process(r + u * stride, gv[u], v[u], old[u]);
+      if (++cnt == 256 / UNR) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) { part[0][e] += sdx[e]; sdx[e] = 0.f; }
         cnt = 0;
       }
+    }
+    for (; r < rows; r += stride) {
+      float gv[VEC], v[VEC], old[VEC];
+      Vec<VEC>::load(g + r * g_cs + g_co + c_first, gv);
+      Vec<VEC>::load(x + r * x_cs + x_co + c_first, v);
+      if (dx_accumulate) load_plain<VEC>(dx + r * dx_cs + dx_co + c_first, old);
+      process(r, gv, v, old);
     }
 #pragma unroll
     for (int e = 0; e < VEC; ++e) part[0][e] += sdx[e];
@@ -407,10 +513,10 @@ extern "C" int crn_brn_stats(const float* x, int64_t rows, int32_t C, int32_t x_
   cudaStream_t st = crn_stream(stream);
   if (vec4_ok(C, x_cs, x_co)) {
     ColGrid g = col_grid(rows, C / 4);
-    brn_stats_kernel<4><<<g.grid, NT, 0, st>>>(x, rows, C, x_cs, x_co, relu_in, acc, g.txc);
+    launch_clustered(brn_stats_kernel<4>, g.grid, g.cluster, st, x, rows, C, x_cs, x_co, relu_in, acc, g.txc);
   } else {
     ColGrid g = col_grid(rows, C);
-    brn_stats_kernel<1><<<g.grid, NT, 0, st>>>(x, rows, C, x_cs, x_co, relu_in, acc, g.txc);
+    launch_clustered(brn_stats_kernel<1>, g.grid, g.cluster, st, x, rows, C, x_cs, x_co, relu_in, acc, g.txc);
   }
   CRN_LAUNCH_CHECK("brn_stats");
   return CRN_OK;
@@ -459,11 +565,11 @@ extern "C" int crn_brn_bwd_reduce(const float* dy, int32_t dy_cs, int32_t dy_co,
   cudaStream_t st = crn_stream(stream);
   if (vec4_ok(C, x_cs, x_co) && dy_cs % 4 == 0 && dy_co % 4 == 0) {
     ColGrid g = col_grid(rows, C / 4);
-    brn_bwd_reduce_kernel<4><<<g.grid, NT, 0, st>>>(dy, dy_cs, dy_co, y_act, g_extra, x, x_cs, x_co, rows,
+    launch_clustered(brn_bwd_reduce_kernel<4>, g.grid, g.cluster, st, dy, dy_cs, dy_co, y_act, g_extra, x, x_cs, x_co, rows,
                                                     C, coef, relu_in, relu_out, g_out, acc, g.txc);
   } else {
     ColGrid g = col_grid(rows, C);
-    brn_bwd_reduce_kernel<1><<<g.grid, NT, 0, st>>>(dy, dy_cs, dy_co, y_act, g_extra, x, x_cs, x_co, rows,
+    launch_clustered(brn_bwd_reduce_kernel<1>, g.grid, g.cluster, st, dy, dy_cs, dy_co, y_act, g_extra, x, x_cs, x_co, rows,
                                                     C, coef, relu_in, relu_out, g_out, acc, g.txc);
   }
   CRN_LAUNCH_CHECK("brn_bwd_reduce");
@@ -481,12 +587,12 @@ extern "C" int crn_brn_bwd_dx(const float* g, int32_t g_cs, int32_t g_co, const 
   cudaStream_t st = crn_stream(stream);
   if (vec4_ok(C, x_cs, x_co) && g_cs % 4 == 0 && g_co % 4 == 0 && dx_cs % 4 == 0 && dx_co % 4 == 0) {
     ColGrid cg = col_grid(rows, C / 4);
-    brn_bwd_dx_kernel<4><<<cg.grid, NT, 0, st>>>(g, g_cs, g_co, x, x_cs, x_co, rows, C, coef, acc, relu_in,
+    launch_clustered(brn_bwd_dx_kernel<4>, cg.grid, cg.cluster, st, g, g_cs, g_co, x, x_cs, x_co, rows, C, coef, acc, relu_in,
                                                  training, dx, dx_cs, dx_co, dx_accumulate, dweight, dbias,
                                                  dxsum, cg.txc);
   } else {
     ColGrid cg = col_grid(rows, C);
-    brn_bwd_dx_kernel<1><<<cg.grid, NT, 0, st>>>(g, g_cs, g_co, x, x_cs, x_co, rows, C, coef, acc, relu_in,
+    launch_clustered(brn_bwd_dx_kernel<1>, cg.grid, cg.cluster, st, g, g_cs, g_co, x, x_cs, x_co, rows, C, coef, acc, relu_in,
                                                  training, dx, dx_cs, dx_co, dx_accumulate, dweight, dbias,
                                                  dxsum, cg.txc);
   }
@@ -501,10 +607,10 @@ extern "C" int crn_colsum(const float* x, int64_t rows, int32_t C, int32_t x_cs,
   cudaMemsetAsync(scratch, 0, sizeof(double) * C, st);
   if (vec4_ok(C, x_cs, x_co)) {
     ColGrid g = col_grid(rows, C / 4);
-    colsum_kernel<4><<<g.grid, NT, 0, st>>>(x, rows, C, x_cs, x_co, scratch, g.txc);
+    launch_clustered(colsum_kernel<4>, g.grid, g.cluster, st, x, rows, C, x_cs, x_co, scratch, g.txc);
   } else {
     ColGrid g = col_grid(rows, C);
-    colsum_kernel<1><<<g.grid, NT, 0, st>>>(x, rows, C, x_cs, x_co, scratch, g.txc);
+    launch_clustered(colsum_kernel<1>, g.grid, g.cluster, st, x, rows, C, x_cs, x_co, scratch, g.txc);
   }
   f64_to_f32_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, out, C);
   crn_count_launches(1);

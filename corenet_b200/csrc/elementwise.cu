@@ -78,15 +78,33 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const int8_t* _
   }
 }
 
-__global__ void spatial_mean_fwd_kernel(const float* __restrict__ x, int N, int HW, int C,
-                                        float* __restrict__ y) {
-  const int i = blockIdx.x * NT + threadIdx.x;
-  if (i >= N * C) return;
-  const int n = i / C, c = i - n * C;
-  const float* p = x + (int64_t)n * HW * C + c;
-  float s = 0.f;
-  for (int k = 0; k < HW; ++k) s += __ldg(p + (int64_t)k * C);
-  y[i] = s / (float)HW;
+// grid (chunks, N): block (g, n) sums its slice of the HW rows of scene n for every channel (threads own channel
+// columns, rows are strided over the remaining threads, 4 loads in flight), then one float atomicAdd per channel.
+__global__ void __launch_bounds__(NT) spatial_mean_fwd_kernel(const float* __restrict__ x, int HW, int C, int txc,
+                                                              float inv, float* __restrict__ y) {
+  __shared__ float red[NT];
+  const int tx = threadIdx.x % txc, ty = threadIdx.x / txc, tyc = NT / txc;
+  const int n = blockIdx.y;
+  const float* base = x + (int64_t)n * HW * C;
+  const int stride = gridDim.x * tyc;
+  for (int c = tx; c < C; c += txc) {                       // uniform trip count per tx; barriers below are block-wide
+    float s = 0.f;
+    int k = blockIdx.x * tyc + ty;
+    for (; k + 3 * stride < HW; k += 4 * stride) {
+      const float a0 = __ldg(base + (int64_t)k * C + c), a1 = __ldg(base + (int64_t)(k + stride) * C + c);
+      const float a2 = __ldg(base + (int64_t)(k + 2 * stride) * C + c), a3 = __ldg(base + (int64_t)(k + 3 * stride) * C + c);
+      s += (a0 + a1) + (a2 + a3);
+    }
+    for (; k < HW; k += stride) s += __ldg(base + (int64_t)k * C + c);
+    red[ty * txc + tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+      float t = 0.f;
+      for (int yy = 0; yy < tyc; ++yy) t += red[yy * txc + tx];
+      atomicAdd(y + (int64_t)n * C + c, t * inv);
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void spatial_mean_bwd_kernel(const float* __restrict__ dy, int N, int HW, int C,
@@ -162,7 +180,19 @@ extern "C" int crn_maxpool_bwd(const float* dy, const int8_t* idx, int32_t N, in
 extern "C" int crn_spatial_mean_fwd(const float* x, int32_t N, int32_t HW, int32_t C, float* y,
                                     void* stream) {
   CRN_REQUIRE(x && y && N > 0 && HW > 0 && C > 0, "crn_spatial_mean_fwd: bad args");
-  spatial_mean_fwd_kernel<<<(N * C + NT - 1) / NT, NT, 0, crn_stream(stream)>>>(x, N, HW, C, y);
+  cudaStream_t st = crn_stream(stream);
+  if (cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * C, st) != cudaSuccess) {
+    crn_set_error("crn_spatial_mean_fwd: memset failed");
+    return CRN_ERR_LAUNCH;
+  }
+  int txc = 1;
+  while (txc < C && txc < NT) txc <<= 1;
+  const int tyc = NT / txc;
+  int chunks = (HW + tyc * 8 - 1) / (tyc * 8);              // >= 8 rows per thread
+  const int target = (2 * kNumSMs + N - 1) / N;
+  if (chunks > target) chunks = target;
+  if (chunks < 1) chunks = 1;
+  spatial_mean_fwd_kernel<<<dim3((unsigned)chunks, (unsigned)N), NT, 0, st>>>(x, HW, C, txc, 1.0f / (float)HW, y);
   CRN_LAUNCH_CHECK("spatial_mean_fwd");
   return CRN_OK;
 }
