@@ -76,6 +76,7 @@ _SIGS = {
     "crn_voxelize_mesh": ([vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "crn_merge_mesh_grids": ([vp, vp, vp, i32, i64, vp, vp], i32),
     "crn_tc_probe": ([vp, vp, vp, i32, i32, i32, vp, vp], i32),
+    "crn_tc_probe_mn": ([vp, vp, vp, i32, i32, i32, i32, vp, vp], i32),
     "crn_tc5_packed_floats": ([i32, i32], i64),
     "crn_tc5_pack": ([vp, i32, i32, i32, vp, vp], i32),
     "crn_conv5_tc": ([_P(ConvDesc), i32, vp, vp, vp, vp, vp, vp], i32),

@@ -25,6 +25,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// ---- MN-major tf32 operands: only the "128-byte swizzle with 32-byte base" layout exists (layout type 1):
+//   element (m, k) at (m/32)*LBO + (k/4)*SBO + (k%4)*128 B + ((((m%32)/8) ^ (k%4))*32 B + (m%8)*4 B
+// (one reduction row = 128 B = 32 MN elements; the XOR is a function of absolute address bits [7,9) -> [5,7)).
+__device__ __forceinline__ uint64_t make_desc_mn32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);
+}
+
 // ---- instruction descriptor for kind::tf32, fp32 accumulate
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                       // c_format = F32

@@ -252,6 +252,10 @@ int crn_merge_mesh_grids(const float* mesh_grids, const int32_t* mesh_scene, con
  * status (device int) is set to 1 if the mbarrier wait timed out. */
 int crn_tc_probe(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode,
                  int32_t* status, void* stream);
+/* Same for MN-major operands (reduction index slow in memory, the weight-gradient case):
+ * D[128,N] = sum_k A[k+shift][m] * B[k][n], A [K+4][128], B [K+4][N]; shift moves the A descriptor by whole rows. */
+int crn_tc_probe_mn(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode, int32_t shift,
+                    int32_t* status, void* stream);
 
 /* Conv3d k=5 s=1 p=2 forward / dgrad on tcgen05 tensor cores (3xTF32, fp32 TMEM accumulators):
  * replaces the cuDNN call behind nn.Conv3d(k=5) at model/reconstruction_decoder.py:66,74,82,91.
