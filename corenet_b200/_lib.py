@@ -37,6 +37,11 @@ class UnpackItem(C.Structure):
               ("CinP", i32), ("CoutP", i32), ("dst_is_transposed", i32)]
 
 
+class GemmTcPackItem(C.Structure):
+  """Mirror of crn_gemm_tc_pack_item."""
+  _fields_ = [("src", vp), ("dst", vp), ("Cout", i32), ("Cin", i32), ("taps", i32), ("dgrad", i32)]
+
+
 _P = C.POINTER
 _SIGS = {
     "crn_version": ([], i32),
@@ -84,6 +89,12 @@ _SIGS = {
     "crn_tct_pack": ([vp, i32, i32, i32, vp, vp], i32),
     "crn_convt7_tc_dgrad": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_convt7_tc": ([_P(ConvDesc), vp, vp, vp, vp, vp, vp], i32),
+    "crn_gemm_tc_packed_floats": ([i32, i32, i32], i64),
+    "crn_gemm_tc_pack": ([vp, vp, i32, i64, vp], i32),
+    "crn_conv_gemm_tc": ([_P(ConvDesc), i32, vp, vp, vp, vp, i32, vp, vp], i32),
+    "crn_gemm_tc_debug_read": ([vp, i32], i32),
+    "crn_conv_wgrad_tc": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
+    "crn_adam_step_dev": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp], i32),
     "crn_adam_step": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp], i32),
 }
 

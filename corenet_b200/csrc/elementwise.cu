@@ -142,6 +142,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// step counter on the device (CUDA-graph replays cannot change a host argument): the counter is bumped by its own
+// one-thread launch, then every thread derives the bias corrections from it
+__global__ void counter_inc_kernel(int32_t* c) { *c += 1; }
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                const int32_t* __restrict__ step, float gscale) {
+  const float st = (float)*step;
+  const float bc1 = 1.f - powf(b1, st);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
 inline unsigned grid_for(int64_t total) {
   int64_t b = crn_ceil_div(total, NT);
   if (b > 16LL * kNumSMs) b = 16LL * kNumSMs;
@@ -223,5 +243,16 @@ extern "C" int crn_adam_step(float* p, const float* g, float* m, float* v, int64
   adam_kernel<<<grid_for(n), NT, 0, crn_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1,
                                                          sqrtf(bc2), grad_scale);
   CRN_LAUNCH_CHECK("adam");
+  return CRN_OK;
+}
+
+extern "C" int crn_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                 float beta2, float eps, int32_t* step_dev, float grad_scale, void* stream) {
+  CRN_REQUIRE(p && g && m && v && n > 0 && step_dev, "crn_adam_step_dev: bad args");
+  counter_inc_kernel<<<1, 1, 0, crn_stream(stream)>>>(step_dev);
+  adam_dev_kernel<<<grid_for(n), NT, 0, crn_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
+                                                             grad_scale);
+  CRN_LAUNCH_CHECK("adam_dev");
+  crn_count_launches(1);
   return CRN_OK;
 }

@@ -54,15 +54,37 @@ def conv_macs(d: ConvDesc) -> int:
   return d.N * pos * taps * d.Cin * d.Cout
 
 
+_ENG = None      # engine whose plan is currently enqueuing (set by Plan.forward / Plan.backward)
+
+
+def _conv_dispatch(kind, layer, d, args):
+  """-> (tag, C-ABI name, argument tuple): wide layers go to the tcgen05 implicit-GEMM kernels
+  (csrc/conv_gemm_tc.cu, csrc/conv_wgrad_tc.cu), everything else to the FFMA kernels."""
+  eng = _ENG
+  if USE_TC and eng is not None:
+    status = eng.tc_status.data_ptr()
+    if kind == "fwd" and layer.name in eng.gt_w:
+      x, _, bias, y, acc, st = args
+      return "fwd_gt", "crn_conv_gemm_tc", (C.byref(d), 0, x, eng.gt_w[layer.name][0].data_ptr(), bias, y, acc, status, st)
+    if kind == "dgrad" and eng.gt_w.get(layer.name, (None, None))[1] is not None:
+      dy, _, dx, acc, st = args
+      return "dgrad_gt", "crn_conv_gemm_tc", (C.byref(d), 1, dy, eng.gt_w[layer.name][1].data_ptr(), None, dx, acc, status, st)
+    if kind == "wgrad" and layer.name in eng.gt_wgrad:
+      x, dy, dw, st = args
+      return "wgrad_tc", "crn_conv_wgrad_tc", (C.byref(d), x, dy, dw, status, st)
+  return kind, _CONV_FN[kind], (C.byref(d),) + tuple(args)
+
+
 def conv_call(kind, layer, d, *args):
+  tag, fn, a = _conv_dispatch(kind, layer, d, args)
   if PROFILE is None:
-    _lib.call(_CONV_FN[kind], C.byref(d), *args)
+    _lib.call(fn, *a)
     return
   e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
   e0.record()
-  _lib.call(_CONV_FN[kind], C.byref(d), *args)
+  _lib.call(fn, *a)
   e1.record()
-  PROFILE.append((kind, layer.name, conv_macs(d), e0, e1))
+  PROFILE.append((tag, layer.name, conv_macs(d), e0, e1))
 
 
 # Conv3d k=5 layers at >= 32^3 run forward/dgrad on the tcgen05 tensor cores (3xTF32, csrc/conv_tc5.cu).
@@ -259,9 +281,56 @@ class Engine:
         mk = lambda dg: t.zeros(lib.crn_tct_packed_floats(mid, t_out, dg), dtype=t.float32, device=dev)
         if fwd_ok or dgrad_ok:
           self.tct_w[l.name] = (mk(0) if fwd_ok else None, mk(1) if dgrad_ok else None)
+    # wide layers (>= 32 channels on both sides): implicit-GEMM forward / dgrad (csrc/conv_gemm_tc.cu) and weight
+    # gradient (csrc/conv_wgrad_tc.cu) on tcgen05
+    self.gt_w = {}
+    self.gt_wgrad = set()
+    for l in self.layers:
+      wide = min(l.cin, l.cout) >= 32 and l.cin % 4 == 0 and l.cout % 4 == 0 and l.src_cin == l.cin
+      enc = l.name.startswith("encoder.") and l.name != "encoder.stage1.conv"
+      dec_c1 = l.name.startswith("decoder.stage_") and l.name.endswith(".c1") and l.name not in self.tc_w
+      # 4.t1 (64 -> 32, 343 taps): the per-tap gather is L2-bound at these narrow channel counts (3.0 ms vs 1.3 FFMA)
+      dec_t1 = l.name in ("decoder.stage_2.t1", "decoder.stage_3.t1")
+      if wide and not l.transposed and (enc or dec_c1):
+        mk = lambda k, n: t.zeros(lib.crn_gemm_tc_packed_floats(k, n, l.taps), dtype=t.float32, device=dev)
+        self.gt_w[l.name] = (mk(l.cin, l.cout), mk(l.cout, l.cin) if l.stride == 1 else None)
+        self.gt_wgrad.add(l.name)
+      elif wide and l.transposed and dec_t1:
+        self.gt_wgrad.add(l.name)
+    self._gt_sig = None
     self.plans = {}
     self._ptr_sig = None
     self._ver_sig = None
+
+  def _pack_gemm_tc(self, P):
+    """ONE launch re-packs every tcgen05 implicit-GEMM weight (item list cached per parameter pointer set)."""
+    if not self.gt_w:
+      return
+    names = sorted(self.gt_w)
+    sig = tuple(P[n + ".weight"].data_ptr() for n in names)
+    if sig != self._gt_sig:
+      lay = {l.name: l for l in self.layers}
+      entries = []
+      for n in names:
+        for dg, buf in enumerate(self.gt_w[n]):
+          if buf is not None:
+            entries.append((lay[n], P[n + ".weight"], dg, buf))
+      items = (_lib.GemmTcPackItem * len(entries))()
+      offs = (C.c_int64 * (len(entries) + 1))()
+      tot = 0
+      for i, (l, w, dg, buf) in enumerate(entries):
+        assert w.is_contiguous() and w.dtype == t.float32 and w.device == self.dev
+        it = items[i]
+        it.src, it.dst, it.Cout, it.Cin, it.taps, it.dgrad = w.data_ptr(), buf.data_ptr(), l.cout, l.cin, l.taps, dg
+        offs[i] = tot
+        tot += buf.numel() // 2
+      offs[len(entries)] = tot
+      self._gt_items = self._to_dev(items, self.dev)
+      self._gt_offs = self._to_dev(offs, self.dev)
+      self._gt_n, self._gt_tot = len(entries), tot
+      self._gt_sig = sig
+    _call("crn_gemm_tc_pack", self._gt_items.data_ptr(), self._gt_offs.data_ptr(), self._gt_n, self._gt_tot,
+          _lib.stream_ptr())
 
   def tensors(self):
     """(name -> parameter, name -> buffer), cached."""
@@ -273,6 +342,8 @@ class Engine:
   def invalidate(self):
     self._pcache = None
     self._ptr_sig = None
+    self._gt_sig = None
+    self._usig = None
 
   @staticmethod
   def _to_dev(ctypes_array, dev):
@@ -315,25 +386,30 @@ class Engine:
             if wt is not None:
               _call("crn_tct_pack", P[l.name + ".weight"].data_ptr(), l.cin, l.cout, dg, wt.data_ptr(),
                     _lib.stream_ptr())
+      self._pack_gemm_tc(P)
       self._ver_sig = ver_sig
 
   def unpack_wgrads(self, grads: Dict[str, t.Tensor]):
-    items = (UnpackItem * len(self.layers))()
-    offs = (C.c_int64 * (len(self.layers) + 1))()
-    tot = 0
-    for i, l in enumerate(self.layers):
-      it = items[i]
-      it.src_packed = self.dw.data_ptr() + 4 * l.off
-      it.dst = grads[l.name + ".weight"].data_ptr()
-      it.Cin, it.Cout, it.taps, it.CinP, it.CoutP = l.src_cin, l.cout, l.taps, l.cinp, l.coutp
-      it.dst_is_transposed = int(l.transposed)
-      offs[i] = tot
-      tot += l.src_cin * l.cout * l.taps
-    offs[len(self.layers)] = tot
-    self._uitems_dev = self._to_dev(items, self.dev)
-    self._uoffs_dev = self._to_dev(offs, self.dev)
+    sig = tuple(grads[l.name + ".weight"].data_ptr() for l in self.layers)
+    if getattr(self, "_usig", None) != sig:          # item list is cached per destination set (graph-capture safe)
+      items = (UnpackItem * len(self.layers))()
+      offs = (C.c_int64 * (len(self.layers) + 1))()
+      tot = 0
+      for i, l in enumerate(self.layers):
+        it = items[i]
+        it.src_packed = self.dw.data_ptr() + 4 * l.off
+        it.dst = grads[l.name + ".weight"].data_ptr()
+        it.Cin, it.Cout, it.taps, it.CinP, it.CoutP = l.src_cin, l.cout, l.taps, l.cinp, l.coutp
+        it.dst_is_transposed = int(l.transposed)
+        offs[i] = tot
+        tot += l.src_cin * l.cout * l.taps
+      offs[len(self.layers)] = tot
+      self._uitems_dev = self._to_dev(items, self.dev)
+      self._uoffs_dev = self._to_dev(offs, self.dev)
+      self._utot = tot
+      self._usig = sig
     _call("crn_unpack_wgrads", self._uitems_dev.data_ptr(), self._uoffs_dev.data_ptr(), len(self.layers),
-          tot, _lib.stream_ptr())
+          self._utot, _lib.stream_ptr())
 
   def wf(self, l):
     return self.w_fwd.data_ptr() + 4 * l.off
@@ -504,6 +580,8 @@ class Plan:
           cmap = self.buf((hw, hw), skip_c)
           st.update(ls=ls, src=src, cmap=cmap, hw=hw)
           st["d_s"] = ls.desc(src.cs, (1, hw, hw), cmap.cs, (1, hw, hw), B, bias_n_stride=skip_c)
+          res = eng.model.config.decoder.resolution
+          st["scale"] = t.diag(t.tensor([res[0] / g2, res[1] / g2, res[2] / g2, 1.0], dtype=t.float32)).to(self.dev)
         cat = nxt
       else:
         cp = _r4(t_out)
@@ -516,7 +594,9 @@ class Plan:
   # ------------------------------------------------------------------ forward
   def forward(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, training: bool,
               want_features: bool = False) -> t.Tensor:
+    global _ENG
     eng, B = self.eng, self.B
+    _ENG = eng
     P, _ = eng.tensors()
     st = _lib.stream_ptr()
     self.training = training
@@ -583,8 +663,7 @@ class Plan:
           sd["sbias"] = sbias
           conv_call("fwd", ls, sd["d_s"], src.p, eng.wf(ls), sbias.data_ptr(), cmap.p, 0, st)
           g2 = 2 * g
-          scale = t.diag(t.tensor([res[0] / g2, res[1] / g2, res[2] / g2, 1.0], dtype=t.float32, device=self.dev))
-          mat = v2s.matmul(scale).contiguous()
+          mat = v2s.matmul(sd["scale"]).contiguous()
           sd["mat"] = mat
           _call("crn_skip_sample_fwd", cmap.p, B, hw, hw, sd["skip_c"], cmap.cs, mat.data_ptr(),
                 self.offs.data_ptr(), g2, g2, g2, nxt.p, nxt.cs, sd["t_out"], st)
@@ -602,7 +681,9 @@ class Plan:
   # ------------------------------------------------------------------ backward
   def backward(self, grad_logits: t.Tensor, grads: Dict[str, t.Tensor], encoder_only_grads=None):
     """grads: name -> zero/empty tensor per parameter (filled here)."""
+    global _ENG
     eng, B = self.eng, self.B
+    _ENG = eng
     P, _ = eng.tensors()
     st = _lib.stream_ptr()
     L = eng.L

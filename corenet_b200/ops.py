@@ -149,6 +149,34 @@ def make_desc(n, cin, cout, idims, odims, k, stride, pad, transposed, x_cs, y_cs
   return d
 
 
+def gemm_tc_pack(weights, dgrads):
+  """Packs conv parameters [Cout][Cin][taps...] for crn_conv_gemm_tc with ONE launch; returns one tensor per item."""
+  import torch as _t
+  dev = weights[0].device
+  lib = _lib.lib()
+  n = len(weights)
+  items = (_lib.GemmTcPackItem * n)()
+  offs = (C.c_int64 * (n + 1))()
+  outs, tot = [], 0
+  for i, (w, dg) in enumerate(zip(weights, dgrads)):
+    assert w.is_cuda and w.is_contiguous() and w.dtype == _t.float32
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    K, N = (cout, cin) if dg else (cin, cout)
+    nfl = lib.crn_gemm_tc_packed_floats(K, N, taps)
+    o = _t.zeros(nfl, dtype=_t.float32, device=dev)
+    outs.append(o)
+    it = items[i]
+    it.src, it.dst, it.Cout, it.Cin, it.taps, it.dgrad = w.data_ptr(), o.data_ptr(), cout, cin, taps, int(dg)
+    offs[i] = tot
+    tot += nfl // 2
+  offs[n] = tot
+  items_d = _t.frombuffer(bytearray(bytes(items)), dtype=_t.uint8).to(dev)
+  offs_d = _t.frombuffer(bytearray(bytes(offs)), dtype=_t.uint8).to(dev)
+  _call("crn_gemm_tc_pack", items_d.data_ptr(), offs_d.data_ptr(), n, tot, _lib.stream_ptr())
+  return outs
+
+
 def _dims3(sp):
   sp = list(sp)
   return tuple([1] * (3 - len(sp)) + sp)

@@ -54,8 +54,14 @@ class Trainer:
   """Owns the flat parameter / gradient / Adam-moment buffers of a CoreNet and runs train steps."""
 
   def __init__(self, model, lr: float = 4e-4, eps: float = 1e-4, betas=(0.9, 0.999),
-               loss: str = "iou_fgbg", process_group=None):
+               loss: str = "iou_fgbg", process_group=None, use_graph: bool = True):
     self.model = model
+    # A step is ~700 kernel launches; enqueuing them from Python costs as much as running them, so after two
+    # eager warm-up steps per input signature the whole step (weight re-pack, forward, loss, backward, and on a
+    # single GPU the Adam update) is captured once in a CUDA graph and replayed.
+    self.use_graph = use_graph
+    self._graphs = {}
+    self.graph_launches = 0      # kernels of this library inside one captured step
     self.lr, self.eps, self.betas = lr, eps, betas
     self.mode = {"iou_fgbg": 0, "xent_times_iou_agnostic": 1}[loss]
     self.pg = process_group
@@ -68,6 +74,7 @@ class Trainer:
     self.m = t.zeros_like(self.flat)
     self.v = t.zeros_like(self.flat)
     self.step_count = 0
+    self.step_dev = t.zeros(1, dtype=t.int32, device=self.flat.device)
     self.names = [n for n, _ in model.named_parameters()]
     self.grads = {}
     for (off, n), (name, p) in zip(self.views, model.named_parameters()):
@@ -83,8 +90,8 @@ class Trainer:
           dlogits=t.empty(b, c, 128, 128, 128, dtype=t.float32, device=dev))
     return self._loss_bufs[key]
 
-  def step(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, gt: t.Tensor) -> t.Tensor:
-    """One optimisation step on this rank's scenes; returns the (device) loss scalar."""
+  def _fwd_bwd(self, image, v2s, offsets, gt):
+    """Enqueues forward, loss and backward on the current stream; gradients land in the flat buffer."""
     model, eng = self.model, self.eng
     st = _lib.stream_ptr()
     b = image.shape[0]
@@ -100,9 +107,50 @@ class Trainer:
     _call("crn_loss_bwd", logits.data_ptr(), gt.data_ptr(), is64, b, c, s, self.mode, lb["coef"].data_ptr(),
           None, lb["dlogits"].data_ptr(), st)
     plan.backward(lb["dlogits"], self.grads)
-    scale = allreduce_flat_grad(self.grad, self.world, self.pg)
-    self.step_count += 1
-    _call("crn_adam_step", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-          self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, scale, st)
-    eng._ver_sig = None        # the fused Adam kernel changed the weights: re-pack on the next forward
     return lb["loss"]
+
+  def _adam(self, scale):
+    _call("crn_adam_step_dev", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+          self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), scale,
+          _lib.stream_ptr())
+    self.eng._ver_sig = None   # the fused Adam kernel changed the weights: re-pack on the next forward
+
+  def _eager_step(self, image, v2s, offsets, gt):
+    loss = self._fwd_bwd(image, v2s, offsets, gt)
+    scale = allreduce_flat_grad(self.grad, self.world, self.pg)
+    self._adam(scale)
+    return loss
+
+  def step(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, gt: t.Tensor) -> t.Tensor:
+    """One optimisation step on this rank's scenes; returns the (device) loss scalar.  In graph mode the inputs
+    may live in (pinned) host memory: they are copied straight into the graph's static device buffers."""
+    self.step_count += 1
+    if not self.use_graph or engine_lib.PROFILE is not None:
+      return self._eager_step(image, v2s, offsets, gt)
+    key = (tuple(image.shape), tuple(gt.shape), gt.dtype, image.device, self.model.training)
+    gs = self._graphs.get(key)
+    if gs is None:
+      gs = {"calls": 0, "graph": None,
+            "in": [t.empty(x.shape, dtype=d or x.dtype, device=self.flat.device)
+                   for x, d in ((image, None), (v2s, t.float32), (offsets, t.float32), (gt, None))]}
+      self._graphs[key] = gs
+    for dst, src in zip(gs["in"], (image, v2s, offsets, gt)):
+      dst.copy_(src, non_blocking=True)
+    if gs["graph"] is None:
+      if gs["calls"] < 2:                       # eager warm-up: lazy initialisation must not happen under capture
+        gs["calls"] += 1
+        return self._eager_step(*gs["in"])
+      n0 = _lib.lib().crn_launch_count()
+      self.eng._ver_sig = None
+      g = t.cuda.CUDAGraph()
+      with t.cuda.graph(g):
+        gs["loss"] = self._fwd_bwd(*gs["in"])
+        if self.world == 1:
+          self._adam(1.0)
+      self.graph_launches = int(_lib.lib().crn_launch_count() - n0)
+      gs["graph"] = g
+    gs["graph"].replay()
+    if self.world > 1:
+      scale = allreduce_flat_grad(self.grad, self.world, self.pg)
+      self._adam(scale)
+    return gs["loss"]

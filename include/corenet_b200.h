@@ -284,9 +284,45 @@ int crn_convt7_tc(const crn_conv_desc* d, const float* x, const float* wtc, cons
 int crn_convt7_tc_dgrad(const crn_conv_desc* d, const float* dy, const float* wtc, float* dx,
                         int32_t* status, void* stream);
 
+/* Implicit-GEMM convolution forward / dgrad on tcgen05 for the wide layers (both channel counts >= 32): the
+ * ResNet-50 encoder's Conv2d 1x1 / 3x3 (model/resnet50.py:61-70,94-108,122-131) and the coarse decoder Conv3d
+ * layers (model/reconstruction_decoder.py:66,74).  3xTF32 with fp32 TMEM accumulators flushed every 72 MMAs.
+ * Weights are pre-split / pre-packed per (output-channel tile, 16-channel K stage) by ONE crn_gemm_tc_pack launch
+ * over a DEVICE item list: src is the PyTorch conv parameter [Cout][Cin][taps], dst holds
+ * crn_gemm_tc_packed_floats(K, N, taps) floats with (K, N) = (Cin, Cout) for the forward operator and
+ * (Cout, Cin) for dgrad != 0 (flipped taps, transposed channels).  offsets: DEVICE int64[n+1] prefix sums of
+ * packed_floats/2 per item, total = offsets[n].
+ * crn_conv_gemm_tc kind 0: y = conv(x) + bias (any stride); kind 1: dx = conv^T(dy), stride-1 convolutions only.
+ * accumulate != 0 adds onto out (bias ignored).  *status is set to 1 if an internal barrier wait timed out. */
+typedef struct {
+  const float* src;
+  float* dst;
+  int32_t Cout, Cin, taps, dgrad;
+} crn_gemm_tc_pack_item;
+int64_t crn_gemm_tc_packed_floats(int32_t K, int32_t N, int32_t taps);
+int crn_gemm_tc_pack(const crn_gemm_tc_pack_item* items, const int64_t* offsets, int32_t n, int64_t total,
+                     void* stream);
+int crn_conv_gemm_tc(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc, const float* bias,
+                     float* out, int32_t accumulate, int32_t* status, void* stream);
+
+/* Debug: with crn_set_flags bit 8 the kernel stamps a per-CTA clock64 timeline; copies n (<= 4096) int64 to host. */
+int crn_gemm_tc_debug_read(long long* host_dst, int32_t n);
+
+/* Weight gradient of the wide layers on tcgen05 (3xTF32; both operands are MN-major tf32 UMMA operands in the
+ * 128B-swizzle / 32B-base layout).  Same contract as crn_conv_wgrad: dWf[tap][ci][co] += sum_rows x * dy, dw zeroed
+ * by the caller before the first call; plain and transposed convolutions, any stride.  Replaces the cuDNN
+ * backward-filter calls behind model/resnet50.py:61-70,94-108,122-131 and model/reconstruction_decoder.py:66-77. */
+int crn_conv_wgrad_tc(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed, int32_t* status,
+                      void* stream);
+
 /* Fused Adam step over a flat list (state.py:65-66) — next-row (f2) op. */
 int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+/* Same with the step counter on the device (*step_dev is incremented by the call, then used for the bias
+ * corrections): the form a captured CUDA graph can replay. */
+int crn_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                      float beta2, float eps, int32_t* step_dev, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

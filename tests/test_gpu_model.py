@@ -216,6 +216,31 @@ def test_trainer_step_matches_reference_adam():
   assert med < 1e-2 and errs[0][0] < 0.25, (med, errs[:3])
 
 
+def test_trainer_cuda_graph_matches_eager():
+  """The captured-and-replayed step must produce the losses / weights of the eagerly enqueued step (train-mode BN,
+  5 steps: two eager warm-ups, capture, two replays).  Only atomics-order noise may differ."""
+  from corenet_b200.trainer import Trainer
+  dev = t.device("cuda", 0)
+  inp = MG.case_inputs("A")
+  gt = MG.synthetic_gt(1, 2)
+  out = []
+  for use_graph in (False, True):
+    m = build_model().to(dev).train()
+    tr = Trainer(m, lr=4e-4, eps=1e-4, loss="iou_fgbg", use_graph=use_graph)
+    args = [inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev), gt.to(dev)]
+    losses = [tr.step(*args).item() for _ in range(5)]
+    assert (tr.graph_launches > 100) == use_graph
+    assert int(tr.eng.tc_status) == 0
+    out.append((losses, tr.flat.detach().clone(), int(tr.step_dev)))
+  (l0, w0, s0), (l1, w1, s1) = out
+  assert s0 == s1 == 5
+  assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-3, (l0, l1)
+  assert l0[-1] < l0[0]                                   # it trains
+  # host inputs (pinned) go straight into the graph's static buffers
+  loss_h = tr.step(inp["image"].pin_memory(), inp["v2s"].pin_memory(), inp["offsets"].pin_memory(), gt.pin_memory())
+  assert t.isfinite(loss_h).all()
+
+
 def test_mean_iou_parity_and_inference_plug():
   """h7-style eval (B=2, C=2): forward -> softmax -> argmax -> confusion matrix -> mean IoU through the CUDA
   kernels vs the oracle (voxel_metrics.py:33-58, evaluation_results.py:262-266): |delta mIoU| <= 0.1 pt."""

@@ -128,6 +128,114 @@ def test_conv5_tcgen05(n, cin, cout, dhw, kind):
   assert rel_err(got, ref) < 2e-4
 
 
+GEMM_TC_CASES = [
+    # (name, x shape, weight shape, stride, pad)
+    ("enc_1x1", (2, 64, 16, 16), (256, 64, 1, 1), 1, 0),
+    ("enc_1x1_s2", (2, 256, 16, 16), (128, 256, 1, 1), 2, 0),
+    ("enc_3x3", (2, 128, 14, 14), (128, 128, 3, 3), 1, 1),
+    ("enc_3x3_splitk", (1, 512, 8, 8), (512, 512, 3, 3), 1, 1),
+    ("enc_1x1_k2048", (1, 2048, 8, 8), (512, 2048, 1, 1), 1, 0),
+    ("dec_k5_112_64", (1, 112, 6, 7, 9), (64, 112, 5, 5, 5), 1, 2),
+    ("dec_k5_224_128", (1, 224, 4, 4, 4), (128, 224, 5, 5, 5), 1, 2),
+    ("odd_channels_36_40", (1, 36, 5, 6, 7), (40, 36, 3, 3, 3), 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_TC_CASES, ids=[c[0] for c in GEMM_TC_CASES])
+@pytest.mark.parametrize("kind", [0, 1], ids=["fwd", "dgrad"])
+def test_conv_gemm_tcgen05(case, kind):
+  """Implicit-GEMM conv on tcgen05 (3xTF32, accumulator flushed every 72 MMAs) against the fp64 oracle.
+  Tolerance 2e-5 of the tensor max, the same as the fp32 FFMA kernels."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  name, xs, ws, stride, pad = case
+  if kind == 1 and stride != 1:
+    pytest.skip("dgrad of strided convolutions stays on the FFMA kernel")
+  g = t.Generator().manual_seed(zlib.crc32(name.encode()) % 1000 + kind)
+  nd = len(xs) - 2
+  conv = F.conv2d if nd == 2 else F.conv3d
+  convt = F.conv_transpose2d if nd == 2 else F.conv_transpose3d
+  cout, cin = ws[0], ws[1]
+  wt = t.randn(ws, generator=g) * 0.05
+  bias = t.randn(cout, generator=g)
+  x = t.randn(xs, generator=g)
+  y_ref = conv(x.double(), wt.double(), bias.double(), stride=stride, padding=pad)
+  if kind == 0:
+    src, ref, K, N = x, y_ref, cin, cout
+  else:
+    src = t.randn(y_ref.shape, generator=g)
+    ref = convt(src.double(), wt.double(), None, stride=1, padding=pad)
+    K, N = cout, cin
+  perm = [0] + list(range(2, nd + 2)) + [1]
+  inv = [0, nd + 1] + list(range(1, nd + 1))
+  xin = src.permute(perm).reshape(-1, K).contiguous().to(dev())
+  out_sp = [ref.shape[0]] + list(ref.shape[2:])
+  rows_out = int(np.prod(out_sp))
+  out = t.full((rows_out, N), float("nan"), device=dev())
+  wtc = ops.gemm_tc_pack([wt.to(dev()).contiguous()], [kind])[0]
+  d3 = lambda sp: tuple([1] * (3 - len(sp)) + list(sp))
+  desc = ops.make_desc(xs[0], cin, cout, d3(xs[2:]), d3(y_ref.shape[2:]), d3(ws[2:]), stride, pad, False, cin, cout)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  b = t.zeros(cout + 1, device=dev())[1:]          # parameters are 4-byte aligned views of a flat buffer
+  b.copy_(bias)
+  _lib.call("crn_conv_gemm_tc", C.byref(desc), kind, xin.data_ptr(), wtc.data_ptr(), b.data_ptr(), out.data_ptr(), 0,
+            status.data_ptr(), _lib.stream_ptr())
+  t.cuda.synchronize()
+  assert int(status) == 0
+  got = out.reshape(out_sp + [N]).permute(inv)
+  assert rel_err(got, ref) < 2e-5
+  # accumulate: out += conv
+  _lib.call("crn_conv_gemm_tc", C.byref(desc), kind, xin.data_ptr(), wtc.data_ptr(), b.data_ptr(), out.data_ptr(), 1,
+            status.data_ptr(), _lib.stream_ptr())
+  t.cuda.synchronize()
+  ref2 = 2 * ref - (bias.double().view([1, -1] + [1] * nd) if kind == 0 else 0)
+  assert rel_err(out.reshape(out_sp + [N]).permute(inv), ref2) < 2e-5
+
+
+WGRAD_TC_CASES = GEMM_TC_CASES + [
+    ("convT_k7_s2_128_64", (1, 128, 4, 4, 4), (128, 64, 7, 7, 7), 2, 3),
+    ("convT_k3_s2_32_20", (2, 32, 4, 5, 6), (32, 20, 3, 3, 3), 2, 1),
+    ("rows_not_multiple_of_16", (1, 64, 5, 7), (96, 64, 3, 3), 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES, ids=[c[0] for c in WGRAD_TC_CASES])
+def test_conv_wgrad_tcgen05(case):
+  """Weight gradient on tcgen05 (MN-major tf32 operands, 3xTF32) against the fp64 oracle; 5e-5 of the tensor max
+  (the FFMA wgrad kernels' tolerance)."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  name, xs, ws, stride, pad = case
+  transposed = name.startswith("convT")
+  g = t.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+  nd = len(xs) - 2
+  x = t.randn(xs, generator=g)
+  wt = (t.randn(ws, generator=g) * 0.05).double().requires_grad_(True)
+  if transposed:
+    cin, cout = ws[0], ws[1]
+    y = F.conv_transpose3d(x.double(), wt, None, stride=stride, padding=pad, output_padding=1)
+  else:
+    cout, cin = ws[0], ws[1]
+    y = (F.conv2d if nd == 2 else F.conv3d)(x.double(), wt, None, stride=stride, padding=pad)
+  gy = t.randn(y.shape, generator=g)
+  y.backward(gy.double())
+  perm = [0] + list(range(2, nd + 2)) + [1]
+  xr = x.permute(perm).reshape(-1, cin).contiguous().to(dev())
+  gr = gy.permute(perm).reshape(-1, cout).contiguous().to(dev())
+  taps = int(np.prod(ws[2:]))
+  dw = t.zeros(taps, cin, cout, device=dev())
+  d3 = lambda sp: tuple([1] * (3 - len(sp)) + list(sp))
+  desc = ops.make_desc(xs[0], cin, cout, d3(xs[2:]), d3(y.shape[2:]), d3(ws[2:]), stride, pad, transposed, cin, cout)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  _lib.call("crn_conv_wgrad_tc", C.byref(desc), xr.data_ptr(), gr.data_ptr(), dw.data_ptr(), status.data_ptr(),
+            _lib.stream_ptr())
+  t.cuda.synchronize()
+  assert int(status) == 0
+  gw = wt.grad.reshape(ws[0], ws[1], taps)
+  ref = gw.permute(2, 0, 1) if transposed else gw.permute(2, 1, 0)     # [tap][ci][co]
+  assert rel_err(dw, ref) < 5e-5
+
+
 @pytest.mark.parametrize("n,cin,cout,dhw,planar", [(1, 8, 2, (8, 16, 8), True), (2, 16, 2, (8, 32, 16), True),
                                                      (1, 12, 3, (8, 16, 8), True), (1, 8, 2, (8, 16, 8), False),
                                                      (1, 32, 16, (8, 16, 16), False), (1, 16, 8, (8, 16, 8), False),
