@@ -94,6 +94,8 @@ _SIGS = {
     "crn_conv_gemm_tc": ([_P(ConvDesc), i32, vp, vp, vp, vp, i32, vp, vp], i32),
     "crn_gemm_tc_debug_read": ([vp, i32], i32),
     "crn_conv_wgrad_tc": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
+    "crn_conv_wgrad_line_supported": ([_P(ConvDesc)], i32),
+    "crn_conv_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_adam_step_dev": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp], i32),
     "crn_adam_step": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp], i32),
 }

@@ -1,0 +1,423 @@
+// Weight gradient of the NARROW Conv3d k=5 s=1 p=2 decoder layers (stage_6.c1: 28 -> 16 at 64^3, stage_5.c1:
+// 56 -> 32 at 32^3; model/reconstruction_decoder.py:82,91) on tcgen05 tensor cores.  Replaces the cuDNN
+// backward-filter call:   dW[tap][ci][co] += sum_vox x[vox + tap - 2][ci] * dy[vox][co].
+//
+// With 16-56 channels a per-tap GEMM would waste the 128 x N tensor-core tile, so filter taps are STACKED into the
+// M and N dimensions of one MMA, using the tf32 MN-major operand layout (descriptor layout type 1: one reduction
+// row = one voxel = one 128-byte line of 32 channels, 32-byte chunks XOR-swizzled by the row index), in which a
+// 32-channel block is addressed as start + block * LBO -- so "block b" can just as well be "the same line shifted
+// by b voxels" (LBO = 128 B) or "the next image row / the lo half" (LBO = one staged line):
+//   * the image row (z, y) of x is staged ONCE as [hi | lo] lines of W + 8 voxel rows (zero halo), dy likewise;
+//   * CB = 1 (Cin <= 32, Cout <= 16):  M = 128 = {hi, lo} x {row y, row y+1} x 32 ci,   dy voxel row = [hi16 | lo16],
+//     N = 160 = 5 kx shifts x 32  ->  ONE MMA per 8 voxels covers 2 ky x 5 kx taps and all four hi/lo products
+//     (x_hi+x_lo)(dy_hi+dy_lo), i.e. full fp32-class products;
+//   * CB = 2 (Cin <= 64, Cout <= 32):  M = 128 = {hi, lo} x 2 channel blocks,  N = 160 = 5 kx shifts x 32 co for the
+//     dy_hi line and again for the dy_lo line (two MMAs into the same accumulator);
+//   * accumulators (3 x 160 TMEM columns) live across all image rows a CTA processes for one PASS (CB = 1: pass = kz,
+//     accumulators = ky pairs; CB = 2: pass = (kz, ky group), accumulators = ky); they are flushed with atomic
+//     adds into dW at pass boundaries and every `flush_every` rows (the tensor core's fp32 accumulate truncates);
+//   * x rows slide through a ring (one new row per step, 5 or 3 resident), so every row is staged once per pass;
+//   * warp roles: 4 epilogue warps (TMEM -> atomics), 4 producer warps (float4 gathers, hi/lo split, swizzled
+//     st.shared), 1 MMA warp (one elected thread).  Persistent grid of one CTA per SM; all waits are bounded.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int NTHREADS = 288;
+constexpr int NACC = 3, ACOLS = 160;
+constexpr int YSLOTS = 3;
+constexpr int MAXX = 9;
+
+struct WLParams {
+  const float* x;
+  const float* dy;
+  float* dw;          // [125][CinP][CoutP]
+  int* status;
+  int N, D, H, W;
+  int Cin, Cout;
+  int x_cs, x_co, y_cs, y_co, CinP, CoutP;
+  int npass;
+  int pass_begin[12];  // prefix sums of line-steps per pass (npass + 1 entries)
+  int flush_every;
+};
+
+struct __align__(8) WLBarriers {
+  uint64_t full_x[MAXX], empty_x[MAXX];
+  uint64_t full_y[YSLOTS], empty_y[YSLOTS];
+  uint64_t acc_full, acc_empty;
+  uint32_t tmem_base;
+  int abort_flag;
+};
+
+template <int CB>
+struct WLCfg {
+  static constexpr int XSLOTS = CB == 1 ? 8 : 6;             // ring (CB = 1: + 1 mirror slot of slot 0)
+};
+
+// one step = one output image row (pass, n, z, y)
+struct Step {
+  int pass, kz, klo, nk;   // ky window [klo, klo + nk)
+  int n, z, y;
+  bool fresh;              // window is (re)loaded completely
+};
+
+template <int CB>
+__device__ __forceinline__ Step decode_step(const WLParams& p, int t, int t0) {
+  Step s;
+  int ps = 0;
+  while (ps + 1 < p.npass && t >= p.pass_begin[ps + 1]) ++ps;
+  s.pass = ps;
+  if (CB == 1) { s.kz = ps; s.klo = 0; s.nk = 5; }
+  else { s.kz = ps >> 1; s.klo = (ps & 1) ? 3 : 0; s.nk = (ps & 1) ? 2 : 3; }
+  const int r = t - p.pass_begin[ps];
+  s.y = r % p.H;
+  const int pl = r / p.H;                                    // plane index among the valid (n, z) of this pass
+  const int zlo = s.kz < 2 ? 2 - s.kz : 0, zcnt = p.D - (s.kz < 2 ? 2 - s.kz : s.kz - 2);
+  s.n = pl / zcnt;
+  s.z = zlo + pl % zcnt;
+  s.fresh = (t == t0) || s.y == 0;
+  return s;
+}
+
+template <int CB, int W>
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams p) {
+  using Cfg = WLCfg<CB>;
+  constexpr int RUNS = (W + 8) / 8;                 // K=8 runs per image row (W + 4 halo voxels, rounded up)
+  constexpr int RS = RUNS * 8;                      // staged voxel rows of an x line (voxel q = row - 4)
+  constexpr int XH = RS * 128;                      // one 32-channel block of a line (LBO of the M operand)
+  constexpr int XL = 2 * CB * XH;                   // x line slot: CB = 1: [h]; CB = 2: [h][cb]
+  constexpr int YROWS = RS + 8;                     // staged voxel rows of a dy line (voxel q = row - 6)
+  constexpr int YL = CB * YROWS * 128;              // dy line slot: CB = 1: [hi16|lo16]; CB = 2: [hi line][lo line]
+  constexpr int XS = Cfg::XSLOTS, XALL = XS + (CB == 1 ? 1 : 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* xring = smem;
+  uint8_t* yring = smem + XALL * XL;
+  WLBarriers* B = reinterpret_cast<WLBarriers*>(yring + YSLOTS * YL);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = p.pass_begin[p.npass];
+  const int t0 = (int)((long long)T * blockIdx.x / gridDim.x), t1 = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
+
+  if (tid == 0) {
+    for (int i = 0; i < MAXX; ++i) { tc::mbar_init(&B->full_x[i], 128); tc::mbar_init(&B->empty_x[i], 1); }
+    for (int i = 0; i < YSLOTS; ++i) { tc::mbar_init(&B->full_y[i], 128); tc::mbar_init(&B->empty_y[i], 1); }
+    tc::mbar_init(&B->acc_full, 1); tc::mbar_init(&B->acc_empty, 128);
+    B->abort_flag = 0;
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&B->tmem_base, 512);
+  // halo rows (and padding channels) are zero for the whole kernel: clear both rings once
+  for (int i = tid; i < (XALL * XL + YSLOTS * YL) / 16; i += NTHREADS)
+    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = B->tmem_base;
+  const uint32_t xring_u32 = tc::smem_u32(xring), yring_u32 = tc::smem_u32(yring);
+  auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
+  volatile int* ab = &B->abort_flag;
+  auto flush_after = [&](int t, const Step& s) -> bool {
+    if (t == t1 - 1) return true;
+    if (t + 1 >= p.pass_begin[s.pass + 1]) return true;                 // next step belongs to the next pass
+    return (t - t0 + 1) % p.flush_every == 0;
+  };
+
+  if (warp < 4) {
+    // ============================ EPILOGUE: TMEM -> atomic adds into dW at every flush point
+    uint32_t nflush = 0;
+    bool dead = false;
+    const int blk = warp;                                     // 32-lane block of the M operand this warp owns
+    for (int t = t0; t < t1 && !dead; ++t) {
+      const Step s = decode_step<CB>(p, t, t0);
+      if (!flush_after(t, s)) continue;
+      if (!tc::mbar_wait(&B->acc_full, nflush & 1, ab)) { fail(); dead = true; break; }
+      tc::fence_after_sync();
+      int ci, kyoff;
+      if (CB == 1) { ci = lane; kyoff = blk >> 1; }           // blocks: (hi, y), (lo, y), (hi, y+1), (lo, y+1)
+      else { ci = (blk & 1) * 32 + lane; kyoff = 0; }         // blocks: (hi, cb0), (hi, cb1), (lo, cb0), (lo, cb1)
+#pragma unroll 1
+      for (int a = 0; a < NACC; ++a) {
+        const int ky = (CB == 1 ? 2 * a : s.klo + a) + kyoff;
+        const bool acc_ok = CB == 1 ? ky <= 4 : a < s.nk;
+#pragma unroll 1
+        for (int sh = 0; sh < 5; ++sh) {
+          const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + a * ACOLS + sh * 32;
+          float v[16], u[16];
+          tc::tmem_ld16(ta, v);
+          tc::tmem_ld16(ta + 16, u);
+          if (!acc_ok || ci >= p.Cin) continue;
+          const int kx = 4 - sh;
+          const int tap = (s.kz * 5 + ky) * 5 + kx;
+          float* dst = p.dw + ((long long)tap * p.CinP + ci) * p.CoutP;
+          if (CB == 1) {                                      // columns [hi16 | lo16] of dy: add the halves
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+              if (c < p.Cout)
+                atomicAdd(reinterpret_cast<float4*>(dst + c),
+                          make_float4(v[c] + u[c], v[c + 1] + u[c + 1], v[c + 2] + u[c + 2], v[c + 3] + u[c + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+              if (c < p.Cout) atomicAdd(reinterpret_cast<float4*>(dst + c), make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+              if (c + 16 < p.Cout)
+                atomicAdd(reinterpret_cast<float4*>(dst + 16 + c), make_float4(u[c], u[c + 1], u[c + 2], u[c + 3]));
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&B->acc_empty);
+      ++nflush;
+    }
+  } else if (warp < 8) {
+    // ============================ PRODUCERS
+    // Work = a stream of line jobs (x lines of the window, then the dy line of the step).  The global loads of job
+    // k+1 are issued before job k is split / stored, so a full load latency is hidden behind every job.
+    const int pt = tid - 128;
+    constexpr int XC4 = 8 * CB;                 // float4 columns of an x voxel (32 channels per block)
+    constexpr int YC4 = CB == 1 ? 4 : 8;        // float4 columns of a dy voxel
+    constexpr int XIT = W * XC4 / 128, YIT = W * YC4 / 128;     // items per thread
+    static_assert(XIT <= 4 && YIT <= 4 && XIT >= 1 && YIT >= 1, "line does not fit the register buffer");
+    struct Job { int kind, n, zi, yi, ok; };    // kind 0: x line, 1: dy line
+    int jt = t0, jj = 0;                        // job iterator: step, index inside the step
+    auto next_job = [&](Job& jb) -> bool {
+      if (jt >= t1) return false;
+      const Step s = decode_step<CB>(p, jt, t0);
+      const int nload = s.fresh ? s.nk : 1;
+      if (jj < nload) {
+        const int ky = s.fresh ? s.klo + jj : s.klo + s.nk - 1;
+        jb.kind = 0; jb.n = s.n; jb.zi = s.z + s.kz - 2; jb.yi = s.y + ky - 2;
+        jb.ok = (unsigned)jb.yi < (unsigned)p.H;             // zi is valid by construction of the pass
+        ++jj;
+      } else {
+        jb.kind = 1; jb.n = s.n; jb.zi = s.z; jb.yi = s.y; jb.ok = 1;
+        jj = 0; ++jt;
+      }
+      return true;
+    };
+    auto issue = [&](const Job& jb, float4 (&buf)[4]) {
+      if (jb.kind == 0) {
+        const float* src = p.x + ((((long long)jb.n * p.D + jb.zi) * p.H + jb.yi) * p.W) * p.x_cs + p.x_co;
+#pragma unroll
+        for (int u = 0; u < XIT; ++u) {
+          const int it = pt + u * 128, v = it / XC4, c4 = it % XC4;
+          buf[u] = (jb.ok && c4 * 4 < p.Cin) ? __ldg(reinterpret_cast<const float4*>(src + (long long)v * p.x_cs + c4 * 4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        const float* src = p.dy + ((((long long)jb.n * p.D + jb.zi) * p.H + jb.yi) * p.W) * p.y_cs + p.y_co;
+#pragma unroll
+        for (int u = 0; u < YIT; ++u) {
+          const int it = pt + u * 128, v = it / YC4, c4 = it % YC4;
+          buf[u] = (c4 * 4 < p.Cout) ? __ldg(reinterpret_cast<const float4*>(src + (long long)v * p.y_cs + c4 * 4))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    uint32_t q = 0, yq = 0;         // x / dy line loads so far
+    bool dead = false;
+    auto store = [&](const Job& jb, const float4 (&buf)[4]) {
+      if (jb.kind == 0) {
+        const int slot = (int)(q % XS);
+        const uint32_t use = q / XS;
+        if (use > 0 && !tc::mbar_wait(&B->empty_x[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+        uint8_t* base = xring + slot * XL;
+#pragma unroll
+        for (int u = 0; u < XIT; ++u) {
+          const int it = pt + u * 128, v = it / XC4, c4 = it % XC4;
+          float4 hi, lo;
+          tc::split_tf32(buf[u].x, hi.x, lo.x); tc::split_tf32(buf[u].y, hi.y, lo.y);
+          tc::split_tf32(buf[u].z, hi.z, lo.z); tc::split_tf32(buf[u].w, hi.w, lo.w);
+          const int row = v + 4, cb = c4 >> 3, cw = c4 & 7;
+          const uint32_t off = (uint32_t)row * 128 + (uint32_t)((((cw >> 1) ^ (row & 3)) << 5) + ((cw & 1) << 4));
+          // CB = 1: blocks [hi][lo];  CB = 2: blocks [hi cb0][hi cb1][lo cb0][lo cb1]
+          uint8_t* dh = base + (CB == 1 ? 0 : cb * XH) + off;
+          uint8_t* dl = base + (CB == 1 ? XH : (2 + cb) * XH) + off;
+          *reinterpret_cast<float4*>(dh) = hi;
+          *reinterpret_cast<float4*>(dl) = lo;
+          if (CB == 1 && slot == 0) {                          // mirror of slot 0 behind the last slot (row pairs)
+            *reinterpret_cast<float4*>(dh + XS * XL) = hi;
+            *reinterpret_cast<float4*>(dl + XS * XL) = lo;
+          }
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&B->full_x[slot]);
+        ++q;
+      } else {
+        const int slot = (int)(yq % YSLOTS);
+        const uint32_t use = yq / YSLOTS;
+        if (use > 0 && !tc::mbar_wait(&B->empty_y[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+        uint8_t* base = yring + slot * YL;
+#pragma unroll
+        for (int u = 0; u < YIT; ++u) {
+          const int it = pt + u * 128, v = it / YC4, c4 = it % YC4;
+          float4 hi, lo;
+          tc::split_tf32(buf[u].x, hi.x, lo.x); tc::split_tf32(buf[u].y, hi.y, lo.y);
+          tc::split_tf32(buf[u].z, hi.z, lo.z); tc::split_tf32(buf[u].w, hi.w, lo.w);
+          const int row = v + 6;
+          if (CB == 1) {                                       // [hi16 | lo16] in one 128-byte row
+            const uint32_t oh = (uint32_t)row * 128 + (uint32_t)((((c4 >> 1) ^ (row & 3)) << 5) + ((c4 & 1) << 4));
+            const uint32_t ol = (uint32_t)row * 128 + (uint32_t)((((2 + (c4 >> 1)) ^ (row & 3)) << 5) + ((c4 & 1) << 4));
+            *reinterpret_cast<float4*>(base + oh) = hi;
+            *reinterpret_cast<float4*>(base + ol) = lo;
+          } else {                                             // hi line, lo line
+            const uint32_t off = (uint32_t)row * 128 + (uint32_t)((((c4 >> 1) ^ (row & 3)) << 5) + ((c4 & 1) << 4));
+            *reinterpret_cast<float4*>(base + off) = hi;
+            *reinterpret_cast<float4*>(base + YROWS * 128 + off) = lo;
+          }
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&B->full_y[slot]);
+        ++yq;
+      }
+    };
+    Job ja, jb2;
+    float4 bufa[4], bufb[4];
+    bool have_a = next_job(ja);
+    if (have_a) issue(ja, bufa);
+    while (have_a && !dead) {
+      const bool have_b = next_job(jb2);
+      if (have_b) issue(jb2, bufb);
+      store(ja, bufa);
+      if (!have_b || dead) break;
+      have_a = next_job(ja);
+      if (have_a) issue(ja, bufa);
+      store(jb2, bufb);
+    }
+  } else {
+    // ============================ MMA ISSUER (one elected thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(128, ACOLS, 1, 1);
+      uint32_t q = 0;               // x line loads consumed so far (mirrors the producers' counter)
+      uint32_t nflush = 0;
+      uint32_t started = 0;         // bit a: accumulator a has been written since the last flush
+      bool dead = false;
+      for (int t = t0; t < t1 && !dead; ++t) {
+        const Step s = decode_step<CB>(p, t, t0);
+        const int nload = s.fresh ? s.nk : 1;
+        for (int j = 0; j < nload; ++j) {
+          const uint32_t l = q + j;
+          if (!tc::mbar_wait(&B->full_x[l % XS], (l / XS) & 1, ab)) { fail(); dead = true; break; }
+        }
+        if (dead) break;
+        q += nload;
+        const int i = t - t0;
+        const int yslot = i % YSLOTS;
+        if (!tc::mbar_wait(&B->full_y[yslot], (uint32_t)(i / YSLOTS) & 1, ab)) { fail(); dead = true; break; }
+        if (started == 0 && nflush > 0) {       // accumulators were handed to the epilogue: wait until it has read them
+          if (!tc::mbar_wait(&B->acc_empty, (nflush - 1) & 1, ab)) { fail(); dead = true; break; }
+        }
+        tc::fence_after_sync();
+        const uint32_t ybase = yring_u32 + yslot * YL;
+        const uint32_t w0 = q - s.nk;           // load index of window line 0
+#pragma unroll 1
+        for (int r = 0; r < RUNS; ++r) {
+          if (CB == 1) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+              const int j = 2 * a;                                         // window lines j, j+1 (ky = j, j+1)
+              // rows outside the image are staged as zero lines (no skipping: every accumulator of the pass is
+              // (re)initialised by the first run after a flush, which the epilogue relies on)
+              const uint32_t slot = (w0 + j) % XS;
+              const uint64_t da = tc::make_desc_mn32(xring_u32 + slot * XL + r * 1024, XH, 512);
+              const uint64_t db = tc::make_desc_mn32(ybase + r * 1024, 128, 512);
+              tc::mma_tf32(tmem + a * ACOLS, da, db, idesc, (started >> a) & 1u);
+              started |= 1u << a;
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+              if (a >= s.nk) continue;
+              const uint32_t slot = (w0 + a) % XS;
+              const uint64_t da = tc::make_desc_mn32(xring_u32 + slot * XL + r * 1024, XH, 512);
+              const uint64_t dbh = tc::make_desc_mn32(ybase + r * 1024, 128, 512);
+              const uint64_t dbl = tc::make_desc_mn32(ybase + YROWS * 128 + r * 1024, 128, 512);
+              tc::mma_tf32(tmem + a * ACOLS, da, dbh, idesc, (started >> a) & 1u);
+              tc::mma_tf32(tmem + a * ACOLS, da, dbl, idesc, 1u);
+              started |= 1u << a;
+            }
+          }
+        }
+        tc::commit(&B->empty_y[yslot]);
+        // release the x lines the next step drops from the window
+        if (t + 1 < t1) {
+          const Step sn = decode_step<CB>(p, t + 1, t0);
+          const int ndrop = sn.fresh ? s.nk : 1;
+          for (int j = 0; j < ndrop; ++j) tc::commit(&B->empty_x[(w0 + j) % XS]);
+        }
+        if (flush_after(t, s)) {
+          tc::commit(&B->acc_full);
+          ++nflush;
+          started = 0;
+        }
+      }
+    }
+  }
+  // ---- teardown
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+namespace {
+template <int CB, int W>
+int launch_wl(WLParams p, cudaStream_t st) {
+  constexpr int RS = ((W + 8) / 8) * 8;
+  constexpr int XL = 2 * CB * RS * 128, YL = CB * (RS + 8) * 128;
+  constexpr int XALL = WLCfg<CB>::XSLOTS + (CB == 1 ? 1 : 0);
+  const size_t smem = (size_t)XALL * XL + (size_t)YSLOTS * YL + sizeof(WLBarriers) + 1024 + 64;
+  auto kern = wgrad_line_kernel<CB, W>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      crn_set_error("conv_wgrad_line: cannot set %zu bytes of dynamic shared memory", smem);
+      return CRN_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  p.npass = CB == 1 ? 5 : 10;
+  int tot = 0;
+  for (int ps = 0; ps < p.npass; ++ps) {
+    const int kz = CB == 1 ? ps : ps >> 1;
+    p.pass_begin[ps] = tot;
+    tot += p.N * (p.D - (kz < 2 ? 2 - kz : kz - 2)) * p.H;
+  }
+  p.pass_begin[p.npass] = tot;
+  p.flush_every = 32;
+  const int grid = tot < kNumSMs ? tot : kNumSMs;
+  kern<<<grid, NTHREADS, smem, st>>>(p);
+  CRN_LAUNCH_CHECK("conv_wgrad_line");
+  return CRN_OK;
+}
+}  // namespace
+
+extern "C" int crn_conv_wgrad_line_supported(const crn_conv_desc* d) {
+  if (!d || d->transposed || d->kD != 5 || d->kH != 5 || d->kW != 5 || d->stride != 1 || d->pad != 2) return 0;
+  if (d->iD != d->oD || d->iH != d->oH || d->iW != d->oW || d->y_planar) return 0;
+  if (d->Cin % 4 || d->Cout % 4 || d->x_cs % 4 || d->x_co % 4 || d->y_cs % 4 || d->y_co % 4 || d->CoutP % 4) return 0;
+  if (d->iD < 3) return 0;
+  if (d->Cin <= 32 && d->Cout <= 16 && (d->iW == 64 || d->iW == 32)) return 1;
+  if (d->Cin <= 64 && d->Cout <= 32 && d->iW == 32) return 1;
+  return 0;
+}
+
+// dWf[tap][ci][co] += sum_vox x * dy for Conv3d k=5 s=1 p=2 with narrow channels (same contract as crn_conv_wgrad).
+extern "C" int crn_conv_wgrad_line(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed,
+                                   int32_t* status, void* stream) {
+  CRN_REQUIRE(d && x && dy && dw_packed && status, "crn_conv_wgrad_line: null pointer");
+  CRN_REQUIRE(crn_conv_wgrad_line_supported(d), "crn_conv_wgrad_line: unsupported layer shape");
+  WLParams p{};
+  p.x = x; p.dy = dy; p.dw = dw_packed; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  p.Cin = d->Cin; p.Cout = d->Cout;
+  p.x_cs = d->x_cs; p.x_co = d->x_co; p.y_cs = d->y_cs; p.y_co = d->y_co; p.CinP = d->CinP; p.CoutP = d->CoutP;
+  cudaStream_t st = crn_stream(stream);
+  if (d->Cin <= 32 && d->Cout <= 16) return d->iW == 64 ? launch_wl<1, 64>(p, st) : launch_wl<1, 32>(p, st);
+  return launch_wl<2, 32>(p, st);
+}

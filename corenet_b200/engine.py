@@ -69,9 +69,27 @@ def _conv_dispatch(kind, layer, d, args):
     if kind == "dgrad" and eng.gt_w.get(layer.name, (None, None))[1] is not None:
       dy, _, dx, acc, st = args
       return "dgrad_gt", "crn_conv_gemm_tc", (C.byref(d), 1, dy, eng.gt_w[layer.name][1].data_ptr(), None, dx, acc, status, st)
+    if kind == "dgrad" and layer.name in eng.gt_td:
+      # dgrad of a transposed convolution IS a strided forward convolution of dy with the same weight tensor
+      # ([Cin][Cout][taps] read as conv weight [Cout'=Cin][Cin'=Cout][taps]): dx[i] = sum_k dy[s*i - pad + k] W[k]
+      dy, _, dx, acc, st = args
+      d2 = ConvDesc()
+      d2.N, d2.Cin, d2.Cout = d.N, d.Cout, d.Cin
+      d2.iD, d2.iH, d2.iW, d2.oD, d2.oH, d2.oW = d.oD, d.oH, d.oW, d.iD, d.iH, d.iW
+      d2.kD, d2.kH, d2.kW, d2.stride, d2.pad, d2.transposed = d.kD, d.kH, d.kW, d.stride, d.pad, 0
+      d2.x_cs, d2.x_co, d2.y_cs, d2.y_co = d.y_cs, d.y_co, d.x_cs, d.x_co
+      d2.CinP, d2.CoutP, d2.y_planar, d2.bias_n_stride = d.CoutP, d.CinP, 0, 0
+      return "dgrad_gt", "crn_conv_gemm_tc", (C.byref(d2), 0, dy, eng.gt_td[layer.name].data_ptr(), None, dx, acc, status, st)
     if kind == "wgrad" and layer.name in eng.gt_wgrad:
       x, dy, dw, st = args
       return "wgrad_tc", "crn_conv_wgrad_tc", (C.byref(d), x, dy, dw, status, st)
+    if kind == "wgrad" and layer.k == (5, 5, 5) and not layer.transposed:
+      ok = eng.wl_ok.get(layer.name)
+      if ok is None:                        # narrow Conv3d k=5 layers: tap-stacked tcgen05 kernel (csrc/conv_wgrad_line.cu)
+        ok = eng.wl_ok[layer.name] = bool(_lib.lib().crn_conv_wgrad_line_supported(C.byref(d)))
+      if ok:
+        x, dy, dw, st = args
+        return "wgrad_tc", "crn_conv_wgrad_line", (C.byref(d), x, dy, dw, status, st)
   return kind, _CONV_FN[kind], (C.byref(d),) + tuple(args)
 
 
@@ -285,6 +303,8 @@ class Engine:
     # gradient (csrc/conv_wgrad_tc.cu) on tcgen05
     self.gt_w = {}
     self.gt_wgrad = set()
+    self.wl_ok = {}
+    self.gt_td = {}
     for l in self.layers:
       wide = min(l.cin, l.cout) >= 32 and l.cin % 4 == 0 and l.cout % 4 == 0 and l.src_cin == l.cin
       enc = l.name.startswith("encoder.") and l.name != "encoder.stage1.conv"
@@ -297,6 +317,10 @@ class Engine:
         self.gt_wgrad.add(l.name)
       elif wide and l.transposed and dec_t1:
         self.gt_wgrad.add(l.name)
+      # transposed-conv dgrad = strided conv of dy: wide layers that the class-channel tcgen05 kernel does not take
+      if (wide and l.transposed and l.name.startswith("decoder.stage_") and l.stride == 2
+          and self.tct_w.get(l.name, (None, None))[1] is None):
+        self.gt_td[l.name] = t.zeros(lib.crn_gemm_tc_packed_floats(l.cout, l.cin, l.taps), dtype=t.float32, device=dev)
     self._gt_sig = None
     self.plans = {}
     self._ptr_sig = None
@@ -304,24 +328,27 @@ class Engine:
 
   def _pack_gemm_tc(self, P):
     """ONE launch re-packs every tcgen05 implicit-GEMM weight (item list cached per parameter pointer set)."""
-    if not self.gt_w:
+    if not self.gt_w and not self.gt_td:
       return
     names = sorted(self.gt_w)
-    sig = tuple(P[n + ".weight"].data_ptr() for n in names)
+    sig = tuple(P[n + ".weight"].data_ptr() for n in names + sorted(self.gt_td))
     if sig != self._gt_sig:
       lay = {l.name: l for l in self.layers}
       entries = []
       for n in names:
         for dg, buf in enumerate(self.gt_w[n]):
           if buf is not None:
-            entries.append((lay[n], P[n + ".weight"], dg, buf))
+            entries.append((lay[n], P[n + ".weight"], dg, buf, False))
+      for n in sorted(self.gt_td):      # (layer, weight, dgrad flag, buffer, swap): convT weight read as [Cout'=Cin][Cin'=Cout]
+        entries.append((lay[n], P[n + ".weight"], 0, self.gt_td[n], True))
       items = (_lib.GemmTcPackItem * len(entries))()
       offs = (C.c_int64 * (len(entries) + 1))()
       tot = 0
-      for i, (l, w, dg, buf) in enumerate(entries):
+      for i, (l, w, dg, buf, swap) in enumerate(entries):
         assert w.is_contiguous() and w.dtype == t.float32 and w.device == self.dev
         it = items[i]
-        it.src, it.dst, it.Cout, it.Cin, it.taps, it.dgrad = w.data_ptr(), buf.data_ptr(), l.cout, l.cin, l.taps, dg
+        co, ci = (l.cin, l.cout) if swap else (l.cout, l.cin)
+        it.src, it.dst, it.Cout, it.Cin, it.taps, it.dgrad = w.data_ptr(), buf.data_ptr(), co, ci, l.taps, dg
         offs[i] = tot
         tot += buf.numel() // 2
       offs[len(entries)] = tot

@@ -315,6 +315,14 @@ int crn_gemm_tc_debug_read(long long* host_dst, int32_t n);
 int crn_conv_wgrad_tc(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed, int32_t* status,
                       void* stream);
 
+/* Weight gradient of the narrow Conv3d k=5 s=1 p=2 layers (Cin <= 32 & Cout <= 16 at W = 64 / 32, or Cin <= 64 &
+ * Cout <= 32 at W = 32) on tcgen05: filter taps are stacked into the M / N dimensions of the MMA through the
+ * MN-major descriptor strides (csrc/conv_wgrad_line.cu).  Same contract as crn_conv_wgrad.  Replaces the cuDNN
+ * backward-filter call behind model/reconstruction_decoder.py:82,91. */
+int crn_conv_wgrad_line_supported(const crn_conv_desc* d);
+int crn_conv_wgrad_line(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed, int32_t* status,
+                        void* stream);
+
 /* Fused Adam step over a flat list (state.py:65-66) — next-row (f2) op. */
 int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream);

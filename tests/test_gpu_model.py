@@ -217,25 +217,50 @@ def test_trainer_step_matches_reference_adam():
 
 
 def test_trainer_cuda_graph_matches_eager():
-  """The captured-and-replayed step must produce the losses / weights of the eagerly enqueued step (train-mode BN,
-  5 steps: two eager warm-ups, capture, two replays).  Only atomics-order noise may differ."""
+  """The captured-and-replayed step must reproduce the eagerly enqueued step.  Adam's first updates are sign-like, so
+  runs diverge from atomics-order noise alone; the test therefore compares ONE step from an identical snapshot:
+  two warm-up steps, snapshot (weights, moments, BN buffers, step counter), step 3 eagerly, restore, step 3 as a
+  captured graph: loss, gradient buffer and updated weights must agree; then two more replays must keep training."""
   from corenet_b200.trainer import Trainer
   dev = t.device("cuda", 0)
   inp = MG.case_inputs("A")
   gt = MG.synthetic_gt(1, 2)
-  out = []
-  for use_graph in (False, True):
-    m = build_model().to(dev).train()
-    tr = Trainer(m, lr=4e-4, eps=1e-4, loss="iou_fgbg", use_graph=use_graph)
+  for train_mode in (False, True):
+    m = build_model().to(dev)
+    m = m.train() if train_mode else m.eval()
+    tr = Trainer(m, lr=4e-4, eps=1e-4, loss="iou_fgbg", use_graph=True)
     args = [inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev), gt.to(dev)]
-    losses = [tr.step(*args).item() for _ in range(5)]
-    assert (tr.graph_launches > 100) == use_graph
-    assert int(tr.eng.tc_status) == 0
-    out.append((losses, tr.flat.detach().clone(), int(tr.step_dev)))
-  (l0, w0, s0), (l1, w1, s1) = out
-  assert s0 == s1 == 5
-  assert max(abs(a - b) for a, b in zip(l0, l1)) < 2e-3, (l0, l1)
-  assert l0[-1] < l0[0]                                   # it trains
+    l12 = [tr.step(*args).item() for _ in range(2)]
+    assert tr.graph_launches == 0
+    bufs = dict(m.named_buffers())
+    snap = (tr.flat.clone(), tr.m.clone(), tr.v.clone(), tr.step_dev.clone(), {k: v.clone() for k, v in bufs.items()})
+
+    def restore():
+      tr.flat.copy_(snap[0]); tr.m.copy_(snap[1]); tr.v.copy_(snap[2]); tr.step_dev.copy_(snap[3])
+      for k, v in snap[4].items():
+        bufs[k].copy_(v)
+      tr.eng._ver_sig = None
+
+    tr.use_graph = False
+    loss_e = tr.step(*args).item()
+    grad_e, flat_e = tr.grad.clone(), tr.flat.clone()
+    nbt_e = int(bufs["decoder.stage_6.b2.num_batches_tracked"])
+    restore()
+    tr.use_graph = True
+    loss_g = tr.step(*args).item()                      # capture + first replay
+    assert tr.graph_launches > 100 and int(tr.eng.tc_status) == 0
+    grad_g, flat_g = tr.grad.clone(), tr.flat.clone()
+    assert int(bufs["decoder.stage_6.b2.num_batches_tracked"]) == nbt_e == (3 if train_mode else 0)
+    assert int(tr.step_dev) == 3
+    gerr = ((grad_e - grad_g).double().norm() / grad_e.double().norm()).item()
+    uerr = ((flat_e - flat_g).double().norm() / (flat_e - snap[0]).double().norm()).item()
+    print(f"{'train' if train_mode else 'eval'}: loss eager {loss_e:.7f} graph {loss_g:.7f}  grad rel-L2 {gerr:.2e}  "
+          f"update rel-L2 {uerr:.2e}")
+    # train-mode BN at init amplifies summation-order noise ~1000x (module docstring)
+    assert abs(loss_e - loss_g) < (2e-4 if train_mode else 2e-6)
+    assert gerr < (5e-2 if train_mode else 1e-4)
+    more = [tr.step(*args).item() for _ in range(2)]    # replays
+    assert all(np.isfinite(more)) and int(tr.step_dev) == 5 and min(more) < l12[0]
   # host inputs (pinned) go straight into the graph's static buffers
   loss_h = tr.step(inp["image"].pin_memory(), inp["v2s"].pin_memory(), inp["offsets"].pin_memory(), gt.pin_memory())
   assert t.isfinite(loss_h).all()

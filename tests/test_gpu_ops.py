@@ -192,6 +192,33 @@ def test_conv_gemm_tcgen05(case, kind):
   assert rel_err(out.reshape(out_sp + [N]).permute(inv), ref2) < 2e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw,k,pad", [(1, 64, 32, (4, 5, 6), 7, 3), (2, 128, 64, (3, 4, 4), 7, 3),
+                                                    (1, 256, 128, (4, 4, 4), 3, 1)])
+def test_conv_transpose_dgrad_as_strided_conv_tcgen05(n, cin, cout, dhw, k, pad):
+  """dgrad of ConvTranspose3d(stride 2) = stride-2 forward convolution of dy with the SAME weight tensor read as
+  [Cout'=Cin][Cin'=Cout][taps] (engine._conv_dispatch): crn_conv_gemm_tc kind 0 against the fp64 oracle."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  g = t.Generator().manual_seed(cin + cout + k)
+  wt = t.randn(cin, cout, k, k, k, generator=g) * 0.05
+  x = t.randn((n, cin) + dhw, generator=g).double().requires_grad_(True)
+  y = F.conv_transpose3d(x, wt.double(), None, stride=2, padding=pad, output_padding=1)
+  gy = t.randn(y.shape, generator=g)
+  y.backward(gy.double())
+  fine = tuple(y.shape[2:])
+  gr = gy.permute(0, 2, 3, 4, 1).reshape(-1, cout).contiguous().to(dev())
+  dx = t.full((n * dhw[0] * dhw[1] * dhw[2], cin), float("nan"), device=dev())
+  wtc = ops.gemm_tc_pack([wt.to(dev()).contiguous()], [0])[0]          # weight read as conv [Cout'=cin][Cin'=cout]
+  desc = ops.make_desc(n, cout, cin, fine, dhw, (k, k, k), 2, pad, False, cout, cin)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  _lib.call("crn_conv_gemm_tc", C.byref(desc), 0, gr.data_ptr(), wtc.data_ptr(), None, dx.data_ptr(), 0,
+            status.data_ptr(), _lib.stream_ptr())
+  t.cuda.synchronize()
+  assert int(status) == 0
+  got = dx.reshape((n,) + dhw + (cin,)).permute(0, 4, 1, 2, 3)
+  assert rel_err(got, x.grad) < 2e-5
+
+
 WGRAD_TC_CASES = GEMM_TC_CASES + [
     ("convT_k7_s2_128_64", (1, 128, 4, 4, 4), (128, 64, 7, 7, 7), 2, 3),
     ("convT_k3_s2_32_20", (2, 32, 4, 5, 6), (32, 20, 3, 3, 3), 2, 1),
@@ -233,6 +260,34 @@ def test_conv_wgrad_tcgen05(case):
   assert int(status) == 0
   gw = wt.grad.reshape(ws[0], ws[1], taps)
   ref = gw.permute(2, 0, 1) if transposed else gw.permute(2, 1, 0)     # [tap][ci][co]
+  assert rel_err(dw, ref) < 5e-5
+
+
+@pytest.mark.parametrize("n,cin,cout,dhw", [(1, 28, 16, (5, 6, 64)), (2, 28, 16, (3, 70, 64)), (1, 12, 8, (4, 5, 32)),
+                                              (2, 56, 32, (4, 6, 32)), (1, 36, 20, (3, 40, 32))])
+def test_conv5_wgrad_line_tcgen05(n, cin, cout, dhw):
+  """Narrow Conv3d k=5 weight gradient with filter taps stacked into the MMA tile (MN-major tf32, all four hi/lo
+  products) against the fp64 oracle; 5e-5 of the tensor max like the FFMA wgrad kernels."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 13 + cout + d)
+  x = t.randn(n, cin, d, h, w, generator=g)
+  wt = (t.randn(cout, cin, 5, 5, 5, generator=g) * 0.05).double().requires_grad_(True)
+  y = F.conv3d(x.double(), wt, None, padding=2)
+  gy = t.randn(y.shape, generator=g)
+  y.backward(gy.double())
+  xr = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).contiguous().to(dev())
+  gr = gy.permute(0, 2, 3, 4, 1).reshape(-1, cout).contiguous().to(dev())
+  dw = t.zeros(125, cin, cout, device=dev())
+  desc = ops.make_desc(n, cin, cout, dhw, dhw, (5, 5, 5), 1, 2, False, cin, cout)
+  assert _lib.lib().crn_conv_wgrad_line_supported(C.byref(desc)) == 1
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  _lib.call("crn_conv_wgrad_line", C.byref(desc), xr.data_ptr(), gr.data_ptr(), dw.data_ptr(), status.data_ptr(),
+            _lib.stream_ptr())
+  t.cuda.synchronize()
+  assert int(status) == 0
+  ref = wt.grad.reshape(cout, cin, 125).permute(2, 1, 0)
   assert rel_err(dw, ref) < 5e-5
 
 
