@@ -96,6 +96,8 @@ _SIGS = {
     "crn_conv_wgrad_tc": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_conv_wgrad_line_supported": ([_P(ConvDesc)], i32),
     "crn_conv_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
+    "crn_convt7_wgrad_line_supported": ([_P(ConvDesc)], i32),
+    "crn_convt7_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_adam_step_dev": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp], i32),
     "crn_adam_step": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp], i32),
 }

@@ -389,7 +389,7 @@ int launch_wl(WLParams p, cudaStream_t st) {
     tot += p.N * (p.D - (kz < 2 ? 2 - kz : kz - 2)) * p.H;
   }
   p.pass_begin[p.npass] = tot;
-  p.flush_every = 32;
+  p.flush_every = 64;
   const int grid = tot < kNumSMs ? tot : kNumSMs;
   kern<<<grid, NTHREADS, smem, st>>>(p);
   CRN_LAUNCH_CHECK("conv_wgrad_line");
@@ -420,4 +420,341 @@ extern "C" int crn_conv_wgrad_line(const crn_conv_desc* d, const float* x, const
   cudaStream_t st = crn_stream(stream);
   if (d->Cin <= 32 && d->Cout <= 16) return d->iW == 64 ? launch_wl<1, 64>(p, st) : launch_wl<1, 32>(p, st);
   return launch_wl<2, 32>(p, st);
+}
+
+// =============================================================================================================
+// ConvTranspose3d k=7 s=2 p=3 (output_padding 1) weight gradient for Cin <= 32, Cout == 16 (stage_5.t1,
+// model/reconstruction_decoder.py:85):   dW[k][ci][co] = sum_i x[i][ci] * dy[2i - 3 + k][co].
+// With o = 2m + c (c = parity class) and j = m - i the filter index is k = 2j + c + 3 per axis, so on the COARSE
+// grid this is a stride-1 weight gradient with 4 shifts j in {-2..1} per axis between x and the class-channel view
+// dyc[m][(cz, cy, cx, co)] = dy[2m + c][co].  One fine voxel PAIR (cx = 0, 1) x 16 co is exactly one 128-byte
+// MN-major row, so block (cz, cy) of a coarse line is simply the fine line (2mz + cz, 2my + cy):
+//   * step = coarse dy line (mz, my): 4 fine lines staged as 4 N-blocks (N = 128), hi and lo copies (2 MMAs);
+//   * M = 128 = {hi, lo} x {x line y_i, y_i + 1} x 32 ci exactly as in the k=5 kernel (ring + mirror slot);
+//   * accumulator a <-> jx = a - 2 (dyc start address shifted by a rows), 4 x 128 TMEM columns;
+//   * pass = (jz, jy pair); all four hi/lo products are formed, taps with k outside 0..6 are dropped in the epilogue.
+namespace {
+
+struct TStep {
+  int pass, jz, g;         // jz in -2..1, g: jy pair (g = 0: jy = 1, 0; g = 1: jy = -1, -2)
+  int n, mz, my;
+  bool fresh;
+};
+
+__device__ __forceinline__ TStep decode_tstep(const WLParams& p, int t, int t0) {
+  TStep s;
+  int ps = 0;
+  while (ps + 1 < p.npass && t >= p.pass_begin[ps + 1]) ++ps;
+  s.pass = ps;
+  s.jz = (ps >> 1) - 2; s.g = ps & 1;
+  const int r = t - p.pass_begin[ps];
+  s.my = r % p.H;
+  const int pl = r / p.H;
+  const int zlo = s.jz > 0 ? s.jz : 0, zcnt = p.D - (s.jz < 0 ? -s.jz : s.jz);
+  s.n = pl / zcnt;
+  s.mz = zlo + pl % zcnt;
+  s.fresh = (t == t0) || s.my == 0;
+  return s;
+}
+
+template <int W>
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_tline_kernel(const WLParams p) {
+  constexpr int RUNS = (W + 8) / 8;
+  constexpr int RS = RUNS * 8;                      // x line rows (coarse voxel i = row - 4)
+  constexpr int XH = RS * 128;
+  constexpr int XL = 2 * XH;                        // [hi][lo]
+  constexpr int YROWS = RS + 8;                     // dyc rows (coarse voxel m = row - 6)
+  constexpr int YB = YROWS * 128;                   // one (cz, cy) block line (LBO of the N operand)
+  constexpr int YL = 8 * YB;                        // [h][b = cz*2 + cy]
+  constexpr int XS = 6, XALL = 7, YS = 2;
+  constexpr int TCOLS = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* xring = smem;
+  uint8_t* yring = smem + XALL * XL;
+  WLBarriers* B = reinterpret_cast<WLBarriers*>(yring + YS * YL);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = p.pass_begin[p.npass];
+  const int t0 = (int)((long long)T * blockIdx.x / gridDim.x), t1 = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
+
+  if (tid == 0) {
+    for (int i = 0; i < MAXX; ++i) { tc::mbar_init(&B->full_x[i], 128); tc::mbar_init(&B->empty_x[i], 1); }
+    for (int i = 0; i < YSLOTS; ++i) { tc::mbar_init(&B->full_y[i], 256); tc::mbar_init(&B->empty_y[i], 1); }
+    tc::mbar_init(&B->acc_full, 1); tc::mbar_init(&B->acc_empty, 128);
+    B->abort_flag = 0;
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&B->tmem_base, 512);
+  for (int i = tid; i < (XALL * XL + YS * YL) / 16; i += NTHREADS)
+    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = B->tmem_base;
+  const uint32_t xring_u32 = tc::smem_u32(xring), yring_u32 = tc::smem_u32(yring);
+  auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
+  volatile int* ab = &B->abort_flag;
+  auto flush_after = [&](int t, const TStep& s) -> bool {
+    if (t == t1 - 1) return true;
+    if (t + 1 >= p.pass_begin[s.pass + 1]) return true;
+    return (t - t0 + 1) % p.flush_every == 0;
+  };
+
+  if (warp < 4) {
+    // ============================ EPILOGUE
+    uint32_t nflush = 0;
+    bool dead = false;
+    const int ya = warp >> 1;                                  // blocks: (hi, y_i), (lo, y_i), (hi, y_i+1), (lo, y_i+1)
+    const int ci = lane;
+    for (int t = t0; t < t1 && !dead; ++t) {
+      const TStep s = decode_tstep(p, t, t0);
+      if (!flush_after(t, s)) continue;
+      if (!tc::mbar_wait(&B->acc_full, nflush & 1, ab)) { fail(); dead = true; break; }
+      tc::fence_after_sync();
+      const int jy = 1 - 2 * s.g - ya;
+#pragma unroll 1
+      for (int a = 0; a < 4; ++a) {
+        const int jx = a - 2;
+#pragma unroll 1
+        for (int b = 0; b < 4; ++b) {                          // N block = (cz, cy); its 32 columns = (cx, co)
+          const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + a * TCOLS + b * 32;
+          float v[16], u[16];
+          tc::tmem_ld16(ta, v);                                // cx = 0
+          tc::tmem_ld16(ta + 16, u);                           // cx = 1
+          const int kz = 2 * s.jz + (b >> 1) + 3, ky = 2 * jy + (b & 1) + 3;
+          if ((unsigned)kz > 6u || (unsigned)ky > 6u || ci >= p.Cin) continue;
+#pragma unroll
+          for (int cx = 0; cx < 2; ++cx) {
+            const int kx = 2 * jx + cx + 3;
+            if ((unsigned)kx > 6u) continue;
+            float* dst = p.dw + ((long long)((kz * 7 + ky) * 7 + kx) * p.CinP + ci) * p.CoutP;
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+              if (c >= p.Cout) break;
+              atomicAdd(reinterpret_cast<float4*>(dst + c),
+                        cx == 0 ? make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]) : make_float4(u[c], u[c + 1], u[c + 2], u[c + 3]));
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&B->acc_empty);
+      ++nflush;
+    }
+  } else if (warp < 8) {
+    // ============================ PRODUCERS (jobs: x line | fine lines cz = 0 | fine lines cz = 1)
+    const int pt = tid - 128;
+    constexpr int XIT = W * 8 / 128;                  // x items per thread (float4)
+    constexpr int FW = 2 * W;                         // fine voxels per fine line
+    constexpr int YIT = 2 * FW * 4 / 128;             // items per thread of one dy job (2 fine lines x FW x 4 float4)
+    static_assert(XIT >= 1 && XIT <= 4 && YIT >= 1 && YIT <= 4, "line does not fit the register buffer");
+    struct Job { int kind, n, z, y, ok; };            // kind 0: x line (z, y coarse); 1, 2: dy fine lines of cz = kind - 1
+    int jt = t0, jj = 0;
+    auto next_job = [&](Job& jb) -> bool {
+      if (jt >= t1) return false;
+      const TStep s = decode_tstep(p, jt, t0);
+      const int nload = s.fresh ? 2 : 1;
+      if (jj < nload) {
+        const int j = s.fresh ? jj : 1;
+        jb.kind = 0; jb.n = s.n; jb.z = s.mz - s.jz; jb.y = s.my - 1 + 2 * s.g + j;
+        jb.ok = (unsigned)jb.y < (unsigned)p.H;
+        ++jj;
+      } else {
+        const int half = jj - nload;
+        jb.kind = 1 + half; jb.n = s.n; jb.z = s.mz; jb.y = s.my; jb.ok = 1;
+        if (half == 1) { jj = 0; ++jt; } else ++jj;
+      }
+      return true;
+    };
+    auto issue = [&](const Job& jb, float4 (&buf)[4]) {
+      if (jb.kind == 0) {
+        const float* src = p.x + ((((long long)jb.n * p.D + jb.z) * p.H + jb.y) * p.W) * p.x_cs + p.x_co;
+#pragma unroll
+        for (int u = 0; u < XIT; ++u) {
+          const int it = pt + u * 128, v = it >> 3, c4 = it & 7;
+          buf[u] = (jb.ok && c4 * 4 < p.Cin) ? __ldg(reinterpret_cast<const float4*>(src + (long long)v * p.x_cs + c4 * 4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        const int cz = jb.kind - 1;
+#pragma unroll
+        for (int u = 0; u < YIT; ++u) {
+          const int it = pt + u * 128, c4 = it & 3, f = (it >> 2) % FW, cy = it / (4 * FW);
+          const float* src = p.dy + ((((long long)jb.n * (2 * p.D) + 2 * jb.z + cz) * (2 * p.H) + 2 * jb.y + cy) * (2 * p.W) + f) *
+                                        p.y_cs + p.y_co;
+          buf[u] = (c4 * 4 < p.Cout) ? __ldg(reinterpret_cast<const float4*>(src + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    uint32_t q = 0, yq = 0;
+    bool dead = false;
+    auto store = [&](const Job& jb, const float4 (&buf)[4]) {
+      if (jb.kind == 0) {
+        const int slot = (int)(q % XS);
+        const uint32_t use = q / XS;
+        if (use > 0 && !tc::mbar_wait(&B->empty_x[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+        uint8_t* base = xring + slot * XL;
+#pragma unroll
+        for (int u = 0; u < XIT; ++u) {
+          const int it = pt + u * 128, v = it >> 3, cw = it & 7;
+          float4 hi, lo;
+          tc::split_tf32(buf[u].x, hi.x, lo.x); tc::split_tf32(buf[u].y, hi.y, lo.y);
+          tc::split_tf32(buf[u].z, hi.z, lo.z); tc::split_tf32(buf[u].w, hi.w, lo.w);
+          const int row = v + 4;
+          const uint32_t off = (uint32_t)row * 128 + (uint32_t)((((cw >> 1) ^ (row & 3)) << 5) + ((cw & 1) << 4));
+          *reinterpret_cast<float4*>(base + off) = hi;
+          *reinterpret_cast<float4*>(base + XH + off) = lo;
+          if (slot == 0) {
+            *reinterpret_cast<float4*>(base + XS * XL + off) = hi;
+            *reinterpret_cast<float4*>(base + XS * XL + XH + off) = lo;
+          }
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&B->full_x[slot]);
+        ++q;
+      } else {
+        const int cz = jb.kind - 1;
+        const int slot = (int)(yq % YS);
+        const uint32_t use = yq / YS;
+        if (cz == 0 && use > 0 && !tc::mbar_wait(&B->empty_y[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+        uint8_t* base = yring + slot * YL;
+#pragma unroll
+        for (int u = 0; u < YIT; ++u) {
+          const int it = pt + u * 128, c4 = it & 3, f = (it >> 2) % FW, cy = it / (4 * FW);
+          float4 hi, lo;
+          tc::split_tf32(buf[u].x, hi.x, lo.x); tc::split_tf32(buf[u].y, hi.y, lo.y);
+          tc::split_tf32(buf[u].z, hi.z, lo.z); tc::split_tf32(buf[u].w, hi.w, lo.w);
+          const int row = (f >> 1) + 6, cx = f & 1, b = cz * 2 + cy;
+          const int chunk = cx * 2 + (c4 >> 1);
+          const uint32_t off = (uint32_t)b * YB + (uint32_t)row * 128 + (uint32_t)(((chunk ^ (row & 3)) << 5) + ((c4 & 1) << 4));
+          *reinterpret_cast<float4*>(base + off) = hi;
+          *reinterpret_cast<float4*>(base + 4 * YB + off) = lo;
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&B->full_y[slot]);       // 256 arrivals: both halves
+        if (cz == 1) ++yq;
+      }
+    };
+    Job ja, jb2;
+    float4 bufa[4], bufb[4];
+    bool have_a = next_job(ja);
+    if (have_a) issue(ja, bufa);
+    while (have_a && !dead) {
+      const bool have_b = next_job(jb2);
+      if (have_b) issue(jb2, bufb);
+      store(ja, bufa);
+      if (!have_b || dead) break;
+      have_a = next_job(ja);
+      if (have_a) issue(ja, bufa);
+      store(jb2, bufb);
+    }
+  } else {
+    // ============================ MMA ISSUER
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(128, 128, 1, 1);
+      uint32_t q = 0, nflush = 0;
+      bool first = true;            // next MMA of every accumulator overwrites (start of a flush interval)
+      bool dead = false;
+      for (int t = t0; t < t1 && !dead; ++t) {
+        const TStep s = decode_tstep(p, t, t0);
+        const int nload = s.fresh ? 2 : 1;
+        for (int j = 0; j < nload; ++j) {
+          const uint32_t l = q + j;
+          if (!tc::mbar_wait(&B->full_x[l % XS], (l / XS) & 1, ab)) { fail(); dead = true; break; }
+        }
+        if (dead) break;
+        q += nload;
+        const int i = t - t0;
+        const int yslot = i % YS;
+        if (!tc::mbar_wait(&B->full_y[yslot], (uint32_t)(i / YS) & 1, ab)) { fail(); dead = true; break; }
+        if (first && nflush > 0) {
+          if (!tc::mbar_wait(&B->acc_empty, (nflush - 1) & 1, ab)) { fail(); dead = true; break; }
+        }
+        tc::fence_after_sync();
+        const uint32_t ybase = yring_u32 + yslot * YL;
+        const uint32_t slot = (q - 2) % XS;                 // window line 0 (line 1 follows; mirror after the last slot)
+#pragma unroll 1
+        for (int r = 0; r < RUNS; ++r) {
+          const uint64_t da = tc::make_desc_mn32(xring_u32 + slot * XL + r * 1024, XH, 512);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const uint64_t dbh = tc::make_desc_mn32(ybase + (r * 8 + a) * 128, YB, 512);
+            const uint64_t dbl = tc::make_desc_mn32(ybase + 4 * YB + (r * 8 + a) * 128, YB, 512);
+            tc::mma_tf32(tmem + a * TCOLS, da, dbh, idesc, (first && r == 0) ? 0u : 1u);
+            tc::mma_tf32(tmem + a * TCOLS, da, dbl, idesc, 1u);
+          }
+        }
+        first = false;
+        tc::commit(&B->empty_y[yslot]);
+        if (t + 1 < t1) {
+          const TStep sn = decode_tstep(p, t + 1, t0);
+          const int ndrop = sn.fresh ? 2 : 1;
+          for (int j = 0; j < ndrop; ++j) tc::commit(&B->empty_x[(q - 2 + j) % XS]);
+        }
+        if (flush_after(t, s)) {
+          tc::commit(&B->acc_full);
+          ++nflush;
+          first = true;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+template <int W>
+int launch_wtl(WLParams p, cudaStream_t st) {
+  constexpr int RS = ((W + 8) / 8) * 8;
+  constexpr int XL = 2 * RS * 128, YL = 8 * (RS + 8) * 128;
+  const size_t smem = (size_t)7 * XL + (size_t)2 * YL + sizeof(WLBarriers) + 1024 + 64;
+  auto kern = wgrad_tline_kernel<W>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      crn_set_error("conv_wgrad_tline: cannot set %zu bytes of dynamic shared memory", smem);
+      return CRN_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  p.npass = 8;
+  int tot = 0;
+  for (int ps = 0; ps < 8; ++ps) {
+    const int jz = (ps >> 1) - 2;
+    p.pass_begin[ps] = tot;
+    tot += p.N * (p.D - (jz < 0 ? -jz : jz)) * p.H;
+  }
+  p.pass_begin[8] = tot;
+  p.flush_every = 64;
+  const int grid = tot < kNumSMs ? tot : kNumSMs;
+  kern<<<grid, NTHREADS, smem, st>>>(p);
+  CRN_LAUNCH_CHECK("conv_wgrad_tline");
+  return CRN_OK;
+}
+}  // namespace
+
+extern "C" int crn_convt7_wgrad_line_supported(const crn_conv_desc* d) {
+  if (!d || !d->transposed || d->kD != 7 || d->kH != 7 || d->kW != 7 || d->stride != 2 || d->pad != 3) return 0;
+  if (d->oD != 2 * d->iD || d->oH != 2 * d->iH || d->oW != 2 * d->iW || d->y_planar) return 0;
+  if (d->Cin % 4 || d->x_cs % 4 || d->x_co % 4 || d->y_cs % 4 || d->y_co % 4 || d->CoutP % 4) return 0;
+  if (d->iD < 3 || d->Cin > 32 || d->Cout != 16) return 0;
+  return d->iW == 32 || d->iW == 16;
+}
+
+// dWf[tap][ci][co] += sum x * dy for ConvTranspose3d k=7 s=2 p=3 with Cin <= 32, Cout == 16 (same contract as
+// crn_conv_wgrad; x is the coarse input [N, D, H, W, x_cs], dy the fine output gradient [N, 2D, 2H, 2W, y_cs]).
+extern "C" int crn_convt7_wgrad_line(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed,
+                                     int32_t* status, void* stream) {
+  CRN_REQUIRE(d && x && dy && dw_packed && status, "crn_convt7_wgrad_line: null pointer");
+  CRN_REQUIRE(crn_convt7_wgrad_line_supported(d), "crn_convt7_wgrad_line: unsupported layer shape");
+  WLParams p{};
+  p.x = x; p.dy = dy; p.dw = dw_packed; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  p.Cin = d->Cin; p.Cout = d->Cout;
+  p.x_cs = d->x_cs; p.x_co = d->x_co; p.y_cs = d->y_cs; p.y_co = d->y_co; p.CinP = d->CinP; p.CoutP = d->CoutP;
+  cudaStream_t st = crn_stream(stream);
+  return d->iW == 32 ? launch_wtl<32>(p, st) : launch_wtl<16>(p, st);
 }

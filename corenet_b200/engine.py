@@ -83,6 +83,13 @@ def _conv_dispatch(kind, layer, d, args):
     if kind == "wgrad" and layer.name in eng.gt_wgrad:
       x, dy, dw, st = args
       return "wgrad_tc", "crn_conv_wgrad_tc", (C.byref(d), x, dy, dw, status, st)
+    if kind == "wgrad" and layer.k == (7, 7, 7) and layer.transposed:
+      ok = eng.wl_ok.get(layer.name)
+      if ok is None:                        # ConvTranspose3d k=7 s=2, Cout == 16: class-channel variant of the same kernel
+        ok = eng.wl_ok[layer.name] = bool(_lib.lib().crn_convt7_wgrad_line_supported(C.byref(d)))
+      if ok:
+        x, dy, dw, st = args
+        return "wgrad_tc", "crn_convt7_wgrad_line", (C.byref(d), x, dy, dw, status, st)
     if kind == "wgrad" and layer.k == (5, 5, 5) and not layer.transposed:
       ok = eng.wl_ok.get(layer.name)
       if ok is None:                        # narrow Conv3d k=5 layers: tap-stacked tcgen05 kernel (csrc/conv_wgrad_line.cu)

@@ -323,6 +323,13 @@ int crn_conv_wgrad_line_supported(const crn_conv_desc* d);
 int crn_conv_wgrad_line(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed, int32_t* status,
                         void* stream);
 
+/* ... and of ConvTranspose3d k=7 s=2 p=3 with Cin <= 32, Cout == 16 at coarse W = 32 / 16 (stage_5.t1,
+ * model/reconstruction_decoder.py:85): the class-channel view of dy on the coarse grid makes it a stride-1 problem
+ * whose N blocks are the fine lines themselves. */
+int crn_convt7_wgrad_line_supported(const crn_conv_desc* d);
+int crn_convt7_wgrad_line(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed, int32_t* status,
+                          void* stream);
+
 /* Fused Adam step over a flat list (state.py:65-66) — next-row (f2) op. */
 int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream);

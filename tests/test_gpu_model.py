@@ -211,9 +211,11 @@ def test_trainer_step_matches_reference_adam():
   errs.sort(reverse=True)
   print("worst update errors:", errs[:6])
   # tiny bias vectors whose gradients are sums over few voxels inherit isolated ReLU sign flips (see module
-  # docstring); bound the distribution: median tight, worst loose
+  # docstring); bound the distribution: median tight, worst loose.  Adam's first updates are lr*sign(g): ONE flipped
+  # near-zero gradient in a 40-element vector is already a relative-L2 error of sqrt(4/40) = 0.32, and which
+  # element flips depends on the atomics order of the run, hence 0.5 for the worst vector.
   med = sorted(e for e, _ in errs)[len(errs) // 2]
-  assert med < 1e-2 and errs[0][0] < 0.25, (med, errs[:3])
+  assert med < 1e-2 and errs[0][0] < 0.5, (med, errs[:3])
 
 
 def test_trainer_cuda_graph_matches_eager():
