@@ -601,12 +601,17 @@ extern "C" int crn_conv_dgrad(const crn_conv_desc* d, const float* dy, const flo
 }
 
 int crn_wgrad_row_try(const crn_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st);
+int crn_wgrad_stem_try(const crn_conv_desc* d, const float* x, const float* dy, float* dw, cudaStream_t st);
 
 extern "C" int crn_conv_wgrad(const crn_conv_desc* d, const float* x, const float* dy,
                               float* dw_packed, void* stream) {
   CRN_REQUIRE(check_desc(d), "crn_conv_wgrad: bad descriptor");
   CRN_REQUIRE(x && dy && dw_packed, "crn_conv_wgrad: null pointer");
   CRN_REQUIRE(!d->y_planar, "crn_conv_wgrad: planar dy unsupported");
+  {   // RGB stem (conv_wgrad_stem.cu)
+    const int rc = crn_wgrad_stem_try(d, x, dy, dw_packed, crn_stream(stream));
+    if (rc != CRN_ERR_UNSUPPORTED) return rc;
+  }
   {   // small-channel 3-D decoder layers: tap-row kernel (conv_wgrad_row.cu)
     const int rc = crn_wgrad_row_try(d, x, dy, dw_packed, crn_stream(stream));
     if (rc != CRN_ERR_UNSUPPORTED) return rc;

@@ -114,6 +114,8 @@ def conv_call(kind, layer, d, *args):
 
 # Conv3d k=5 layers at >= 32^3 run forward/dgrad on the tcgen05 tensor cores (3xTF32, csrc/conv_tc5.cu).
 USE_TC = True
+# weight-gradient launches go to a second stream (see Plan.backward)
+WGRAD_SIDE_STREAM = True
 
 
 def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
@@ -525,6 +527,7 @@ class Plan:
     self.arena_bwd = t.zeros(max(self._n["bwd"], 1), dtype=t.float64, device=self.dev)
     self.training = True
     self.launches = 0
+    self.side_stream = t.cuda.Stream(device=self.dev)
 
   def f32(self, n):
     return t.zeros(n, dtype=t.float32, device=self.dev)
@@ -730,8 +733,21 @@ class Plan:
       n = n if n is not None else grads[name].numel()
       grads[name].copy_(v[lo:lo + n])
 
+    # Weight gradients only feed the final un-pack, so they run on a side stream concurrently with the dgrad /
+    # BatchRenorm chain (fork: event after dy is final; join: before crn_unpack_wgrads).  The small encoder launches
+    # (16-160 CTAs) no longer serialise behind each other; inside a captured graph this becomes a parallel branch.
+    main = t.cuda.current_stream()
+    side = self.side_stream if WGRAD_SIDE_STREAM else None
+
     def wgrad(l, d, x_ptr, dy_ptr):
-      conv_call("wgrad", l, d, x_ptr, dy_ptr, eng.dwp(l), st)
+      if side is None:
+        conv_call("wgrad", l, d, x_ptr, dy_ptr, eng.dwp(l), st)
+        return
+      ev = t.cuda.Event()
+      ev.record(main)
+      side.wait_event(ev)
+      with t.cuda.stream(side):
+        conv_call("wgrad", l, d, x_ptr, dy_ptr, eng.dwp(l), side.cuda_stream)
 
     def dgrad(l, d, dy_ptr, dx_ptr, acc=0):
       conv_call("dgrad", l, d, dy_ptr, eng.wd(l), dx_ptr, acc, st)
@@ -836,6 +852,8 @@ class Plan:
     bias_from(dxs, stem.name + ".bias")
     wgrad(stem, self.d_stem, self.img4.p, self.s1.gp)
     # ---- weight gradients back to the parameters' layout (one launch)
+    if side is not None:
+      main.wait_stream(side)
     eng.unpack_wgrads(grads)
     # offset-channel columns of the skip compress convs (the GEMM ran without them)
     for sd in self.stages:

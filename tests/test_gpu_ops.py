@@ -37,6 +37,8 @@ CONV_CASES = [
     ("1x1_s2", (2, 64, 16, 16), (128, 64, 1, 1), 2, 0, False, 0),
     ("3x3", (2, 32, 14, 14), (48, 32, 3, 3), 1, 1, False, 0),
     ("stem7x7_s2_cin3", (2, 3, 40, 40), (64, 3, 7, 7), 2, 3, False, 0),
+    ("stem7x7_s2_ow64_stemkernel", (2, 3, 128, 128), (64, 3, 7, 7), 2, 3, False, 0),
+    ("stem7x7_s2_ow128_stemkernel", (1, 3, 256, 256), (64, 3, 7, 7), 2, 3, False, 0),
     ("small_cout", (1, 28, 12, 12, 12), (16, 28, 5, 5, 5), 1, 2, False, 0),
     ("3d_k3", (2, 16, 6, 6, 6), (24, 16, 3, 3, 3), 1, 1, False, 0),
     ("3d_k5_wide", (1, 56, 8, 8, 8), (132, 56, 5, 5, 5), 1, 2, False, 0),
