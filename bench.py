@@ -231,8 +231,10 @@ def run_native(args):
   # per-kernel roofline pass: the same step enqueued eagerly with CUDA events around every convolution launch
   # (a replayed graph has no per-launch events); same inputs, same process, right after the timed region
   engine.PROFILE = []
+  engine.WGRAD_SIDE_STREAM = False          # kernels timed alone (in the graph the weight gradients run concurrently)
   timed(dev_step, args.steps)
   prof, engine.PROFILE = engine.PROFILE, None
+  engine.WGRAD_SIDE_STREAM = True
   tc_status = int(engine.get_engine(model).tc_status)
   if tc_status != 0:
     raise RuntimeError("tcgen05 conv kernel reported a barrier timeout: results are invalid")

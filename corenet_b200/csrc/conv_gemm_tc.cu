@@ -295,33 +295,41 @@ __device__ __forceinline__ int gt_find_item(const int64_t* offsets, int n, int64
   return lo;
 }
 
+// one thread = the 4 K values (e) of one (channel tile, stage, kq, row): <= 4 reads, one float4 hi + one float4 lo
+// store (consecutive threads = consecutive rows = consecutive 16-byte slots of the packed block)
 __global__ void gemm_tc_pack_kernel(const crn_gemm_tc_pack_item* items, const int64_t* offsets, int n, int64_t total) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int li = gt_find_item(offsets, n, i);
+  const int64_t total4 = total >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int li = gt_find_item(offsets, n, i << 2);
     const crn_gemm_tc_pack_item it = items[li];
-    int64_t r = i - offsets[li];                      // (nt, stage, kq, nrow, e)
+    int64_t r = i - (offsets[li] >> 2);                // (nt, stage, kq, nrow)
     const int K = it.dgrad ? it.Cout : it.Cin, Nn = it.dgrad ? it.Cin : it.Cout;
     const int BN = Nn <= 64 ? 64 : 128;
     const int kchunks = (K + KS - 1) / KS;
-    const int e = (int)(r & 3); r >>= 2;
     const int nrow = (int)(r % BN); r /= BN;
     const int kq = (int)(r & 3); r >>= 2;
     const int nstages = it.taps * kchunks;
     const int s = (int)(r % nstages); const int nt = (int)(r / nstages);
     const int tap = s / kchunks, kc = s - tap * kchunks;
-    const int k = kc * KS + kq * 4 + e, nn = nt * BN + nrow;
-    float v = 0.f;
-    if (k < K && nn < Nn) {
-      const int co = it.dgrad ? k : nn, ci = it.dgrad ? nn : k;
-      const int ts = it.dgrad ? it.taps - 1 - tap : tap;
-      v = it.src[((int64_t)co * it.Cin + ci) * it.taps + ts];
+    const int k0 = kc * KS + kq * 4, nn = nt * BN + nrow;
+    const int ts = it.dgrad ? it.taps - 1 - tap : tap;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (nn < Nn) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + e;
+        if (k < K) {
+          const int co = it.dgrad ? k : nn, ci = it.dgrad ? nn : k;
+          v[e] = __ldg(it.src + ((int64_t)co * it.Cin + ci) * it.taps + ts);
+        }
+      }
     }
-    float hi, lo;
-    tc::split_tf32(v, hi, lo);
-    const int64_t blk = ((int64_t)nt * nstages + s) * (2 * 4 * BN * 4);
-    const int64_t off = ((int64_t)kq * BN + nrow) * 4 + e;
-    it.dst[blk + off] = hi;
-    it.dst[blk + 4 * BN * 4 + off] = lo;
+    float4 hi, lo;
+    tc::split_tf32(v[0], hi.x, lo.x); tc::split_tf32(v[1], hi.y, lo.y);
+    tc::split_tf32(v[2], hi.z, lo.z); tc::split_tf32(v[3], hi.w, lo.w);
+    float* blk = it.dst + ((int64_t)nt * nstages + s) * (2 * 4 * BN * 4) + ((int64_t)kq * BN + nrow) * 4;
+    *reinterpret_cast<float4*>(blk) = hi;
+    *reinterpret_cast<float4*>(blk + 4 * BN * 4) = lo;
   }
 }
 
@@ -356,8 +364,8 @@ extern "C" int64_t crn_gemm_tc_packed_floats(int32_t K, int32_t N, int32_t taps)
 extern "C" int crn_gemm_tc_pack(const crn_gemm_tc_pack_item* items, const int64_t* offsets, int32_t n, int64_t total,
                                 void* stream) {
   CRN_REQUIRE(items && offsets && n > 0 && total > 0, "crn_gemm_tc_pack: bad args");
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  int64_t blocks = (total / 4 + 255) / 256;
+  if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
   gemm_tc_pack_kernel<<<(unsigned)blocks, 256, 0, crn_stream(stream)>>>(items, offsets, n, total);
   CRN_LAUNCH_CHECK("gemm_tc_pack");
   return CRN_OK;

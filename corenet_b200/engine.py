@@ -392,25 +392,35 @@ class Engine:
     ptr_sig = tuple(w.data_ptr() for w in ws)
     ver_sig = tuple(w._version for w in ws)
     if ptr_sig != self._ptr_sig:
-      items = (PackItem * len(self.layers))()
-      offs = (C.c_int64 * (len(self.layers) + 1))()
-      for i, (l, w) in enumerate(zip(self.layers, ws)):
+      entries = []
+      for l, w in zip(self.layers, ws):
         assert w.is_contiguous() and w.dtype == t.float32 and w.device == self.dev
+        # layers served by the tcgen05 implicit-GEMM kernels do not read the FFMA arenas
+        tc_f = USE_TC and l.name in self.gt_w
+        tc_d = USE_TC and (self.gt_w.get(l.name, (None, None))[1] is not None or l.name in self.gt_td)
+        if not (tc_f and tc_d):
+          entries.append((l, w, tc_f, tc_d))
+      items = (PackItem * len(entries))()
+      offs = (C.c_int64 * (len(entries) + 1))()
+      tot = 0
+      for i, (l, w, tc_f, tc_d) in enumerate(entries):
         it = items[i]
         it.src = w.data_ptr()
-        it.dst_fwd = self.w_fwd.data_ptr() + 4 * l.off
-        it.dst_dgrad = self.w_dgrad.data_ptr() + 4 * l.off
+        it.dst_fwd = None if tc_f else self.w_fwd.data_ptr() + 4 * l.off
+        it.dst_dgrad = None if tc_d else self.w_dgrad.data_ptr() + 4 * l.off
         it.Cin, it.Cout, it.taps, it.CinP, it.CoutP = l.src_cin, l.cout, l.taps, l.cinp, l.coutp
         it.src_is_transposed = int(l.transposed)
-        offs[i] = l.off
-      offs[len(self.layers)] = self.total
+        offs[i] = tot
+        tot += l.size
+      offs[len(entries)] = tot
       self._items_dev = self._to_dev(items, self.dev)
       self._offs_dev = self._to_dev(offs, self.dev)
+      self._pack_n, self._pack_tot = len(entries), tot
       self._ptr_sig = ptr_sig
       self._ver_sig = None
     if ver_sig != self._ver_sig:
-      _call("crn_pack_weights", self._items_dev.data_ptr(), self._offs_dev.data_ptr(), len(self.layers),
-            self.total, _lib.stream_ptr())
+      _call("crn_pack_weights", self._items_dev.data_ptr(), self._offs_dev.data_ptr(), self._pack_n,
+            self._pack_tot, _lib.stream_ptr())
       for l in self.layers:
         if l.name in self.tc_w:
           w = P[l.name + ".weight"]
