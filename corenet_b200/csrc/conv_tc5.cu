@@ -731,5 +731,7 @@ extern "C" int crn_convt7_tc_dgrad(const crn_conv_desc* d, const float* dy, cons
     return launch_tc5<16, 8, false, 4, false, true>(p, st);
   }
   if (p.gN <= 32) return launch_tc5<32, 8, false, 4, false, true>(p, st);
+  // small grids (stage_4.t1 at 16^3: 32 work items with 4 planes each): one output plane per item fills the machine
+  if ((long long)p.N * p.tiles_x * p.tiles_y * (p.D / 4) < kNumSMs / 2) return launch_tc5<64, 1, false, 4, false, true>(p, st);
   return launch_tc5<64, 4, false, 4, false, true>(p, st);
 }

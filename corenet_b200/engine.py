@@ -299,15 +299,21 @@ class Engine:
                              t.zeros(lib.crn_tc5_packed_floats(mid, cin), dtype=t.float32, device=dev))
     # ... and per eligible ConvTranspose3d(k=7, s=2) layer a packed copy for the forward (csrc/conv_tc5.cu, KT=4)
     self.tct_w = {}
+    self.tct_slices = {}
     for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
       l = self.L[f"stage_{stage}.t1"]
       if l.k == (7, 7, 7) and g >= 16 and g % 16 == 0 and mid % 4 == 0:
         fwd_ok = t_out <= 16                          # 8 * Cout accumulator columns <= 128
-        # float4 class-channel gathers, N = Cin <= 64; at 16^3 the 32 work items leave most SMs idle (FFMA wins)
-        dgrad_ok = t_out % 4 == 0 and mid <= 64 and g >= 32
+        # float4 class-channel gathers, N = Cin <= 64 (on small grids the C side takes one z-plane per work item)
+        dgrad_ok = t_out % 4 == 0 and mid <= 64
         mk = lambda dg: t.zeros(lib.crn_tct_packed_floats(mid, t_out, dg), dtype=t.float32, device=dev)
         if fwd_ok or dgrad_ok:
           self.tct_w[l.name] = (mk(0) if fwd_ok else None, mk(1) if dgrad_ok else None)
+        # wider outputs: the forward runs once per 16-channel slice of Cout (each slice = 128 accumulator columns)
+        if not fwd_ok and t_out % 16 == 0 and t_out <= 64:
+          self.tct_slices[l.name] = [
+              (t.zeros(lib.crn_tct_packed_floats(mid, 16, 0), dtype=t.float32, device=dev),
+               t.zeros(mid, 16, 7, 7, 7, dtype=t.float32, device=dev), co0) for co0 in range(0, t_out, 16)]
     # wide layers (>= 32 channels on both sides): implicit-GEMM forward / dgrad (csrc/conv_gemm_tc.cu) and weight
     # gradient (csrc/conv_wgrad_tc.cu) on tcgen05
     self.gt_w = {}
@@ -427,6 +433,9 @@ class Engine:
           wf, wd = self.tc_w[l.name]
           _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 0, wf.data_ptr(), _lib.stream_ptr())
           _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 1, wd.data_ptr(), _lib.stream_ptr())
+        for wt, wslice, co0 in self.tct_slices.get(l.name, ()):
+          wslice.copy_(P[l.name + ".weight"][:, co0:co0 + 16])
+          _call("crn_tct_pack", wslice.data_ptr(), l.cin, 16, 0, wt.data_ptr(), _lib.stream_ptr())
         if l.name in self.tct_w:
           for dg, wt in enumerate(self.tct_w[l.name]):
             if wt is not None:
@@ -700,6 +709,16 @@ class Plan:
         if USE_TC and eng.tct_w.get(sd["lt"].name, (None, None))[0] is not None:
           convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name][0].data_ptr(), bias(sd["lt"]), nxt.p,
                          eng.tc_status.data_ptr(), st)
+        elif USE_TC and sd["lt"].name in eng.tct_slices:
+          if "d_t_slices" not in sd:
+            sd["d_t_slices"] = []
+            for _, _, co0 in eng.tct_slices[sd["lt"].name]:
+              ds = ConvDesc.from_buffer_copy(bytes(sd["d_t"]))
+              ds.Cout, ds.y_co = 16, sd["d_t"].y_co + co0
+              sd["d_t_slices"].append(ds)
+          for (wt, _, co0), ds in zip(eng.tct_slices[sd["lt"].name], sd["d_t_slices"]):
+            convt7_tc_call(sd["lt"], ds, sd["z2"].p, wt.data_ptr(), bias(sd["lt"]) + 4 * co0, nxt.p,
+                           eng.tc_status.data_ptr(), st)
         else:
           conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]), nxt.p, 0, st)
         if sd["skip_c"]:
