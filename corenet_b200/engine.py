@@ -100,16 +100,49 @@ def _conv_dispatch(kind, layer, d, args):
   return kind, _CONV_FN[kind], (C.byref(d),) + tuple(args)
 
 
+def _wgrad_t7_slices(eng, layer, d, args):
+  """ConvTranspose3d k=7 s=2 weight gradient of a layer wider than the class-channel tcgen05 kernel takes
+  (Cin <= 32, Cout == 16): one launch per (32-channel Cin block, 16-channel Cout block), each writing its own block
+  of the packed dW.  Returns the list of calls, or None when the layer does not decompose."""
+  key = (layer.name, d.N)
+  calls = eng.wl_split.get(key)
+  if calls is None:
+    calls = []
+    if d.Cin % 32 == 0 and d.Cout % 16 == 0 and d.Cin <= 64 and d.Cout <= 32 and (d.Cin > 32 or d.Cout > 16):
+      for ci0 in range(0, d.Cin, 32):
+        for co0 in range(0, d.Cout, 16):
+          ds = ConvDesc.from_buffer_copy(bytes(d))
+          ds.Cin, ds.x_co, ds.Cout, ds.y_co = 32, d.x_co + ci0, 16, d.y_co + co0
+          if not _lib.lib().crn_convt7_wgrad_line_supported(C.byref(ds)):
+            calls = []
+            break
+          calls.append((ds, 4 * (ci0 * d.CoutP + co0)))
+        if not calls:
+          break
+    eng.wl_split[key] = calls
+  if not calls:
+    return None
+  x, dy, dw, st = args
+  status = eng.tc_status.data_ptr()
+  return [("wgrad_tc", "crn_convt7_wgrad_line", (C.byref(ds), x, dy, dw + off, status, st), ds) for ds, off in calls]
+
+
 def conv_call(kind, layer, d, *args):
-  tag, fn, a = _conv_dispatch(kind, layer, d, args)
-  if PROFILE is None:
+  calls = None
+  if kind == "wgrad" and USE_TC and _ENG is not None and layer.transposed and layer.k == (7, 7, 7):
+    calls = _wgrad_t7_slices(_ENG, layer, d, args)
+  if calls is None:
+    tag, fn, a = _conv_dispatch(kind, layer, d, args)
+    calls = [(tag, fn, a, d)]
+  for tag, fn, a, dd in calls:
+    if PROFILE is None:
+      _lib.call(fn, *a)
+      continue
+    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    e0.record()
     _lib.call(fn, *a)
-    return
-  e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-  e0.record()
-  _lib.call(fn, *a)
-  e1.record()
-  PROFILE.append((tag, layer.name, conv_macs(d), e0, e1))
+    e1.record()
+    PROFILE.append((tag, layer.name, conv_macs(dd), e0, e1))
 
 
 # Conv3d k=5 layers at >= 32^3 run forward/dgrad on the tcgen05 tensor cores (3xTF32, csrc/conv_tc5.cu).
@@ -319,6 +352,7 @@ class Engine:
     self.gt_w = {}
     self.gt_wgrad = set()
     self.wl_ok = {}
+    self.wl_split = {}
     self.gt_td = {}
     for l in self.layers:
       wide = min(l.cin, l.cout) >= 32 and l.cin % 4 == 0 and l.cout % 4 == 0 and l.src_cin == l.cin

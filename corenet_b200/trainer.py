@@ -61,6 +61,8 @@ class Trainer:
     # single GPU the Adam update) is captured once in a CUDA graph and replayed.
     self.use_graph = use_graph
     self._graphs = {}
+    self._copy_stream = None
+    self._prefetched = None
     self.graph_launches = 0      # kernels of this library inside one captured step
     self.lr, self.eps, self.betas = lr, eps, betas
     self.mode = {"iou_fgbg": 0, "xent_times_iou_agnostic": 1}[loss]
@@ -121,21 +123,57 @@ class Trainer:
     self._adam(scale)
     return loss
 
-  def step(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, gt: t.Tensor) -> t.Tensor:
-    """One optimisation step on this rank's scenes; returns the (device) loss scalar.  In graph mode the inputs
-    may live in (pinned) host memory: they are copied straight into the graph's static device buffers."""
-    self.step_count += 1
-    if not self.use_graph or engine_lib.PROFILE is not None:
-      return self._eager_step(image, v2s, offsets, gt)
-    key = (tuple(image.shape), tuple(gt.shape), gt.dtype, image.device, self.model.training)
+  def _gstate(self, image, v2s, offsets, gt):
+    key = (tuple(image.shape), tuple(gt.shape), gt.dtype, self.flat.device, self.model.training)
     gs = self._graphs.get(key)
     if gs is None:
-      gs = {"calls": 0, "graph": None,
-            "in": [t.empty(x.shape, dtype=d or x.dtype, device=self.flat.device)
-                   for x, d in ((image, None), (v2s, t.float32), (offsets, t.float32), (gt, None))]}
+      mk = lambda: [t.empty(x.shape, dtype=d or x.dtype, device=self.flat.device)
+                    for x, d in ((image, None), (v2s, t.float32), (offsets, t.float32), (gt, None))]
+      gs = {"calls": 0, "graph": None, "in": mk(), "stage": mk(), "ready": None, "consumed": None}
       self._graphs[key] = gs
-    for dst, src in zip(gs["in"], (image, v2s, offsets, gt)):
-      dst.copy_(src, non_blocking=True)
+    return gs
+
+  def prefetch(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, gt: t.Tensor) -> None:
+    """Starts the host->device copy of the NEXT step's inputs on a copy stream (into staging buffers), so that it
+    overlaps the step that is currently running -- what the reference's DataLoader prefetch + .cuda() do
+    (pipeline.py:215-223).  The following `step()` (called without arguments) consumes them."""
+    gs = self._gstate(image, v2s, offsets, gt)
+    if self._copy_stream is None:
+      self._copy_stream = t.cuda.Stream(device=self.flat.device)
+    cs = self._copy_stream
+    if gs["consumed"] is not None:
+      cs.wait_event(gs["consumed"])            # the previous step has copied the staging buffers out
+    with t.cuda.stream(cs):
+      for dst, src in zip(gs["stage"], (image, v2s, offsets, gt)):
+        dst.copy_(src, non_blocking=True)
+      gs["ready"] = t.cuda.Event()
+      gs["ready"].record(cs)
+    self._prefetched = gs
+
+  def step(self, image: Optional[t.Tensor] = None, v2s: Optional[t.Tensor] = None,
+           offsets: Optional[t.Tensor] = None, gt: Optional[t.Tensor] = None) -> t.Tensor:
+    """One optimisation step on this rank's scenes; returns the (device) loss scalar.  In graph mode the inputs
+    may live in (pinned) host memory: they are copied straight into the graph's static device buffers.  Called
+    without arguments it consumes the batch started by `prefetch()`."""
+    self.step_count += 1
+    if image is None:
+      gs = self._prefetched
+      assert gs is not None, "step() without arguments needs a preceding prefetch()"
+      self._prefetched = None
+      main = t.cuda.current_stream()
+      main.wait_event(gs["ready"])
+      for dst, src in zip(gs["in"], gs["stage"]):
+        dst.copy_(src, non_blocking=True)        # device-to-device, ~10 us
+      gs["consumed"] = t.cuda.Event()
+      gs["consumed"].record(main)
+      if not self.use_graph or engine_lib.PROFILE is not None:
+        return self._eager_step(*gs["in"])
+    else:
+      if not self.use_graph or engine_lib.PROFILE is not None:
+        return self._eager_step(image, v2s, offsets, gt)
+      gs = self._gstate(image, v2s, offsets, gt)
+      for dst, src in zip(gs["in"], (image, v2s, offsets, gt)):
+        dst.copy_(src, non_blocking=True)
     if gs["graph"] is None:
       if gs["calls"] < 2:                       # eager warm-up: lazy initialisation must not happen under capture
         gs["calls"] += 1

@@ -264,8 +264,15 @@ def test_trainer_cuda_graph_matches_eager():
     more = [tr.step(*args).item() for _ in range(2)]    # replays
     assert all(np.isfinite(more)) and int(tr.step_dev) == 5 and min(more) < l12[0]
   # host inputs (pinned) go straight into the graph's static buffers
-  loss_h = tr.step(inp["image"].pin_memory(), inp["v2s"].pin_memory(), inp["offsets"].pin_memory(), gt.pin_memory())
+  host = [inp["image"].pin_memory(), inp["v2s"].pin_memory(), inp["offsets"].pin_memory(), gt.pin_memory()]
+  loss_h = tr.step(*host)
   assert t.isfinite(loss_h).all()
+  # prefetch path: H2D on the copy stream into staging buffers, consumed by an argument-less step()
+  tr.prefetch(*host)
+  l1 = tr.step().item()
+  tr.prefetch(*host)
+  l2 = tr.step().item()
+  assert np.isfinite([l1, l2]).all() and int(tr.step_dev) == 8
 
 
 def test_mean_iou_parity_and_inference_plug():
