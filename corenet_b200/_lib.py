@@ -37,6 +37,11 @@ class UnpackItem(C.Structure):
               ("CinP", i32), ("CoutP", i32), ("dst_is_transposed", i32)]
 
 
+class F64CopyItem(C.Structure):
+  """Mirror of crn_f64_copy_item."""
+  _fields_ = [("src", vp), ("dst", vp)]
+
+
 class GemmTcPackItem(C.Structure):
   """Mirror of crn_gemm_tc_pack_item."""
   _fields_ = [("src", vp), ("dst", vp), ("Cout", i32), ("Cin", i32), ("taps", i32), ("dgrad", i32)]
@@ -98,6 +103,7 @@ _SIGS = {
     "crn_conv_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_convt7_wgrad_line_supported": ([_P(ConvDesc)], i32),
     "crn_convt7_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
+    "crn_gather_f64_to_f32": ([vp, vp, i32, i64, vp], i32),
     "crn_adam_step_dev": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp], i32),
     "crn_adam_step": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp], i32),
 }

@@ -204,14 +204,18 @@ __global__ void brn_finalize_kernel(const double* __restrict__ acc, int64_t rows
                                     const float* __restrict__ weight, const float* __restrict__ bias,
                                     float* running_mean, float* running_var, int64_t* nbt, float eps,
                                     float momentum, int training, float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  // ONE block: every thread reads the step counter, the block synchronises, then thread 0 increments it
+  // (num_batches_tracked += 1, batch_renorm.py:58) -- no separate launch
+  const long long nt_now = training ? *nbt : 0;
+  __syncthreads();
+  if (training && threadIdx.x == 0) *nbt = nt_now + 1;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
   const float w = weight[c], bz = bias[c];
   const float rm = running_mean[c], rv = running_var[c];
   const float rstd = sqrtf(rv + eps);
   float a, b, mean, invstd, r, d;
   if (training) {
-    const long long nt = *nbt;
+    const long long nt = nt_now;
     float dmax = 5.0f * (float)(nt - 5000) / 20000.0f;
     dmax = fminf(fmaxf(dmax, 0.f), 5.f);
     float rmax = 2.0f * (float)(nt - 5000) / 35000.0f;
@@ -239,9 +243,8 @@ __global__ void brn_finalize_kernel(const double* __restrict__ acc, int64_t rows
   }
   coef[c] = a; coef[C + c] = b; coef[2 * C + c] = mean; coef[3 * C + c] = invstd;
   coef[4 * C + c] = r; coef[5 * C + c] = d;
+  }
 }
-// separate launch: every thread of finalize reads *nbt, so the increment must happen after that grid
-__global__ void brn_bump_counter(int64_t* nbt) { *nbt += 1; }
 
 // ---------------------------------------------------------------- apply
 template <int VEC>
@@ -529,10 +532,9 @@ extern "C" int crn_brn_finalize(const double* acc, int64_t rows, int32_t C, cons
   CRN_REQUIRE(weight && bias && running_mean && running_var && coef && C > 0, "crn_brn_finalize: bad args");
   CRN_REQUIRE(!training || (acc && num_batches_tracked && rows > 0), "crn_brn_finalize: bad training args");
   cudaStream_t st = crn_stream(stream);
-  brn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, rows, C, weight, bias, running_mean,
-                                                       running_var, num_batches_tracked, eps, momentum,
-                                                       training, coef);
-  if (training) { brn_bump_counter<<<1, 1, 0, st>>>(num_batches_tracked); crn_count_launches(1); }
+  const int threads = C >= 1024 ? 1024 : ((C + 31) / 32 * 32);
+  brn_finalize_kernel<<<1, threads, 0, st>>>(acc, rows, C, weight, bias, running_mean, running_var,
+                                             num_batches_tracked, eps, momentum, training, coef);
   CRN_LAUNCH_CHECK("brn_finalize");
   return CRN_OK;
 }

@@ -80,7 +80,10 @@ template <int NPAD, int ZT, bool ND, int KT, bool SCAT, bool GATH>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p) {
   constexpr int HLO = (KT == 5 || GATH) ? 2 : 1;           // most negative tap offset
   constexpr int KZG = (KT == 4) ? 2 : 1;                   // kz planes per flush group (chain <= 96 MMAs)
-  constexpr bool RACC = SCAT && NPAD == 16;                // epilogue keeps the running sums in registers
+  // epilogue keeps the running sums of all ZT planes in registers (16 columns: ZT * 16 floats per thread) -> no
+  // global read-modify-write per flush group, one store per item.  (With the per-group RMW the 4 epilogue warps,
+  // not the tensor pipe, bounded the N = 16 forward layer.)
+  constexpr bool RACC = NPAD == 16 && (SCAT || ZT <= 8);
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NSLOT = ZT + 1;                            // plane ring
   constexpr int NPLANE = ZT + KT - 1;                      // planes loaded per pass
@@ -226,7 +229,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
                 }
               }
               if (last) {
-                scatter_chunk(zz, 0, sum[zz], true);
+                if constexpr (SCAT) {
+                  scatter_chunk(zz, 0, sum[zz], true);
+                } else {
+                  const long long pos = (((long long)n * p.D + (z0 + zz)) * p.H + y) * p.W + x;
+                  float* dst = p.out + pos * p.out_cs + p.out_co;
+#pragma unroll
+                  for (int qd = 0; qd < 4; ++qd) {
+                    const int c = qd * 4;
+                    if (c < p.gN) {                        // gN is a multiple of 4
+                      float4 o = make_float4(sum[zz][c], sum[zz][c + 1], sum[zz][c + 2], sum[zz][c + 3]);
+                      if (p.bias) {
+                        o.x += __ldg(p.bias + c); o.y += __ldg(p.bias + c + 1);
+                        o.z += __ldg(p.bias + c + 2); o.w += __ldg(p.bias + c + 3);
+                      }
+                      *reinterpret_cast<float4*>(dst + c) = o;
+                    }
+                  }
+                }
 #pragma unroll
                 for (int e = 0; e < 16; ++e) sum[zz][e] = 0.f;
               }

@@ -275,85 +275,104 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
         ++yq;
       }
     };
-    Job ja, jb2;
-    float4 bufa[4], bufb[4];
-    bool have_a = next_job(ja);
-    if (have_a) issue(ja, bufa);
-    while (have_a && !dead) {
-      const bool have_b = next_job(jb2);
-      if (have_b) issue(jb2, bufb);
-      store(ja, bufa);
-      if (!have_b || dead) break;
-      have_a = next_job(ja);
-      if (have_a) issue(ja, bufa);
-      store(jb2, bufb);
+    constexpr int PD = 4;             // jobs in flight (load latency under HBM streaming ~ 2 steps)
+    Job jobs[PD];
+    float4 bufs[PD][4];
+    bool have[PD];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) {
+      have[k] = next_job(jobs[k]);
+      if (have[k]) issue(jobs[k], bufs[k]);
+    }
+    while (have[0] && !dead) {
+#pragma unroll
+      for (int k = 0; k < PD; ++k) {
+        if (!have[k] || dead) { have[0] = false; break; }
+        store(jobs[k], bufs[k]);
+        have[k] = next_job(jobs[k]);
+        if (have[k]) issue(jobs[k], bufs[k]);
+      }
     }
   } else {
     // ============================ MMA ISSUER (one elected thread)
+    // This single thread is the critical path (its instruction latency, not the tensor pipe, bounded the first
+    // version): no divisions, no per-step decode -- the step state is carried incrementally, descriptors are built
+    // once per step and advanced by adding the run offset to the 14-bit start-address field.
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, ACOLS, 1, 1);
       uint32_t q = 0;               // x line loads consumed so far (mirrors the producers' counter)
       uint32_t nflush = 0;
-      uint32_t started = 0;         // bit a: accumulator a has been written since the last flush
+      bool first = true;            // the next MMA of every accumulator overwrites (start of a flush interval)
       bool dead = false;
+      const Step s0 = decode_step<CB>(p, t0, t0);
+      int pass = s0.pass, y = s0.y;
+      int pass_end = p.pass_begin[pass + 1];
+      int mod_ctr = 0;                           // (t - t0 + 1) % flush_every, the epilogue's periodic flush rule
+      uint32_t xslot = 0, xphase = 0;            // ring position / phase of the next x line load to consume
+      uint32_t yslot = 0, yphase = 0;
       for (int t = t0; t < t1 && !dead; ++t) {
-        const Step s = decode_step<CB>(p, t, t0);
-        const int nload = s.fresh ? s.nk : 1;
+        const int nk = CB == 1 ? 5 : ((pass & 1) ? 2 : 3);
+        const bool fresh = (t == t0) || y == 0;
+        const int nload = fresh ? nk : 1;
         for (int j = 0; j < nload; ++j) {
-          const uint32_t l = q + j;
-          if (!tc::mbar_wait(&B->full_x[l % XS], (l / XS) & 1, ab)) { fail(); dead = true; break; }
+          if (!tc::mbar_wait(&B->full_x[xslot], xphase, ab)) { fail(); dead = true; break; }
+          if (++xslot == XS) { xslot = 0; xphase ^= 1; }
         }
         if (dead) break;
         q += nload;
-        const int i = t - t0;
-        const int yslot = i % YSLOTS;
-        if (!tc::mbar_wait(&B->full_y[yslot], (uint32_t)(i / YSLOTS) & 1, ab)) { fail(); dead = true; break; }
-        if (started == 0 && nflush > 0) {       // accumulators were handed to the epilogue: wait until it has read them
+        if (!tc::mbar_wait(&B->full_y[yslot], yphase, ab)) { fail(); dead = true; break; }
+        if (first && nflush > 0) {              // accumulators were handed to the epilogue: wait until it has read them
           if (!tc::mbar_wait(&B->acc_empty, (nflush - 1) & 1, ab)) { fail(); dead = true; break; }
         }
         tc::fence_after_sync();
         const uint32_t ybase = yring_u32 + yslot * YL;
-        const uint32_t w0 = q - s.nk;           // load index of window line 0
-#pragma unroll 1
+        // window line 0 sits nk slots behind the ring head
+        uint32_t w0slot = xslot + XS - nk; if (w0slot >= XS) w0slot -= XS;
+        uint64_t da[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          uint32_t sl = w0slot + (CB == 1 ? 2 * a : a); if (sl >= XS) sl -= XS;
+          // rows outside the image are staged as zero lines (no skipping: every accumulator of the pass is
+          // (re)initialised by the first run after a flush, which the epilogue relies on)
+          da[a] = tc::make_desc_mn32(xring_u32 + sl * XL, XH, 512);
+        }
+        const uint64_t dbh = tc::make_desc_mn32(ybase, 128, 512);
+        const uint64_t dbl = tc::make_desc_mn32(ybase + YROWS * 128, 128, 512);
+#pragma unroll
         for (int r = 0; r < RUNS; ++r) {
-          if (CB == 1) {
+          const uint32_t acc = (first && r == 0) ? 0u : 1u;
+          const uint64_t ro = (uint64_t)(r * 64);            // 1024 bytes >> 4
 #pragma unroll
-            for (int a = 0; a < NACC; ++a) {
-              const int j = 2 * a;                                         // window lines j, j+1 (ky = j, j+1)
-              // rows outside the image are staged as zero lines (no skipping: every accumulator of the pass is
-              // (re)initialised by the first run after a flush, which the epilogue relies on)
-              const uint32_t slot = (w0 + j) % XS;
-              const uint64_t da = tc::make_desc_mn32(xring_u32 + slot * XL + r * 1024, XH, 512);
-              const uint64_t db = tc::make_desc_mn32(ybase + r * 1024, 128, 512);
-              tc::mma_tf32(tmem + a * ACOLS, da, db, idesc, (started >> a) & 1u);
-              started |= 1u << a;
-            }
-          } else {
-#pragma unroll
-            for (int a = 0; a < NACC; ++a) {
-              if (a >= s.nk) continue;
-              const uint32_t slot = (w0 + a) % XS;
-              const uint64_t da = tc::make_desc_mn32(xring_u32 + slot * XL + r * 1024, XH, 512);
-              const uint64_t dbh = tc::make_desc_mn32(ybase + r * 1024, 128, 512);
-              const uint64_t dbl = tc::make_desc_mn32(ybase + YROWS * 128 + r * 1024, 128, 512);
-              tc::mma_tf32(tmem + a * ACOLS, da, dbh, idesc, (started >> a) & 1u);
-              tc::mma_tf32(tmem + a * ACOLS, da, dbl, idesc, 1u);
-              started |= 1u << a;
+          for (int a = 0; a < NACC; ++a) {
+            if (CB == 1) {
+              tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbh + ro, idesc, acc);
+            } else if (a < nk) {
+              tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbh + ro, idesc, acc);
+              tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbl + ro, idesc, 1u);
             }
           }
         }
+        first = false;
         tc::commit(&B->empty_y[yslot]);
+        if (++yslot == YSLOTS) { yslot = 0; yphase ^= 1; }
         // release the x lines the next step drops from the window
+        const bool next_fresh = (y + 1 == p.H);
         if (t + 1 < t1) {
-          const Step sn = decode_step<CB>(p, t + 1, t0);
-          const int ndrop = sn.fresh ? s.nk : 1;
-          for (int j = 0; j < ndrop; ++j) tc::commit(&B->empty_x[(w0 + j) % XS]);
+          const int ndrop = next_fresh ? nk : 1;
+          uint32_t sl = w0slot;
+          for (int j = 0; j < ndrop; ++j) {
+            tc::commit(&B->empty_x[sl]);
+            if (++sl == XS) sl = 0;
+          }
         }
-        if (flush_after(t, s)) {
+        if (++mod_ctr == p.flush_every) mod_ctr = 0;
+        if (t == t1 - 1 || t + 1 >= pass_end || mod_ctr == 0) {
           tc::commit(&B->acc_full);
           ++nflush;
-          started = 0;
+          first = true;
         }
+        if (++y == p.H) y = 0;
+        if (t + 1 >= pass_end && t + 1 < t1) { ++pass; pass_end = p.pass_begin[pass + 1]; }
       }
     }
   }
@@ -637,67 +656,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tline_kernel(const WLParams
         if (cz == 1) ++yq;
       }
     };
-    Job ja, jb2;
-    float4 bufa[4], bufb[4];
-    bool have_a = next_job(ja);
-    if (have_a) issue(ja, bufa);
-    while (have_a && !dead) {
-      const bool have_b = next_job(jb2);
-      if (have_b) issue(jb2, bufb);
-      store(ja, bufa);
-      if (!have_b || dead) break;
-      have_a = next_job(ja);
-      if (have_a) issue(ja, bufa);
-      store(jb2, bufb);
+    constexpr int PD = 4;             // jobs in flight (load latency under HBM streaming ~ 2 steps)
+    Job jobs[PD];
+    float4 bufs[PD][4];
+    bool have[PD];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) {
+      have[k] = next_job(jobs[k]);
+      if (have[k]) issue(jobs[k], bufs[k]);
+    }
+    while (have[0] && !dead) {
+#pragma unroll
+      for (int k = 0; k < PD; ++k) {
+        if (!have[k] || dead) { have[0] = false; break; }
+        store(jobs[k], bufs[k]);
+        have[k] = next_job(jobs[k]);
+        if (have[k]) issue(jobs[k], bufs[k]);
+      }
     }
   } else {
-    // ============================ MMA ISSUER
+    // ============================ MMA ISSUER (incremental step state, see wgrad_line_kernel)
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, 128, 1, 1);
-      uint32_t q = 0, nflush = 0;
+      uint32_t nflush = 0;
       bool first = true;            // next MMA of every accumulator overwrites (start of a flush interval)
       bool dead = false;
+      const TStep s0 = decode_tstep(p, t0, t0);
+      int pass = s0.pass, y = s0.my, mod_ctr = 0;
+      int pass_end = p.pass_begin[pass + 1];
+      uint32_t xslot = 0, xphase = 0, yslot = 0, yphase = 0;
       for (int t = t0; t < t1 && !dead; ++t) {
-        const TStep s = decode_tstep(p, t, t0);
-        const int nload = s.fresh ? 2 : 1;
+        const bool fresh = (t == t0) || y == 0;
+        const int nload = fresh ? 2 : 1;
         for (int j = 0; j < nload; ++j) {
-          const uint32_t l = q + j;
-          if (!tc::mbar_wait(&B->full_x[l % XS], (l / XS) & 1, ab)) { fail(); dead = true; break; }
+          if (!tc::mbar_wait(&B->full_x[xslot], xphase, ab)) { fail(); dead = true; break; }
+          if (++xslot == XS) { xslot = 0; xphase ^= 1; }
         }
         if (dead) break;
-        q += nload;
-        const int i = t - t0;
-        const int yslot = i % YS;
-        if (!tc::mbar_wait(&B->full_y[yslot], (uint32_t)(i / YS) & 1, ab)) { fail(); dead = true; break; }
+        if (!tc::mbar_wait(&B->full_y[yslot], yphase, ab)) { fail(); dead = true; break; }
         if (first && nflush > 0) {
           if (!tc::mbar_wait(&B->acc_empty, (nflush - 1) & 1, ab)) { fail(); dead = true; break; }
         }
         tc::fence_after_sync();
         const uint32_t ybase = yring_u32 + yslot * YL;
-        const uint32_t slot = (q - 2) % XS;                 // window line 0 (line 1 follows; mirror after the last slot)
-#pragma unroll 1
+        uint32_t w0slot = xslot + XS - 2; if (w0slot >= XS) w0slot -= XS;   // window line 0 (line 1 follows; mirror)
+        const uint64_t da0 = tc::make_desc_mn32(xring_u32 + w0slot * XL, XH, 512);
+        const uint64_t dbh0 = tc::make_desc_mn32(ybase, YB, 512);
+        const uint64_t dbl0 = tc::make_desc_mn32(ybase + 4 * YB, YB, 512);
+#pragma unroll
         for (int r = 0; r < RUNS; ++r) {
-          const uint64_t da = tc::make_desc_mn32(xring_u32 + slot * XL + r * 1024, XH, 512);
+          const uint32_t acc = (first && r == 0) ? 0u : 1u;
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
-            const uint64_t dbh = tc::make_desc_mn32(ybase + (r * 8 + a) * 128, YB, 512);
-            const uint64_t dbl = tc::make_desc_mn32(ybase + 4 * YB + (r * 8 + a) * 128, YB, 512);
-            tc::mma_tf32(tmem + a * TCOLS, da, dbh, idesc, (first && r == 0) ? 0u : 1u);
-            tc::mma_tf32(tmem + a * TCOLS, da, dbl, idesc, 1u);
+            const uint64_t bo = (uint64_t)((r * 8 + a) * 8);    // (r*8 + a) rows of 128 bytes, >> 4
+            tc::mma_tf32(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbh0 + bo, idesc, acc);
+            tc::mma_tf32(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbl0 + bo, idesc, 1u);
           }
         }
         first = false;
         tc::commit(&B->empty_y[yslot]);
+        if (++yslot == YS) { yslot = 0; yphase ^= 1; }
+        const bool next_fresh = (y + 1 == p.H);
         if (t + 1 < t1) {
-          const TStep sn = decode_tstep(p, t + 1, t0);
-          const int ndrop = sn.fresh ? 2 : 1;
-          for (int j = 0; j < ndrop; ++j) tc::commit(&B->empty_x[(q - 2 + j) % XS]);
+          const int ndrop = next_fresh ? 2 : 1;
+          uint32_t sl = w0slot;
+          for (int j = 0; j < ndrop; ++j) {
+            tc::commit(&B->empty_x[sl]);
+            if (++sl == XS) sl = 0;
+          }
         }
-        if (flush_after(t, s)) {
+        if (++mod_ctr == p.flush_every) mod_ctr = 0;
+        if (t == t1 - 1 || t + 1 >= pass_end || mod_ctr == 0) {
           tc::commit(&B->acc_full);
           ++nflush;
           first = true;
         }
+        if (++y == p.H) y = 0;
+        if (t + 1 >= pass_end && t + 1 < t1) { ++pass; pass_end = p.pass_begin[pass + 1]; }
       }
     }
   }
@@ -736,11 +771,315 @@ int launch_wtl(WLParams p, cudaStream_t st) {
 }
 }  // namespace
 
+// =============================================================================================================
+// Same operator for the LAST decoder layer (stage_6.t1: Cin <= 16, Cout <= 4 stored with channel stride 4, i.e. the
+// 2-class logits gradient; model/reconstruction_decoder.py:95).  Everything is narrower, so more taps are stacked:
+//   * x voxel row = [hi16 | lo16] (one 128-byte row), M = 128 = FOUR consecutive x lines y_i = my-1 .. my+2, i.e.
+//     all four jy shifts in one MMA (ring of 8 lines + 3 mirror slots keeps any 4 consecutive lines contiguous);
+//   * dyc voxel row = 8 classes x 4 co = 32 floats = one 128-byte row gathered from the 4 fine lines (cz, cy)
+//     (32-byte chunk b = cz*2 + cy holds the fine voxel pair cx = 0, 1), hi line and lo line; N = 128 = the 4 jx
+//     shifts stacked through LBO = 128 B;
+//   * ONE accumulator (128 columns) per pass jz: 2 MMAs per 8 coarse voxels cover 16 shifts x 8 classes.
+namespace {
+
+template <int W>
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_t2line_kernel(const WLParams p) {
+  constexpr int RUNS = (W + 8) / 8;
+  constexpr int RS = RUNS * 8;
+  constexpr int XL = RS * 128;                      // one x line ([hi16|lo16] rows) = LBO of the M operand
+  constexpr int YROWS = RS + 8;
+  constexpr int YH = YROWS * 128;                   // hi (or lo) dyc line
+  constexpr int YL = 2 * YH;
+  constexpr int XS = 8, XALL = 11, YS = 3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* xring = smem;
+  uint8_t* yring = smem + XALL * XL;
+  WLBarriers* B = reinterpret_cast<WLBarriers*>(yring + YS * YL);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = p.pass_begin[p.npass];
+  const int t0 = (int)((long long)T * blockIdx.x / gridDim.x), t1 = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
+
+  if (tid == 0) {
+    for (int i = 0; i < MAXX; ++i) { tc::mbar_init(&B->full_x[i], 128); tc::mbar_init(&B->empty_x[i], 1); }
+    for (int i = 0; i < YSLOTS; ++i) { tc::mbar_init(&B->full_y[i], 128); tc::mbar_init(&B->empty_y[i], 1); }
+    tc::mbar_init(&B->acc_full, 1); tc::mbar_init(&B->acc_empty, 128);
+    B->abort_flag = 0;
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&B->tmem_base, 128);
+  for (int i = tid; i < (XALL * XL + YS * YL) / 16; i += NTHREADS)
+    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = B->tmem_base;
+  const uint32_t xring_u32 = tc::smem_u32(xring), yring_u32 = tc::smem_u32(yring);
+  auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
+  volatile int* ab = &B->abort_flag;
+  // pass = jz (npass = 4): decode_tstep's (jz, g) split is not used here
+  auto decode = [&](int t) -> TStep {
+    TStep s;
+    int ps = 0;
+    while (ps + 1 < p.npass && t >= p.pass_begin[ps + 1]) ++ps;
+    s.pass = ps; s.jz = ps - 2; s.g = 0;
+    const int r = t - p.pass_begin[ps];
+    s.my = r % p.H;
+    const int pl = r / p.H;
+    const int zlo = s.jz > 0 ? s.jz : 0, zcnt = p.D - (s.jz < 0 ? -s.jz : s.jz);
+    s.n = pl / zcnt; s.mz = zlo + pl % zcnt;
+    s.fresh = (t == t0) || s.my == 0;
+    return s;
+  };
+  auto flush_after = [&](int t, const TStep& s) -> bool {
+    if (t == t1 - 1) return true;
+    if (t + 1 >= p.pass_begin[s.pass + 1]) return true;
+    return (t - t0 + 1) % p.flush_every == 0;
+  };
+
+  if (warp < 4) {
+    // ============================ EPILOGUE
+    uint32_t nflush = 0;
+    bool dead = false;
+    const int jy = 1 - warp;                                   // M block = x line y_i = my - 1 + warp
+    const int ci = lane & 15;                                  // lanes 0-15: hi, 16-31: lo (both add)
+    for (int t = t0; t < t1 && !dead; ++t) {
+      const TStep s = decode(t);
+      if (!flush_after(t, s)) continue;
+      if (!tc::mbar_wait(&B->acc_full, nflush & 1, ab)) { fail(); dead = true; break; }
+      tc::fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        if (ci >= p.Cin) continue;
+        const int jx = (c0 >> 5) - 2;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {                        // 4-column group = (class b, cx): the 4 co
+          const int col = c0 + gq * 4;
+          const int b = (col >> 3) & 3, cx = (col >> 2) & 1;
+          const int kz = 2 * s.jz + (b >> 1) + 3, ky = 2 * jy + (b & 1) + 3, kx = 2 * jx + cx + 3;
+          if ((unsigned)kz > 6u || (unsigned)ky > 6u || (unsigned)kx > 6u) continue;
+          float* dst = p.dw + ((long long)((kz * 7 + ky) * 7 + kx) * p.CinP + ci) * p.CoutP;
+          atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[gq * 4], v[gq * 4 + 1], v[gq * 4 + 2], v[gq * 4 + 3]));
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&B->acc_empty);
+      ++nflush;
+    }
+  } else if (warp < 8) {
+    // ============================ PRODUCERS (jobs: x line only | x line + dyc line of the step)
+    // The MMA work per step is short here (18 MMAs), so a step's loads are ONE job (one load latency per step, issued
+    // a full step ahead); only the 3 extra x lines of a fresh window are separate jobs.
+    const int pt = tid - 128;
+    constexpr int XIT = W * 4 / 128;                  // x: W voxels x 4 float4
+    constexpr int FW = 2 * W;
+    constexpr int YIT = 4 * FW / 128;                 // dy: 4 fine lines x FW voxels x 1 float4
+    constexpr int NB = XIT + YIT;
+    static_assert(XIT >= 1 && YIT >= 1 && NB <= 6, "line does not fit the register buffer");
+    struct Job { int with_y, n, z, y, ok, yz, yy; };
+    int jt = t0, jj = 0;
+    auto next_job = [&](Job& jb) -> bool {
+      if (jt >= t1) return false;
+      const TStep s = decode(jt);
+      const int nload = s.fresh ? 4 : 1;
+      const int j = s.fresh ? jj : 3;
+      jb.n = s.n; jb.z = s.mz - s.jz; jb.y = s.my - 1 + j;
+      jb.ok = (unsigned)jb.y < (unsigned)p.H;
+      jb.yz = s.mz; jb.yy = s.my;
+      if (jj + 1 < nload) { jb.with_y = 0; ++jj; }
+      else { jb.with_y = 1; jj = 0; ++jt; }
+      return true;
+    };
+    auto issue = [&](const Job& jb, float4 (&buf)[NB]) {
+      const float* src = p.x + ((((long long)jb.n * p.D + jb.z) * p.H + jb.y) * p.W) * p.x_cs + p.x_co;
+#pragma unroll
+      for (int u = 0; u < XIT; ++u) {
+        const int it = pt + u * 128, v = it >> 2, c4 = it & 3;
+        buf[u] = (jb.ok && c4 * 4 < p.Cin) ? __ldg(reinterpret_cast<const float4*>(src + (long long)v * p.x_cs + c4 * 4))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (jb.with_y) {
+#pragma unroll
+        for (int u = 0; u < YIT; ++u) {
+          const int it = pt + u * 128, f = it % FW, b = it / FW;
+          const float* sy = p.dy + ((((long long)jb.n * (2 * p.D) + 2 * jb.yz + (b >> 1)) * (2 * p.H) + 2 * jb.yy + (b & 1)) *
+                                        (2 * p.W) + f) * p.y_cs + p.y_co;
+          buf[XIT + u] = __ldg(reinterpret_cast<const float4*>(sy));
+        }
+      }
+    };
+    uint32_t q = 0, yq = 0;
+    bool dead = false;
+    auto store = [&](const Job& jb, const float4 (&buf)[NB]) {
+      {
+        const int slot = (int)(q % XS);
+        const uint32_t use = q / XS;
+        if (use > 0 && !tc::mbar_wait(&B->empty_x[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+        uint8_t* base = xring + slot * XL;
+#pragma unroll
+        for (int u = 0; u < XIT; ++u) {
+          const int it = pt + u * 128, v = it >> 2, c4 = it & 3;
+          float4 hi, lo;
+          tc::split_tf32(buf[u].x, hi.x, lo.x); tc::split_tf32(buf[u].y, hi.y, lo.y);
+          tc::split_tf32(buf[u].z, hi.z, lo.z); tc::split_tf32(buf[u].w, hi.w, lo.w);
+          const int row = v + 4;
+          const uint32_t oh = (uint32_t)row * 128 + (uint32_t)((((c4 >> 1) ^ (row & 3)) << 5) + ((c4 & 1) << 4));
+          const uint32_t ol = (uint32_t)row * 128 + (uint32_t)((((2 + (c4 >> 1)) ^ (row & 3)) << 5) + ((c4 & 1) << 4));
+          *reinterpret_cast<float4*>(base + oh) = hi;
+          *reinterpret_cast<float4*>(base + ol) = lo;
+          if (slot < 3) {                                      // mirrors of slots 0..2 behind the last slot
+            *reinterpret_cast<float4*>(base + XS * XL + oh) = hi;
+            *reinterpret_cast<float4*>(base + XS * XL + ol) = lo;
+          }
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&B->full_x[slot]);
+        ++q;
+      }
+      if (jb.with_y) {
+        const int slot = (int)(yq % YS);
+        const uint32_t use = yq / YS;
+        if (use > 0 && !tc::mbar_wait(&B->empty_y[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+        uint8_t* base = yring + slot * YL;
+#pragma unroll
+        for (int u = 0; u < YIT; ++u) {
+          const int it = pt + u * 128, f = it % FW, b = it / FW;
+          float4 hi, lo;
+          tc::split_tf32(buf[XIT + u].x, hi.x, lo.x); tc::split_tf32(buf[XIT + u].y, hi.y, lo.y);
+          tc::split_tf32(buf[XIT + u].z, hi.z, lo.z); tc::split_tf32(buf[XIT + u].w, hi.w, lo.w);
+          const int row = (f >> 1) + 6, cx = f & 1;
+          const uint32_t off = (uint32_t)row * 128 + (uint32_t)(((b ^ (row & 3)) << 5) + (cx << 4));
+          *reinterpret_cast<float4*>(base + off) = hi;
+          *reinterpret_cast<float4*>(base + YH + off) = lo;
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&B->full_y[slot]);
+        ++yq;
+      }
+    };
+    // PD jobs in flight: the loads of a job are issued PD - 1 jobs (~ steps) before they are needed, which covers the
+    // DRAM latency under load (the lines stream from HBM: 4 passes over 200 MB do not stay in L2)
+    constexpr int PD = 4;
+    Job jobs[PD];
+    float4 bufs[PD][NB];
+    bool have[PD];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) {
+      have[k] = next_job(jobs[k]);
+      if (have[k]) issue(jobs[k], bufs[k]);
+    }
+    while (have[0] && !dead) {
+#pragma unroll
+      for (int k = 0; k < PD; ++k) {
+        if (!have[k] || dead) { have[0] = false; break; }
+        store(jobs[k], bufs[k]);
+        have[k] = next_job(jobs[k]);
+        if (have[k]) issue(jobs[k], bufs[k]);
+      }
+    }
+  } else {
+    // ============================ MMA ISSUER (incremental step state, see wgrad_line_kernel)
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(128, 128, 1, 1);
+      uint32_t nflush = 0;
+      bool first = true;
+      bool dead = false;
+      const TStep s0 = decode(t0);
+      int pass = s0.pass, y = s0.my, mod_ctr = 0;
+      int pass_end = p.pass_begin[pass + 1];
+      uint32_t xslot = 0, xphase = 0, yslot = 0, yphase = 0;
+      for (int t = t0; t < t1 && !dead; ++t) {
+        const bool fresh = (t == t0) || y == 0;
+        const int nload = fresh ? 4 : 1;
+        for (int j = 0; j < nload; ++j) {
+          if (!tc::mbar_wait(&B->full_x[xslot], xphase, ab)) { fail(); dead = true; break; }
+          if (++xslot == XS) { xslot = 0; xphase ^= 1; }
+        }
+        if (dead) break;
+        if (!tc::mbar_wait(&B->full_y[yslot], yphase, ab)) { fail(); dead = true; break; }
+        if (first && nflush > 0) {
+          if (!tc::mbar_wait(&B->acc_empty, (nflush - 1) & 1, ab)) { fail(); dead = true; break; }
+        }
+        tc::fence_after_sync();
+        const uint32_t ybase = yring_u32 + yslot * YL;
+        uint32_t w0slot = xslot + XS - 4; if (w0slot >= XS) w0slot -= XS;   // window line 0; 1..3 follow (mirrors)
+        const uint64_t da0 = tc::make_desc_mn32(xring_u32 + w0slot * XL, XL, 512);
+        const uint64_t dbh0 = tc::make_desc_mn32(ybase, 128, 512);
+        const uint64_t dbl0 = tc::make_desc_mn32(ybase + YH, 128, 512);
+#pragma unroll
+        for (int r = 0; r < RUNS; ++r) {
+          tc::mma_tf32(tmem, da0 + (uint64_t)(r * 64), dbh0 + (uint64_t)(r * 64), idesc, (first && r == 0) ? 0u : 1u);
+          tc::mma_tf32(tmem, da0 + (uint64_t)(r * 64), dbl0 + (uint64_t)(r * 64), idesc, 1u);
+        }
+        first = false;
+        tc::commit(&B->empty_y[yslot]);
+        if (++yslot == YS) { yslot = 0; yphase ^= 1; }
+        const bool next_fresh = (y + 1 == p.H);
+        if (t + 1 < t1) {
+          const int ndrop = next_fresh ? 4 : 1;
+          uint32_t sl = w0slot;
+          for (int j = 0; j < ndrop; ++j) {
+            tc::commit(&B->empty_x[sl]);
+            if (++sl == XS) sl = 0;
+          }
+        }
+        if (++mod_ctr == p.flush_every) mod_ctr = 0;
+        if (t == t1 - 1 || t + 1 >= pass_end || mod_ctr == 0) {
+          tc::commit(&B->acc_full);
+          ++nflush;
+          first = true;
+        }
+        if (++y == p.H) y = 0;
+        if (t + 1 >= pass_end && t + 1 < t1) { ++pass; pass_end = p.pass_begin[pass + 1]; }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 128);
+}
+
+template <int W>
+int launch_wt2l(WLParams p, cudaStream_t st) {
+  constexpr int RS = ((W + 8) / 8) * 8;
+  constexpr int XL = RS * 128, YL = 2 * (RS + 8) * 128;
+  const size_t smem = (size_t)11 * XL + (size_t)3 * YL + sizeof(WLBarriers) + 1024 + 64;
+  auto kern = wgrad_t2line_kernel<W>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      crn_set_error("conv_wgrad_t2line: cannot set %zu bytes of dynamic shared memory", smem);
+      return CRN_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  p.npass = 4;
+  int tot = 0;
+  for (int ps = 0; ps < 4; ++ps) {
+    const int jz = ps - 2;
+    p.pass_begin[ps] = tot;
+    tot += p.N * (p.D - (jz < 0 ? -jz : jz)) * p.H;
+  }
+  p.pass_begin[4] = tot;
+  p.flush_every = 64;
+  const int grid = tot < kNumSMs ? tot : kNumSMs;
+  kern<<<grid, NTHREADS, smem, st>>>(p);
+  CRN_LAUNCH_CHECK("conv_wgrad_t2line");
+  return CRN_OK;
+}
+}  // namespace
+
 extern "C" int crn_convt7_wgrad_line_supported(const crn_conv_desc* d) {
   if (!d || !d->transposed || d->kD != 7 || d->kH != 7 || d->kW != 7 || d->stride != 2 || d->pad != 3) return 0;
   if (d->oD != 2 * d->iD || d->oH != 2 * d->iH || d->oW != 2 * d->iW || d->y_planar) return 0;
   if (d->Cin % 4 || d->x_cs % 4 || d->x_co % 4 || d->y_cs % 4 || d->y_co % 4 || d->CoutP % 4) return 0;
-  if (d->iD < 3 || d->Cin > 32 || d->Cout != 16) return 0;
+  if (d->iD < 3) return 0;
+  if (d->Cin <= 16 && d->Cout <= 4 && d->y_cs == 4 && d->y_co == 0 && d->CoutP == 4 && (d->iW == 64 || d->iW == 32)) return 2;
+  if (d->Cin > 32 || d->Cout != 16) return 0;
   return d->iW == 32 || d->iW == 16;
 }
 
@@ -756,5 +1095,6 @@ extern "C" int crn_convt7_wgrad_line(const crn_conv_desc* d, const float* x, con
   p.Cin = d->Cin; p.Cout = d->Cout;
   p.x_cs = d->x_cs; p.x_co = d->x_co; p.y_cs = d->y_cs; p.y_co = d->y_co; p.CinP = d->CinP; p.CoutP = d->CoutP;
   cudaStream_t st = crn_stream(stream);
+  if (crn_convt7_wgrad_line_supported(d) == 2) return d->iW == 64 ? launch_wt2l<64>(p, st) : launch_wt2l<32>(p, st);
   return d->iW == 32 ? launch_wtl<32>(p, st) : launch_wtl<16>(p, st);
 }

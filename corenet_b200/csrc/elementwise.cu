@@ -256,3 +256,28 @@ extern "C" int crn_adam_step_dev(float* p, const float* g, float* m, float* v, i
   crn_count_launches(1);
   return CRN_OK;
 }
+
+// Batched fp64 -> fp32 copies (bias gradients = per-channel column sums kept in fp64 accumulator slots): one launch
+// for all of a backward pass instead of one tiny copy per layer.
+namespace {
+__global__ void gather_f64_kernel(const crn_f64_copy_item* __restrict__ items, const int64_t* __restrict__ offsets,
+                                  int n, int64_t total) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (offsets[mid] <= e) lo = mid; else hi = mid;
+    }
+    const int64_t i = e - offsets[lo];
+    items[lo].dst[i] = (float)items[lo].src[i];
+  }
+}
+}  // namespace
+
+extern "C" int crn_gather_f64_to_f32(const crn_f64_copy_item* items, const int64_t* offsets, int32_t n,
+                                     int64_t total, void* stream) {
+  CRN_REQUIRE(items && offsets && n > 0 && total > 0, "crn_gather_f64_to_f32: bad args");
+  gather_f64_kernel<<<grid_for(total), NT, 0, crn_stream(stream)>>>(items, offsets, n, total);
+  CRN_LAUNCH_CHECK("gather_f64");
+  return CRN_OK;
+}

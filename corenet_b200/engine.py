@@ -791,10 +791,12 @@ class Plan:
     self.arena_bwd.zero_()
     eng.dw.zero_()
 
+    # bias gradients = fp64 column sums in accumulator slots: collected here, moved by ONE batched launch at the end
+    bias_jobs = []
+
     def bias_from(slot: Slot, name, lo=0, n=None):
-      v = slot.view()
       n = n if n is not None else grads[name].numel()
-      grads[name].copy_(v[lo:lo + n])
+      bias_jobs.append((slot.data_ptr() + 8 * lo, grads[name].data_ptr(), n))
 
     # Weight gradients only feed the final un-pack, so they run on a side stream concurrently with the dgrad /
     # BatchRenorm chain (fork: event after dy is final; join: before crn_unpack_wgrads).  The small encoder launches
@@ -914,6 +916,22 @@ class Plan:
     stem = L["stem"]
     bias_from(dxs, stem.name + ".bias")
     wgrad(stem, self.d_stem, self.img4.p, self.s1.gp)
+    # ---- bias gradients (one launch; item list cached per pointer set)
+    sig = tuple(bias_jobs)
+    if getattr(self, "_bias_sig", None) != sig:
+      items = (_lib.F64CopyItem * len(bias_jobs))()
+      offs = (C.c_int64 * (len(bias_jobs) + 1))()
+      tot = 0
+      for i, (src, dst, n) in enumerate(bias_jobs):
+        items[i].src, items[i].dst = src, dst
+        offs[i] = tot
+        tot += n
+      offs[len(bias_jobs)] = tot
+      self._bias_items = eng._to_dev(items, self.dev)
+      self._bias_offs = eng._to_dev(offs, self.dev)
+      self._bias_tot, self._bias_sig = tot, sig
+    _call("crn_gather_f64_to_f32", self._bias_items.data_ptr(), self._bias_offs.data_ptr(), len(bias_jobs),
+          self._bias_tot, st)
     # ---- weight gradients back to the parameters' layout (one launch)
     if side is not None:
       main.wait_stream(side)

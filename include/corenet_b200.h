@@ -334,6 +334,15 @@ int crn_convt7_wgrad_line(const crn_conv_desc* d, const float* x, const float* d
 int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream);
 
+/* Batched fp64 -> fp32 copies: items / offsets are DEVICE arrays (offsets = int64[n+1] prefix sums of the item
+ * lengths, total = offsets[n]); used to move all bias gradients (fp64 column sums) of a backward pass at once. */
+typedef struct {
+  const double* src;
+  float* dst;
+} crn_f64_copy_item;
+int crn_gather_f64_to_f32(const crn_f64_copy_item* items, const int64_t* offsets, int32_t n, int64_t total,
+                          void* stream);
+
 /* Same with the step counter on the device (*step_dev is incremented by the call, then used for the bias
  * corrections): the form a captured CUDA graph can replay. */
 int crn_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

@@ -293,13 +293,14 @@ def test_conv5_wgrad_line_tcgen05(n, cin, cout, dhw):
   assert rel_err(dw, ref) < 5e-5
 
 
-@pytest.mark.parametrize("n,cin,dhw,ycs", [(1, 32, (4, 5, 32), 16), (2, 32, (3, 37, 32), 28), (1, 20, (5, 4, 16), 16)])
-def test_convt7_wgrad_line_tcgen05(n, cin, dhw, ycs):
-  """ConvTranspose3d k=7 s=2 (Cout = 16) weight gradient through the class-channel tap-stacked tcgen05 kernel against
-  the fp64 oracle; dy may sit inside a wider concat buffer (channel stride ycs)."""
+@pytest.mark.parametrize("n,cin,cout,dhw,ycs", [(1, 32, 16, (4, 5, 32), 16), (2, 32, 16, (3, 37, 32), 28),
+                                                  (1, 20, 16, (5, 4, 16), 16), (1, 16, 2, (4, 5, 64), 4),
+                                                  (2, 12, 3, (3, 6, 32), 4)])
+def test_convt7_wgrad_line_tcgen05(n, cin, cout, dhw, ycs):
+  """ConvTranspose3d k=7 s=2 weight gradient through the class-channel tap-stacked tcgen05 kernels (Cout = 16, and the
+  narrow logits layer with Cout <= 4) against the fp64 oracle; dy may sit inside a wider concat buffer (stride ycs)."""
   import ctypes as C
   from corenet_b200 import _lib, ops
-  cout = 16
   g = t.Generator().manual_seed(cin + dhw[1])
   x = t.randn((n, cin) + dhw, generator=g)
   wt = (t.randn(cin, cout, 7, 7, 7, generator=g) * 0.05).double().requires_grad_(True)
@@ -308,19 +309,23 @@ def test_convt7_wgrad_line_tcgen05(n, cin, dhw, ycs):
   y.backward(gy.double())
   fine = tuple(y.shape[2:])
   xr = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).contiguous().to(dev())
-  gr = t.randn(gy.numel() // cout, ycs, generator=g)                      # other channels of the concat buffer: noise
+  if cout == 16:
+    gr = t.randn(gy.numel() // cout, ycs, generator=g)                    # other channels of the concat buffer: noise
+  else:
+    gr = t.zeros(gy.numel() // cout, ycs)                                 # padded logits-gradient rows
   gr[:, :cout] = gy.permute(0, 2, 3, 4, 1).reshape(-1, cout)
   gr = gr.to(dev())
-  dw = t.zeros(343, cin, cout, device=dev())
+  coutp = (cout + 3) // 4 * 4
+  dw = t.zeros(343, cin, coutp, device=dev())
   desc = ops.make_desc(n, cin, cout, dhw, fine, (7, 7, 7), 2, 3, True, cin, ycs)
-  assert _lib.lib().crn_convt7_wgrad_line_supported(C.byref(desc)) == 1
+  assert _lib.lib().crn_convt7_wgrad_line_supported(C.byref(desc)) == (1 if cout == 16 else 2)
   status = t.zeros(1, dtype=t.int32, device=dev())
   _lib.call("crn_convt7_wgrad_line", C.byref(desc), xr.data_ptr(), gr.data_ptr(), dw.data_ptr(), status.data_ptr(),
             _lib.stream_ptr())
   t.cuda.synchronize()
   assert int(status) == 0
   ref = wt.grad.reshape(cin, cout, 343).permute(2, 0, 1)
-  assert rel_err(dw, ref) < 5e-5
+  assert rel_err(dw[:, :, :cout], ref) < 5e-5
 
 
 @pytest.mark.parametrize("n,cin,cout,dhw,planar", [(1, 8, 2, (8, 16, 8), True), (2, 16, 2, (8, 32, 16), True),
