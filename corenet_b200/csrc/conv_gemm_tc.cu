@@ -46,7 +46,13 @@ struct GTParams {
   int nstages;                      // taps * kchunks
   int ksplit, accumulate;
   int dbg;                          // debug bits: 1 timeline stamps, 2 skip epilogue stores, 4 skip gathers, 8 skip MMAs
-  long long rows;                   // output rows
+  // transposed-gather mode (tmode = 1): out[o] = sum_k in[(o + pad - k) / ts] W[k] over the taps with an exact
+  // quotient (ConvTranspose forward = dgrad of a strided convolution).  Output positions are ordered by parity
+  // class c = o mod ts so that a 128-row tile has ONE tap set: (oD, oH, oW) hold the per-class extents O / ts,
+  // (fD, fH, fW) the real output extents, tiles_per_class the row tiles of one class; the packed weights hold all
+  // taps in flipped order (crn_gemm_tc_pack with dgrad != 0).
+  int tmode, ts, tsD, tsH, tsW, fD, fH, fW, tiles_per_class;
+  long long rows;                   // output rows (tmode: rows of ONE class)
 };
 
 struct __align__(8) GTBarriers {
@@ -79,9 +85,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
   if (tid == 0) GT_STAMP(0);
-  const int s0 = (int)((long long)p.nstages * z / p.ksplit);
-  const int s1 = (int)((long long)p.nstages * (z + 1) / p.ksplit);
+  // transposed-gather mode: parity class of this tile, its taps per axis (k = r + ts*j, j < K_c) and the input
+  // offset q of tap j = 0 (i = m + q - j)
+  int mtile = mt, cls_z = 0, cls_y = 0, cls_x = 0;
+  int rz = 0, ry = 0, rx = 0, Kz = p.kD, Ky = p.kH, Kx = p.kW, qz = 0, qy = 0, qx = 0;
+  int nstages = p.nstages;
+  if (p.tmode) {
+    const int cls = mt / p.tiles_per_class;
+    mtile = mt - cls * p.tiles_per_class;
+    cls_x = cls % p.tsW; cls_y = (cls / p.tsW) % p.tsH; cls_z = cls / (p.tsW * p.tsH);
+    rz = (cls_z + p.pD) % p.tsD; ry = (cls_y + p.pH) % p.tsH; rx = (cls_x + p.pW) % p.tsW;
+    Kz = p.kD > rz ? (p.kD - rz + p.tsD - 1) / p.tsD : 0;
+    Ky = p.kH > ry ? (p.kH - ry + p.tsH - 1) / p.tsH : 0;
+    Kx = p.kW > rx ? (p.kW - rx + p.tsW - 1) / p.tsW : 0;
+    qz = (cls_z + p.pD - rz) / p.tsD; qy = (cls_y + p.pH - ry) / p.tsH; qx = (cls_x + p.pW - rx) / p.tsW;
+    nstages = Kz * Ky * Kx * p.kchunks;
+  }
+  const int s0 = (int)((long long)nstages * z / p.ksplit);
+  const int s1 = (int)((long long)nstages * (z + 1) / p.ksplit);
   const int nst = s1 - s0;
+  // stage -> (filter tap, 16-channel chunk); tmode: tap of the class list -> real filter tap
+  auto stage_tap = [&](int s, int& kz, int& ky, int& kx, int& kc) {
+    const int tap = s / p.kchunks;
+    kc = s - tap * p.kchunks;
+    if (p.tmode) {
+      const int jx = tap % Kx; const int t2 = tap / Kx;
+      const int jy = t2 % Ky, jz = t2 / Ky;
+      kz = jz; ky = jy; kx = jx;                      // class-local tap indices j
+    } else {
+      kx = tap % p.kW; const int t2 = tap / p.kW;
+      ky = t2 % p.kH; kz = t2 / p.kH;
+    }
+  };
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
@@ -145,10 +180,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
 #pragma unroll 4
         for (int r0 = 0; r0 < 32; r0 += RPI) {
           const int r = r0 + rsub;
-          const long long row = (long long)mt * BM + warp * 32 + r;
+          long long row = (long long)mtile * BM + warp * 32 + r;
           if (row >= p.rows) break;
           float4 o = *reinterpret_cast<const float4*>(tile + r * LDS + col);
           o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          if (p.tmode) {                                  // class row (n, m) -> output position ts*m + c
+            long long t = row;
+            const int mx = (int)(t % p.oW); t /= p.oW;
+            const int my = (int)(t % p.oH); t /= p.oH;
+            const int mz = (int)(t % p.oD); const long long nn = t / p.oD;
+            row = ((nn * p.fD + (mz * p.tsD + cls_z)) * p.fH + (my * p.tsH + cls_y)) * p.fW + (mx * p.tsW + cls_x);
+          }
           float* dst = p.out + row * p.out_cs + p.out_co + nt * BN + col;
           if (p.ksplit > 1) {
             atomicAdd(reinterpret_cast<float4*>(dst), o);
@@ -165,7 +207,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
   } else if (warp < 8) {
     // ============================ PRODUCERS: thread = output row; gather + hi/lo split into the A ring
     const int m = tid - 128;
-    const long long row = (long long)mt * BM + m;
+    const long long row = (long long)mtile * BM + m;
     const bool row_ok = row < p.rows;
     int n = 0, oz = 0, oy = 0, ox = 0;
     if (row_ok) {
@@ -176,10 +218,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
     }
     const int bz = oz * p.sD - p.pD, by = oy * p.sH - p.pH, bx = ox * p.sW - p.pW;
     auto load_stage = [&](int s, float4 (&v)[4]) {
-      const int tap = s / p.kchunks, kc = s - tap * p.kchunks;
-      const int kx = tap % p.kW; const int t2 = tap / p.kW;
-      const int ky = t2 % p.kH, kz = t2 / p.kH;
-      const int iz = bz + kz, iy = by + ky, ix = bx + kx;
+      int kz, ky, kx, kc;
+      stage_tap(s, kz, ky, kx, kc);
+      // normal: i = o*stride - pad + k;   transposed gather: i = m + q - j
+      const int iz = p.tmode ? oz + qz - kz : bz + kz;
+      const int iy = p.tmode ? oy + qy - ky : by + ky;
+      const int ix = p.tmode ? ox + qx - kx : bx + kx;
       const bool ok = row_ok && (unsigned)iz < (unsigned)p.iD && (unsigned)iy < (unsigned)p.iH &&
                       (unsigned)ix < (unsigned)p.iW;
       const long long off = ((((long long)n * p.iD + iz) * p.iH + iy) * p.iW + ix) * p.in_cs + p.in_co + kc * KS;
@@ -260,7 +304,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
         const int slot = i % NSTAGE;
         const uint32_t use = (uint32_t)(i / NSTAGE);
         if (use > 0 && !tc::mbar_wait(&B->empty[slot], (use - 1) & 1, ab)) { fail(); dead = true; break; }
-        const float* src = p.wtc + ((size_t)nt * p.nstages + (size_t)(s0 + i)) * (B_STAGE_BYTES / 4);
+        size_t blk = (size_t)(s0 + i);
+        if (p.tmode) {                          // class-local tap j -> filter tap k = r + ts*j -> packed (flipped) block
+          int kz, ky, kx, kc;
+          stage_tap(s0 + i, kz, ky, kx, kc);
+          const int t = ((rz + p.tsD * kz) * p.kH + (ry + p.tsH * ky)) * p.kW + (rx + p.tsW * kx);
+          blk = (size_t)(p.kD * p.kH * p.kW - 1 - t) * p.kchunks + kc;
+        }
+        const float* src = p.wtc + ((size_t)nt * p.nstages + blk) * (B_STAGE_BYTES / 4);
         const uint32_t bar = tc::smem_u32(&B->full_b[slot]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)B_STAGE_BYTES)
                      : "memory");
@@ -334,7 +385,7 @@ __global__ void gemm_tc_pack_kernel(const crn_gemm_tc_pack_item* items, const in
 }
 
 template <int BN>
-int launch_gt(const GTParams& p, cudaStream_t st) {
+int launch_gt(const GTParams& p, dim3 grid, cudaStream_t st) {
   constexpr int NSTAGE = BN == 128 ? 6 : 8;
   constexpr int B_STAGE_BYTES = 2 * 4 * BN * 16;
   const size_t smem = (size_t)NSTAGE * (A_STAGE_BYTES + B_STAGE_BYTES) + sizeof(GTBarriers) + 64;
@@ -347,7 +398,6 @@ int launch_gt(const GTParams& p, cudaStream_t st) {
     }
     configured = true;
   }
-  dim3 grid((unsigned)crn_ceil_div(p.rows, BM), (unsigned)crn_ceil_div(p.gN, BN), (unsigned)p.ksplit);
   kern<<<grid, NTHREADS, smem, st>>>(p);
   CRN_LAUNCH_CHECK("conv_gemm_tc");
   return CRN_OK;
@@ -371,11 +421,15 @@ extern "C" int crn_gemm_tc_pack(const crn_gemm_tc_pack_item* items, const int64_
   return CRN_OK;
 }
 
-// kind 0: y = conv(x) + bias (any stride); kind 1: dx = conv^T(dy) of a stride-1 convolution.
+// kind 0: y = conv(x) + bias (any stride) or, for a transposed descriptor, y = conv_transpose(x) + bias;
+// kind 1: dx = conv^T(dy) of a plain convolution (any stride).  The two "transposed gather" cases (transposed forward,
+// strided dgrad) need weights packed with dgrad != 0 (flipped taps; for the transposed conv the [Cin][Cout][taps]
+// parameter is passed as Cout' = Cin, Cin' = Cout).
 extern "C" int crn_conv_gemm_tc(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc,
                                 const float* bias, float* out, int32_t accumulate, int32_t* status, void* stream) {
   CRN_REQUIRE(d && in && wtc && out && status, "crn_conv_gemm_tc: null pointer");
-  CRN_REQUIRE(!d->transposed && !d->y_planar && !d->bias_n_stride, "crn_conv_gemm_tc: plain convolutions only");
+  CRN_REQUIRE(!d->y_planar && !d->bias_n_stride, "crn_conv_gemm_tc: planar output / per-scene bias unsupported");
+  CRN_REQUIRE(!(d->transposed && kind == 1), "crn_conv_gemm_tc: dgrad of a transposed conv = kind 0 on dy (see engine)");
   CRN_REQUIRE(d->Cin % 4 == 0 && d->Cout % 4 == 0 && d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 &&
                   d->y_co % 4 == 0,
               "crn_conv_gemm_tc: channels, strides and offsets must be multiples of 4");
@@ -390,6 +444,9 @@ extern "C" int crn_conv_gemm_tc(const crn_conv_desc* d, int32_t kind, const floa
     s3[a] = trivial ? 1 : d->stride;
     p3[a] = K3[a] > 1 ? d->pad : 0;
   }
+  const bool strided = s3[0] > 1 || s3[1] > 1 || s3[2] > 1;
+  const bool tgather = (kind == 0 && d->transposed) || (kind == 1 && strided);
+  p.ts = 1; p.tsD = p.tsH = p.tsW = 1;
   if (kind == 0) {
     p.bias = accumulate ? nullptr : bias;
     p.gK = d->Cin; p.gN = d->Cout;
@@ -397,7 +454,6 @@ extern "C" int crn_conv_gemm_tc(const crn_conv_desc* d, int32_t kind, const floa
     p.iD = d->iD; p.iH = d->iH; p.iW = d->iW; p.oD = d->oD; p.oH = d->oH; p.oW = d->oW;
     p.sD = s3[0]; p.sH = s3[1]; p.sW = s3[2]; p.pD = p3[0]; p.pH = p3[1]; p.pW = p3[2];
   } else {
-    CRN_REQUIRE(d->stride == 1 || (s3[0] == 1 && s3[1] == 1 && s3[2] == 1), "crn_conv_gemm_tc: dgrad needs stride 1");
     p.bias = nullptr;
     p.gK = d->Cout; p.gN = d->Cin;
     p.in_cs = d->y_cs; p.in_co = d->y_co; p.out_cs = d->x_cs; p.out_co = d->x_co;
@@ -405,26 +461,45 @@ extern "C" int crn_conv_gemm_tc(const crn_conv_desc* d, int32_t kind, const floa
     p.sD = p.sH = p.sW = 1;
     p.pD = K3[0] - 1 - p3[0]; p.pH = K3[1] - 1 - p3[1]; p.pW = K3[2] - 1 - p3[2];
   }
+  int nclasses = 1;
+  if (tgather) {
+    // output = the FINE grid (p.o*), ordered by parity class; (p.o*) become the per-class extents
+    CRN_REQUIRE(p.oD % s3[0] == 0 && p.oH % s3[1] == 0 && p.oW % s3[2] == 0,
+                "crn_conv_gemm_tc: transposed gather needs output extents divisible by the stride");
+    p.tmode = 1; p.ts = d->stride; p.tsD = s3[0]; p.tsH = s3[1]; p.tsW = s3[2];
+    p.fD = p.oD; p.fH = p.oH; p.fW = p.oW;
+    p.oD /= s3[0]; p.oH /= s3[1]; p.oW /= s3[2];
+    p.sD = p.sH = p.sW = 1; p.pD = p3[0]; p.pH = p3[1]; p.pW = p3[2];
+    nclasses = s3[0] * s3[1] * s3[2];
+  }
   p.rows = (long long)p.N * p.oD * p.oH * p.oW;
   if (p.rows <= 0) return CRN_OK;
+  p.tiles_per_class = (int)crn_ceil_div(p.rows, BM);
   p.kchunks = (p.gK + KS - 1) / KS;
   p.nstages = d->kD * d->kH * d->kW * p.kchunks;
   const int BN = gt_bn(p.gN);
   // split-K when the tile grid cannot fill the machine; needs a dense, exclusively owned output to zero first
   p.ksplit = 1;
-  const long long blocks = crn_ceil_div(p.rows, BM) * crn_ceil_div(p.gN, BN);
+  const long long blocks = (long long)nclasses * p.tiles_per_class * crn_ceil_div(p.gN, BN);
+  long long min_stages = p.nstages;
+  if (tgather) {           // the smallest class: floor(K / ts) taps per axis
+    min_stages = p.kchunks;
+    for (int a = 0; a < 3; ++a) min_stages *= (K3[a] / s3[a] > 0 ? K3[a] / s3[a] : 1);
+  }
+  const long long out_rows = p.rows * nclasses;
   const bool dense_out = p.out_co == 0 && p.out_cs == p.gN;
-  if (blocks < kNumSMs && p.nstages >= 8 && dense_out && !(crn_get_flags() & 16)) {
+  if (blocks < kNumSMs && min_stages >= 8 && dense_out && !(crn_get_flags() & 16)) {
     long long ks = kNumSMs / blocks;                      // one wave: a second one costs a full CTA set-up
-    if (ks > p.nstages / 4) ks = p.nstages / 4;
+    if (ks > min_stages / 4) ks = min_stages / 4;
     if (ks > 32) ks = 32;
     if (ks > 1) {
       p.ksplit = (int)ks;
-      if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * p.rows * p.out_cs, crn_stream(stream));
+      if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * out_rows * p.out_cs, crn_stream(stream));
     }
   }
   cudaStream_t st = crn_stream(stream);
-  return BN == 64 ? launch_gt<64>(p, st) : launch_gt<128>(p, st);
+  dim3 grid((unsigned)(nclasses * p.tiles_per_class), (unsigned)crn_ceil_div(p.gN, BN), (unsigned)p.ksplit);
+  return BN == 64 ? launch_gt<64>(p, grid, st) : launch_gt<128>(p, grid, st);
 }
 
 extern "C" int crn_gemm_tc_debug_read(long long* host_dst, int32_t n) {

@@ -66,6 +66,9 @@ def _conv_dispatch(kind, layer, d, args):
     if kind == "fwd" and layer.name in eng.gt_w:
       x, _, bias, y, acc, st = args
       return "fwd_gt", "crn_conv_gemm_tc", (C.byref(d), 0, x, eng.gt_w[layer.name][0].data_ptr(), bias, y, acc, status, st)
+    if kind == "fwd" and layer.name in eng.gt_tf:
+      x, _, bias, y, acc, st = args
+      return "fwd_gt", "crn_conv_gemm_tc", (C.byref(d), 0, x, eng.gt_tf[layer.name].data_ptr(), bias, y, acc, status, st)
     if kind == "dgrad" and eng.gt_w.get(layer.name, (None, None))[1] is not None:
       dy, _, dx, acc, st = args
       return "dgrad_gt", "crn_conv_gemm_tc", (C.byref(d), 1, dy, eng.gt_w[layer.name][1].data_ptr(), None, dx, acc, status, st)
@@ -354,6 +357,7 @@ class Engine:
     self.wl_ok = {}
     self.wl_split = {}
     self.gt_td = {}
+    self.gt_tf = {}
     for l in self.layers:
       wide = min(l.cin, l.cout) >= 32 and l.cin % 4 == 0 and l.cout % 4 == 0 and l.src_cin == l.cin
       enc = l.name.startswith("encoder.") and l.name != "encoder.stage1.conv"
@@ -362,10 +366,14 @@ class Engine:
       dec_t1 = l.name in ("decoder.stage_2.t1", "decoder.stage_3.t1")
       if wide and not l.transposed and (enc or dec_c1):
         mk = lambda k, n: t.zeros(lib.crn_gemm_tc_packed_floats(k, n, l.taps), dtype=t.float32, device=dev)
-        self.gt_w[l.name] = (mk(l.cin, l.cout), mk(l.cout, l.cin) if l.stride == 1 else None)
+        self.gt_w[l.name] = (mk(l.cin, l.cout), mk(l.cout, l.cin))     # strided dgrad = transposed-gather mode
         self.gt_wgrad.add(l.name)
       elif wide and l.transposed and dec_t1:
         self.gt_wgrad.add(l.name)
+      # transposed-conv forward through the class-ordered transposed-gather mode of the implicit-GEMM kernel
+      if (wide and l.transposed and l.name.startswith("decoder.stage_") and l.stride == 2
+          and self.tct_w.get(l.name, (None, None))[0] is None and l.name not in self.tct_slices):
+        self.gt_tf[l.name] = t.zeros(lib.crn_gemm_tc_packed_floats(l.cin, l.cout, l.taps), dtype=t.float32, device=dev)
       # transposed-conv dgrad = strided conv of dy: wide layers that the class-channel tcgen05 kernel does not take
       if (wide and l.transposed and l.name.startswith("decoder.stage_") and l.stride == 2
           and self.tct_w.get(l.name, (None, None))[1] is None):
@@ -377,10 +385,10 @@ class Engine:
 
   def _pack_gemm_tc(self, P):
     """ONE launch re-packs every tcgen05 implicit-GEMM weight (item list cached per parameter pointer set)."""
-    if not self.gt_w and not self.gt_td:
+    if not self.gt_w and not self.gt_td and not self.gt_tf:
       return
     names = sorted(self.gt_w)
-    sig = tuple(P[n + ".weight"].data_ptr() for n in names + sorted(self.gt_td))
+    sig = tuple(P[n + ".weight"].data_ptr() for n in names + sorted(self.gt_td) + sorted(self.gt_tf))
     if sig != self._gt_sig:
       lay = {l.name: l for l in self.layers}
       entries = []
@@ -390,6 +398,8 @@ class Engine:
             entries.append((lay[n], P[n + ".weight"], dg, buf, False))
       for n in sorted(self.gt_td):      # (layer, weight, dgrad flag, buffer, swap): convT weight read as [Cout'=Cin][Cin'=Cout]
         entries.append((lay[n], P[n + ".weight"], 0, self.gt_td[n], True))
+      for n in sorted(self.gt_tf):      # convT forward: K = Cin, N = Cout, flipped taps (transposed-gather mode)
+        entries.append((lay[n], P[n + ".weight"], 1, self.gt_tf[n], True))
       items = (_lib.GemmTcPackItem * len(entries))()
       offs = (C.c_int64 * (len(entries) + 1))()
       tot = 0

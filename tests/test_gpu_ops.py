@@ -151,8 +151,6 @@ def test_conv_gemm_tcgen05(case, kind):
   import ctypes as C
   from corenet_b200 import _lib, ops
   name, xs, ws, stride, pad = case
-  if kind == 1 and stride != 1:
-    pytest.skip("dgrad of strided convolutions stays on the FFMA kernel")
   g = t.Generator().manual_seed(zlib.crc32(name.encode()) % 1000 + kind)
   nd = len(xs) - 2
   conv = F.conv2d if nd == 2 else F.conv3d
@@ -166,7 +164,12 @@ def test_conv_gemm_tcgen05(case, kind):
     src, ref, K, N = x, y_ref, cin, cout
   else:
     src = t.randn(y_ref.shape, generator=g)
-    ref = convt(src.double(), wt.double(), None, stride=1, padding=pad)
+    if stride == 1:
+      ref = convt(src.double(), wt.double(), None, stride=1, padding=pad)
+    else:                                        # strided dgrad: class-ordered transposed-gather mode
+      xg = x.double().requires_grad_(True)
+      conv(xg, wt.double(), None, stride=stride, padding=pad).backward(src.double())
+      ref = xg.grad
     K, N = cout, cin
   perm = [0] + list(range(2, nd + 2)) + [1]
   inv = [0, nd + 1] + list(range(1, nd + 1))
@@ -219,6 +222,33 @@ def test_conv_transpose_dgrad_as_strided_conv_tcgen05(n, cin, cout, dhw, k, pad)
   assert int(status) == 0
   got = dx.reshape((n,) + dhw + (cin,)).permute(0, 4, 1, 2, 3)
   assert rel_err(got, x.grad) < 2e-5
+
+
+@pytest.mark.parametrize("n,cin,cout,dhw,k,pad", [(1, 128, 64, (4, 4, 4), 7, 3), (2, 64, 32, (3, 5, 4), 7, 3),
+                                                    (1, 256, 128, (4, 4, 4), 3, 1), (2, 40, 36, (2, 3, 5), 3, 1)])
+def test_conv_transpose_fwd_gemm_tcgen05(n, cin, cout, dhw, k, pad):
+  """ConvTranspose3d(stride 2) forward through the class-ordered transposed-gather mode of the implicit-GEMM tcgen05
+  kernel (weights packed with flipped taps, [Cin][Cout][taps] passed as Cout' = Cin, Cin' = Cout) vs the fp64 oracle."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  g = t.Generator().manual_seed(cin + cout + k)
+  wt = t.randn(cin, cout, k, k, k, generator=g) * 0.05
+  bias = t.randn(cout, generator=g)
+  x = t.randn((n, cin) + dhw, generator=g)
+  ref = F.conv_transpose3d(x.double(), wt.double(), bias.double(), stride=2, padding=pad, output_padding=1)
+  fine = tuple(ref.shape[2:])
+  xr = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).contiguous().to(dev())
+  out = t.full((n * fine[0] * fine[1] * fine[2], cout), float("nan"), device=dev())
+  wtc = ops.gemm_tc_pack([wt.to(dev()).contiguous()], [1])[0]          # shape[0] = Cin read as Cout', flipped taps
+  desc = ops.make_desc(n, cin, cout, dhw, fine, (k, k, k), 2, pad, True, cin, cout)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  b = bias.to(dev())
+  _lib.call("crn_conv_gemm_tc", C.byref(desc), 0, xr.data_ptr(), wtc.data_ptr(), b.data_ptr(), out.data_ptr(), 0,
+            status.data_ptr(), _lib.stream_ptr())
+  t.cuda.synchronize()
+  assert int(status) == 0
+  got = out.reshape((n,) + fine + (cout,)).permute(0, 4, 1, 2, 3)
+  assert rel_err(got, ref) < 2e-5
 
 
 WGRAD_TC_CASES = GEMM_TC_CASES + [
