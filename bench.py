@@ -271,8 +271,18 @@ def run_native(args):
     conv_ms = sum(v[0] for v in fam.values())
     achieved = dom[1][1] / (dom[1][0] * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/ncu_traffic.json:
+    # {family: {"bytes_per_launch": ..., "source": ...}}), null if that family has no capture
+    traffic, traffic_src = None, None
+    try:
+      tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+      if dom[0] in tj:
+        traffic, traffic_src = tj[dom[0]]["bytes_per_launch"], tj[dom[0]]["source"]
+    except Exception:
+      pass
     roof = {"bound": "tensor", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": f"{pk_src} bf16 sustained",
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": f"{pk_src} bf16 sustained",
             "launches": dom[1][2], "kernel_ms_per_step": dom[1][0] / args.steps,
             "all_conv_ms_per_step": conv_ms / args.steps,
             "families": {k: {"ms_per_step": v[0] / args.steps, "tflops": v[1] / (v[0] * 1e-3) / 1e12}

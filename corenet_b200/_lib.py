@@ -101,6 +101,8 @@ _SIGS = {
     "crn_conv_wgrad_tc": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_conv_wgrad_line_supported": ([_P(ConvDesc)], i32),
     "crn_conv_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
+    "crn_conv_wgrad_xline_supported": ([_P(ConvDesc)], i32),
+    "crn_conv_wgrad_xline": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_convt7_wgrad_line_supported": ([_P(ConvDesc)], i32),
     "crn_convt7_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_gather_f64_to_f32": ([vp, vp, i32, i64, vp], i32),

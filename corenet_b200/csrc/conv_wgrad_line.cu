@@ -1098,3 +1098,271 @@ extern "C" int crn_convt7_wgrad_line(const crn_conv_desc* d, const float* x, con
   if (crn_convt7_wgrad_line_supported(d) == 2) return d->iW == 64 ? launch_wt2l<64>(p, st) : launch_wt2l<32>(p, st);
   return d->iW == 32 ? launch_wtl<32>(p, st) : launch_wtl<16>(p, st);
 }
+
+// =============================================================================================================
+// Conv3d k=5 s=1 p=2 weight gradient for the WIDE coarse layers (stage_4.c1: 112 -> 64 at 16^3, stage_3.c1:
+// 224 -> 128 at 8^3; model/reconstruction_decoder.py:66,74).  The per-tap gather GEMM (conv_wgrad_tc.cu) re-reads
+// x and dy for each of the 125 taps and is L2-bound there (1.0 ms); here a CTA owns one (kz, ky) pair, stages an
+// image row of x (W + 4 voxels) and the matching dy row ONCE, and gets the 5 kx taps from five start-address
+// shifts of the same staged x rows (MN-major rows are whole 128-byte lines, so a shift is just +128 B):
+//   M = 128 input channels (4 x 32-channel blocks, hi and lo copies), N = 64 / 128 output channels,
+//   5 accumulators (kx) x N TMEM columns, 3xTF32, flushed with float4 atomics.
+namespace {
+
+struct WXParams {
+  const float* x; const float* dy; float* dw; int* status;
+  int N, D, H, W, Cin, Cout, x_cs, x_co, y_cs, y_co, CinP, CoutP;
+  int mtiles, ntiles;      // 128-channel Cin tiles, BN-channel Cout tiles
+  int lines;               // N * D * H image rows per (kz, ky) pass
+  int flush_every;
+};
+
+template <int W, int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) wgrad_xline_kernel(const WXParams p) {
+  constexpr int XR = W + 8;                         // staged x rows (voxel q = row - 2; rows beyond W + 3 unused)
+  constexpr int XB = XR * 128;                      // one 32-channel block of the x line (LBO)
+  constexpr int XP = 4 * XB;                        // hi (or lo) part: 128 channels
+  constexpr int QB = BN / 32;
+  constexpr int YB = W * 128;                       // one 32-channel block of the dy line
+  constexpr int YP = QB * YB;
+  constexpr int STAGE = 2 * XP + 2 * YP;
+  constexpr int NS = 5;                             // stages in the ring
+  constexpr int RUNS = W / 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  WLBarriers* B = reinterpret_cast<WLBarriers*>(smem + NS * STAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // blockIdx.y = (m tile, n tile); blockIdx.x splits the 25 * lines steps
+  const int mt = blockIdx.y / p.ntiles, nt = blockIdx.y % p.ntiles;
+  const long long T = 25LL * p.lines;
+  const int t0 = (int)(T * blockIdx.x / gridDim.x), t1 = (int)(T * (blockIdx.x + 1) / gridDim.x);
+
+  if (tid == 0) {
+    for (int i = 0; i < MAXX; ++i) { tc::mbar_init(&B->full_x[i], 128); tc::mbar_init(&B->empty_x[i], 1); }
+    tc::mbar_init(&B->acc_full, 1); tc::mbar_init(&B->acc_empty, 128);
+    B->abort_flag = 0;
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&B->tmem_base, 512);
+  for (int i = tid; i < NS * STAGE / 16; i += NTHREADS)            // halo rows stay zero
+    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = B->tmem_base;
+  const uint32_t smem_u32 = tc::smem_u32(smem);
+  auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
+  volatile int* ab = &B->abort_flag;
+  auto flush_after = [&](int t) -> bool {
+    return t == t1 - 1 || (t + 1) % p.lines == 0 || (t - t0 + 1) % p.flush_every == 0;
+  };
+
+  if (warp < 4) {
+    // ============================ EPILOGUE: lane = ci, accumulator a = kx, columns = co
+    uint32_t nflush = 0;
+    bool dead = false;
+    const int ci = mt * 128 + warp * 32 + lane;
+    for (int t = t0; t < t1 && !dead; ++t) {
+      if (!flush_after(t)) continue;
+      if (!tc::mbar_wait(&B->acc_full, nflush & 1, ab)) { fail(); dead = true; break; }
+      tc::fence_after_sync();
+      const int pass = t / p.lines;                  // = kz * 5 + ky
+#pragma unroll 1
+      for (int a = 0; a < 5; ++a) {
+        float* dst = p.dw + ((long long)(pass * 5 + a) * p.CinP + ci) * p.CoutP + nt * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + a * BN + c0, v);
+          if (ci >= p.Cin) continue;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4)
+            if (nt * BN + c0 + c < p.Cout)
+              atomicAdd(reinterpret_cast<float4*>(dst + c0 + c), make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(&B->acc_empty);
+      ++nflush;
+    }
+  } else if (warp < 8) {
+    // ============================ PRODUCERS: one job = x line (128 channels) + dy line (BN channels) of a step
+    const int pt = tid - 128;
+    constexpr int XIT = W * 32 / 128, YIT = W * (BN / 4) / 128, NB = XIT + YIT;
+    static_assert(NB <= 8, "line does not fit the register buffer");
+    struct Job { int n, z, y, xz, xy, ok; };
+    int jt = t0;
+    auto next_job = [&](Job& jb) -> bool {
+      if (jt >= t1) return false;
+      const int pass = jt / p.lines, l = jt - pass * p.lines;
+      const int kz = pass / 5, ky = pass - kz * 5;
+      jb.y = l % p.H; const int r2 = l / p.H;
+      jb.z = r2 % p.D; jb.n = r2 / p.D;
+      jb.xz = jb.z + kz - 2; jb.xy = jb.y + ky - 2;
+      jb.ok = (unsigned)jb.xz < (unsigned)p.D && (unsigned)jb.xy < (unsigned)p.H;
+      ++jt;
+      return true;
+    };
+    auto issue = [&](const Job& jb, float4 (&buf)[NB]) {
+      const float* sx = p.x + ((((long long)jb.n * p.D + jb.xz) * p.H + jb.xy) * p.W) * p.x_cs + p.x_co + mt * 128;
+#pragma unroll
+      for (int u = 0; u < XIT; ++u) {
+        const int it = pt + u * 128, v = it >> 5, c4 = it & 31;
+        buf[u] = (jb.ok && mt * 128 + c4 * 4 < p.Cin) ? __ldg(reinterpret_cast<const float4*>(sx + (long long)v * p.x_cs + c4 * 4))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const float* sy = p.dy + ((((long long)jb.n * p.D + jb.z) * p.H + jb.y) * p.W) * p.y_cs + p.y_co + nt * BN;
+#pragma unroll
+      for (int u = 0; u < YIT; ++u) {
+        const int it = pt + u * 128, v = it / (BN / 4), c4 = it % (BN / 4);
+        buf[XIT + u] = (jb.ok && nt * BN + c4 * 4 < p.Cout) ? __ldg(reinterpret_cast<const float4*>(sy + (long long)v * p.y_cs + c4 * 4))
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    uint32_t q = 0;
+    bool dead = false;
+    auto store = [&](const Job& jb, const float4 (&buf)[NB]) {
+      const int slot = (int)(q % NS);
+      const uint32_t use = q / NS;
+      if (use > 0 && !tc::mbar_wait(&B->empty_x[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+      uint8_t* base = smem + slot * STAGE;
+#pragma unroll
+      for (int u = 0; u < XIT; ++u) {
+        const int it = pt + u * 128, v = it >> 5, c4 = it & 31;
+        float4 hi, lo;
+        tc::split_tf32(buf[u].x, hi.x, lo.x); tc::split_tf32(buf[u].y, hi.y, lo.y);
+        tc::split_tf32(buf[u].z, hi.z, lo.z); tc::split_tf32(buf[u].w, hi.w, lo.w);
+        const int row = v + 2, cb = c4 >> 3, cw = c4 & 7;
+        const uint32_t off = (uint32_t)cb * XB + (uint32_t)row * 128 + (uint32_t)((((cw >> 1) ^ (row & 3)) << 5) + ((cw & 1) << 4));
+        *reinterpret_cast<float4*>(base + off) = hi;
+        *reinterpret_cast<float4*>(base + XP + off) = lo;
+      }
+#pragma unroll
+      for (int u = 0; u < YIT; ++u) {
+        const int it = pt + u * 128, v = it / (BN / 4), c4 = it % (BN / 4);
+        float4 hi, lo;
+        tc::split_tf32(buf[XIT + u].x, hi.x, lo.x); tc::split_tf32(buf[XIT + u].y, hi.y, lo.y);
+        tc::split_tf32(buf[XIT + u].z, hi.z, lo.z); tc::split_tf32(buf[XIT + u].w, hi.w, lo.w);
+        const int row = v, cb = c4 >> 3, cw = c4 & 7;
+        const uint32_t off = (uint32_t)cb * YB + (uint32_t)row * 128 + (uint32_t)((((cw >> 1) ^ (row & 3)) << 5) + ((cw & 1) << 4));
+        *reinterpret_cast<float4*>(base + 2 * XP + off) = hi;
+        *reinterpret_cast<float4*>(base + 2 * XP + YP + off) = lo;
+      }
+      tc::fence_async_smem();
+      tc::mbar_arrive(&B->full_x[slot]);
+      ++q;
+    };
+    constexpr int PD = 3;
+    Job jobs[PD];
+    float4 bufs[PD][NB];
+    bool have[PD];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) {
+      have[k] = next_job(jobs[k]);
+      if (have[k]) issue(jobs[k], bufs[k]);
+    }
+    while (have[0] && !dead) {
+#pragma unroll
+      for (int k = 0; k < PD; ++k) {
+        if (!have[k] || dead) { have[0] = false; break; }
+        store(jobs[k], bufs[k]);
+        have[k] = next_job(jobs[k]);
+        if (have[k]) issue(jobs[k], bufs[k]);
+      }
+    }
+  } else {
+    // ============================ MMA ISSUER
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_tf32(128, BN, 1, 1);
+      uint32_t nflush = 0, slot = 0, phase = 0;
+      bool first = true, dead = false;
+      int mod_ctr = 0;
+      int line = t0 % p.lines;
+      for (int t = t0; t < t1 && !dead; ++t) {
+        if (!tc::mbar_wait(&B->full_x[slot], phase, ab)) { fail(); dead = true; break; }
+        if (first && nflush > 0) {
+          if (!tc::mbar_wait(&B->acc_empty, (nflush - 1) & 1, ab)) { fail(); dead = true; break; }
+        }
+        tc::fence_after_sync();
+        const uint32_t base = smem_u32 + slot * STAGE;
+        const uint64_t dxh = tc::make_desc_mn32(base, XB, 512), dxl = tc::make_desc_mn32(base + XP, XB, 512);
+        const uint64_t dyh = tc::make_desc_mn32(base + 2 * XP, YB, 512), dyl = tc::make_desc_mn32(base + 2 * XP + YP, YB, 512);
+#pragma unroll
+        for (int r = 0; r < RUNS; ++r) {
+#pragma unroll
+          for (int a = 0; a < 5; ++a) {                    // kx = a: x rows shifted by a
+            const uint64_t xo = (uint64_t)((r * 8 + a) * 8), yo = (uint64_t)(r * 64);
+            tc::mma_tf32(tmem + a * BN, dxh + xo, dyh + yo, idesc, (first && r == 0) ? 0u : 1u);
+            tc::mma_tf32(tmem + a * BN, dxl + xo, dyh + yo, idesc, 1u);
+            tc::mma_tf32(tmem + a * BN, dxh + xo, dyl + yo, idesc, 1u);
+          }
+        }
+        first = false;
+        tc::commit(&B->empty_x[slot]);
+        if (++slot == NS) { slot = 0; phase ^= 1; }
+        if (++mod_ctr == p.flush_every) mod_ctr = 0;
+        if (++line == p.lines) line = 0;
+        if (t == t1 - 1 || line == 0 || mod_ctr == 0) {
+          tc::commit(&B->acc_full);
+          ++nflush;
+          first = true;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+template <int W, int BN>
+int launch_wx(WXParams p, cudaStream_t st) {
+  constexpr int STAGE = 2 * 4 * (W + 8) * 128 + 2 * (BN / 32) * W * 128;
+  const size_t smem = (size_t)5 * STAGE + sizeof(WLBarriers) + 1024 + 64;
+  auto kern = wgrad_xline_kernel<W, BN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      crn_set_error("conv_wgrad_xline: cannot set %zu bytes of dynamic shared memory", smem);
+      return CRN_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  p.flush_every = 64;
+  const int tiles = p.mtiles * p.ntiles;
+  long long gx = kNumSMs / tiles;
+  if (gx < 1) gx = 1;
+  if (gx > 25LL * p.lines) gx = 25LL * p.lines;
+  dim3 grid((unsigned)gx, (unsigned)tiles);
+  kern<<<grid, NTHREADS, smem, st>>>(p);
+  CRN_LAUNCH_CHECK("conv_wgrad_xline");
+  return CRN_OK;
+}
+}  // namespace
+
+extern "C" int crn_conv_wgrad_xline_supported(const crn_conv_desc* d) {
+  if (!d || d->transposed || d->kD != 5 || d->kH != 5 || d->kW != 5 || d->stride != 1 || d->pad != 2) return 0;
+  if (d->iD != d->oD || d->iH != d->oH || d->iW != d->oW || d->y_planar) return 0;
+  if (d->Cin % 4 || d->Cout % 4 || d->x_cs % 4 || d->x_co % 4 || d->y_cs % 4 || d->y_co % 4 || d->CoutP % 4) return 0;
+  if (d->Cin < 64 || d->Cout < 32 || d->Cout > 128) return 0;
+  return d->iW == 16 || d->iW == 8;
+}
+
+// dWf[tap][ci][co] += sum_vox x * dy for wide Conv3d k=5 layers on 16^3 / 8^3 grids (same contract as crn_conv_wgrad).
+extern "C" int crn_conv_wgrad_xline(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed,
+                                    int32_t* status, void* stream) {
+  CRN_REQUIRE(d && x && dy && dw_packed && status, "crn_conv_wgrad_xline: null pointer");
+  CRN_REQUIRE(crn_conv_wgrad_xline_supported(d), "crn_conv_wgrad_xline: unsupported layer shape");
+  WXParams p{};
+  p.x = x; p.dy = dy; p.dw = dw_packed; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  p.Cin = d->Cin; p.Cout = d->Cout;
+  p.x_cs = d->x_cs; p.x_co = d->x_co; p.y_cs = d->y_cs; p.y_co = d->y_co; p.CinP = d->CinP; p.CoutP = d->CoutP;
+  p.lines = d->N * d->iD * d->iH;
+  // 5 accumulators (kx) x 64 columns = 320 of the 512 TMEM columns: Cout is tiled by 64
+  p.mtiles = (d->Cin + 127) / 128; p.ntiles = (d->Cout + 63) / 64;
+  cudaStream_t st = crn_stream(stream);
+  return d->iW == 16 ? launch_wx<16, 64>(p, st) : launch_wx<8, 64>(p, st);
+}

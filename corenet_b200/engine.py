@@ -83,6 +83,13 @@ def _conv_dispatch(kind, layer, d, args):
       d2.x_cs, d2.x_co, d2.y_cs, d2.y_co = d.y_cs, d.y_co, d.x_cs, d.x_co
       d2.CinP, d2.CoutP, d2.y_planar, d2.bias_n_stride = d.CoutP, d.CinP, 0, 0
       return "dgrad_gt", "crn_conv_gemm_tc", (C.byref(d2), 0, dy, eng.gt_td[layer.name].data_ptr(), None, dx, acc, status, st)
+    if kind == "wgrad" and layer.k == (5, 5, 5) and not layer.transposed and layer.name in eng.gt_wgrad:
+      ok = eng.wl_ok.get(layer.name)
+      if ok is None:                        # wide coarse Conv3d k=5: one staged image row serves the 5 kx taps
+        ok = eng.wl_ok[layer.name] = bool(_lib.lib().crn_conv_wgrad_xline_supported(C.byref(d)))
+      if ok:
+        x, dy, dw, st = args
+        return "wgrad_tc", "crn_conv_wgrad_xline", (C.byref(d), x, dy, dw, status, st)
     if kind == "wgrad" and layer.name in eng.gt_wgrad:
       x, dy, dw, st = args
       return "wgrad_tc", "crn_conv_wgrad_tc", (C.byref(d), x, dy, dw, status, st)

@@ -39,7 +39,9 @@ const char* crn_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (bench.py gpu_launches). */
 int64_t crn_launch_count(void);
 /* Debug / A-B switches: bit0 = disable the row-direct conv kernels, bit1 = disable the tap-row wgrad
- * kernel (both fall back to the generic implicit-GEMM kernels), bit4 = disable split-K in the generic kernel. */
+ * kernel (both fall back to the generic implicit-GEMM kernels), bit4 = disable split-K in the generic and the
+ * tcgen05 implicit-GEMM kernels, bit5 = disable the stem wgrad kernel, bit6 = 3 narrow MMAs instead of N doubling in
+ * conv_tc5, bits 8-11 = gemm_tc_kernel debug (timeline stamps / skip stores / skip gathers / skip MMAs). */
 void crn_set_flags(int32_t flags);
 
 /* ------------------------------------------------------------------------
@@ -323,6 +325,11 @@ int crn_conv_wgrad_line_supported(const crn_conv_desc* d);
 int crn_conv_wgrad_line(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed, int32_t* status,
                         void* stream);
 
+/* ... of the wide coarse Conv3d k=5 layers (Cin >= 64, 32 <= Cout <= 128 at W = 16 / 8: stage_4.c1, stage_3.c1): one
+ * CTA per (kz, ky), the 5 kx taps are start-address shifts of the image row staged once. */
+int crn_conv_wgrad_xline_supported(const crn_conv_desc* d);
+int crn_conv_wgrad_xline(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed, int32_t* status,
+                         void* stream);
 /* ... and of ConvTranspose3d k=7 s=2 p=3 with Cin <= 32, Cout == 16 at coarse W = 32 / 16 (stage_5.t1,
  * model/reconstruction_decoder.py:85): the class-channel view of dy on the coarse grid makes it a stride-1 problem
  * whose N blocks are the fine lines themselves. */

@@ -323,6 +323,33 @@ def test_conv5_wgrad_line_tcgen05(n, cin, cout, dhw):
   assert rel_err(dw, ref) < 5e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw", [(1, 112, 64, (4, 5, 16)), (2, 224, 128, (3, 4, 8)), (1, 64, 32, (5, 3, 16)),
+                                              (1, 132, 68, (3, 3, 8))])
+def test_conv5_wgrad_xline_tcgen05(n, cin, cout, dhw):
+  """Wide coarse Conv3d k=5 weight gradient: one staged image row per step, 5 kx taps as row shifts (MN-major tf32,
+  3xTF32) against the fp64 oracle; 5e-5 of the tensor max."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  g = t.Generator().manual_seed(cin + cout)
+  x = t.randn((n, cin) + dhw, generator=g)
+  wt = (t.randn(cout, cin, 5, 5, 5, generator=g) * 0.05).double().requires_grad_(True)
+  y = F.conv3d(x.double(), wt, None, padding=2)
+  gy = t.randn(y.shape, generator=g)
+  y.backward(gy.double())
+  xr = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).contiguous().to(dev())
+  gr = gy.permute(0, 2, 3, 4, 1).reshape(-1, cout).contiguous().to(dev())
+  dw = t.zeros(125, cin, cout, device=dev())
+  desc = ops.make_desc(n, cin, cout, dhw, dhw, (5, 5, 5), 1, 2, False, cin, cout)
+  assert _lib.lib().crn_conv_wgrad_xline_supported(C.byref(desc)) == 1
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  _lib.call("crn_conv_wgrad_xline", C.byref(desc), xr.data_ptr(), gr.data_ptr(), dw.data_ptr(), status.data_ptr(),
+            _lib.stream_ptr())
+  t.cuda.synchronize()
+  assert int(status) == 0
+  ref = wt.grad.reshape(cout, cin, 125).permute(2, 1, 0)
+  assert rel_err(dw, ref) < 5e-5
+
+
 @pytest.mark.parametrize("n,cin,cout,dhw,ycs", [(1, 32, 16, (4, 5, 32), 16), (2, 32, 16, (3, 37, 32), 28),
                                                   (1, 20, 16, (5, 4, 16), 16), (1, 16, 2, (4, 5, 64), 4),
                                                   (2, 12, 3, (3, 6, 32), 4)])
