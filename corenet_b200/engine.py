@@ -386,6 +386,8 @@ class Engine:
           and self.tct_w.get(l.name, (None, None))[1] is None):
         self.gt_td[l.name] = t.zeros(lib.crn_gemm_tc_packed_floats(l.cout, l.cin, l.taps), dtype=t.float32, device=dev)
     self._gt_sig = None
+    self._pack_stream = None
+    self._pack_ev = None
     self.plans = {}
     self._ptr_sig = None
     self._ver_sig = None
@@ -478,6 +480,29 @@ class Engine:
     if ver_sig != self._ver_sig:
       _call("crn_pack_weights", self._items_dev.data_ptr(), self._offs_dev.data_ptr(), self._pack_n,
             self._pack_tot, _lib.stream_ptr())
+      # the tcgen05 re-packs (~0.5 ms) are first needed by the encoder blocks / the decoder: they run on a side
+      # stream concurrently with preprocessing, the stem and its BatchRenorm (Plan.forward joins before the blocks)
+      main = t.cuda.current_stream()
+      if self._pack_stream is None:
+        self._pack_stream = t.cuda.Stream(device=self.dev)
+      ev = t.cuda.Event()
+      ev.record(main)
+      self._pack_stream.wait_event(ev)
+      with t.cuda.stream(self._pack_stream):
+        self._pack_tc(P)
+        self._pack_ev = t.cuda.Event()
+        self._pack_ev.record(self._pack_stream)
+      self._ver_sig = ver_sig
+
+  def join_packs(self):
+    """Main stream waits for the side-stream weight re-packs of this forward (no-op if none were launched)."""
+    if self._pack_ev is not None:
+      t.cuda.current_stream().wait_event(self._pack_ev)
+      self._pack_ev = None
+
+  def _pack_tc(self, P):
+    """tcgen05 weight re-packs (conv_tc5 / class-scatter / implicit-GEMM layouts) on the current stream."""
+    if True:
       for l in self.layers:
         if l.name in self.tc_w:
           w = P[l.name + ".weight"]
@@ -493,7 +518,6 @@ class Engine:
               _call("crn_tct_pack", P[l.name + ".weight"].data_ptr(), l.cin, l.cout, dg, wt.data_ptr(),
                     _lib.stream_ptr())
       self._pack_gemm_tc(P)
-      self._ver_sig = ver_sig
 
   def unpack_wgrads(self, grads: Dict[str, t.Tensor]):
     sig = tuple(grads[l.name + ".weight"].data_ptr() for l in self.layers)
@@ -717,6 +741,7 @@ class Plan:
               self.s1.p, 0, st)
     self.brn_stem.fwd(training)
     _call("crn_maxpool_fwd", self.s1a.p, B, 128, 128, 64, self.p1.p, self.p1_idx.data_ptr(), st)
+    eng.join_packs()
     for blk in self.blocks:
       x = blk["x"]
       if blk["down"]:
