@@ -90,6 +90,9 @@ _SIGS = {
     "crn_tc5_packed_floats": ([i32, i32], i64),
     "crn_tc5_pack": ([vp, i32, i32, i32, vp, vp], i32),
     "crn_conv5_tc": ([_P(ConvDesc), i32, vp, vp, vp, vp, vp, vp], i32),
+    "crn_tc5s_packed_floats": ([i32], i64),
+    "crn_tc5s_pack": ([vp, i32, i32, vp, vp], i32),
+    "crn_conv5_tcs": ([_P(ConvDesc), vp, vp, vp, vp, vp, vp], i32),
     "crn_tct_packed_floats": ([i32, i32, i32], i64),
     "crn_tct_pack": ([vp, i32, i32, i32, vp, vp], i32),
     "crn_convt7_tc_dgrad": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),

@@ -1,0 +1,351 @@
+// Conv3d k=5 s=1 p=2 FORWARD for <= 16 output channels (stage_6.c1: 28 -> 16 at 64^3, the single most expensive
+// launch; model/reconstruction_decoder.py:91) with the 5 kz taps STACKED INTO N.
+//
+// conv_tc5_kernel issues one 128 x 32 x 8 MMA per (tap, output plane): ncu shows its tensor pipe 16 % busy -- the
+// kernel is bound by re-fetching the 4 KB A tile (one staged input plane, tap-shifted) from shared memory for every
+// MMA.  But one staged input plane q contributes to the FIVE output planes z = q - kz (+2), whose accumulators are
+// adjacent TMEM columns: stacking the weights of kz = 4..0 as consecutive B rows turns those five MMAs into ONE with
+// N = 5 x 32, i.e. one A fetch per 5x more columns (2.5x fewer, wider MMAs per output voxel).
+//   * item = (8 x 16) xy tile x ZT = 4 output planes; the ZT + 4 = 8 input planes of a K pass (8 channels) are all
+//     resident (ring of 8 slots, refilled plane by plane during the last ky sweep of the previous pass);
+//   * loop: pass -> ky (weights of all kz, kx for this ky: one 50 KB cp.async.bulk, 2-stage ring) -> input plane q
+//     -> kx -> {A_hi x [W_hi | W_lo], A_lo x [W_hi | 0]} over the stack of valid output planes;
+//   * the first MMA that touches a not-yet-started accumulator of the (pass, ky) flush group overwrites it; the
+//     not-started planes are always the upper end of the stack, so that MMA is split in two at most once per q;
+//   * epilogue: register-resident running sums (4 planes x 16 columns), one flush per (pass, ky) group (80 MMAs),
+//     one store per item; warp roles and bounded waits as in conv_tc5.cu.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TX = 8, TY = 16;
+constexpr int XS = TX + 4, YS = TY + 4;
+constexpr int CHUNK_BYTES = YS * XS * 16;        // one 4-channel chunk of a plane  (3840)
+constexpr int PART_BYTES = 2 * CHUNK_BYTES;      // 8 channels                       (7680)
+constexpr int PLANE_BYTES = 2 * PART_BYTES;      // hi + lo                          (15360)
+constexpr int ZT = 4, NPLANE = ZT + 4, NSLOT = NPLANE;
+constexpr int NP = 16;                           // padded output channels
+constexpr int BLK = 2 * NP;                      // B rows / accumulator columns per output plane: [hi | lo]
+constexpr int SROWS = 5 * BLK;                   // rows of one stacked part (kz = 4..0)
+constexpr int KC_BYTES = 2 * SROWS * 16;         // one 4-channel K chunk of a tap: part 0 rows + part 1 rows (LBO)
+constexpr int TAP_BYTES = 2 * KC_BYTES;          // 10240
+constexpr int WROW_BYTES = 5 * TAP_BYTES;        // the 5 kx taps of one ky (all kz)   (51200)
+constexpr int WSTAGES = 2;
+constexpr int NTHREADS = 320;
+constexpr int ACOLS = BLK;                       // 32 accumulator columns per plane
+constexpr int TMEM_COLS = 256;                   // 2 stages x 4 planes x 32 columns
+
+struct TC5SParams {
+  const float* in; const float* wtc; const float* bias; float* out; int* status;
+  int N, D, H, W, gK, gN, in_cs, in_co, out_cs, out_co, P;
+  int tiles_x, tiles_y, tiles_z, nitems;
+};
+
+struct __align__(8) Barriers {
+  uint64_t plane_full[NSLOT], plane_empty[NSLOT];
+  uint64_t w_full[WSTAGES], w_empty[WSTAGES];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  int abort_flag;
+};
+
+__device__ __forceinline__ void decode_item(const TC5SParams& p, int item, int& n, int& z0, int& y0, int& x0) {
+  int t = item;
+  x0 = (t % p.tiles_x) * TX; t /= p.tiles_x;
+  y0 = (t % p.tiles_y) * TY; t /= p.tiles_y;
+  z0 = (t % p.tiles_z) * ZT; n = t / p.tiles_z;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;
+  uint8_t* wring = smem + NSLOT * PLANE_BYTES;
+  Barriers* B = reinterpret_cast<Barriers*>(wring + WSTAGES * WROW_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&B->plane_full[i], 128); tc::mbar_init(&B->plane_empty[i], 1); }
+    for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&B->w_full[i], 1); tc::mbar_init(&B->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&B->acc_full[i], 1); tc::mbar_init(&B->acc_empty[i], 128); }
+    B->abort_flag = 0;
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&B->tmem_base, TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = B->tmem_base;
+  const uint32_t ring_u32 = tc::smem_u32(ring), wring_u32 = tc::smem_u32(wring);
+  auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
+  volatile int* ab = &B->abort_flag;
+
+  if (warp < 4) {
+    // ============================ EPILOGUE: one flush per (pass, ky) group into register sums, one store per item
+    long long G = 0;
+    bool dead = false;
+    for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
+      int n, z0, y0, x0;
+      decode_item(p, item, n, z0, y0, x0);
+      const int m = warp * 32 + lane;
+      const int y = y0 + (m >> 3), x = x0 + (m & 7);
+      float sum[ZT][16];
+#pragma unroll
+      for (int zz = 0; zz < ZT; ++zz)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) sum[zz][e] = 0.f;
+      for (int pass = 0; pass < p.P && !dead; ++pass) {
+        for (int ky = 0; ky < 5; ++ky, ++G) {
+          const int st = (int)(G & 1);
+          if (!tc::mbar_wait(&B->acc_full[st], (uint32_t)(G >> 1) & 1, ab)) { fail(); dead = true; break; }
+          tc::fence_after_sync();
+#pragma unroll
+          for (int zz = 0; zz < ZT; ++zz) {
+            // plane zz always receives at least its kz = 2 contribution (input plane z0 + zz is inside the volume)
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + st * (ZT * ACOLS) + zz * ACOLS;
+            float v[16];
+            tc::tmem_ld16(ta, v);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sum[zz][e] += v[e];
+            tc::tmem_ld16(ta + NP, v);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sum[zz][e] += v[e];
+          }
+          tc::fence_before_sync();
+          tc::mbar_arrive(&B->acc_empty[st]);
+        }
+      }
+      if (dead) break;
+#pragma unroll
+      for (int zz = 0; zz < ZT; ++zz) {
+        const long long pos = (((long long)n * p.D + (z0 + zz)) * p.H + y) * p.W + x;
+        float* dst = p.out + pos * p.out_cs + p.out_co;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const int c = qd * 4;
+          if (c < p.gN) {                          // gN is a multiple of 4
+            float4 o = make_float4(sum[zz][c], sum[zz][c + 1], sum[zz][c + 2], sum[zz][c + 3]);
+            if (p.bias) {
+              o.x += __ldg(p.bias + c); o.y += __ldg(p.bias + c + 1); o.z += __ldg(p.bias + c + 2); o.w += __ldg(p.bias + c + 3);
+            }
+            *reinterpret_cast<float4*>(dst + c) = o;
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ============================ PRODUCERS: halo gather + hi/lo split; plane r of every pass goes to slot r
+    const int pt = tid - 128;
+    long long L = 0;                               // running plane-load index (slot = L % NSLOT = r)
+    bool dead = false;
+    for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
+      int n, z0, y0, x0;
+      decode_item(p, item, n, z0, y0, x0);
+      for (int pass = 0; pass < p.P && !dead; ++pass) {
+        for (int r = 0; r < NPLANE; ++r, ++L) {
+          const int slot = (int)(L % NSLOT);
+          const uint32_t use = (uint32_t)(L / NSLOT);
+          if (use > 0 && !tc::mbar_wait(&B->plane_empty[slot], (use - 1) & 1, ab)) { fail(); dead = true; break; }
+          const int q = z0 - 2 + r;
+          if (q >= 0 && q < p.D) {
+            uint8_t* dst = ring + slot * PLANE_BYTES;
+            for (int u = pt; u < YS * XS * 2; u += 128) {
+              const int kc = u & 1; const int v = u >> 1;
+              const int xs = v % XS, ys = v / XS;
+              const int y = y0 - 2 + ys, x = x0 - 2 + xs;
+              const int k = pass * 8 + kc * 4;
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
+                const long long off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
+                a = __ldg(reinterpret_cast<const float4*>(p.in + off));
+              }
+              float4 hi, lo;
+              tc::split_tf32(a.x, hi.x, lo.x); tc::split_tf32(a.y, hi.y, lo.y);
+              tc::split_tf32(a.z, hi.z, lo.z); tc::split_tf32(a.w, hi.w, lo.w);
+              const int o = kc * CHUNK_BYTES + v * 16;
+              *reinterpret_cast<float4*>(dst + o) = hi;
+              *reinterpret_cast<float4*>(dst + PART_BYTES + o) = lo;
+            }
+            tc::fence_async_smem();
+          }
+          tc::mbar_arrive(&B->plane_full[slot]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ============================ MMA ISSUER (one elected thread)
+    if (lane == 0) {
+      constexpr uint32_t A_DESC_HI = (uint32_t)((XS * 16) >> 4) | (1u << 14);   // SBO field | version 1 (bit 46)
+      long long L0 = 0;                             // plane-load index of r = 0 of the current pass
+      long long Wn = 0;                             // running weight-row (ky) index
+      long long G = 0;                              // running (pass, ky) group index -> accumulator stage
+      bool dead = false;
+      for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
+        int n, z0, y0, x0;
+        decode_item(p, item, n, z0, y0, x0);
+        for (int pass = 0; pass < p.P && !dead; ++pass, L0 += NPLANE) {
+          for (int ky = 0; ky < 5 && !dead; ++ky, ++G, ++Wn) {
+            const int st = (int)(G & 1);
+            if (G >= 2 && !tc::mbar_wait(&B->acc_empty[st], (uint32_t)((G >> 1) - 1) & 1, ab)) { fail(); dead = true; break; }
+            const int ws = (int)(Wn % WSTAGES);
+            if (!tc::mbar_wait(&B->w_full[ws], (uint32_t)(Wn / WSTAGES) & 1, ab)) { fail(); dead = true; break; }
+            tc::fence_after_sync();
+            const uint32_t wbase = wring_u32 + ws * WROW_BYTES;
+            const uint32_t acc0 = tmem + st * (ZT * ACOLS);
+            int ns = 0;                             // accumulators [0, ns) of this group have been written
+#pragma unroll 1
+            for (int q = 0; q < NPLANE; ++q) {
+              const long long L = L0 + q;
+              const int slot = (int)(L % NSLOT);
+              if (ky == 0) {                        // planes arrive during the first sweep of a pass
+                if (!tc::mbar_wait(&B->plane_full[slot], (uint32_t)(L / NSLOT) & 1, ab)) { fail(); dead = true; break; }
+                tc::fence_after_sync();
+              }
+              const int zin = z0 - 2 + q;
+              if (zin >= 0 && zin < p.D) {
+                // output planes zz = q - kz, kz = 0..4, clipped to the item: the stack [zlo, zhi]
+                const int zlo = q > 4 ? q - 4 : 0, zhi = q < ZT - 1 ? q : ZT - 1;
+                // B rows: block b holds kz = 4 - b; plane zlo needs kz = q - zlo -> first block 4 - (q - zlo)
+                const uint32_t boff = (uint32_t)(4 - (q - zlo)) * (BLK * 16);
+                const uint32_t alo0 = ((ring_u32 + (uint32_t)slot * PLANE_BYTES) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+#pragma unroll
+                  for (int part = 0; part < 2; ++part) {
+                    const uint32_t alo = alo0 + (ky * XS + kx) + (part == 1 ? (PART_BYTES >> 4) : 0);
+                    const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
+                    const uint32_t bb = wbase + kx * TAP_BYTES + (part == 1 ? SROWS * 16 : 0) + boff;
+                    if (kx == 0 && part == 0 && ns <= zhi) {
+                      // planes [max(zlo, ns), zhi] get their first contribution of the group: overwrite them
+                      const int zs = ns > zlo ? ns : zlo;
+                      if (zs > zlo) {
+                        const int cnt = zs - zlo;
+                        tc::mma_tf32(acc0 + zlo * ACOLS, da, tc::make_desc(bb, KC_BYTES, 128),
+                                     tc::make_idesc_tf32(128, BLK * cnt, 0, 0), 1u);
+                      }
+                      const int cnt2 = zhi - zs + 1;
+                      tc::mma_tf32(acc0 + zs * ACOLS, da, tc::make_desc(bb + (uint32_t)(zs - zlo) * (BLK * 16), KC_BYTES, 128),
+                                   tc::make_idesc_tf32(128, BLK * cnt2, 0, 0), 0u);
+                      ns = zhi + 1;
+                    } else {
+                      const int cnt = zhi - zlo + 1;
+                      tc::mma_tf32(acc0 + zlo * ACOLS, da, tc::make_desc(bb, KC_BYTES, 128),
+                                   tc::make_idesc_tf32(128, BLK * cnt, 0, 0), 1u);
+                    }
+                  }
+                }
+              }
+              if (ky == 4) tc::commit(&B->plane_empty[slot]);      // last sweep of the pass: plane q is dead
+            }
+            if (dead) break;
+            tc::commit(&B->w_empty[ws]);
+            tc::commit(&B->acc_full[st]);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================ WEIGHT COPIES: one cp.async.bulk per (pass, ky)
+    if (lane == 0) {
+      long long Wn = 0;
+      bool dead = false;
+      for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
+        for (int pass = 0; pass < p.P && !dead; ++pass) {
+          for (int ky = 0; ky < 5; ++ky, ++Wn) {
+            const int ws = (int)(Wn % WSTAGES);
+            const uint32_t use = (uint32_t)(Wn / WSTAGES);
+            if (use > 0 && !tc::mbar_wait(&B->w_empty[ws], (use - 1) & 1, ab)) { fail(); dead = true; break; }
+            const float* src = p.wtc + ((size_t)pass * 5 + ky) * (WROW_BYTES / 4);
+            const uint32_t bar = tc::smem_u32(&B->w_full[ws]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WROW_BYTES)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    wring_u32 + ws * WROW_BYTES),
+                "l"(src), "r"((uint32_t)WROW_BYTES), "r"(bar)
+                : "memory");
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// pack: PyTorch conv weight [Cout][Cin][125] -> wtc[P][ky][kx][kc][part][blk = 4 - kz][32 rows][4 floats]
+//   part 0 rows: [hi(co 0..15) | lo(co 0..15)],  part 1 rows: [hi(co 0..15) | 0]
+__global__ void tc5s_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int P, float* __restrict__ out) {
+  const long long total = (long long)P * 25 * 2 * 5 * 16 * 4;      // (pass, ky, kx, kc, kz, co, e)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 3); long long r = i >> 2;
+    const int co = (int)(r & 15); r >>= 4;
+    const int kz = (int)(r % 5); r /= 5;
+    const int kc = (int)(r & 1); r >>= 1;
+    const int kx = (int)(r % 5); r /= 5;
+    const int ky = (int)(r % 5); const int pass = (int)(r / 5);
+    const int ci = pass * 8 + kc * 4 + e;
+    float v = 0.f;
+    if (ci < Cin && co < Cout) v = w[((long long)co * Cin + ci) * 125 + (kz * 5 + ky) * 5 + kx];
+    float hi, lo;
+    tc::split_tf32(v, hi, lo);
+    const long long tap = (((long long)pass * 5 + ky) * 5 + kx) * (TAP_BYTES / 4);
+    const long long kcb = tap + (long long)kc * (KC_BYTES / 4);
+    const int blk = 4 - kz;
+    const long long row0 = kcb + ((long long)blk * BLK + co) * 4 + e;                  // part 0, hi
+    out[row0] = hi;
+    out[row0 + NP * 4] = lo;                                                           // part 0, lo
+    const long long row1 = kcb + (long long)SROWS * 4 + ((long long)blk * BLK + co) * 4 + e;   // part 1, hi
+    out[row1] = hi;
+    out[row1 + NP * 4] = 0.f;
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t crn_tc5s_packed_floats(int32_t Cin) { return (int64_t)((Cin + 7) / 8) * 5 * (WROW_BYTES / 4); }
+
+extern "C" int crn_tc5s_pack(const float* w, int32_t Cout, int32_t Cin, float* out, void* stream) {
+  CRN_REQUIRE(w && out && Cout > 0 && Cout <= 16 && Cin > 0, "crn_tc5s_pack: bad args (Cout <= 16)");
+  const int P = (Cin + 7) / 8;
+  const long long total = (long long)P * 25 * 2 * 5 * 16 * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  tc5s_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cout, Cin, P, out);
+  CRN_LAUNCH_CHECK("tc5s_pack");
+  return CRN_OK;
+}
+
+// y = conv5(x) + bias for Cout <= 16; the grid must tile by 8 (x) x 16 (y) x 4 (z).
+extern "C" int crn_conv5_tcs(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
+                             int32_t* status, void* stream) {
+  CRN_REQUIRE(d && x && wtc && y && status, "crn_conv5_tcs: null pointer");
+  CRN_REQUIRE(!d->transposed && d->kD == 5 && d->kH == 5 && d->kW == 5 && d->stride == 1 && d->pad == 2,
+              "crn_conv5_tcs: only Conv3d k=5 s=1 p=2");
+  CRN_REQUIRE(d->iD == d->oD && d->iH == d->oH && d->iW == d->oW, "crn_conv5_tcs: shape mismatch");
+  CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % ZT == 0 && d->iD >= 5, "crn_conv5_tcs: grid must tile by 8x16x4");
+  CRN_REQUIRE(!d->y_planar && !d->bias_n_stride && d->Cout <= 16 && d->Cout % 4 == 0 && d->Cin % 4 == 0,
+              "crn_conv5_tcs: Cout <= 16, channels multiples of 4, channels-last output");
+  CRN_REQUIRE(d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
+              "crn_conv5_tcs: channel strides/offsets must be multiples of 4");
+  TC5SParams p{};
+  p.in = x; p.wtc = wtc; p.bias = bias; p.out = y; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  p.gK = d->Cin; p.gN = d->Cout; p.in_cs = d->x_cs; p.in_co = d->x_co; p.out_cs = d->y_cs; p.out_co = d->y_co;
+  p.P = (p.gK + 7) / 8;
+  p.tiles_x = p.W / TX; p.tiles_y = p.H / TY; p.tiles_z = p.D / ZT;
+  p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
+  const size_t smem = (size_t)NSLOT * PLANE_BYTES + (size_t)WSTAGES * WROW_BYTES + sizeof(Barriers) + 64;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_tc5s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      crn_set_error("conv_tc5s: cannot set %zu bytes of dynamic shared memory", smem);
+      return CRN_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const int grid = p.nitems < kNumSMs ? p.nitems : kNumSMs;
+  conv_tc5s_kernel<<<grid, NTHREADS, smem, crn_stream(stream)>>>(p);
+  CRN_LAUNCH_CHECK("conv_tc5s");
+  return CRN_OK;
+}

@@ -159,6 +159,8 @@ def conv_call(kind, layer, d, *args):
 USE_TC = True
 # weight-gradient launches go to a second stream (see Plan.backward)
 WGRAD_SIDE_STREAM = True
+# stage_6.c1 forward through the kz-stacked kernel (csrc/conv_tc5s.cu)
+USE_TC5S = True
 
 
 def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
@@ -183,6 +185,18 @@ def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st):
   _lib.call("crn_convt7_tc_dgrad", C.byref(d), dy, wtc, dx, status, st)
   e1.record()
   PROFILE.append(("dgrad_tc", layer.name, conv_macs(d), e0, e1))
+
+
+def conv5_tcs_call(layer, d, inp, wtc, bias, out, status, st):
+  """Conv3d k=5 forward, Cout <= 16, through crn_conv5_tcs (kz taps stacked into N)."""
+  if PROFILE is None:
+    _lib.call("crn_conv5_tcs", C.byref(d), inp, wtc, bias, out, status, st)
+    return
+  e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+  e0.record()
+  _lib.call("crn_conv5_tcs", C.byref(d), inp, wtc, bias, out, status, st)
+  e1.record()
+  PROFILE.append(("fwd_tc", layer.name, conv_macs(d), e0, e1))
 
 
 def conv5_tc_call(kind, layer, d, inp, wtc, bias, out, status, st):
@@ -340,6 +354,13 @@ class Engine:
       if l.k == (5, 5, 5) and g >= 32 and g % 16 == 0 and cin <= 64 and mid <= 64:
         self.tc_w[l.name] = (t.zeros(lib.crn_tc5_packed_floats(cin, mid), dtype=t.float32, device=dev),
                              t.zeros(lib.crn_tc5_packed_floats(mid, cin), dtype=t.float32, device=dev))
+    # forward of the <= 16-output-channel layers: kz taps stacked into N (csrc/conv_tc5s.cu)
+    self.tcs_w = {}
+    if USE_TC5S:
+      for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
+        l = self.L[f"stage_{stage}.c1"]
+        if l.name in self.tc_w and mid <= 16 and mid % 4 == 0 and g % 16 == 0:
+          self.tcs_w[l.name] = t.zeros(lib.crn_tc5s_packed_floats(cin), dtype=t.float32, device=dev)
     # ... and per eligible ConvTranspose3d(k=7, s=2) layer a packed copy for the forward (csrc/conv_tc5.cu, KT=4)
     self.tct_w = {}
     self.tct_slices = {}
@@ -507,7 +528,10 @@ class Engine:
         if l.name in self.tc_w:
           w = P[l.name + ".weight"]
           wf, wd = self.tc_w[l.name]
-          _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 0, wf.data_ptr(), _lib.stream_ptr())
+          if l.name in self.tcs_w:
+            _call("crn_tc5s_pack", w.data_ptr(), l.cout, l.cin, self.tcs_w[l.name].data_ptr(), _lib.stream_ptr())
+          else:
+            _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 0, wf.data_ptr(), _lib.stream_ptr())
           _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 1, wd.data_ptr(), _lib.stream_ptr())
         for wt, wslice, co0 in self.tct_slices.get(l.name, ()):
           wslice.copy_(P[l.name + ".weight"][:, co0:co0 + 16])
@@ -774,7 +798,10 @@ class Plan:
     for sd in self.stages:
       g = sd["g"]
       sd["bn1"].fwd(training)
-      if USE_TC and sd["lc"].name in eng.tc_w:
+      if USE_TC and sd["lc"].name in eng.tcs_w:
+        conv5_tcs_call(sd["lc"], sd["d_c"], sd["z"].p, eng.tcs_w[sd["lc"].name].data_ptr(), bias(sd["lc"]), sd["c"].p,
+                       eng.tc_status.data_ptr(), st)
+      elif USE_TC and sd["lc"].name in eng.tc_w:
         conv5_tc_call("fwd", sd["lc"], sd["d_c"], sd["z"].p, eng.tc_w[sd["lc"].name][0].data_ptr(), bias(sd["lc"]),
                       sd["c"].p, eng.tc_status.data_ptr(), st)
       else:

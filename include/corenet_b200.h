@@ -271,6 +271,15 @@ int crn_tc5_pack(const float* w, int32_t Cout, int32_t Cin, int32_t dgrad, float
 int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc, const float* bias,
                  float* out, int32_t* status, void* stream);
 
+/* Conv3d k=5 forward for Cout <= 16 with the 5 kz taps stacked into N (csrc/conv_tc5s.cu): one staged input plane
+ * feeds the accumulators of the five output planes it contributes to in ONE tcgen05.mma (N = 5 x 32), which amortises
+ * the shared-memory A fetch that bounds crn_conv5_tc at these channel counts.  Same contract as crn_conv5_tc kind 0;
+ * the grid must tile by 8 (x) x 16 (y) x 4 (z).  Replaces the cuDNN call behind model/reconstruction_decoder.py:91. */
+int64_t crn_tc5s_packed_floats(int32_t Cin);
+int crn_tc5s_pack(const float* w, int32_t Cout, int32_t Cin, float* out, void* stream);
+int crn_conv5_tcs(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
+                  int32_t* status, void* stream);
+
 /* ConvTranspose3d k=7 s=2 p=3 output_padding=1 forward on the same tcgen05 kernel: seen from the input
  * grid all 8 output parity classes form one stride-1 4x4x4-tap convolution with 8*Cout columns, whose
  * epilogue scatters column (class, co) of input voxel i to output voxel 2i+class.  Replaces the cuDNN

@@ -385,6 +385,34 @@ def test_convt7_wgrad_line_tcgen05(n, cin, cout, dhw, ycs):
   assert rel_err(dw[:, :, :cout], ref) < 5e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw", [(1, 8, 16, (8, 16, 8)), (2, 28, 16, (12, 32, 16)), (1, 12, 8, (4, 16, 24)),
+                                              (1, 28, 16, (20, 16, 8))])
+def test_conv5_kz_stacked_tcgen05(n, cin, cout, dhw):
+  """Conv3d k=5 forward with the kz taps stacked into N (csrc/conv_tc5s.cu) against the fp64 oracle; same tolerance
+  as the plain tcgen05 kernel (2e-4 of the tensor max)."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 5 + cout + d)
+  wt = t.randn(cout, cin, 5, 5, 5, generator=g) * 0.05
+  bias = t.randn(cout, generator=g)
+  x = t.randn(n, cin, d, h, w, generator=g)
+  ref = F.conv3d(x.double(), wt.double(), bias.double(), padding=2)
+  xin = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).contiguous().to(dev())
+  out = t.full((n * d * h * w, cout), float("nan"), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tc5s_packed_floats(cin), device=dev())
+  st = _lib.stream_ptr()
+  _lib.call("crn_tc5s_pack", wt.to(dev()).contiguous().data_ptr(), cout, cin, wtc.data_ptr(), st)
+  desc = ops.make_desc(n, cin, cout, dhw, dhw, (5, 5, 5), 1, 2, False, cin, cout)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  b = bias.to(dev())
+  _lib.call("crn_conv5_tcs", C.byref(desc), xin.data_ptr(), wtc.data_ptr(), b.data_ptr(), out.data_ptr(), status.data_ptr(), st)
+  t.cuda.synchronize()
+  assert int(status) == 0
+  got = out.reshape(n, d, h, w, cout).permute(0, 4, 1, 2, 3)
+  assert rel_err(got, ref) < 2e-4
+
+
 @pytest.mark.parametrize("n,cin,cout,dhw,planar", [(1, 8, 2, (8, 16, 8), True), (2, 16, 2, (8, 32, 16), True),
                                                      (1, 12, 3, (8, 16, 8), True), (1, 8, 2, (8, 16, 8), False),
                                                      (1, 32, 16, (8, 16, 16), False), (1, 16, 8, (8, 16, 8), False),
