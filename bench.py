@@ -228,11 +228,11 @@ def run_native(args):
   ms = timed(dev_step, args.steps)
   # kernels of this library per step: counted at graph capture (replays do not pass through the C-ABI counter)
   launches = trainer.graph_launches * args.steps + (_lib.lib().crn_launch_count() - n0)
-  clocks = sampler.stop()
   trainer.prefetch(*h_in)
   for _ in range(2):
     e2e_step()
   ms_e2e = timed(e2e_step, args.steps)
+  clocks = sampler.stop()                           # sampled across both timed regions (device-resident and e2e)
   trainer.step()                                    # drain the last prefetched batch
   # per-kernel roofline pass: the same step enqueued eagerly with CUDA events around every convolution launch
   # (a replayed graph has no per-launch events); same inputs, same process, right after the timed region

@@ -523,7 +523,7 @@ class Engine:
 
   def _pack_tc(self, P):
     """tcgen05 weight re-packs (conv_tc5 / class-scatter / implicit-GEMM layouts) on the current stream."""
-    if True:
+    if self.layers:
       for l in self.layers:
         if l.name in self.tc_w:
           w = P[l.name + ".weight"]
