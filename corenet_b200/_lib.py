@@ -93,6 +93,8 @@ _SIGS = {
     "crn_tc5s_packed_floats": ([i32], i64),
     "crn_tc5s_pack": ([vp, i32, i32, vp, vp], i32),
     "crn_conv5_tcs": ([_P(ConvDesc), vp, vp, vp, vp, vp, vp], i32),
+    "crn_tc5s_pack2": ([vp, i32, i32, i32, vp, vp], i32),
+    "crn_conv5_tcs2": ([_P(ConvDesc), i32, vp, vp, vp, vp, vp, vp], i32),
     "crn_tct_packed_floats": ([i32, i32, i32], i64),
     "crn_tct_pack": ([vp, i32, i32, i32, vp, vp], i32),
     "crn_convt7_tc_dgrad": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),

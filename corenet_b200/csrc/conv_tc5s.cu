@@ -14,6 +14,10 @@
 //     not-started planes are always the upper end of the stack, so that MMA is split in two at most once per q;
 //   * epilogue: register-resident running sums (4 planes x 16 columns), one flush per (pass, ky) group (80 MMAs),
 //     one store per item; warp roles and bounded waits as in conv_tc5.cu.
+// WIDE variant (17..32 output channels: stage_6.c1 dgrad 16 -> 28, stage_5.c1 forward 56 -> 32): the 32 columns of a
+// plane are 32 channels, the stacked B regions are [W_hi] and [W_lo] (same 10 KB per tap) and the three products
+// A_hi x W_hi, A_lo x W_hi, A_hi x W_lo are three stacked MMAs.  dgrad = the same kernel on dy with the flipped,
+// transposed filter (packed that way).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -57,7 +61,9 @@ __device__ __forceinline__ void decode_item(const TC5SParams& p, int item, int& 
   z0 = (t % p.tiles_z) * ZT; n = t / p.tiles_z;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams p) {
+  constexpr int NOUT = WIDE ? 32 : 16;             // output channels held per plane
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;
   uint8_t* wring = smem + NSLOT * PLANE_BYTES;
@@ -88,11 +94,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
       decode_item(p, item, n, z0, y0, x0);
       const int m = warp * 32 + lane;
       const int y = y0 + (m >> 3), x = x0 + (m & 7);
-      float sum[ZT][16];
+      float sum[ZT][NOUT];
 #pragma unroll
       for (int zz = 0; zz < ZT; ++zz)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) sum[zz][e] = 0.f;
+        for (int e = 0; e < NOUT; ++e) sum[zz][e] = 0.f;
       for (int pass = 0; pass < p.P && !dead; ++pass) {
         for (int ky = 0; ky < 5; ++ky, ++G) {
           const int st = (int)(G & 1);
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
             for (int e = 0; e < 16; ++e) sum[zz][e] += v[e];
             tc::tmem_ld16(ta + NP, v);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) sum[zz][e] += v[e];
+            for (int e = 0; e < 16; ++e) sum[zz][WIDE ? 16 + e : e] += v[e];   // ND16: hi*lo half folds onto the same 16
           }
           tc::fence_before_sync();
           tc::mbar_arrive(&B->acc_empty[st]);
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
         const long long pos = (((long long)n * p.D + (z0 + zz)) * p.H + y) * p.W + x;
         float* dst = p.out + pos * p.out_cs + p.out_co;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
+        for (int qd = 0; qd < NOUT / 4; ++qd) {
           const int c = qd * 4;
           if (c < p.gN) {                          // gN is a multiple of 4
             float4 o = make_float4(sum[zz][c], sum[zz][c + 1], sum[zz][c + 2], sum[zz][c + 3]);
@@ -209,11 +215,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
                 const uint32_t alo0 = ((ring_u32 + (uint32_t)slot * PLANE_BYTES) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
 #pragma unroll
                 for (int kx = 0; kx < 5; ++kx) {
+                  // ND16: (A_hi, [W_hi|W_lo]), (A_lo, [W_hi|0]);   WIDE: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
 #pragma unroll
-                  for (int part = 0; part < 2; ++part) {
-                    const uint32_t alo = alo0 + (ky * XS + kx) + (part == 1 ? (PART_BYTES >> 4) : 0);
+                  for (int part = 0; part < (WIDE ? 3 : 2); ++part) {
+                    const bool a_lo = part == 1;
+                    const bool b_r1 = WIDE ? part == 2 : part == 1;
+                    const uint32_t alo = alo0 + (ky * XS + kx) + (a_lo ? (PART_BYTES >> 4) : 0);
                     const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
-                    const uint32_t bb = wbase + kx * TAP_BYTES + (part == 1 ? SROWS * 16 : 0) + boff;
+                    const uint32_t bb = wbase + kx * TAP_BYTES + (b_r1 ? SROWS * 16 : 0) + boff;
                     if (kx == 0 && part == 0 && ns <= zhi) {
                       // planes [max(zlo, ns), zhi] get their first contribution of the group: overwrite them
                       const int zs = ns > zlo ? ns : zlo;
@@ -273,79 +282,115 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
   if (warp == 8) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// pack: PyTorch conv weight [Cout][Cin][125] -> wtc[P][ky][kx][kc][part][blk = 4 - kz][32 rows][4 floats]
-//   part 0 rows: [hi(co 0..15) | lo(co 0..15)],  part 1 rows: [hi(co 0..15) | 0]
-__global__ void tc5s_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int P, float* __restrict__ out) {
-  const long long total = (long long)P * 25 * 2 * 5 * 16 * 4;      // (pass, ky, kx, kc, kz, co, e)
+// pack: PyTorch conv weight [Cout][Cin][125] -> wtc[P][ky][kx][kc][region][blk = 4 - kz][32 rows][4 floats]
+//   ND16 (N <= 16): region 0 rows [hi(n 0..15) | lo(n 0..15)], region 1 rows [hi(n 0..15) | 0]
+//   WIDE (N <= 32): region 0 rows hi(n 0..31),                 region 1 rows lo(n 0..31)
+//   fwd: k = ci, n = co, tap t;   dgrad: k = co, n = ci, tap 124 - t
+__global__ void tc5s_pack_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, int wide, int P,
+                                 float* __restrict__ out) {
+  const int K = dgrad ? Cout : Cin, Nn = dgrad ? Cin : Cout;
+  const long long total = (long long)P * 25 * 2 * 5 * 32 * 4;      // (pass, ky, kx, kc, kz, n, e)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int e = (int)(i & 3); long long r = i >> 2;
-    const int co = (int)(r & 15); r >>= 4;
+    const int n = (int)(r & 31); r >>= 5;
     const int kz = (int)(r % 5); r /= 5;
     const int kc = (int)(r & 1); r >>= 1;
     const int kx = (int)(r % 5); r /= 5;
     const int ky = (int)(r % 5); const int pass = (int)(r / 5);
-    const int ci = pass * 8 + kc * 4 + e;
+    if (!wide && n >= 16) continue;
+    const int k = pass * 8 + kc * 4 + e;
     float v = 0.f;
-    if (ci < Cin && co < Cout) v = w[((long long)co * Cin + ci) * 125 + (kz * 5 + ky) * 5 + kx];
+    if (k < K && n < Nn) {
+      const int co = dgrad ? k : n, ci = dgrad ? n : k;
+      const int t = (kz * 5 + ky) * 5 + kx;
+      v = w[((long long)co * Cin + ci) * 125 + (dgrad ? 124 - t : t)];
+    }
     float hi, lo;
     tc::split_tf32(v, hi, lo);
-    const long long tap = (((long long)pass * 5 + ky) * 5 + kx) * (TAP_BYTES / 4);
-    const long long kcb = tap + (long long)kc * (KC_BYTES / 4);
-    const int blk = 4 - kz;
-    const long long row0 = kcb + ((long long)blk * BLK + co) * 4 + e;                  // part 0, hi
-    out[row0] = hi;
-    out[row0 + NP * 4] = lo;                                                           // part 0, lo
-    const long long row1 = kcb + (long long)SROWS * 4 + ((long long)blk * BLK + co) * 4 + e;   // part 1, hi
-    out[row1] = hi;
-    out[row1 + NP * 4] = 0.f;
+    const long long kcb = (((long long)pass * 5 + ky) * 5 + kx) * (TAP_BYTES / 4) + (long long)kc * (KC_BYTES / 4);
+    const long long row0 = kcb + ((long long)(4 - kz) * BLK + n) * 4 + e;              // region 0
+    const long long row1 = row0 + (long long)SROWS * 4;                               // region 1
+    if (wide) {
+      out[row0] = hi;
+      out[row1] = lo;
+    } else {
+      out[row0] = hi; out[row0 + NP * 4] = lo;
+      out[row1] = hi; out[row1 + NP * 4] = 0.f;
+    }
   }
 }
 
-}  // namespace
-
-extern "C" int64_t crn_tc5s_packed_floats(int32_t Cin) { return (int64_t)((Cin + 7) / 8) * 5 * (WROW_BYTES / 4); }
-
-extern "C" int crn_tc5s_pack(const float* w, int32_t Cout, int32_t Cin, float* out, void* stream) {
-  CRN_REQUIRE(w && out && Cout > 0 && Cout <= 16 && Cin > 0, "crn_tc5s_pack: bad args (Cout <= 16)");
-  const int P = (Cin + 7) / 8;
-  const long long total = (long long)P * 25 * 2 * 5 * 16 * 4;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  tc5s_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cout, Cin, P, out);
-  CRN_LAUNCH_CHECK("tc5s_pack");
-  return CRN_OK;
-}
-
-// y = conv5(x) + bias for Cout <= 16; the grid must tile by 8 (x) x 16 (y) x 4 (z).
-extern "C" int crn_conv5_tcs(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
-                             int32_t* status, void* stream) {
-  CRN_REQUIRE(d && x && wtc && y && status, "crn_conv5_tcs: null pointer");
-  CRN_REQUIRE(!d->transposed && d->kD == 5 && d->kH == 5 && d->kW == 5 && d->stride == 1 && d->pad == 2,
-              "crn_conv5_tcs: only Conv3d k=5 s=1 p=2");
-  CRN_REQUIRE(d->iD == d->oD && d->iH == d->oH && d->iW == d->oW, "crn_conv5_tcs: shape mismatch");
-  CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % ZT == 0 && d->iD >= 5, "crn_conv5_tcs: grid must tile by 8x16x4");
-  CRN_REQUIRE(!d->y_planar && !d->bias_n_stride && d->Cout <= 16 && d->Cout % 4 == 0 && d->Cin % 4 == 0,
-              "crn_conv5_tcs: Cout <= 16, channels multiples of 4, channels-last output");
-  CRN_REQUIRE(d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
-              "crn_conv5_tcs: channel strides/offsets must be multiples of 4");
-  TC5SParams p{};
-  p.in = x; p.wtc = wtc; p.bias = bias; p.out = y; p.status = status;
-  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
-  p.gK = d->Cin; p.gN = d->Cout; p.in_cs = d->x_cs; p.in_co = d->x_co; p.out_cs = d->y_cs; p.out_co = d->y_co;
-  p.P = (p.gK + 7) / 8;
-  p.tiles_x = p.W / TX; p.tiles_y = p.H / TY; p.tiles_z = p.D / ZT;
-  p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
+template <bool WIDE>
+int launch_tc5s(const TC5SParams& p, cudaStream_t st) {
   const size_t smem = (size_t)NSLOT * PLANE_BYTES + (size_t)WSTAGES * WROW_BYTES + sizeof(Barriers) + 64;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc5s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc5s_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       crn_set_error("conv_tc5s: cannot set %zu bytes of dynamic shared memory", smem);
       return CRN_ERR_LAUNCH;
     }
     configured = true;
   }
   const int grid = p.nitems < kNumSMs ? p.nitems : kNumSMs;
-  conv_tc5s_kernel<<<grid, NTHREADS, smem, crn_stream(stream)>>>(p);
+  conv_tc5s_kernel<WIDE><<<grid, NTHREADS, smem, st>>>(p);
   CRN_LAUNCH_CHECK("conv_tc5s");
   return CRN_OK;
+}
+
+}  // namespace
+
+// K = reduction channels (Cin for the forward operator, Cout for dgrad)
+extern "C" int64_t crn_tc5s_packed_floats(int32_t K) { return (int64_t)((K + 7) / 8) * 5 * (WROW_BYTES / 4); }
+
+extern "C" int crn_tc5s_pack2(const float* w, int32_t Cout, int32_t Cin, int32_t dgrad, float* out, void* stream) {
+  CRN_REQUIRE(w && out && Cout > 0 && Cin > 0, "crn_tc5s_pack2: bad args");
+  const int K = dgrad ? Cout : Cin, N = dgrad ? Cin : Cout;
+  CRN_REQUIRE(N <= 32, "crn_tc5s_pack2: N > 32 unsupported");
+  const int P = (K + 7) / 8;
+  const long long total = (long long)P * 25 * 2 * 5 * 32 * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  tc5s_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cout, Cin, dgrad ? 1 : 0, N > 16 ? 1 : 0, P, out);
+  CRN_LAUNCH_CHECK("tc5s_pack");
+  return CRN_OK;
+}
+
+extern "C" int crn_tc5s_pack(const float* w, int32_t Cout, int32_t Cin, float* out, void* stream) {
+  CRN_REQUIRE(Cout <= 16, "crn_tc5s_pack: Cout <= 16 (use crn_tc5s_pack2)");
+  return crn_tc5s_pack2(w, Cout, Cin, 0, out, stream);
+}
+
+// kind 0: y = conv5(x) + bias (gK = Cin, gN = Cout); kind 1: dx = conv5^T(dy) (gK = Cout, gN = Cin); gN <= 32.
+// The grid must tile by 8 (x) x 16 (y) x 4 (z).
+extern "C" int crn_conv5_tcs2(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc, const float* bias,
+                              float* out, int32_t* status, void* stream) {
+  CRN_REQUIRE(d && in && wtc && out && status, "crn_conv5_tcs: null pointer");
+  CRN_REQUIRE(!d->transposed && d->kD == 5 && d->kH == 5 && d->kW == 5 && d->stride == 1 && d->pad == 2,
+              "crn_conv5_tcs: only Conv3d k=5 s=1 p=2");
+  CRN_REQUIRE(d->iD == d->oD && d->iH == d->oH && d->iW == d->oW, "crn_conv5_tcs: shape mismatch");
+  CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % ZT == 0 && d->iD >= 5, "crn_conv5_tcs: grid must tile by 8x16x4");
+  CRN_REQUIRE(!d->y_planar && !d->bias_n_stride && d->Cout % 4 == 0 && d->Cin % 4 == 0,
+              "crn_conv5_tcs: channels multiples of 4, channels-last output");
+  CRN_REQUIRE(d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
+              "crn_conv5_tcs: channel strides/offsets must be multiples of 4");
+  TC5SParams p{};
+  p.in = in; p.wtc = wtc; p.bias = kind == 0 ? bias : nullptr; p.out = out; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  if (kind == 0) {
+    p.gK = d->Cin; p.gN = d->Cout; p.in_cs = d->x_cs; p.in_co = d->x_co; p.out_cs = d->y_cs; p.out_co = d->y_co;
+  } else {
+    p.gK = d->Cout; p.gN = d->Cin; p.in_cs = d->y_cs; p.in_co = d->y_co; p.out_cs = d->x_cs; p.out_co = d->x_co;
+  }
+  CRN_REQUIRE(p.gN <= 32, "crn_conv5_tcs: at most 32 output channels");
+  p.P = (p.gK + 7) / 8;
+  p.tiles_x = p.W / TX; p.tiles_y = p.H / TY; p.tiles_z = p.D / ZT;
+  p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
+  cudaStream_t st = crn_stream(stream);
+  return p.gN <= 16 ? launch_tc5s<false>(p, st) : launch_tc5s<true>(p, st);
+}
+
+extern "C" int crn_conv5_tcs(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
+                             int32_t* status, void* stream) {
+  CRN_REQUIRE(d && d->Cout <= 16, "crn_conv5_tcs: Cout <= 16 (use crn_conv5_tcs2)");
+  return crn_conv5_tcs2(d, 0, x, wtc, bias, y, status, stream);
 }

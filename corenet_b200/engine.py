@@ -187,16 +187,17 @@ def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st):
   PROFILE.append(("dgrad_tc", layer.name, conv_macs(d), e0, e1))
 
 
-def conv5_tcs_call(layer, d, inp, wtc, bias, out, status, st):
-  """Conv3d k=5 forward, Cout <= 16, through crn_conv5_tcs (kz taps stacked into N)."""
+def conv5_tcs_call(layer, d, inp, wtc, bias, out, status, st, kind=0):
+  """Conv3d k=5 forward (kind 0) / dgrad (kind 1) with <= 32 output channels through crn_conv5_tcs2 (kz taps
+  stacked into N)."""
   if PROFILE is None:
-    _lib.call("crn_conv5_tcs", C.byref(d), inp, wtc, bias, out, status, st)
+    _lib.call("crn_conv5_tcs2", C.byref(d), kind, inp, wtc, bias, out, status, st)
     return
   e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
   e0.record()
-  _lib.call("crn_conv5_tcs", C.byref(d), inp, wtc, bias, out, status, st)
+  _lib.call("crn_conv5_tcs2", C.byref(d), kind, inp, wtc, bias, out, status, st)
   e1.record()
-  PROFILE.append(("fwd_tc", layer.name, conv_macs(d), e0, e1))
+  PROFILE.append(("fwd_tc" if kind == 0 else "dgrad_tc", layer.name, conv_macs(d), e0, e1))
 
 
 def conv5_tc_call(kind, layer, d, inp, wtc, bias, out, status, st):
@@ -355,12 +356,17 @@ class Engine:
         self.tc_w[l.name] = (t.zeros(lib.crn_tc5_packed_floats(cin, mid), dtype=t.float32, device=dev),
                              t.zeros(lib.crn_tc5_packed_floats(mid, cin), dtype=t.float32, device=dev))
     # forward of the <= 16-output-channel layers: kz taps stacked into N (csrc/conv_tc5s.cu)
+    # (<= 32 output channels; the dgrad of a layer is the same kernel with N = Cin)
     self.tcs_w = {}
+    self.tcs_wd = {}
     if USE_TC5S:
       for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
         l = self.L[f"stage_{stage}.c1"]
-        if l.name in self.tc_w and mid <= 16 and mid % 4 == 0 and g % 16 == 0:
-          self.tcs_w[l.name] = t.zeros(lib.crn_tc5s_packed_floats(cin), dtype=t.float32, device=dev)
+        if l.name in self.tc_w and mid % 4 == 0 and cin % 4 == 0 and g % 16 == 0:
+          if mid <= 32:
+            self.tcs_w[l.name] = t.zeros(lib.crn_tc5s_packed_floats(cin), dtype=t.float32, device=dev)
+          if cin <= 32:
+            self.tcs_wd[l.name] = t.zeros(lib.crn_tc5s_packed_floats(mid), dtype=t.float32, device=dev)
     # ... and per eligible ConvTranspose3d(k=7, s=2) layer a packed copy for the forward (csrc/conv_tc5.cu, KT=4)
     self.tct_w = {}
     self.tct_slices = {}
@@ -529,10 +535,13 @@ class Engine:
           w = P[l.name + ".weight"]
           wf, wd = self.tc_w[l.name]
           if l.name in self.tcs_w:
-            _call("crn_tc5s_pack", w.data_ptr(), l.cout, l.cin, self.tcs_w[l.name].data_ptr(), _lib.stream_ptr())
+            _call("crn_tc5s_pack2", w.data_ptr(), l.cout, l.cin, 0, self.tcs_w[l.name].data_ptr(), _lib.stream_ptr())
           else:
             _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 0, wf.data_ptr(), _lib.stream_ptr())
-          _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 1, wd.data_ptr(), _lib.stream_ptr())
+          if l.name in self.tcs_wd:
+            _call("crn_tc5s_pack2", w.data_ptr(), l.cout, l.cin, 1, self.tcs_wd[l.name].data_ptr(), _lib.stream_ptr())
+          else:
+            _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 1, wd.data_ptr(), _lib.stream_ptr())
         for wt, wslice, co0 in self.tct_slices.get(l.name, ()):
           wslice.copy_(P[l.name + ".weight"][:, co0:co0 + 16])
           _call("crn_tct_pack", wslice.data_ptr(), l.cin, 16, 0, wt.data_ptr(), _lib.stream_ptr())
@@ -923,7 +932,10 @@ class Plan:
       dxs = sd["bn2"].bwd(tr, grads, sd["z2"].gp, sd["z2"].cs, sd["c"].gp, sd["c"].cs)
       bias_from(dxs, lc.name + ".bias")
       wgrad(lc, sd["d_c"], sd["z"].p, sd["c"].gp)
-      if USE_TC and lc.name in eng.tc_w:
+      if USE_TC and lc.name in eng.tcs_wd:
+        conv5_tcs_call(lc, sd["d_c"], sd["c"].gp, eng.tcs_wd[lc.name].data_ptr(), None, sd["z"].gp,
+                       eng.tc_status.data_ptr(), st, kind=1)
+      elif USE_TC and lc.name in eng.tc_w:
         conv5_tc_call("dgrad", lc, sd["d_c"], sd["c"].gp, eng.tc_w[lc.name][1].data_ptr(), None, sd["z"].gp,
                       eng.tc_status.data_ptr(), st)
       else:

@@ -275,10 +275,15 @@ int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* in, const fl
  * feeds the accumulators of the five output planes it contributes to in ONE tcgen05.mma (N = 5 x 32), which amortises
  * the shared-memory A fetch that bounds crn_conv5_tc at these channel counts.  Same contract as crn_conv5_tc kind 0;
  * the grid must tile by 8 (x) x 16 (y) x 4 (z).  Replaces the cuDNN call behind model/reconstruction_decoder.py:91. */
-int64_t crn_tc5s_packed_floats(int32_t Cin);
+int64_t crn_tc5s_packed_floats(int32_t K);   /* K = reduction channels: Cin (forward) / Cout (dgrad) */
 int crn_tc5s_pack(const float* w, int32_t Cout, int32_t Cin, float* out, void* stream);
 int crn_conv5_tcs(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
                   int32_t* status, void* stream);
+/* General form: up to 32 output channels (17..32: the three hi/lo products as three stacked MMAs) and dgrad
+ * (kind 1: dx = conv5^T(dy), weights packed with dgrad != 0 = flipped taps, transposed channels). */
+int crn_tc5s_pack2(const float* w, int32_t Cout, int32_t Cin, int32_t dgrad, float* out, void* stream);
+int crn_conv5_tcs2(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc, const float* bias,
+                   float* out, int32_t* status, void* stream);
 
 /* ConvTranspose3d k=7 s=2 p=3 output_padding=1 forward on the same tcgen05 kernel: seen from the input
  * grid all 8 output parity classes form one stride-1 4x4x4-tap convolution with 8*Cout columns, whose

