@@ -300,7 +300,10 @@ def run_native(args):
                        "scenes_per_sec": value / VOX},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "note": "Trainer.step()/prefetch() with pinned HOST inputs: every timed step issues the full H2D of a "
+                            "batch (copy stream, overlapping the running step like a prefetching data loader) and "
+                            "synchronously reads the step's loss back"},
             "gpu_launches": int(launches), "roofline": roof}
     if world == 1 and not args.no_cpu_baseline:
       line["cpu_baseline"] = cpu_baseline()
