@@ -81,6 +81,7 @@ _SIGS = {
     "crn_loss_bwd": ([vp, vp, i32, i32, i32, i64, i32, vp, vp, vp, vp], i32),
     "crn_softmax_planar": ([vp, i32, i32, i64, vp, vp], i32),
     "crn_argmax_confusion": ([vp, vp, i32, i32, i32, i64, vp, vp], i32),
+    "crn_argmax_confusion_labeled": ([vp, vp, i32, i32, i32, i64, vp, i32, vp, vp], i32),
     "crn_fill_workspace_bytes": ([i32, i32, i32, i32], i64),
     "crn_fill_inside": ([vp, vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "crn_voxelize_mesh": ([vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp], i32),
@@ -112,6 +113,8 @@ _SIGS = {
     "crn_convt7_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_gather_f64_to_f32": ([vp, vp, i32, i64, vp], i32),
     "crn_adam_step_dev": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, f32, vp], i32),
+    "crn_adam_step_guarded": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, i32, f32, vp, vp], i32),
+    "crn_status_poison": ([vp, vp, i64, i32, vp], i32),
     "crn_adam_step": ([vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp], i32),
 }
 

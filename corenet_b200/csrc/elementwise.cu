@@ -162,6 +162,51 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+__global__ void counter_inc_guarded_kernel(int32_t* c, const int32_t* status) {
+  if (status == nullptr || *status == 0) *c += 1;
+}
+
+__global__ void adam_guarded_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                    float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                    const int32_t* __restrict__ step, float gscale,
+                                    const int32_t* __restrict__ status) {
+  if (status != nullptr && *status != 0) return;
+  const float st = (float)*step;
+  const float bc1 = 1.f - powf(b1, st);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                       reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 ? n / 4 : 0;
+  const float a = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += (int64_t)gridDim.x * NT) {
+    float4 gi = reinterpret_cast<const float4*>(g)[i];
+    float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+    float4 pi = reinterpret_cast<float4*>(p)[i];
+#define CRN_ADAM1(c)                                              \
+    { const float gg = gi.c * gscale;                               \
+      mi.c = b1 * mi.c + (1.f - b1) * gg;                           \
+      vi.c = b2 * vi.c + (1.f - b2) * gg * gg;                      \
+      pi.c -= a * (mi.c / (sqrtf(vi.c) / bc2_sqrt + eps)); }
+    CRN_ADAM1(x) CRN_ADAM1(y) CRN_ADAM1(z) CRN_ADAM1(w)
+#undef CRN_ADAM1
+    reinterpret_cast<float4*>(m)[i] = mi;
+    reinterpret_cast<float4*>(v)[i] = vi;
+    reinterpret_cast<float4*>(p)[i] = pi;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= a * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
+__global__ void status_poison_kernel(const int32_t* status, float* out, int64_t stride, int n) {
+  if (*status == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[(int64_t)i * stride] = __int_as_float(0x7fc00000);
+}
+
 inline unsigned grid_for(int64_t total) {
   int64_t b = crn_ceil_div(total, NT);
   if (b > 16LL * kNumSMs) b = 16LL * kNumSMs;
@@ -254,6 +299,27 @@ extern "C" int crn_adam_step_dev(float* p, const float* g, float* m, float* v, i
                                                              grad_scale);
   CRN_LAUNCH_CHECK("adam_dev");
   crn_count_launches(1);
+  return CRN_OK;
+}
+
+extern "C" int crn_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                     float beta2, float eps, int32_t* step_dev, int32_t bump_step, float grad_scale,
+                                     const int32_t* status, void* stream) {
+  CRN_REQUIRE(p && g && m && v && n > 0 && step_dev, "crn_adam_step_guarded: bad args");
+  if (bump_step) {
+    counter_inc_guarded_kernel<<<1, 1, 0, crn_stream(stream)>>>(step_dev, status);
+    crn_count_launches(1);
+  }
+  adam_guarded_kernel<<<grid_for(crn_ceil_div(n, 4)), NT, 0, crn_stream(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, step_dev, grad_scale, status);
+  CRN_LAUNCH_CHECK("adam_guarded");
+  return CRN_OK;
+}
+
+extern "C" int crn_status_poison(const int32_t* status, float* out, int64_t stride, int32_t n, void* stream) {
+  CRN_REQUIRE(status && out && n > 0, "crn_status_poison: bad args");
+  status_poison_kernel<<<(n + 63) / 64, 64, 0, crn_stream(stream)>>>(status, out, stride, n);
+  CRN_LAUNCH_CHECK("status_poison");
   return CRN_OK;
 }
 

@@ -9,9 +9,12 @@ namespace {
 constexpr int NT = 256;
 constexpr int MAXC = 32;
 
+// labels outside [0, C) would index logits out of bounds: clamped here (the reference's one_hot raises on them,
+// model/losses.py:36; the host wrappers validate the dtype, range validation needs a device sync and is opt-in)
 template <typename GT>
-__device__ __forceinline__ int load_gt(const void* gt, int64_t i) {
-  return (int)reinterpret_cast<const GT*>(gt)[i];
+__device__ __forceinline__ int load_gt(const void* gt, int64_t i, int C) {
+  const GT v = reinterpret_cast<const GT*>(gt)[i];
+  return v < (GT)0 ? 0 : (v >= (GT)C ? C - 1 : (int)v);
 }
 
 // per-voxel softmax into s[], returns log-sum-exp pieces
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(NT) loss_sums_kernel(const float* __restrict__
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < S; i += (int64_t)gridDim.x * NT) {
     float s[MAXC], mx, sum;
     softmax_c(base + i, C, S, s, mx, sum);
-    const int L = load_gt<GT>(gt, (int64_t)n * S + i);
+    const int L = load_gt<GT>(gt, (int64_t)n * S + i, C);
     if (mode == 0) {
       float pfg = 0.f;
       for (int c = 1; c < C; ++c) pfg += s[c];
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(NT) loss_bwd_kernel(const float* __restrict__ 
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < S; i += (int64_t)gridDim.x * NT) {
     float s[MAXC], mx, sum;
     softmax_c(base + i, C, S, s, mx, sum);
-    const int L = load_gt<GT>(gt, (int64_t)n * S + i);
+    const int L = load_gt<GT>(gt, (int64_t)n * S + i, C);
     if (mode == 0) {
       float pfg = 0.f;
       for (int c = 1; c < C; ++c) pfg += s[c];
@@ -151,11 +154,14 @@ __global__ void __launch_bounds__(NT) softmax_planar_kernel(const float* __restr
 template <typename GT>
 __global__ void __launch_bounds__(NT) argmax_confusion_kernel(const float* __restrict__ logits, const void* gt,
                                                               int N, int C, int64_t S,
+                                                              const int32_t* __restrict__ scene_label, int K,
                                                               unsigned long long* cm) {
-  extern __shared__ unsigned int hist[];   // C*C
-  for (int k = threadIdx.x; k < C * C; k += NT) hist[k] = 0u;
+  extern __shared__ unsigned int hist[];   // K*K
+  for (int k = threadIdx.x; k < K * K; k += NT) hist[k] = 0u;
   __syncthreads();
   const int n = blockIdx.y;
+  // FG_BG evaluation (evaluation_results.py:40-51): labels 0/1 are scaled by the scene's dataset class
+  const int mul = scene_label ? __ldg(scene_label + n) : 1;
   const float* base = logits + (int64_t)n * C * S;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < S; i += (int64_t)gridDim.x * NT) {
     float best = __ldg(base + i);
@@ -164,11 +170,11 @@ __global__ void __launch_bounds__(NT) argmax_confusion_kernel(const float* __res
       const float v = __ldg(base + i + (int64_t)c * S);
       if (v > best) { best = v; bi = c; }   // first max wins, like torch.argmax
     }
-    const int L = load_gt<GT>(gt, (int64_t)n * S + i);
-    atomicAdd(&hist[L * C + bi], 1u);
+    const int L = load_gt<GT>(gt, (int64_t)n * S + i, C);
+    atomicAdd(&hist[(L * mul) * K + bi * mul], 1u);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < C * C; k += NT)
+  for (int k = threadIdx.x; k < K * K; k += NT)
     if (hist[k]) atomicAdd(cm + k, (unsigned long long)hist[k]);
 }
 
@@ -221,17 +227,25 @@ extern "C" int crn_softmax_planar(const float* logits, int32_t N, int32_t C, int
   return CRN_OK;
 }
 
-extern "C" int crn_argmax_confusion(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N,
-                                    int32_t C, int64_t S, int64_t* cm, void* stream) {
-  CRN_REQUIRE(logits && gt && cm && N > 0 && C >= 1 && C <= MAXC && S > 0, "crn_argmax_confusion: bad args");
+extern "C" int crn_argmax_confusion_labeled(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N,
+                                            int32_t C, int64_t S, const int32_t* scene_label, int32_t K,
+                                            int64_t* cm, void* stream) {
+  CRN_REQUIRE(logits && gt && cm && N > 0 && C >= 1 && C <= MAXC && S > 0 && K >= C && K <= 64,
+              "crn_argmax_confusion: bad args");
+  CRN_REQUIRE(scene_label || K == C, "crn_argmax_confusion: K != C needs scene labels");
   cudaStream_t st = crn_stream(stream);
-  const size_t sh = sizeof(unsigned int) * C * C;
+  const size_t sh = sizeof(unsigned int) * K * K;
   if (gt_is_i64)
     argmax_confusion_kernel<int64_t><<<grid_ns(N, S), NT, sh, st>>>(
-        logits, gt, N, C, S, reinterpret_cast<unsigned long long*>(cm));
+        logits, gt, N, C, S, scene_label, K, reinterpret_cast<unsigned long long*>(cm));
   else
     argmax_confusion_kernel<int32_t><<<grid_ns(N, S), NT, sh, st>>>(
-        logits, gt, N, C, S, reinterpret_cast<unsigned long long*>(cm));
+        logits, gt, N, C, S, scene_label, K, reinterpret_cast<unsigned long long*>(cm));
   CRN_LAUNCH_CHECK("argmax_confusion");
   return CRN_OK;
+}
+
+extern "C" int crn_argmax_confusion(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N,
+                                    int32_t C, int64_t S, int64_t* cm, void* stream) {
+  return crn_argmax_confusion_labeled(logits, gt, gt_is_i64, N, C, S, nullptr, C, cm, stream);
 }

@@ -17,6 +17,7 @@ reconstruction_decoder.py:119-152.  Design (DESIGN.md "Engine"):
     are the model's parameters, so DDP hooks / optimisers see ordinary grads.
 """
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch as t
@@ -35,6 +36,18 @@ ENC_STAGE_OF = {2048: "stage5", 1024: "stage4", 512: "stage3", 256: "stage2"}
 
 def _r4(c: int) -> int:
   return (c + 3) // 4 * 4
+
+
+# Gradient chunks in the order the backward pass completes them (prefixes of parameter names).  In
+# named_parameters() order they are three contiguous ranges of the flat buffer: [2 | 1 | 0].
+GRAD_CHUNKS = (("decoder.",), ("encoder.stage4.", "encoder.stage5."), ("encoder.",))
+
+
+def grad_chunk_of(name: str) -> int:
+  for i, prefixes in enumerate(GRAD_CHUNKS):
+    if name.startswith(prefixes):
+      return i
+  raise KeyError(name)
 
 
 def _call(name, *args):
@@ -153,6 +166,16 @@ def conv_call(kind, layer, d, *args):
     _lib.call(fn, *a)
     e1.record()
     PROFILE.append((tag, layer.name, conv_macs(dd), e0, e1))
+
+
+# The module path (CoreNet.forward + autograd) replays CUDA graphs: a step is ~600 launches whose Python/ctypes
+# enqueue alone takes as long as their execution.  CRN_NO_GRAPH=1 (or an active PROFILE) keeps it eager.
+USE_GRAPHS = os.environ.get("CRN_NO_GRAPH", "0") != "1"
+GRAPH_WARMUP = 2
+
+
+def graphs_enabled() -> bool:
+  return USE_GRAPHS and PROFILE is None and not t.cuda.is_current_stream_capturing()
 
 
 # Conv3d k=5 layers at >= 32^3 run forward/dgrad on the tcgen05 tensor cores (3xTF32, csrc/conv_tc5.cu).
@@ -288,6 +311,9 @@ class Engine:
     self._ptr_sig = None
     self._ver_sig = None
     self._pcache = None
+    # bumped by anything that changes the weights through raw pointers (the fused Adam kernel, also inside replayed
+    # CUDA graphs, never touches tensor._version): part of the re-pack signature
+    self.weights_epoch = 0
     self._build_layers()
 
   # ------------------------------------------------------------------ layers
@@ -465,7 +491,7 @@ class Engine:
     self._pcache = None
     self._ptr_sig = None
     self._gt_sig = None
-    self._usig = None
+    self.__dict__.pop("_ucache", None)
 
   @staticmethod
   def _to_dev(ctypes_array, dev):
@@ -476,7 +502,7 @@ class Engine:
     P, _ = self.tensors()
     ws = [P[l.name + ".weight"] for l in self.layers]
     ptr_sig = tuple(w.data_ptr() for w in ws)
-    ver_sig = tuple(w._version for w in ws)
+    ver_sig = (self.weights_epoch,) + tuple(w._version for w in ws)
     if ptr_sig != self._ptr_sig:
       entries = []
       for l, w in zip(self.layers, ws):
@@ -552,13 +578,22 @@ class Engine:
                     _lib.stream_ptr())
       self._pack_gemm_tc(P)
 
-  def unpack_wgrads(self, grads: Dict[str, t.Tensor]):
-    sig = tuple(grads[l.name + ".weight"].data_ptr() for l in self.layers)
-    if getattr(self, "_usig", None) != sig:          # item list is cached per destination set (graph-capture safe)
-      items = (UnpackItem * len(self.layers))()
-      offs = (C.c_int64 * (len(self.layers) + 1))()
+  def chunk_layers(self, ci: int):
+    """Conv layers of gradient chunk ci (GRAD_CHUNKS order)."""
+    if getattr(self, "_chunk_layers", None) is None:
+      self._chunk_layers = [[l for l in self.layers if grad_chunk_of(l.name) == c] for c in range(len(GRAD_CHUNKS))]
+    return self._chunk_layers[ci]
+
+  def unpack_wgrads(self, grads: Dict[str, t.Tensor], layers=None, key=-1):
+    layers = self.layers if layers is None else layers
+    sig = tuple(grads[l.name + ".weight"].data_ptr() for l in layers)
+    cache = self.__dict__.setdefault("_ucache", {})
+    ent = cache.get(key)
+    if ent is None or ent[0] != sig:                 # item list is cached per destination set (graph-capture safe)
+      items = (UnpackItem * len(layers))()
+      offs = (C.c_int64 * (len(layers) + 1))()
       tot = 0
-      for i, l in enumerate(self.layers):
+      for i, l in enumerate(layers):
         it = items[i]
         it.src_packed = self.dw.data_ptr() + 4 * l.off
         it.dst = grads[l.name + ".weight"].data_ptr()
@@ -566,13 +601,9 @@ class Engine:
         it.dst_is_transposed = int(l.transposed)
         offs[i] = tot
         tot += l.src_cin * l.cout * l.taps
-      offs[len(self.layers)] = tot
-      self._uitems_dev = self._to_dev(items, self.dev)
-      self._uoffs_dev = self._to_dev(offs, self.dev)
-      self._utot = tot
-      self._usig = sig
-    _call("crn_unpack_wgrads", self._uitems_dev.data_ptr(), self._uoffs_dev.data_ptr(), len(self.layers),
-          self._utot, _lib.stream_ptr())
+      offs[len(layers)] = tot
+      ent = cache[key] = (sig, self._to_dev(items, self.dev), self._to_dev(offs, self.dev), tot)
+    _call("crn_unpack_wgrads", ent[1].data_ptr(), ent[2].data_ptr(), len(layers), ent[3], _lib.stream_ptr())
 
   def wf(self, l):
     return self.w_fwd.data_ptr() + 4 * l.off
@@ -655,6 +686,14 @@ class Plan:
     self.training = True
     self.launches = 0
     self.side_stream = t.cuda.Stream(device=self.dev)
+    self.gen = 0
+    # the module path (CoreNet.forward / autograd backward) replays captured CUDA graphs after GRAPH_WARMUP eager calls
+    self._graphs = {}
+    self.in_image = t.zeros(batch, 3, 256, 256, dtype=t.uint8, device=self.dev)
+    self.in_v2s = t.zeros(batch, 4, 4, dtype=t.float32, device=self.dev)
+    self.in_offs = t.zeros(batch, 3, dtype=t.float32, device=self.dev)
+    self.in_glog = None
+    self.gflat = None
 
   def f32(self, n):
     return t.zeros(n, dtype=t.float32, device=self.dev)
@@ -746,6 +785,10 @@ class Plan:
           st["d_s"] = ls.desc(src.cs, (1, hw, hw), cmap.cs, (1, hw, hw), B, bias_n_stride=skip_c)
           res = eng.model.config.decoder.resolution
           st["scale"] = t.diag(t.tensor([res[0] / g2, res[1] / g2, res[2] / g2, 1.0], dtype=t.float32)).to(self.dev)
+          st["sbias"] = t.zeros(B, skip_c, dtype=t.float32, device=self.dev)
+          st["mat"] = t.zeros(B, 4, 4, dtype=t.float32, device=self.dev)
+          st["ssum"] = t.zeros(B, skip_c, dtype=t.float32, device=self.dev)
+          st["dwoff"] = t.zeros(skip_c, 3, dtype=t.float32, device=self.dev)
         cat = nxt
       else:
         cp = _r4(t_out)
@@ -754,10 +797,18 @@ class Plan:
         st["d_t_bwd"] = st["lt"].desc(z2.cs, (g, g, g), cp, (g2, g2, g2), B, planar=False)
       self.stages.append(st)
     self.scratch64 = t.zeros(4096, dtype=t.float64, device=self.dev)
+    self.offs = t.zeros(B, 3, dtype=t.float32, device=self.dev)
+    res = eng.model.config.decoder.resolution
+    self.logits = t.zeros(B, eng.model.config.decoder.num_output_channels, *res, dtype=t.float32, device=self.dev)
 
   # ------------------------------------------------------------------ forward
   def forward(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, training: bool,
-              want_features: bool = False) -> t.Tensor:
+              want_features: bool = False, pack: bool = True, run_encoder: bool = True) -> t.Tensor:
+    """Enqueues the forward pass on the current stream and returns the plan-owned logits buffer
+    float32[B,C,D,H,W] (overwritten by the next forward of this plan).  pack=False: the caller has already
+    re-packed the weights (graph replays pack outside the captured region when the weights did not change);
+    run_encoder=False: reuse the encoder activations of the previous forward of this plan (same image; the
+    encoder does not depend on the sample offsets -- super_resolution.py:92-126)."""
     global _ENG
     eng, B = self.eng, self.B
     _ENG = eng
@@ -765,9 +816,21 @@ class Plan:
     st = _lib.stream_ptr()
     self.training = training
     bias = lambda l: P[l.name + ".bias"].data_ptr()
-    eng.pack_weights()
-    if training:
-      self.arena_fwd.zero_()
+    if pack:
+      eng.pack_weights()
+    if run_encoder:
+      if training:
+        self.arena_fwd.zero_()
+      self._forward_encoder(image, training, P, bias, st)
+    else:
+      assert not training, "run_encoder=False is an inference-only path"
+      eng.join_packs()
+    if want_features:
+      return None
+    return self._forward_decoder(v2s, offsets, training, P, bias, st)
+
+  def _forward_encoder(self, image, training, P, bias, st):
+    eng, B = self.eng, self.B
     # ---- encoder
     _call("crn_preprocess_image", image.data_ptr(), B, 256, 256, self.img4.p, st)
     conv_call("fwd", eng.L["stem"], self.d_stem, self.img4.p, eng.wf(eng.L["stem"]), bias(eng.L["stem"]),
@@ -789,8 +852,9 @@ class Plan:
                 blk["c_c"].p, 0, st)
       blk["bn_c"].fwd(training)
     _call("crn_spatial_mean_fwd", self.enc_out.p, B, 64, 2048, self.feat.p, st)
-    if want_features:
-      return None
+
+  def _forward_decoder(self, v2s, offsets, training, P, bias, st):
+    eng, B = self.eng, self.B
     # ---- decoder
     L = eng.L
     lat = eng.lat
@@ -801,8 +865,7 @@ class Plan:
     conv_call("fwd", L["stage_1.t1"], self.d_s1t, self.z1.p, eng.wf(L["stage_1.t1"]), bias(L["stage_1.t1"]),
               self.x1.p, 0, st)
     # per-scale layer matrices (reconstruction_decoder.py:111-115) and offsets
-    self.offs = offsets.contiguous()
-    res = eng.model.config.decoder.resolution
+    self.offs.copy_(offsets)
     logits = None
     for sd in self.stages:
       g = sd["g"]
@@ -837,28 +900,34 @@ class Plan:
           ls, src, cmap, hw = sd["ls"], sd["src"], sd["cmap"], sd["hw"]
           w = P[ls.name + ".weight"]
           # the 3 offset channels are constant per scene -> exact per-scene bias
-          sbias = (P[ls.name + ".bias"][None, :] + offsets @ w[:, ls.cin:, 0, 0].t()).contiguous()
-          sd["sbias"] = sbias
+          sbias, mat = sd["sbias"], sd["mat"]
+          t.addmm(P[ls.name + ".bias"], self.offs, w[:, ls.cin:, 0, 0].t(), out=sbias)
           conv_call("fwd", ls, sd["d_s"], src.p, eng.wf(ls), sbias.data_ptr(), cmap.p, 0, st)
           g2 = 2 * g
-          mat = v2s.matmul(sd["scale"]).contiguous()
-          sd["mat"] = mat
+          t.matmul(v2s, sd["scale"], out=mat)
           _call("crn_skip_sample_fwd", cmap.p, B, hw, hw, sd["skip_c"], cmap.cs, mat.data_ptr(),
                 self.offs.data_ptr(), g2, g2, g2, nxt.p, nxt.cs, sd["t_out"], st)
       else:
-        g2 = 2 * g
-        logits = t.empty(B, sd["t_out"], g2, g2, g2, dtype=t.float32, device=self.dev)
+        logits = self.logits
         if USE_TC and eng.tct_w.get(sd["lt"].name, (None, None))[0] is not None:
           convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name][0].data_ptr(), bias(sd["lt"]),
                          logits.data_ptr(), eng.tc_status.data_ptr(), st)
         else:
           conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]),
                     logits.data_ptr(), 0, st)
+    # a tcgen05 barrier timeout (status word != 0) must not go unnoticed: NaN in every scene's logits
+    _call("crn_status_poison", eng.tc_status.data_ptr(), logits.data_ptr(), logits[0].numel(), B, st)
     return logits
 
   # ------------------------------------------------------------------ backward
-  def backward(self, grad_logits: t.Tensor, grads: Dict[str, t.Tensor], encoder_only_grads=None):
-    """grads: name -> zero/empty tensor per parameter (filled here)."""
+  def backward(self, grad_logits: t.Tensor, grads: Dict[str, t.Tensor], chunk_cb=None, comm_stream=None):
+    """grads: name -> zero/empty tensor per parameter (filled here).
+
+    chunk_cb(i): data-parallel hook.  The parameters are finished in three chunks in backward order -- GRAD_CHUNKS:
+    0 = decoder, 1 = encoder stage4+5, 2 = the rest -- and as soon as every gradient of chunk i is final its
+    un-pack / bias-gather launches and chunk_cb(i) (the all-reduce + optimiser update of that slice of the flat
+    buffer) are enqueued on comm_stream, overlapping the rest of the backward pass (the reference: DDP's bucketed
+    all-reduce, pipeline.py:199-200,229).  Without a callback everything is finished by one launch set at the end."""
     global _ENG
     eng, B = self.eng, self.B
     _ENG = eng
@@ -871,10 +940,39 @@ class Plan:
 
     # bias gradients = fp64 column sums in accumulator slots: collected here, moved by ONE batched launch at the end
     bias_jobs = []
+    mark = [0]
 
     def bias_from(slot: Slot, name, lo=0, n=None):
       n = n if n is not None else grads[name].numel()
       bias_jobs.append((slot.data_ptr() + 8 * lo, grads[name].data_ptr(), n))
+
+    def finish(ci, final=False):
+      """Bias gather + weight-gradient un-pack (+ the skip convs' offset columns) of chunk ci; see the docstring."""
+      if chunk_cb is None and not final:
+        return
+      jobs = tuple(bias_jobs[mark[0]:])
+      mark[0] = len(bias_jobs)
+      layers = eng.layers if chunk_cb is None else eng.chunk_layers(ci)
+      where = main if chunk_cb is None else comm_stream
+      if chunk_cb is not None:
+        where.wait_stream(main)
+      if side is not None:
+        where.wait_stream(side)
+      with t.cuda.stream(where):
+        if jobs:
+          self._gather_bias(ci if chunk_cb is not None else -1, jobs)
+        eng.unpack_wgrads(grads, layers, ci if chunk_cb is not None else -1)
+        if chunk_cb is None or ci == 0:
+          # offset-channel columns of the skip compress convs (the GEMM ran without them)
+          for sd in self.stages:
+            if sd["stage"] < 6 and sd["skip_c"]:
+              ls = sd["ls"]
+              t.matmul(sd["ssum"].t(), self.offs, out=sd["dwoff"])
+              grads[ls.name + ".weight"][:, ls.cin:, 0, 0].copy_(sd["dwoff"])
+        if chunk_cb is not None:
+          chunk_cb(ci)
+      if chunk_cb is not None and final:
+        main.wait_stream(comm_stream)
 
     # Weight gradients only feed the final un-pack, so they run on a side stream concurrently with the dgrad /
     # BatchRenorm chain (fork: event after dy is final; join: before crn_unpack_wgrads).  The small encoder launches
@@ -920,10 +1018,9 @@ class Plan:
           wgrad(ls, sd["d_s"], src.p, cmap.gp)
           dgrad(ls, sd["d_s"], cmap.gp, src.gp, 0)
           # per-scene sums of d(cmap) -> bias and offset-channel weight grads (tiny glue)
-          ssum = t.empty(B, sd["skip_c"], dtype=t.float32, device=self.dev)
+          ssum = sd["ssum"]
           _call("crn_spatial_mean_fwd", cmap.gp, B, hw * hw, cmap.cs, ssum.data_ptr(), st)
-          ssum = ssum * float(hw * hw)
-          sd["ssum"] = ssum
+          ssum.mul_(float(hw * hw))
       wgrad(lt, d_t, sd["z2"].p, dy_ptr)
       if USE_TC and eng.tct_w.get(lt.name, (None, None))[1] is not None:
         convt7_tc_dgrad_call(lt, d_t, dy_ptr, eng.tct_w[lt.name][1].data_ptr(), sd["z2"].gp, eng.tc_status.data_ptr(), st)
@@ -950,8 +1047,7 @@ class Plan:
         bias_from(nxt_sd["dxs_cat"], sd["lt"].name + ".bias", 0, sd["t_out"])
         if sd["skip_c"]:
           ls = sd["ls"]
-          ssum = sd["ssum"]
-          grads[ls.name + ".bias"].copy_(ssum.sum(0))
+          t.sum(sd["ssum"], 0, out=grads[ls.name + ".bias"])
     bias_from(self.stages[0]["dxs_cat"], L["stage_1.t1"].name + ".bias")
     # ---- stage_1 / stage_0
     l1 = L["stage_1.t1"]
@@ -962,6 +1058,7 @@ class Plan:
     bias_from(dxs, l0.name + ".bias", 0, eng.lat)
     wgrad(l0, self.d_s0, self.feat.p, self.latb.gp)
     dgrad(l0, self.d_s0, self.latb.gp, self.feat.gp, 0)
+    finish(0)
     _call("crn_spatial_mean_bwd", self.feat.gp, B, 64, 2048, self.enc_out.gp, 0, st)
     # ---- encoder, last block first
     for blk in reversed(self.blocks):
@@ -991,37 +1088,112 @@ class Plan:
         dgrad(la, blk["d_a"], blk["a_c"].gp, x.gp, 1)
       else:
         dgrad(la, blk["d_a"], blk["a_c"].gp, x.gp, 1)
+      if blk["p"] == "encoder.stage4.a.":
+        finish(1)
     # ---- stem
     _call("crn_maxpool_bwd", self.p1.gp, self.p1_idx.data_ptr(), B, 128, 128, 64, self.s1a.gp, st)
     dxs = self.brn_stem.bwd(tr, grads, self.s1a.gp, self.s1a.cs, self.s1.gp, self.s1.cs)
     stem = L["stem"]
     bias_from(dxs, stem.name + ".bias")
     wgrad(stem, self.d_stem, self.img4.p, self.s1.gp)
-    # ---- bias gradients (one launch; item list cached per pointer set)
-    sig = tuple(bias_jobs)
-    if getattr(self, "_bias_sig", None) != sig:
-      items = (_lib.F64CopyItem * len(bias_jobs))()
-      offs = (C.c_int64 * (len(bias_jobs) + 1))()
+    finish(2, final=True)
+
+  def _gather_bias(self, key, jobs):
+    """ONE launch moves the fp64 column sums of `jobs` into the bias gradients (item list cached per pointer set)."""
+    eng = self.eng
+    cache = self.__dict__.setdefault("_bias_cache", {})
+    ent = cache.get(key)
+    if ent is None or ent[0] != jobs:
+      items = (_lib.F64CopyItem * len(jobs))()
+      offs = (C.c_int64 * (len(jobs) + 1))()
       tot = 0
-      for i, (src, dst, n) in enumerate(bias_jobs):
+      for i, (src, dst, n) in enumerate(jobs):
         items[i].src, items[i].dst = src, dst
         offs[i] = tot
         tot += n
-      offs[len(bias_jobs)] = tot
-      self._bias_items = eng._to_dev(items, self.dev)
-      self._bias_offs = eng._to_dev(offs, self.dev)
-      self._bias_tot, self._bias_sig = tot, sig
-    _call("crn_gather_f64_to_f32", self._bias_items.data_ptr(), self._bias_offs.data_ptr(), len(bias_jobs),
-          self._bias_tot, st)
-    # ---- weight gradients back to the parameters' layout (one launch)
-    if side is not None:
-      main.wait_stream(side)
-    eng.unpack_wgrads(grads)
-    # offset-channel columns of the skip compress convs (the GEMM ran without them)
-    for sd in self.stages:
-      if sd["stage"] < 6 and sd["skip_c"]:
-        ls = sd["ls"]
-        grads[ls.name + ".weight"][:, ls.cin:, 0, 0] = sd["ssum"].t() @ self.offs
+      offs[len(jobs)] = tot
+      ent = cache[key] = (jobs, eng._to_dev(items, self.dev), eng._to_dev(offs, self.dev), tot)
+    _call("crn_gather_f64_to_f32", ent[1].data_ptr(), ent[2].data_ptr(), len(jobs), ent[3], _lib.stream_ptr())
+
+  # ------------------------------------------------------------------ graph-replayed entry points (module path)
+  def _sig(self):
+    """Everything a captured graph bakes in: parameter / buffer addresses and the kernel routing switches."""
+    P, Bf = self.eng.tensors()
+    return (tuple(p.data_ptr() for p in P.values()), tuple(b.data_ptr() for b in Bf.values()), USE_TC, USE_TC5S,
+            WGRAD_SIDE_STREAM)
+
+  def _graph_state(self, key):
+    sig = self._sig()
+    gs = self._graphs.get(key)
+    if gs is None or gs["sig"] != sig:
+      gs = self._graphs[key] = {"sig": sig, "calls": 0, "graph": None}
+    return gs
+
+  def run_forward(self, image, v2s, offsets, training, run_encoder=True):
+    """forward() through a CUDA graph: inputs are copied into the plan's static buffers; the first GRAPH_WARMUP calls
+    per (mode, parameter set) run eagerly (lazy initialisation must not happen under capture), the next one captures,
+    later ones replay.  The weight re-pack stays outside the graph: it is skipped when the weights did not change."""
+    eng = self.eng
+    if not graphs_enabled():
+      return self.forward(image, v2s, offsets, training, run_encoder=run_encoder)
+    self.training = training
+    if run_encoder:
+      self.in_image.copy_(image)
+    self.in_v2s.copy_(v2s)
+    self.in_offs.copy_(offsets)
+    args = (self.in_image, self.in_v2s, self.in_offs, training)
+    gs = self._graph_state(("fwd", training, run_encoder))
+    if gs["graph"] is None:
+      if gs["calls"] < GRAPH_WARMUP:
+        gs["calls"] += 1
+        return self.forward(*args, run_encoder=run_encoder)
+      eng.pack_weights()
+      eng.join_packs()
+      g = t.cuda.CUDAGraph()
+      with t.cuda.graph(g, capture_error_mode="thread_local"):
+        self.forward(*args, pack=False, run_encoder=run_encoder)
+      gs["graph"] = g
+    eng.pack_weights()
+    eng.join_packs()
+    gs["graph"].replay()
+    return self.logits
+
+  def run_backward(self, grad_logits, names):
+    """backward() through a CUDA graph; returns name -> gradient (fresh tensors: views of one flat copy)."""
+    eng = self.eng
+    P, _ = eng.tensors()
+    if self.gflat is None or self._gnames != names:
+      sizes = [P[n].numel() for n in names]
+      self.gflat = t.zeros(sum(sizes), dtype=t.float32, device=self.dev)
+      self._gnames, self._gviews, off = list(names), {}, 0
+      for n, sz in zip(names, sizes):
+        self._gviews[n] = (off, sz, P[n].shape)
+        off += sz
+      self.gstatic = {n: self.gflat[o:o + sz].view(shp) for n, (o, sz, shp) in self._gviews.items()}
+      self.in_glog = t.zeros_like(self.logits)
+      self._graphs = {k: v for k, v in self._graphs.items() if k[0] != "bwd"}
+
+    def enqueue(glog):
+      self.gflat.zero_()
+      self.backward(glog, self.gstatic)
+
+    if not graphs_enabled():
+      enqueue(grad_logits)
+    else:
+      self.in_glog.copy_(grad_logits)
+      gs = self._graph_state(("bwd", self.training))
+      if gs["graph"] is None and gs["calls"] < GRAPH_WARMUP:
+        gs["calls"] += 1
+        enqueue(self.in_glog)
+      else:
+        if gs["graph"] is None:
+          g = t.cuda.CUDAGraph()
+          with t.cuda.graph(g, capture_error_mode="thread_local"):
+            enqueue(self.in_glog)
+          gs["graph"] = g
+        gs["graph"].replay()
+    out = self.gflat.clone()
+    return {n: out[o:o + sz].view(shp) for n, (o, sz, shp) in self._gviews.items()}
 
   # ------------------------------------------------------------------ features (NCHW copies)
   def features_nchw(self):
@@ -1034,30 +1206,48 @@ class Plan:
 
 
 # ====================================================================== autograd bridge
+class _Lease:
+  """Marks a plan busy between a grad-enabled forward and its backward.  If the autograd node dies without a
+  backward (an eval loop without no_grad, an exception) the lease is released by its destructor, so the plan is
+  reused instead of a new ~0.5 GB plan being built on every such call."""
+
+  def __init__(self, plan):
+    plan.busy = True
+    plan.gen += 1
+    self.plan, self.gen = plan, plan.gen
+
+  def release(self):
+    plan, self.plan = self.plan, None
+    if plan is not None and plan.gen == self.gen:
+      plan.busy = False
+
+  __del__ = release
+
+
 class _CoreNetFn(t.autograd.Function):
   @staticmethod
   def forward(ctx, model, need_grad, image, v2s, offsets, *params):
     eng = get_engine(model)
     plan = eng.get_plan(image.shape[0], image.device, need_grad)
-    logits = plan.forward(image, v2s, offsets, model.training)
+    logits = plan.run_forward(image, v2s, offsets, model.training)
     if need_grad:
-      plan.busy = True
-      ctx.plan = plan
+      ctx.lease = _Lease(plan)
       ctx.model = model
     ctx.nparams = len(params)
-    return logits
+    # the plan owns its logits buffer (the next forward overwrites it): hand out a copy
+    return logits.clone()
 
   @staticmethod
   def backward(ctx, grad_logits):
-    plan, model = ctx.plan, ctx.model
-    eng = plan.eng
+    lease, model = ctx.lease, ctx.model
+    plan = lease.plan
+    if plan is None:
+      raise RuntimeError("corenet_b200: backward through the same CoreNet forward twice is not supported")
     names = [n for n, _ in model.named_parameters()]
-    P, _ = eng.tensors()
-    grads = {n: t.zeros_like(P[n]) for n in names}
     try:
-      plan.backward(grad_logits, grads)
+      grads = plan.run_backward(grad_logits, names)
     finally:
-      plan.busy = False
+      lease.release()
     return (None, None, None, None, None) + tuple(grads[n] for n in names)
 
 
@@ -1069,7 +1259,7 @@ def get_engine(model) -> Engine:
   return eng
 
 
-def corenet_forward(model, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor) -> t.Tensor:
+def _check_inputs(image, v2s, offsets):
   if not image.is_cuda:
     raise RuntimeError("corenet_b200.CoreNet runs on CUDA only (no CPU fallback); move the module and "
                        "its inputs to a B200")
@@ -1077,6 +1267,10 @@ def corenet_forward(model, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor) ->
     raise AssertionError("image must be uint8[B,3,H,W]")
   if tuple(image.shape[2:]) != (256, 256):
     raise ValueError("the encoder feature pyramid (256 -> 8) is fixed: image must be 256x256")
+
+
+def corenet_forward(model, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor) -> t.Tensor:
+  _check_inputs(image, v2s, offsets)
   b = image.shape[0]
   v2s = v2s.to(dtype=t.float32)
   offsets = offsets.to(dtype=t.float32)
@@ -1085,6 +1279,32 @@ def corenet_forward(model, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor) ->
   need_grad = t.is_grad_enabled() and any(p.requires_grad for p in params)
   return _CoreNetFn.apply(model, need_grad, image.contiguous(), v2s.contiguous(), offsets.contiguous(),
                           *params)
+
+
+def corenet_multi_offset_pmf(model, image: t.Tensor, v2s: t.Tensor, grid_offsets: t.Tensor) -> t.Tensor:
+  """Class probabilities for several sample offsets of the same images: float32[n_off, B, 3] offsets ->
+  float32[n_off, B, C, D, H, W].  The encoder does not depend on the offsets (super_resolution.py:92-126 of the
+  reference re-runs it mult^3 times): in eval mode it runs ONCE and only the decoder + skip connections + softmax
+  are replayed per offset.  In train mode BatchRenorm statistics are batch statistics, so the reference's loop is
+  kept as is."""
+  from corenet_b200 import ops
+  _check_inputs(image, v2s, grid_offsets)
+  b, n_off = image.shape[0], grid_offsets.shape[0]
+  v2s = v2s.to(dtype=t.float32).contiguous()
+  grid_offsets = grid_offsets.to(dtype=t.float32)
+  assert v2s.shape == (b, 4, 4) and grid_offsets.shape[1:] == (b, 3)
+  with t.no_grad():
+    if model.training:
+      return t.stack([ops.softmax_channels(model(image, v2s, o)) for o in grid_offsets], 0)
+    eng = get_engine(model)
+    plan = eng.get_plan(b, image.device, False)
+    c = model.config.decoder.num_output_channels
+    out = t.empty((n_off, b, c) + tuple(model.config.decoder.resolution), dtype=t.float32, device=image.device)
+    for i in range(n_off):
+      logits = plan.run_forward(image.contiguous(), v2s, grid_offsets[i], False, run_encoder=(i == 0))
+      _call("crn_softmax_planar", logits.data_ptr(), b, c, logits[0, 0].numel(), out[i].data_ptr(),
+            _lib.stream_ptr())
+    return out
 
 
 def encoder_forward(encoder, image_f32: t.Tensor):

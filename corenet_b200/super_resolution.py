@@ -9,13 +9,33 @@ from typing import Tuple
 
 import torch as t
 
-from corenet_b200 import ops
 from corenet_b200.geometry import transformations
 
 
 class InferenceFn:
   def __call__(self, input_image, camera_transform, view_to_voxel_transform, grid_offsets, output_resolution):
     raise NotImplementedError()
+
+
+class MultiOffsetInferenceFn:
+  """grid_offsets float32[n_off, B, 3] -> pmf float32[n_off, B, C, D, H, W] (super_resolution.py:28-43)."""
+
+  def __call__(self, input_image, camera_transform, view_to_voxel_transform, grid_offsets):
+    raise NotImplementedError()
+
+
+class CoreNetMultiOffsetInferenceFn(MultiOffsetInferenceFn):
+  """The B200 model as a multi-offset inference function: the encoder runs once per image batch, the decoder +
+  ray-traced skips + softmax once per offset, each as a replayed CUDA graph (engine.corenet_multi_offset_pmf).
+  The reference re-runs the whole model per offset (super_resolution.py:118-126)."""
+
+  def __init__(self, model):
+    self.model = model
+
+  def __call__(self, input_image, camera_transform, view_to_voxel_transform, grid_offsets):
+    from corenet_b200 import engine
+    v2s = camera_transform @ view_to_voxel_transform.inverse()
+    return engine.corenet_multi_offset_pmf(self.model, input_image, v2s, grid_offsets)
 
 
 class SuperResolutionInference(InferenceFn):
@@ -49,8 +69,9 @@ class SuperResolutionInference(InferenceFn):
 
 def super_resolution_from_model(model) -> SuperResolutionInference:
   """Plugs a corenet_b200 CoreNet into the eval pipeline (super_resolution.py:115-129)."""
-  def inference_fn(input_image, camera_transform, view_to_voxel_transform, grid_offsets):
-    v2s = camera_transform @ view_to_voxel_transform.inverse()
-    with t.no_grad():
-      return t.stack([ops.softmax_channels(model(input_image, v2s, o)) for o in grid_offsets], 0)
-  return SuperResolutionInference(inference_fn, model.config.decoder.resolution)
+  return SuperResolutionInference(CoreNetMultiOffsetInferenceFn(model), model.config.decoder.resolution)
+
+
+def super_resolution_from_state(state) -> SuperResolutionInference:
+  """Same name and argument as the reference's (super_resolution.py:115): `state.model` is the CoreNet."""
+  return super_resolution_from_model(state.model)

@@ -1,11 +1,13 @@
 """Data-parallel training step (SURVEY §8 rows e, f2): one process per GPU, scenes sharded by rank,
-ONE NCCL all-reduce over a flat fp32 gradient buffer, one fused Adam launch.
+the gradient exchange as NCCL all-reduces over slices of ONE flat fp32 gradient buffer that overlap the
+backward pass, fused Adam per slice.
 
 Host-side mirror of TrainPipeline._process_batch (src/corenet/pipeline.py:215-240 of the reference:
-zero_grad -> model -> loss -> backward [DDP all-reduce] -> Adam step) and of the fixed-seed index
-shard of distributed.DistributedSampler (src/corenet/distributed.py:204-230).
+zero_grad -> model -> loss -> backward [DDP all-reduce] -> Adam step), of DDP's construction-time
+parameter/buffer broadcast (pipeline.py:199-200) and of the fixed-seed index shard of
+distributed.DistributedSampler (src/corenet/distributed.py:204-230).
 """
-from typing import Optional
+from typing import List, Optional
 
 import torch as t
 
@@ -14,23 +16,39 @@ from corenet_b200 import engine as engine_lib
 
 _call = _lib.call
 
+SAMPLER_SEED = 0x1234       # distributed.py:216
 
-def shard_indices(num_items: int, rank: int, world: int, pad: bool = True):
-  """Rank-strided shard of range(num_items) (distributed.py:204-224): rank r gets r, r+world, ...;
-  with pad=True the tail is padded by wrapping so that every rank gets the same count."""
-  idx = list(range(num_items))
-  if pad and num_items % world:
-    idx += idx[:world - num_items % world]
-  return idx[rank::world]
+
+def shard_indices(num_items: int, rank: int, world: int, pad: bool = True) -> List[int]:
+  """Indices of `range(num_items)` that rank `rank` of `world` processes iterates over: the algorithm of the
+  reference's DistributedSampler (distributed.py:204-224) -- a randperm seeded with 0x1234, zero-padded at the
+  end to a multiple of `world` when pad=True (training; evaluation does not pad), split into contiguous blocks
+  [rank*total//world, (rank+1)*total//world)."""
+  total = (num_items + world - 1) // world * world if pad else num_items
+  g = t.Generator()
+  g.manual_seed(SAMPLER_SEED)
+  indices = t.randperm(num_items, generator=g)
+  indices = t.constant_pad_nd(indices, [0, total - indices.shape[0]])
+  start = rank * total // world
+  end = (rank + 1) * total // world
+  return indices[start:end].tolist()
 
 
 def allreduce_flat_grad(flat_grad: t.Tensor, world: int, group=None) -> float:
-  """The path's single exchange step: in-place sum-all-reduce of the flat gradient buffer (NCCL on the
-  GPU box, gloo in the CPU tests).  Returns the scale (1/world) the optimiser kernel must apply to get
-  DDP's rank average."""
+  """The path's exchange step on one (slice of the) flat gradient buffer: in-place sum-all-reduce (NCCL on the
+  GPU box, gloo in the CPU tests).  Returns the scale (1/world) the optimiser kernel must apply to get DDP's
+  rank average."""
   if world > 1:
     t.distributed.all_reduce(flat_grad, op=t.distributed.ReduceOp.SUM, group=group)
   return 1.0 / world
+
+
+def broadcast_from_rank0(tensors, world: int, group=None) -> None:
+  """What DistributedDataParallel does at construction (pipeline.py:199-200): every rank starts from rank 0's
+  parameters and buffers."""
+  if world > 1:
+    for x in tensors:
+      t.distributed.broadcast(x, src=0, group=group)
 
 
 def flatten_parameters(model: t.nn.Module):
@@ -50,15 +68,28 @@ def flatten_parameters(model: t.nn.Module):
   return flat, views
 
 
+def grad_chunk_ranges(names, views):
+  """[(lo, hi)] of the flat buffer per engine.GRAD_CHUNKS entry (each chunk is one contiguous range)."""
+  ranges = []
+  for ci in range(len(engine_lib.GRAD_CHUNKS)):
+    idx = [i for i, n in enumerate(names) if engine_lib.grad_chunk_of(n) == ci]
+    assert idx == list(range(idx[0], idx[-1] + 1)), "gradient chunk is not contiguous in parameter order"
+    ranges.append((views[idx[0]][0], views[idx[-1]][0] + views[idx[-1]][1]))
+  return ranges
+
+
 class Trainer:
   """Owns the flat parameter / gradient / Adam-moment buffers of a CoreNet and runs train steps."""
 
+  STATUS_EVERY = 1      # steps between (asynchronous, one step late) reads of the tcgen05 status word
+
   def __init__(self, model, lr: float = 4e-4, eps: float = 1e-4, betas=(0.9, 0.999),
-               loss: str = "iou_fgbg", process_group=None, use_graph: bool = True):
+               loss: str = "iou_fgbg", process_group=None, use_graph: bool = True,
+               overlap_allreduce: bool = True, collective_in_graph: Optional[bool] = None):
     self.model = model
-    # A step is ~700 kernel launches; enqueuing them from Python costs as much as running them, so after two
-    # eager warm-up steps per input signature the whole step (weight re-pack, forward, loss, backward, and on a
-    # single GPU the Adam update) is captured once in a CUDA graph and replayed.
+    # A step is ~600 kernel launches; enqueuing them from Python costs as much as running them, so after two
+    # eager warm-up steps per input signature the whole step (weight re-pack, forward, loss, backward, the
+    # gradient all-reduces when the backend can be captured, Adam) is captured once in a CUDA graph and replayed.
     self.use_graph = use_graph
     self._graphs = {}
     self._copy_stream = None
@@ -67,22 +98,57 @@ class Trainer:
     self.lr, self.eps, self.betas = lr, eps, betas
     self.mode = {"iou_fgbg": 0, "xent_times_iou_agnostic": 1}[loss]
     self.pg = process_group
-    self.world = t.distributed.get_world_size(process_group) if t.distributed.is_initialized() else 1
+    dist_on = t.distributed.is_available() and t.distributed.is_initialized()
+    self.world = t.distributed.get_world_size(process_group) if dist_on else 1
+    self.backend = t.distributed.get_backend(process_group) if dist_on else None
+    # NCCL collectives are stream-ordered and capturable; gloo's are host-synchronous
+    self.collective_in_graph = (self.backend == "nccl") if collective_in_graph is None else collective_in_graph
+    self.overlap_allreduce = overlap_allreduce and self.world > 1
     self.flat, self.views = flatten_parameters(model)
     eng = engine_lib.get_engine(model)
     eng.invalidate()
     self.eng = eng
+    dev = self.flat.device
+    broadcast_from_rank0([self.flat] + [b for _, b in model.named_buffers()], self.world, process_group)
     self.grad = t.zeros_like(self.flat)
     self.m = t.zeros_like(self.flat)
     self.v = t.zeros_like(self.flat)
     self.step_count = 0
-    self.step_dev = t.zeros(1, dtype=t.int32, device=self.flat.device)
+    self.step_dev = t.zeros(1, dtype=t.int32, device=dev)
     self.names = [n for n, _ in model.named_parameters()]
     self.grads = {}
     for (off, n), (name, p) in zip(self.views, model.named_parameters()):
       self.grads[name] = self.grad[off:off + n].view(p.shape)
+    self.chunks = grad_chunk_ranges(self.names, self.views)
+    self._comm_stream = t.cuda.Stream(device=dev) if self.overlap_allreduce else None
     self._loss_bufs = {}
+    # tcgen05 status word: copied to pinned host memory after every STATUS_EVERY-th step and checked, without
+    # blocking, at the start of the next one
+    self._status_host = t.zeros(1, dtype=t.int32).pin_memory()
+    self._status_ev = None
 
+  # ------------------------------------------------------------------ failure surfacing
+  def check_status(self, wait: bool = False) -> None:
+    """Raises if a tcgen05 kernel reported an mbarrier timeout (the guarded Adam kernel has skipped the update of
+    that step, the logits / loss of that step are NaN)."""
+    ev = self._status_ev
+    if ev is None:
+      return
+    if wait:
+      ev.synchronize()
+    if ev.query():
+      self._status_ev = None
+      if int(self._status_host[0]) != 0:
+        raise RuntimeError("corenet_b200: a tcgen05 kernel reported an mbarrier timeout; the step was skipped "
+                           "(weights unchanged). Reset with trainer.eng.tc_status.zero_() after fixing the cause.")
+
+  def _post_status_read(self):
+    if self.step_count % self.STATUS_EVERY == 0 and self.eng.dev is not None:
+      self._status_host.copy_(self.eng.tc_status, non_blocking=True)
+      self._status_ev = t.cuda.Event()
+      self._status_ev.record()
+
+  # ------------------------------------------------------------------ one step, enqueued on the current stream
   def _bufs(self, b, c, dev):
     key = (b, c)
     if key not in self._loss_bufs:
@@ -92,8 +158,21 @@ class Trainer:
           dlogits=t.empty(b, c, 128, 128, 128, dtype=t.float32, device=dev))
     return self._loss_bufs[key]
 
-  def _fwd_bwd(self, image, v2s, offsets, gt):
-    """Enqueues forward, loss and backward on the current stream; gradients land in the flat buffer."""
+  def _adam(self, lo, hi, bump, scale):
+    """Guarded fused Adam over flat[lo:hi) on the current stream."""
+    n = hi - lo
+    _call("crn_adam_step_guarded", self.flat.data_ptr() + 4 * lo, self.grad.data_ptr() + 4 * lo,
+          self.m.data_ptr() + 4 * lo, self.v.data_ptr() + 4 * lo, n, self.lr, self.betas[0], self.betas[1],
+          self.eps, self.step_dev.data_ptr(), int(bump), scale, self.eng.tc_status.data_ptr(), _lib.stream_ptr())
+
+  def _chunk_cb(self, ci):
+    """Called by the engine on the comm stream as soon as chunk ci of the flat gradient is final."""
+    lo, hi = self.chunks[ci]
+    scale = allreduce_flat_grad(self.grad[lo:hi], self.world, self.pg)
+    self._adam(lo, hi, ci == 0, scale)
+
+  def _step_body(self, image, v2s, offsets, gt, with_update: bool):
+    """forward + loss + backward (+ all-reduce + Adam when with_update)."""
     model, eng = self.model, self.eng
     st = _lib.stream_ptr()
     b = image.shape[0]
@@ -108,22 +187,38 @@ class Trainer:
           lb["coef"].data_ptr(), st)
     _call("crn_loss_bwd", logits.data_ptr(), gt.data_ptr(), is64, b, c, s, self.mode, lb["coef"].data_ptr(),
           None, lb["dlogits"].data_ptr(), st)
-    plan.backward(lb["dlogits"], self.grads)
+    if with_update and self.overlap_allreduce:
+      plan.backward(lb["dlogits"], self.grads, chunk_cb=self._chunk_cb, comm_stream=self._comm_stream)
+    else:
+      plan.backward(lb["dlogits"], self.grads)
+      if with_update:
+        self._update_all()
     return lb["loss"]
 
-  def _adam(self, scale):
-    _call("crn_adam_step_dev", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-          self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev.data_ptr(), scale,
-          _lib.stream_ptr())
-    self.eng._ver_sig = None   # the fused Adam kernel changed the weights: re-pack on the next forward
+  def _update_all(self):
+    scale = allreduce_flat_grad(self.grad, self.world, self.pg)
+    self._adam(0, self.flat.numel(), True, scale)
+
+  def _weights_changed(self):
+    # the fused Adam kernel writes the parameters through raw pointers (tensor._version does not move, graph
+    # replays run no Python): the engine's re-pack signature is keyed on this counter
+    self.eng.weights_epoch += 1
 
   def _eager_step(self, image, v2s, offsets, gt):
-    loss = self._fwd_bwd(image, v2s, offsets, gt)
-    scale = allreduce_flat_grad(self.grad, self.world, self.pg)
-    self._adam(scale)
+    loss = self._step_body(image, v2s, offsets, gt, True)
+    self._weights_changed()
     return loss
 
+  # ------------------------------------------------------------------ graph / prefetch plumbing
+  @staticmethod
+  def _check_inputs(image, v2s, offsets, gt):
+    if gt.dtype not in (t.int32, t.int64):
+      raise AssertionError(f"ground-truth grid must be int32 or int64 (model/losses.py:36), got {gt.dtype}")
+    if image.dtype != t.uint8:
+      raise AssertionError("image must be uint8[B,3,H,W]")
+
   def _gstate(self, image, v2s, offsets, gt):
+    self._check_inputs(image, v2s, offsets, gt)
     key = (tuple(image.shape), tuple(gt.shape), gt.dtype, self.flat.device, self.model.training)
     gs = self._graphs.get(key)
     if gs is None:
@@ -152,9 +247,10 @@ class Trainer:
 
   def step(self, image: Optional[t.Tensor] = None, v2s: Optional[t.Tensor] = None,
            offsets: Optional[t.Tensor] = None, gt: Optional[t.Tensor] = None) -> t.Tensor:
-    """One optimisation step on this rank's scenes; returns the (device) loss scalar.  In graph mode the inputs
-    may live in (pinned) host memory: they are copied straight into the graph's static device buffers.  Called
-    without arguments it consumes the batch started by `prefetch()`."""
+    """One optimisation step on this rank's scenes; returns the (device) loss scalar.  Inputs may live in (pinned)
+    host memory: they are always copied into the step's static device buffers first.  Called without arguments it
+    consumes the batch started by `prefetch()`."""
+    self.check_status()
     self.step_count += 1
     if image is None:
       gs = self._prefetched
@@ -166,29 +262,31 @@ class Trainer:
         dst.copy_(src, non_blocking=True)        # device-to-device, ~10 us
       gs["consumed"] = t.cuda.Event()
       gs["consumed"].record(main)
-      if not self.use_graph or engine_lib.PROFILE is not None:
-        return self._eager_step(*gs["in"])
     else:
-      if not self.use_graph or engine_lib.PROFILE is not None:
-        return self._eager_step(image, v2s, offsets, gt)
       gs = self._gstate(image, v2s, offsets, gt)
       for dst, src in zip(gs["in"], (image, v2s, offsets, gt)):
         dst.copy_(src, non_blocking=True)
+    loss = self._run(gs)
+    self._post_status_read()
+    return loss
+
+  def _run(self, gs):
+    if not self.use_graph or engine_lib.PROFILE is not None:
+      return self._eager_step(*gs["in"])
     if gs["graph"] is None:
       if gs["calls"] < 2:                       # eager warm-up: lazy initialisation must not happen under capture
         gs["calls"] += 1
         return self._eager_step(*gs["in"])
+      in_graph = self.world == 1 or self.collective_in_graph
       n0 = _lib.lib().crn_launch_count()
-      self.eng._ver_sig = None
+      self.eng._ver_sig = None                  # the captured step re-packs the weights unconditionally
       g = t.cuda.CUDAGraph()
-      with t.cuda.graph(g):
-        gs["loss"] = self._fwd_bwd(*gs["in"])
-        if self.world == 1:
-          self._adam(1.0)
+      with t.cuda.graph(g, capture_error_mode="thread_local"):
+        gs["loss"] = self._step_body(*gs["in"], in_graph)
       self.graph_launches = int(_lib.lib().crn_launch_count() - n0)
-      gs["graph"] = g
+      gs["graph"], gs["update_in_graph"] = g, in_graph
     gs["graph"].replay()
-    if self.world > 1:
-      scale = allreduce_flat_grad(self.grad, self.world, self.pg)
-      self._adam(scale)
+    if not gs["update_in_graph"]:
+      self._update_all()
+    self._weights_changed()
     return gs["loss"]

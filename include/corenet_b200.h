@@ -219,6 +219,11 @@ int crn_softmax_planar(const float* logits, int32_t N, int32_t C, int64_t S, flo
                        void* stream);
 int crn_argmax_confusion(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N,
                          int32_t C, int64_t S, int64_t* cm, void* stream);
+/* FG_BG evaluation form (evaluation_results.py:40-51): predicted and ground-truth labels (0/1) of scene n are
+ * multiplied by scene_label[n] (device int32[N], values in [0, K/(C-1))) before counting into cm int64[K, K];
+ * scene_label == NULL requires K == C and is crn_argmax_confusion. */
+int crn_argmax_confusion_labeled(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N, int32_t C,
+                                 int64_t S, const int32_t* scene_label, int32_t K, int64_t* cm, void* stream);
 
 /* ------------------------------------------------------------------------
  * fill_inside_voxels.  Replaces cc/fill_voxels_gpu.cu:136-171 (kernels
@@ -368,6 +373,16 @@ int crn_gather_f64_to_f32(const crn_f64_copy_item* items, const int64_t* offsets
  * corrections): the form a captured CUDA graph can replay. */
 int crn_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                       float beta2, float eps, int32_t* step_dev, float grad_scale, void* stream);
+/* Guarded form: when *status (device word the tcgen05 kernels set on an mbarrier timeout; may be NULL) is non-zero the
+ * step is skipped entirely (weights, moments and the counter stay as they were), so a failed step cannot reach the
+ * parameters.  Works on a sub-range too: the counter is only bumped when bump_step != 0 (chunked updates call it once
+ * per chunk with bump_step set on the first chunk only). */
+int crn_adam_step_guarded(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                          float beta2, float eps, int32_t* step_dev, int32_t bump_step, float grad_scale,
+                          const int32_t* status, void* stream);
+/* Failure surfacing: if *status != 0 writes NaN to out[i * stride] for i < n (one element per scene of the logits is
+ * enough to turn every loss into NaN).  No-op otherwise. */
+int crn_status_poison(const int32_t* status, float* out, int64_t stride, int32_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,273 @@
+"""Parity on BASELINE.json's own configurations, against fixtures generated from the REAL reference
+(oracle/make_golden_configs.py -> tests/golden/corenet_reference_configs.npz):
+
+  C  h5 per-GPU batch   B=4, C=2,  train, iou_fgbg
+  D  h7                 B=8, C=2,  eval, softmax + argmax + confusion matrix / mean IoU
+  E  m7 / m9            B=2, C=15, train, xent_times_iou_agnostic
+
+Kernel routing depends on the batch size and the channel counts (engine._conv_dispatch), so these are different
+code paths from the B=1/B=2 cases of test_gpu_model.py.  Tolerances: forward 1e-3 of the tensor maximum (logits and
+every decoder / encoder tap), mean IoU 0.1 pt, gradients "as accurate as the reference's own fp32 gradients" measured
+against the fp64 answer (train mode at random init is chaotic, see test_gpu_model.py).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch as t
+
+pytestmark = pytest.mark.gpu
+
+from oracle import make_golden_configs as MGC
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FWD_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def cfg_golden():
+  return np.load(os.path.join(ROOT, "tests", "golden", "corenet_reference_configs.npz"), allow_pickle=False)
+
+
+def build_model(classes):
+  from corenet_b200 import configuration as C
+  from corenet_b200.model.core_net import CoreNet
+  t.manual_seed(0)
+  return CoreNet(C.default_config(classes))
+
+
+def check_samples(golden, key, ten, tol=FWD_TOL):
+  idx, val, mx = golden[key + ".idx"], golden[key + ".val"], float(golden[key + ".max"])
+  got = ten.detach().double().cpu().reshape(-1)[idx].numpy()
+  err = np.abs(got - val).max() / mx
+  assert err <= tol, f"{key}: {err:.3e}"
+  return err
+
+
+def plan_tap(plan, key):
+  """Reference-layout (NCDHW / NCHW) copy of an engine buffer named like the oracle's taps."""
+  def grid(buf, c):
+    g = buf.spatial[0]
+    return buf.v.view(plan.B, g, g, g, buf.cs)[..., :c].permute(0, 4, 1, 2, 3).contiguous()
+  for sd in plan.stages:
+    k = sd["stage"]
+    if key == f"cat_{k}":
+      return grid(sd["cat"], sd["cin"])
+    if key == f"stage_{k}.c1":
+      return grid(sd["c"], sd["mid"])
+    if key == f"stage_{k}" and k < 6:
+      return grid(sd["next"], sd["t_out"])
+  raise KeyError(key)
+
+
+def check_forward(golden, case, model, logits, need_grad):
+  from corenet_b200 import engine
+  eng = engine.get_engine(model)
+  assert int(eng.tc_status) == 0, "tcgen05 conv kernel reported a barrier timeout"
+  errs = {"logits": check_samples(golden, f"{case}.logits", logits)}
+  plan = eng.plans[(logits.shape[0], need_grad)][0]
+  for k in ("cat_3", "cat_4", "cat_5", "cat_6", "stage_2", "stage_3", "stage_4", "stage_5", "stage_3.c1",
+            "stage_4.c1", "stage_5.c1", "stage_6.c1"):
+    errs[k] = check_samples(golden, f"{case}.tap.{k}", plan_tap(plan, k))
+  feats = plan.features_nchw()
+  for name, f in zip(("stage1_64x128x128", "stage2_256x64x64", "stage3_512x32x32", "stage4_1024x16x16",
+                      "stage5_2048x8x8", "global_average_2048"), feats):
+    errs[name] = check_samples(golden, f"{case}.tap.{name}", f)
+  worst = max(errs, key=errs.get)
+  print(f"\n[{case}] forward: logits {errs['logits']:.2e}, worst tap {worst} {errs[worst]:.2e}")
+
+
+def check_gradients(golden, case, model):
+  """Sampled relative-L2 error per tensor against the fp64 gradients, next to the same error of the reference's own
+  fp32 gradients: the CUDA path must be as accurate as the reference (<= 4x its error + 3e-3 for >= 90 % of the
+  tensors, comparable median) -- the acceptance rule of test_gpu_model.test_forward_backward_parity."""
+  e_mine, e_ref, names = [], [], []
+  gscale = max(float(golden[f"{case}.grad.{n}.norm64"]) for n, _ in model.named_parameters())
+  for n, p in model.named_parameters():
+    assert p.grad is not None, n
+    idx = golden[f"{case}.grad.{n}.idx"]
+    g64, g32 = golden[f"{case}.grad.{n}.f64"], golden[f"{case}.grad.{n}.ref32"]
+    mine = p.grad.detach().double().cpu().reshape(-1)[idx].numpy()
+    den = np.linalg.norm(g64)
+    if float(golden[f"{case}.grad.{n}.norm64"]) <= 1e-12 * gscale or den == 0.0:
+      assert np.abs(mine).max() <= 1e-5 * gscale, n
+      continue
+    e_mine.append(np.linalg.norm(mine - g64) / den)
+    e_ref.append(np.linalg.norm(g32 - g64) / den)
+    names.append(n)
+  e_mine, e_ref = np.array(e_mine), np.array(e_ref)
+  worst = int(np.argmax(e_mine))
+  print(f"[{case}] grad rel-L2 (sampled) vs fp64: CUDA median {np.median(e_mine):.2e} max {e_mine.max():.2e} "
+        f"({names[worst]}); reference fp32 median {np.median(e_ref):.2e} max {e_ref.max():.2e}")
+  ok = e_mine <= 4 * e_ref + 3e-3
+  assert ok.mean() >= 0.9, f"only {ok.mean():.2%} of the gradient tensors are as accurate as the reference's"
+  assert np.median(e_mine) <= 3 * np.median(e_ref) + 1e-3
+
+
+@pytest.mark.parametrize("case", ["C", "E"])
+def test_train_configs_match_reference(cfg_golden, case):
+  from corenet_b200.model import losses
+  dev = t.device("cuda", 0)
+  inp = MGC.config_inputs(case)
+  m = build_model(inp["classes"]).to(dev).train()
+  logits = m(inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev))
+  loss = getattr(losses, MGC.LOSS[case])(inp["gt"].to(dev), logits)
+  loss.backward()
+  check_forward(cfg_golden, case, m, logits, True)
+  ref_loss = float(cfg_golden[f"{case}.loss"])
+  print(f"[{case}] loss {loss.item():.7f} vs reference {ref_loss:.7f}")
+  assert abs(loss.item() - ref_loss) <= 1e-4 * max(1.0, abs(ref_loss))
+  check_gradients(cfg_golden, case, m)
+  bufs = dict(m.named_buffers())
+  for k, v in bufs.items():
+    if k.endswith("num_batches_tracked"):
+      assert int(v) == 1
+    else:
+      idx, val = cfg_golden[f"{case}.buf.{k}.idx"], cfg_golden[f"{case}.buf.{k}.val"]
+      got = v.detach().double().cpu().reshape(-1)[idx].numpy()
+      assert np.abs(got - val).max() <= 3e-4 * float(cfg_golden[f"{case}.buf.{k}.max"]), k
+
+
+def test_h7_eval_batch8_confusion_and_miou(cfg_golden):
+  """B=8 eval forward + softmax + argmax + confusion through the Evaluator (eager, eager, captured graph, replay):
+  the counts of every pass must equal the reference's up to near-tie voxels, mean IoU within 0.1 pt."""
+  from corenet_b200.evaluator import Evaluator
+  dev = t.device("cuda", 0)
+  inp = MGC.config_inputs("D")
+  m = build_model(2).to(dev).eval()
+  ev = Evaluator(m)
+  args = [inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev), inp["gt"].to(dev)]
+  cm_ref = t.from_numpy(cfg_golden["D.cm"])
+  from oracle import corenet_oracle as O
+  for i in range(4):
+    if ev.confusion_matrix is not None:
+      ev.confusion_matrix.zero_()
+    pmf = ev.add_batch(*args)
+    cm = ev.confusion_matrix.cpu()
+    assert int(cm.sum()) == inp["gt"].numel()
+    assert (cm - cm_ref).abs().sum().item() <= 1e-5 * inp["gt"].numel(), (i, cm, cm_ref)
+    assert abs(ev.mean_iou() - float(cfg_golden["D.miou"])) <= 1e-3
+    assert abs(ev.mean_iou() - O.mean_iou(cm)) < 1e-12
+  assert ev.graph_launches > 100, "the fourth batch must have been a graph replay"
+  ev.check_status()
+  eng = ev.eng
+  plan = eng.plans[(8, False)][0]
+  check_forward(cfg_golden, "D", m, plan.logits, False)
+  assert t.allclose(pmf, plan.logits.softmax(1), atol=1e-6)
+  assert t.allclose(pmf.sum(1), t.ones_like(pmf[:, 0]), atol=1e-5)
+  # prefetch path with pinned host inputs
+  host = [x.pin_memory() for x in (inp["image"], inp["v2s"], inp["offsets"], inp["gt"])]
+  ev.confusion_matrix.zero_()
+  ev.prefetch(*host)
+  ev.add_batch()
+  assert (ev.confusion_matrix.cpu() - cm_ref).abs().sum().item() <= 1e-5 * inp["gt"].numel()
+
+
+def test_fgbg_labeled_confusion_matches_reference_rule():
+  """FG_BG evaluation scales 0/1 labels by the scene's dataset class (evaluation_results.py:40-51)."""
+  from corenet_b200 import _lib
+  dev = t.device("cuda", 0)
+  g = t.Generator().manual_seed(5)
+  b, c, k, s = 3, 2, 6, 4096
+  logits = t.randn(b, c, 16, 16, 16, generator=g)
+  gt = t.randint(0, 2, (b, 16, 16, 16), generator=g, dtype=t.int32)
+  labels = t.tensor([1, 5, 3], dtype=t.int32)
+  pred = logits.argmax(1).to(t.int64) * labels[:, None, None, None]
+  gts = gt.to(t.int64) * labels[:, None, None, None]
+  exp = t.bincount((gts * k + pred).reshape(-1), minlength=k * k).reshape(k, k)
+  cm = t.zeros(k, k, dtype=t.int64, device=dev)
+  _lib.call("crn_argmax_confusion_labeled", logits.to(dev).data_ptr(), gt.to(dev).data_ptr(), 0, b, c, s,
+            labels.to(dev).data_ptr(), k, cm.data_ptr(), _lib.stream_ptr())
+  assert t.equal(cm.cpu(), exp)
+
+
+def test_module_path_graph_replay_matches_eager():
+  """CoreNet.forward + autograd backward: calls 1-2 enqueue eagerly, call 3 captures CUDA graphs, call 4 replays.
+  In eval mode (well conditioned) all four must agree; weights changed in between (optimizer.step through torch)
+  must be picked up by the replay (re-pack outside the graph)."""
+  from corenet_b200 import engine
+  from corenet_b200.model import losses
+  from oracle import make_golden as MG
+  dev = t.device("cuda", 0)
+  inp = MG.case_inputs("B")
+  gt = MG.synthetic_gt(2, 2).to(dev)
+  m = build_model(2).to(dev).eval()
+  args = [inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev)]
+  outs = []
+  for i in range(4):
+    m.zero_grad()
+    logits = m(*args)
+    losses.iou_fgbg(gt, logits).backward()
+    outs.append((logits.detach().clone(), t.cat([p.grad.reshape(-1) for p in m.parameters()])))
+  plan = engine.get_engine(m).plans[(2, True)][0]
+  assert any(k[0] == "fwd" and v["graph"] is not None for k, v in plan._graphs.items())
+  assert any(k[0] == "bwd" and v["graph"] is not None for k, v in plan._graphs.items())
+  for lo, g in outs[1:]:
+    assert (lo - outs[0][0]).abs().max().item() <= 1e-5 * outs[0][0].abs().max().item()
+    assert ((g - outs[0][1]).norm() / outs[0][1].norm()).item() <= 1e-4
+  # change the weights through torch: the replayed graph must see them
+  with t.no_grad():
+    for p in m.parameters():
+      p.mul_(1.01)
+  lo2 = m(*args).detach()
+  t.cuda.synchronize()
+  engine.USE_GRAPHS = False
+  try:
+    lo2_eager = m(*args).detach()
+  finally:
+    engine.USE_GRAPHS = True
+  assert (lo2 - outs[0][0]).abs().max().item() > 1e-4 * outs[0][0].abs().max().item()
+  assert (lo2 - lo2_eager).abs().max().item() <= 1e-5 * lo2_eager.abs().max().item()
+  # a forward with grad that is never back-propagated must release its plan (no new plan per call)
+  for _ in range(3):
+    m(*args)
+  assert len(engine.get_engine(m).plans[(2, True)]) <= 2
+
+
+def test_eval_forward_between_trainer_steps_sees_new_weights():
+  """the fused Adam kernel updates the weights through raw pointers (also inside graph replays); an eval
+  forward between training steps must re-pack them."""
+  from corenet_b200 import engine
+  from corenet_b200.trainer import Trainer
+  from oracle import make_golden as MG
+  dev = t.device("cuda", 0)
+  inp = MG.case_inputs("A")
+  gt = MG.synthetic_gt(1, 2).to(dev)
+  m = build_model(2).to(dev).eval()
+  tr = Trainer(m, lr=1e-2, eps=1e-4)
+  args = [inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev)]
+  for i in range(5):
+    tr.step(*args, gt)
+    with t.no_grad():
+      a = m(*args).clone()
+    eng = engine.get_engine(m)
+    eng._ver_sig = None            # force a fresh pack: the reference answer for the current weights
+    with t.no_grad():
+      b = m(*args).clone()
+    assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item(), f"stale weights after step {i + 1}"
+  assert tr.graph_launches > 100
+  tr.check_status(wait=True)
+
+
+def test_trainer_rejects_bad_label_dtype_and_guards_failed_steps():
+  from corenet_b200.trainer import Trainer
+  from oracle import make_golden as MG
+  dev = t.device("cuda", 0)
+  inp = MG.case_inputs("A")
+  m = build_model(2).to(dev).train()
+  tr = Trainer(m, use_graph=False)
+  args = [inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev)]
+  with pytest.raises(AssertionError):
+    tr.step(*args, MG.synthetic_gt(1, 2).to(dev).to(t.uint8))
+  gt = MG.synthetic_gt(1, 2).to(dev)
+  tr.step(*args, gt)
+  before = tr.flat.clone()
+  tr.eng.tc_status.fill_(1)          # simulate an mbarrier timeout reported by a tcgen05 kernel
+  loss = tr.step(*args, gt)
+  assert t.isnan(loss).all(), "a failed step must surface as a NaN loss"
+  assert t.equal(tr.flat, before) and int(tr.step_dev) == 1, "the guarded Adam kernel must skip a failed step"
+  with pytest.raises(RuntimeError):
+    tr.check_status(wait=True)
+  tr.eng.tc_status.zero_()
+  tr.step(*args, gt)
+  assert int(tr.step_dev) == 2 and not t.equal(tr.flat, before)

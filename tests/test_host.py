@@ -55,12 +55,108 @@ def test_engine_layer_table():
   assert eng.dec_plan[-1][0] == 6
 
 
-def test_shard_indices():
+def test_shard_indices_follow_reference_sampler(monkeypatch):
+  """Vector computed with the reference's DistributedSampler (distributed.py:204-224: randperm seeded 0x1234,
+  zero-padded, contiguous blocks); re-checked against the class itself when a reference checkout is present."""
   from corenet_b200.trainer import shard_indices
-  assert shard_indices(10, 0, 4) == [0, 4, 8]
-  assert shard_indices(10, 3, 4) == [3, 7, 1]
+  assert shard_indices(10, 0, 4) == [6, 1, 0]
+  assert shard_indices(10, 3, 4) == [3, 0, 0]                      # padded with index 0
+  assert shard_indices(10, 1, 4, pad=False) == [0, 7, 5]
   parts = [shard_indices(10, r, 4, pad=False) for r in range(4)]
   assert sorted(sum(parts, [])) == list(range(10))
+  from baseline import ref_import
+  if ref_import.import_reference() is not None:
+    from corenet import distributed as ref_dist
+    # torch >= 2.x: Sampler.__init__ no longer takes the data source the reference passes (distributed.py:209)
+    monkeypatch.setattr(t.utils.data.Sampler, "__init__", lambda self, *a, **k: None, raising=False)
+    for n, world, pad in ((10, 4, True), (10, 4, False), (37, 8, True), (5, 2, False), (64, 8, True)):
+      for r in range(world):
+        smp = ref_dist.DistributedSampler(list(range(n)), r, world, pad)
+        assert [int(i) for i in smp] == shard_indices(n, r, world, pad), (n, world, pad, r)
+
+
+def test_reference_state_roundtrip_with_dropin_module():
+  """The reference's own state.py (encode_state / decode_state, :74-97) over the overlaid module (CPU: no forward)."""
+  from baseline import ref_import
+  if ref_import.import_reference() is None:
+    pytest.skip("no reference checkout")
+  from corenet_b200 import compat
+  compat.install()
+  from corenet import configuration as ref_cfg
+  from corenet import state as ref_state
+  from corenet.model import core_net
+  assert core_net.CoreNet is CoreNet
+  cfg = ref_cfg.CoreNetConfig(decoder=ref_cfg.DecoderConfig(
+      resolution=(128, 128, 128), num_output_channels=15, last_upscale_factor=2, latent_channels=64,
+      skip_fraction=0.75))
+  t.manual_seed(1)
+  m = core_net.CoreNet(cfg)
+  opt = t.optim.Adam(m.parameters(), lr=4e-4, eps=1e-4)
+  st = ref_state.State(global_step=7, model=m, optimizer=opt, extra_metadata={"note": 1})
+  st2 = ref_state.decode_state(ref_state.encode_state(st), "cpu")
+  assert isinstance(st2.model, CoreNet) and st2.global_step == 7 and st2.extra_metadata == {"note": 1}
+  assert st2.model.config.decoder.num_output_channels == 15
+  for (k1, v1), (k2, v2) in zip(m.state_dict().items(), st2.model.state_dict().items()):
+    assert k1 == k2 and t.equal(v1, v2)
+  # the encoder checkpoint interface of create_initial_state (state.py:69): 371 keys
+  enc = m.encoder.state_dict()
+  assert len(enc) == 371
+  st2.model.encoder.load_state_dict(enc)
+
+
+def test_json5_config_surface():
+  text = """// generated
+  {
+    string_templates: [{key: "data_dir", value: "data"}, {key: 'out', value: "{data_dir}/o",},],
+    train: {
+      data: {
+        datasets: [{dataset_path: "{data_dir}/a.json", /* c */ high_realism: true,},],
+        data_loader: {num_data_workers: 6, batch_size: 4, prefetch_factor: 2,},
+        voxelization_config: {
+          task_type: "SEMANTIC",
+          resolution: {depth: 128, height: 128, width: 128,},
+          sub_grid_sampling: false, conservative_rasterization: false,
+          voxelization_image_resolution_multiplier: 8, voxelization_projection_depth_multiplier: 1,
+        },
+      },
+      initial_learning_rate: 0.0004, adam_epsilon: 0.0001, note: "a, } b // not a comment",
+    },
+    output_path: "{out}/m7",
+  }"""
+  cfg = C.expand_templates(C.parse_json5(text))
+  assert cfg["output_path"] == "data/o/m7" and cfg["train"]["note"] == "a, } b // not a comment"
+  assert cfg["train"]["data"]["datasets"][0]["dataset_path"] == "data/a.json"
+  hp = C.hot_path_settings(cfg)
+  assert hp["batch_size"] == 4 and hp["loss"] == "xent_times_iou_agnostic" and hp["resolution"] == (128, 128, 128)
+  v = hp["voxelization_config"]
+  assert v.task_type == C.TaskType.SEMANTIC and v.voxelization_image_resolution_multiplier == 8
+  assert not v.conservative_rasterization
+  import glob
+  for p in glob.glob("/root/reference/configs/*/*.json5"):        # build container only
+    hp = C.hot_path_settings(C.load_config(p))
+    assert hp["resolution"] == (128, 128, 128) and hp["batch_size"] in (4, 8)
+
+
+def test_super_resolution_host_logic_32_to_128():
+  """y1-style plumbing without a GPU: SuperResolutionInference over a stub 32^3 model (super_resolution.py:45-112)."""
+  from corenet_b200.super_resolution import SuperResolutionInference
+  from oracle import corenet_oracle as O
+  seen = []
+
+  def stub(image, cam, v2x, grid_offsets):
+    seen.append((v2x, grid_offsets))
+    n_off, b = grid_offsets.shape[:2]
+    return grid_offsets.sum(-1)[:, :, None, None, None, None] + t.zeros(n_off, b, 3, 32, 32, 32)
+  sr = SuperResolutionInference(stub, (32, 32, 32))
+  go = t.tensor([[0.5, 0.25, 0.75], [0.1, 0.2, 0.3]])
+  v2x = t.eye(4)[None].expand(2, 4, 4)
+  out = sr(t.zeros(2, 3, 8, 8, dtype=t.uint8), v2x, v2x, go, (128, 128, 128))
+  native = O.native_offsets(4, go)
+  assert t.allclose(seen[0][1], native) and t.allclose(seen[0][0], v2x @ O.scale([0.25] * 3))
+  want = O.interleave_pmfs(native.sum(-1)[:, :, None, None, None, None] + t.zeros(64, 2, 3, 32, 32, 32), 4)
+  assert t.equal(out, want) and tuple(out.shape) == (2, 3, 128, 128, 128)
+  with pytest.raises(ValueError):
+    sr.get_resolution_multiplier((100, 128, 128))
 
 
 def test_transformations_match_oracle():
