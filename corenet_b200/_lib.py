@@ -75,6 +75,9 @@ _SIGS = {
     "crn_planar_to_rows": ([vp, i32, i32, i64, i32, vp, vp], i32),
     "crn_skip_sample_fwd": ([vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, i32, i32, vp], i32),
     "crn_skip_sample_bwd": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp], i32),
+    "crn_skip_lists_workspace_bytes": ([i32, i32, i32, i32, i32, i32], i64),
+    "crn_skip_build_lists": ([i32, i32, i32, vp, vp, i32, i32, i32, vp, i64, vp, vp, vp], i32),
+    "crn_skip_sample_bwd_sorted": ([vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], i32),
     "crn_skip_indices": ([i32, i32, i32, vp, vp, i32, i32, i32, vp, vp], i32),
     "crn_loss_sums": ([vp, vp, i32, i32, i32, i64, i32, vp, vp], i32),
     "crn_loss_finalize": ([vp, i32, i32, i64, i32, vp, vp, vp], i32),

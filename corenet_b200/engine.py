@@ -50,8 +50,49 @@ def grad_chunk_of(name: str) -> int:
   raise KeyError(name)
 
 
-def _call(name, *args):
+def _call(name, *args, hbm=None):
+  """C-ABI launch on the current stream.  Under PROFILE the HBM-bound kernels of the path are bracketed with CUDA
+  events: entries ("hbm", family, algorithmic bytes, start, end) -- bench.py turns them into achieved GB/s.
+  hbm = (label, bytes) overrides the per-function table."""
+  fam = (hbm and (lambda a: hbm)) or HBM_BYTES.get(name) if PROFILE is not None else None
+  if fam is None:
+    _lib.call(name, *args)
+    return
+  e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+  e0.record()
   _lib.call(name, *args)
+  e1.record()
+  label, nbytes = fam(args)
+  PROFILE.append(("hbm", label, nbytes, e0, e1))
+
+
+def _b_skip_fwd(a):      # (cmap, B, h, w, Cs, cmap_cs, mat, offs, gd, gh, gw, out, out_cs, out_co, st)
+  b, h, w, cs, gd, gh, gw = a[1], a[2], a[3], a[4], a[8], a[9], a[10]
+  return f"skip_fwd g={gd}", 4 * cs * b * (gd * gh * gw + h * w)
+
+
+def _b_skip_bwd(a):      # (dy, dy_cs, dy_co, B, h, w, Cs, cmap_cs, mat, offs, gd, gh, gw, dmap, st)
+  b, h, w, cs, gd, gh, gw = a[3], a[4], a[5], a[6], a[10], a[11], a[12]
+  return f"skip_bwd g={gd}", 4 * cs * b * (gd * gh * gw + h * w)
+
+
+# C-ABI name -> args -> (family label, algorithmic bytes): compulsory reads + writes of the op (SURVEY 8d, DESIGN 3)
+HBM_BYTES = {
+    "crn_skip_sample_fwd": _b_skip_fwd,
+    "crn_skip_sample_bwd": _b_skip_bwd,
+    "crn_brn_stats": lambda a: ("brn_stats", 4 * a[1] * a[2]),
+    "crn_brn_apply": lambda a: ("brn_apply", (8 + (4 if a[6] else 0) + (4 if a[12] else 0)) * a[1] * a[2]),
+    "crn_brn_bwd_reduce": lambda a: ("brn_bwd_reduce", (8 + (4 if a[3] else 0) + (4 if a[4] else 0)
+                                                          + (4 if a[13] else 0)) * a[8] * a[9]),
+    "crn_brn_bwd_dx": lambda a: ("brn_bwd_dx", 12 * a[6] * a[7]),
+    "crn_loss_sums": lambda a: ("loss_sums", (4 * a[4] + (8 if a[2] else 4)) * a[3] * a[5]),
+    "crn_loss_bwd": lambda a: ("loss_bwd", (8 * a[4] + (8 if a[2] else 4)) * a[3] * a[5]),
+    "crn_softmax_planar": lambda a: ("softmax", 8 * a[1] * a[2] * a[3]),
+    "crn_argmax_confusion_labeled": lambda a: ("argmax_confusion", (4 * a[4] + (8 if a[2] else 4)) * a[3] * a[5]),
+    "crn_adam_step_guarded": lambda a: ("adam", 28 * a[4]),
+    "crn_unpack_wgrads": lambda a: ("unpack_wgrads", 8 * a[3]),
+    "crn_planar_to_rows": lambda a: ("planar_to_rows", 8 * a[1] * a[2] * a[3]),
+}
 
 
 # bench.py sets this to a list to time every convolution launch with CUDA events:
@@ -184,6 +225,8 @@ USE_TC = True
 WGRAD_SIDE_STREAM = True
 # stage_6.c1 forward through the kz-stacked kernel (csrc/conv_tc5s.cu)
 USE_TC5S = True
+# ray-traced skip backward as a sorted per-pixel gather (bit-reproducible) instead of float atomics
+DETERMINISTIC_SKIP_BWD = True
 
 
 def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
@@ -789,6 +832,11 @@ class Plan:
           st["mat"] = t.zeros(B, 4, 4, dtype=t.float32, device=self.dev)
           st["ssum"] = t.zeros(B, skip_c, dtype=t.float32, device=self.dev)
           st["dwoff"] = t.zeros(skip_c, 3, dtype=t.float32, device=self.dev)
+          if self.need_grad:
+            nb = _lib.lib().crn_skip_lists_workspace_bytes(B, hw, hw, g2, g2, g2)
+            st["lists_ws"] = t.empty(nb, dtype=t.uint8, device=self.dev)
+            st["sorted_vox"] = t.empty(B * g2 ** 3, dtype=t.int32, device=self.dev)
+            st["starts"] = t.empty(B * hw * hw + 1, dtype=t.int32, device=self.dev)
         cat = nxt
       else:
         cp = _r4(t_out)
@@ -866,6 +914,25 @@ class Plan:
               self.x1.p, 0, st)
     # per-scale layer matrices (reconstruction_decoder.py:111-115) and offsets
     self.offs.copy_(offsets)
+    # per-scale layer matrices v2s @ scale(res / g) (reconstruction_decoder.py:111-115)
+    skips = [sd for sd in self.stages if sd["stage"] < 6 and sd["skip_c"]]
+    for sd in skips:
+      t.matmul(v2s, sd["scale"], out=sd["mat"])
+    if self.need_grad and DETERMINISTIC_SKIP_BWD:
+      # voxel lists per pixel for the atomics-free skip backward: they depend on (v2s, offsets) only and are built on
+      # the side stream while the decoder runs
+      main, side = t.cuda.current_stream(), self.side_stream
+      ev = t.cuda.Event()
+      ev.record(main)
+      side.wait_event(ev)
+      with t.cuda.stream(side):
+        for sd in skips:
+          g2, hw = 2 * sd["g"], sd["hw"]
+          _call("crn_skip_build_lists", B, hw, hw, sd["mat"].data_ptr(), self.offs.data_ptr(), g2, g2, g2,
+                sd["lists_ws"].data_ptr(), sd["lists_ws"].numel(), sd["sorted_vox"].data_ptr(),
+                sd["starts"].data_ptr(), side.cuda_stream, hbm=(f"skip_lists g={g2}", 40 * B * g2 ** 3))
+        lists_ev = t.cuda.Event()
+        lists_ev.record(side)
     logits = None
     for sd in self.stages:
       g = sd["g"]
@@ -904,7 +971,6 @@ class Plan:
           t.addmm(P[ls.name + ".bias"], self.offs, w[:, ls.cin:, 0, 0].t(), out=sbias)
           conv_call("fwd", ls, sd["d_s"], src.p, eng.wf(ls), sbias.data_ptr(), cmap.p, 0, st)
           g2 = 2 * g
-          t.matmul(v2s, sd["scale"], out=mat)
           _call("crn_skip_sample_fwd", cmap.p, B, hw, hw, sd["skip_c"], cmap.cs, mat.data_ptr(),
                 self.offs.data_ptr(), g2, g2, g2, nxt.p, nxt.cs, sd["t_out"], st)
       else:
@@ -915,6 +981,8 @@ class Plan:
         else:
           conv_call("fwd", sd["lt"], sd["d_t"], sd["z2"].p, eng.wf(sd["lt"]), bias(sd["lt"]),
                     logits.data_ptr(), 0, st)
+    if self.need_grad and DETERMINISTIC_SKIP_BWD:
+      t.cuda.current_stream().wait_event(lists_ev)
     # a tcgen05 barrier timeout (status word != 0) must not go unnoticed: NaN in every scene's logits
     _call("crn_status_poison", eng.tc_status.data_ptr(), logits.data_ptr(), logits[0].numel(), B, st)
     return logits
@@ -1011,10 +1079,15 @@ class Plan:
         dy_ptr, d_t = nxt.gp, sd["d_t"]
         if sd["skip_c"]:
           ls, src, cmap, hw = sd["ls"], sd["src"], sd["cmap"], sd["hw"]
-          cmap.g.zero_()
           g2 = 2 * g
-          _call("crn_skip_sample_bwd", nxt.gp, nxt.cs, sd["t_out"], B, hw, hw, sd["skip_c"], cmap.cs,
-                sd["mat"].data_ptr(), self.offs.data_ptr(), g2, g2, g2, cmap.gp, st)
+          if DETERMINISTIC_SKIP_BWD:
+            _call("crn_skip_sample_bwd_sorted", nxt.gp, nxt.cs, sd["t_out"], B, hw, hw, sd["skip_c"], cmap.cs,
+                  sd["sorted_vox"].data_ptr(), sd["starts"].data_ptr(), cmap.gp, st,
+                  hbm=(f"skip_bwd g={g2}", 4 * sd["skip_c"] * B * (g2 ** 3 + hw * hw) + 4 * B * g2 ** 3))
+          else:
+            cmap.g.zero_()
+            _call("crn_skip_sample_bwd", nxt.gp, nxt.cs, sd["t_out"], B, hw, hw, sd["skip_c"], cmap.cs,
+                  sd["mat"].data_ptr(), self.offs.data_ptr(), g2, g2, g2, cmap.gp, st)
           wgrad(ls, sd["d_s"], src.p, cmap.gp)
           dgrad(ls, sd["d_s"], cmap.gp, src.gp, 0)
           # per-scene sums of d(cmap) -> bias and offset-channel weight grads (tiny glue)

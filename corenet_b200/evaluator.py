@@ -14,7 +14,7 @@ import torch as t
 from corenet_b200 import _lib
 from corenet_b200 import engine as engine_lib
 
-_call = _lib.call
+_call = engine_lib._call     # C-ABI launch (bracketed with CUDA events under engine.PROFILE)
 
 
 class Evaluator:

@@ -39,9 +39,9 @@ def voxelize_mesh(triangles, mesh_num_tri, resolution: Tuple[int, int, int], vie
   if sub_grid_sampling and projection_depth_multiplier == 0:
     raise ValueError("projection_depth_multiplier must be 1 if sub_grid_sampling is True")
   assert int(mesh_num_tri.sum()) == triangles.shape[0]
-  tri_mesh = _dynamic_tile(mesh_num_tri).to(dev)
-  return ops.voxelize_mesh(triangles.to(dev), tri_mesh, len(mesh_num_tri), tuple(resolution),
-                           view2voxel.to(dev).contiguous(), sub_grid_sampling,
+  tri_mesh = _dynamic_tile(mesh_num_tri).to(dev, non_blocking=True)
+  return ops.voxelize_mesh(triangles.to(dev, non_blocking=True), tri_mesh, len(mesh_num_tri), tuple(resolution),
+                           view2voxel.to(dev, non_blocking=True).contiguous(), sub_grid_sampling,
                            image_resolution_multiplier, conservative_rasterization,
                            projection_depth_multiplier)
 

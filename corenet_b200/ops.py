@@ -273,10 +273,26 @@ class _SkipGatherFn(t.autograd.Function):
     b, c, h, w, gd, gh, gw = ctx.meta
     st = _lib.stream_ptr()
     g, _, _ = _to_rows(gy)
-    dmap = t.zeros(b * h * w, c, dtype=t.float32, device=g.device)
-    _call("crn_skip_sample_bwd", g.data_ptr(), c, 0, b, h, w, c, c, m.data_ptr(), o.data_ptr(), gd, gh, gw,
-          dmap.data_ptr(), st)
+    dmap = skip_scatter_sorted(g, c, 0, b, h, w, c, m, o, (gd, gh, gw))
     return _from_rows(dmap, (b, c, h, w)), None, None, None
+
+
+def skip_scatter_sorted(dout_rows, out_cs, out_co, b, h, w, c, matrix, offsets, res3d):
+  """Deterministic backward of the gather: dmap rows [b*h*w, c] = per-pixel sums of the voxel gradients, voxels
+  visited in sorted order (no atomics; ray_traced_skip_connection.py:135-142 under autograd is an atomic index_put)."""
+  gd, gh, gw = res3d
+  st = _lib.stream_ptr()
+  dev = dout_rows.device
+  nb = _lib.lib().crn_skip_lists_workspace_bytes(b, h, w, gd, gh, gw)
+  ws = t.empty(nb, dtype=t.uint8, device=dev)
+  sorted_vox = t.empty(b * gd * gh * gw, dtype=t.int32, device=dev)
+  starts = t.empty(b * h * w + 1, dtype=t.int32, device=dev)
+  _call("crn_skip_build_lists", b, h, w, matrix.data_ptr(), offsets.data_ptr(), gd, gh, gw, ws.data_ptr(), nb,
+        sorted_vox.data_ptr(), starts.data_ptr(), st)
+  dmap = t.empty(b * h * w, c, dtype=t.float32, device=dev)
+  _call("crn_skip_sample_bwd_sorted", dout_rows.data_ptr(), out_cs, out_co, b, h, w, c, c, sorted_vox.data_ptr(),
+        starts.data_ptr(), dmap.data_ptr(), st)
+  return dmap
 
 
 def sample_grid2d(grid2d, weight, bias, res3d, matrix, offsets):

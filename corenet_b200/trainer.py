@@ -14,7 +14,7 @@ import torch as t
 from corenet_b200 import _lib
 from corenet_b200 import engine as engine_lib
 
-_call = _lib.call
+_call = engine_lib._call     # C-ABI launch (bracketed with CUDA events under engine.PROFILE)
 
 SAMPLER_SEED = 0x1234       # distributed.py:216
 
@@ -228,14 +228,20 @@ class Trainer:
       self._graphs[key] = gs
     return gs
 
-  def prefetch(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, gt: t.Tensor) -> None:
+  def prefetch(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, gt) -> None:
     """Starts the host->device copy of the NEXT step's inputs on a copy stream (into staging buffers), so that it
     overlaps the step that is currently running -- what the reference's DataLoader prefetch + .cuda() do
-    (pipeline.py:215-223).  The following `step()` (called without arguments) consumes them."""
-    gs = self._gstate(image, v2s, offsets, gt)
+    (pipeline.py:215-223).  `gt` may be a callable returning the device grid: it is invoked with the copy stream
+    current, which puts the device-resident ground-truth pipeline (data.batched_example.voxelize: rasterise + fill +
+    label merge, the reference's voxelize_batch, pipeline.py:126-150) of step k+1 next to step k.
+    The following `step()` (called without arguments) consumes the batch."""
     if self._copy_stream is None:
       self._copy_stream = t.cuda.Stream(device=self.flat.device)
     cs = self._copy_stream
+    if callable(gt):
+      with t.cuda.stream(cs):
+        gt = gt()
+    gs = self._gstate(image, v2s, offsets, gt)
     if gs["consumed"] is not None:
       cs.wait_event(gs["consumed"])            # the previous step has copied the staging buffers out
     with t.cuda.stream(cs):

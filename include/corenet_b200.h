@@ -193,6 +193,19 @@ int crn_skip_sample_fwd(const float* map, int32_t N, int32_t h, int32_t w, int32
 int crn_skip_sample_bwd(const float* dout, int32_t out_cs, int32_t out_co, int32_t N, int32_t h,
                         int32_t w, int32_t C, int32_t map_cs, const float* m, const float* offs,
                         int32_t gD, int32_t gH, int32_t gW, float* dmap, void* stream);
+/* Deterministic backward (no atomics): crn_skip_build_lists sorts the voxels of all N scenes by the pixel they sample
+ * (stable radix sort of the keys n*h*w + pixel; voxels that sample nothing go last) into sorted_vox int32[N*g^3] and
+ * writes starts int32[N*h*w + 1] (the voxels of pixel p are sorted_vox[starts[p] .. starts[p+1])).  The lists depend
+ * only on (m, offs): build them once per step, off the critical path.  crn_skip_sample_bwd_sorted then WRITES
+ * dmap[p] = sum over the list of p of dout channels [out_co, out_co+C), in list order: bit-reproducible.
+ * The reference's backward is an atomic index_put (ray_traced_skip_connection.py:135-142 under autograd). */
+int64_t crn_skip_lists_workspace_bytes(int32_t N, int32_t h, int32_t w, int32_t gD, int32_t gH, int32_t gW);
+int crn_skip_build_lists(int32_t N, int32_t h, int32_t w, const float* m, const float* offs, int32_t gD, int32_t gH,
+                         int32_t gW, void* workspace, int64_t workspace_bytes, int32_t* sorted_vox, int32_t* starts,
+                         void* stream);
+int crn_skip_sample_bwd_sorted(const float* dout, int32_t out_cs, int32_t out_co, int32_t N, int32_t h, int32_t w,
+                               int32_t C, int32_t map_cs, const int32_t* sorted_vox, const int32_t* starts,
+                               float* dmap, void* stream);
 /* The int32 pixel index (iy*(w+2)+ix into the padded map, or -1 behind the
  * camera) for every voxel: test/debug hook for bit-exact index parity. */
 int crn_skip_indices(int32_t N, int32_t h, int32_t w, const float* m, const float* offs,

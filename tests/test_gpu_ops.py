@@ -665,6 +665,51 @@ def test_skip_gather_bit_exact():
   assert t.equal(got, exp)
 
 
+@pytest.mark.parametrize("g3,hw,c", [(64, 64, 12), (32, 32, 24), (16, 16, 48), (8, 8, 96), (16, 8, 20)])
+def test_skip_backward_sorted_is_exact_and_reproducible(g3, hw, c):
+  """The atomics-free backward (voxels sorted by sampled pixel, per-pixel gather in list order): equals a float64
+  index_add of the same scatter to fp32 rounding, equals the atomic kernel to rounding, covers every voxel exactly
+  once, and two runs are bit-identical."""
+  from corenet_b200 import _lib, ops
+  b = 3
+  v2s, offs = _skip_inputs(b, g3 + c, dense=True)
+  mat = v2s.matmul(O.scale([128.0 / g3] * 3)).contiguous()
+  ix, iy, front = O.sample_grid2d_indices(b, (g3,) * 3, (hw, hw), mat, offs)
+  valid = front & (ix >= 1) & (ix <= hw) & (iy >= 1) & (iy <= hw)
+  pix = (t.arange(b)[:, None, None, None] * hw + (iy - 1)) * hw + (ix - 1)
+  cs, co = c + 8, 4                         # gradient rows wider than the slice, like a concat buffer
+  g = t.Generator().manual_seed(g3)
+  dout = t.randn(b * g3 ** 3, cs, generator=g)
+  exp = t.zeros(b * hw * hw, c, dtype=t.float64)
+  exp.index_add_(0, pix[valid].reshape(-1), dout.reshape(b, g3, g3, g3, cs)[valid][:, co:co + c].double())
+  d = dev()
+  args = (dout.to(d), cs, co, b, hw, hw, c, mat.to(d), offs.to(d), (g3,) * 3)
+  got = ops.skip_scatter_sorted(*args)
+  got2 = ops.skip_scatter_sorted(*args)
+  assert t.equal(got, got2)
+  assert rel_err(got, exp) < 1e-5
+  # the lists: a permutation of all voxels, segment p holds exactly the voxels that sample pixel p, ascending
+  nb = _lib.lib().crn_skip_lists_workspace_bytes(b, hw, hw, g3, g3, g3)
+  ws = t.empty(nb, dtype=t.uint8, device=d)
+  sv = t.empty(b * g3 ** 3, dtype=t.int32, device=d)
+  starts = t.empty(b * hw * hw + 1, dtype=t.int32, device=d)
+  _lib.call("crn_skip_build_lists", b, hw, hw, args[7].data_ptr(), args[8].data_ptr(), g3, g3, g3, ws.data_ptr(), nb,
+            sv.data_ptr(), starts.data_ptr(), _lib.stream_ptr())
+  sv, starts = sv.cpu().long(), starts.cpu().long()
+  assert t.equal(sv.sort().values, t.arange(b * g3 ** 3))
+  key = t.where(valid, pix, t.full_like(pix, b * hw * hw)).reshape(-1)
+  assert t.equal(key[sv], key[sv].sort().values)                       # sorted by pixel
+  assert t.equal(starts, t.searchsorted(key[sv], t.arange(b * hw * hw + 1)))
+  seg = key[sv]
+  same = seg[1:] == seg[:-1]
+  assert bool((sv[1:][same] > sv[:-1][same]).all())                    # stable: ascending voxel index per pixel
+  # the atomic kernel computes the same sums (different order)
+  dmap = t.zeros(b * hw * hw, c, dtype=t.float32, device=d)
+  _lib.call("crn_skip_sample_bwd", args[0].data_ptr(), cs, co, b, hw, hw, c, c, args[7].data_ptr(),
+            args[8].data_ptr(), g3, g3, g3, dmap.data_ptr(), _lib.stream_ptr())
+  assert rel_err(dmap, exp) < 1e-5
+
+
 # ---------------------------------------------------------------------------- losses
 def test_losses_known_answers():
   """src/corenet/test/losses_test.py:72-88 through the CUDA kernels."""
