@@ -6,13 +6,19 @@
 // global-memory union-find (16 B/voxel scratch); here
 //   A. pack:   grid -> empty-mask bits E (1 bit/voxel) + seed bits R = E on the
 //              x=0 / y=0 / z=0 faces (near-face rule)      [HBM read]
-//   B. flood:  R <- fixpoint of "R spreads through E" using bit-parallel row
-//              fills (carry-chain trick, 128 voxels per add) and register-
-//              carried sweeps along +-y and +-z; loops until nothing changes,
-//              so the result is the exact connected component      [L2 resident]
+//   B. flood:  R <- fixpoint of "R spreads through E", so the result is the exact
+//              connected component.  Grids whose bit planes fit the shared memory
+//              of a thread-block cluster (up to 8 CTAs x 128 KB: 128^3 and smaller)
+//              run fill_flood_cluster_kernel: each CTA keeps a z-slab of E, R and
+//              two pass-through masks in shared memory; x spreads by carry chains
+//              (128 voxels per add), y and z by log2(extent) doubling steps
+//              (segmented OR-scan on whole bit rows; z steps read the neighbour
+//              slabs through distributed shared memory).  Larger grids fall back to
+//              register-/global-memory line sweeps (fill_flood_kernel, any W).
 //   C. unpack: out = R ? 0 : 1 in the element type                   [HBM write]
 // Algorithmic bytes: read T + write T per voxel; scratch is 0.25 B/voxel.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 constexpr int NT = 256;
@@ -176,6 +182,238 @@ __global__ void __launch_bounds__(1024) fill_flood_kernel(const uint32_t* __rest
   }
 }
 
+// Any row width: the same line sweeps with the row words streamed from global memory (W > 256).
+__global__ void __launch_bounds__(1024) fill_flood_wide_kernel(const uint32_t* __restrict__ E, uint32_t* R, int D,
+                                                               int H, int nw) {
+  const int64_t base = (int64_t)blockIdx.x * D * H * nw;
+  const uint32_t* Eg = E + base;
+  uint32_t* Rg = R + base;
+  const int t = threadIdx.x;
+  // in-row fill of row `off` given that R was OR-ed with `prev & E` already; returns true if the row changed
+  auto fill_row = [&](int64_t off, const uint32_t* prev_row) -> bool {
+    bool grew = false;
+    for (int w = 0; w < nw; ++w) {
+      const uint32_t e = __ldg(Eg + off + w), r0 = Rg[off + w];
+      const uint32_t r = r0 | (prev_row ? (e & prev_row[w]) : 0u);
+      if (r != r0) { Rg[off + w] = r; grew = true; }
+    }
+    if (!grew && prev_row) return false;
+    uint64_t carry = 0;
+    bool any = grew;
+    for (int w = 0; w < nw; ++w) {
+      const uint32_t e = __ldg(Eg + off + w), r = Rg[off + w];
+      const uint64_t s = (uint64_t)e + (uint64_t)r + carry;
+      carry = s >> 32;
+      const uint32_t up = r | (e & ((uint32_t)s ^ e));
+      if (up != r) { Rg[off + w] = up; any = true; }
+    }
+    carry = 0;
+    for (int w = nw - 1; w >= 0; --w) {
+      const uint32_t e = __ldg(Eg + off + w), r = Rg[off + w];
+      const uint32_t er = __brev(e), rr = __brev(r);
+      const uint64_t s = (uint64_t)er + (uint64_t)rr + carry;
+      carry = s >> 32;
+      const uint32_t dn = __brev(rr | (er & ((uint32_t)s ^ er)));
+      if (dn != r) { Rg[off + w] = dn; any = true; }
+    }
+    return any;
+  };
+  for (int row = t; row < D * H; row += blockDim.x) fill_row((int64_t)row * nw, nullptr);
+  __syncthreads();
+  auto sweep = [&](int line, int len, int64_t line_stride, int64_t step_stride, bool reverse) -> bool {
+    bool changed = false;
+    const uint32_t* prev = nullptr;
+    for (int k = 0; k < len; ++k) {
+      const int i = reverse ? len - 1 - k : k;
+      const int64_t off = ((int64_t)line * line_stride + (int64_t)i * step_stride) * nw;
+      if (prev) changed |= fill_row(off, prev);
+      prev = Rg + off;
+    }
+    return changed;
+  };
+  for (;;) {
+    bool changed = false;
+    for (int z = t; z < D; z += blockDim.x) changed |= sweep(z, H, H, 1, false);
+    __syncthreads();
+    for (int y = t; y < H; y += blockDim.x) changed |= sweep(y, D, 1, H, false);
+    __syncthreads();
+    for (int z = t; z < D; z += blockDim.x) changed |= sweep(z, H, H, 1, true);
+    __syncthreads();
+    for (int y = t; y < H; y += blockDim.x) changed |= sweep(y, D, 1, H, true);
+    if (!__syncthreads_or(changed ? 1 : 0)) break;
+  }
+}
+
+// ---- shared-memory / cluster flood ---------------------------------------------------------------------------
+// One cluster of CS CTAs per grid; CTA `rank` owns the z-slab [rank*zs, rank*zs + zs).  Shared memory per CTA:
+// E, R and the two pass-through masks Tu, Td of the slab ([zs][H][NW] words each, <= CL_WPT * CL_NT words).
+//   doubling step d along an axis (a segmented OR-scan of whole 128-bit rows):
+//     R[i]  |= Tu[i] & R[i-d]  |  Td[i] & R[i+d]
+//     Tu[i] &= Tu[i-d]           (Tu[i] = "the d rows ending at i are all empty")      Td likewise upwards
+//   after ceil(log2(extent)) steps every bit reachable from a reached bit along that axis through empty voxels is set.
+// y steps are CTA-local; z steps read rows of other slabs through distributed shared memory (cluster.sync between the
+// read and the write half of a step).  Iterated with the x carry chains until no bit changes in a whole round.
+constexpr int CL_NT = 512;
+constexpr int CL_WPT = 16;                       // words per thread kept in registers during a doubling step
+namespace cg = cooperative_groups;
+
+template <int NW>
+__global__ void __launch_bounds__(CL_NT) fill_flood_cluster_kernel(const uint32_t* __restrict__ E, uint32_t* R, int D,
+                                                                   int H, int zs) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int64_t gbase = (int64_t)(blockIdx.x / CS) * D * H * NW;
+  extern __shared__ uint32_t sm[];
+  const int cap = zs * H * NW;                   // words per slab array (same in every CTA)
+  uint32_t* Es = sm;
+  uint32_t* Rs = Es + cap;
+  uint32_t* Tu = Rs + cap;
+  uint32_t* Td = Tu + cap;
+  __shared__ int flags[2];
+  const int z0 = rank * zs;
+  const int nz = max(0, min(zs, D - z0));
+  const int words = nz * H * NW;
+  const int rows = nz * H;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < words; i += CL_NT) {
+    Es[i] = __ldg(E + gbase + (int64_t)z0 * H * NW + i);
+    Rs[i] = R[gbase + (int64_t)z0 * H * NW + i];
+  }
+  if (tid < 2) flags[tid] = 0;
+  __syncthreads();
+
+  auto x_fill = [&]() -> bool {                  // carry chains along x, one row per thread iteration
+    bool ch = false;
+    for (int row = tid; row < rows; row += CL_NT) {
+      uint32_t e[NW], r[NW], r0[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { e[w] = Es[row * NW + w]; r0[w] = r[w] = Rs[row * NW + w]; }
+      row_fill<NW>(r, e);
+      bool c = false;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) c |= r[w] != r0[w];
+      if (c) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) Rs[row * NW + w] = r[w];
+        ch = true;
+      }
+    }
+    return ch;
+  };
+
+  bool changed = x_fill();
+  __syncthreads();
+  for (int it = 0;; ++it) {
+    // ---- y: CTA-local doubling
+    for (int i = tid; i < words; i += CL_NT) { const uint32_t e = Es[i]; Tu[i] = e; Td[i] = e; }
+    __syncthreads();
+    for (int d = 1; d < H; d <<= 1) {
+      uint32_t r[CL_WPT], tu[CL_WPT], td[CL_WPT];
+#pragma unroll
+      for (int k = 0; k < CL_WPT; ++k) {
+        const int i = tid + k * CL_NT;
+        if (i < words) {
+          const int y = (i / NW) % H;
+          uint32_t rr = Rs[i], a = Tu[i], b = Td[i];
+          const uint32_t r0 = rr;
+          if (y >= d) { rr |= a & Rs[i - d * NW]; a &= Tu[i - d * NW]; }
+          if (y + d < H) { rr |= b & Rs[i + d * NW]; b &= Td[i + d * NW]; }
+          changed |= rr != r0;
+          r[k] = rr; tu[k] = a; td[k] = b;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < CL_WPT; ++k) {
+        const int i = tid + k * CL_NT;
+        if (i < words) { Rs[i] = r[k]; Tu[i] = tu[k]; Td[i] = td[k]; }
+      }
+      __syncthreads();
+    }
+    changed |= x_fill();
+    __syncthreads();
+    // ---- z: doubling across the slabs of the cluster
+    for (int i = tid; i < words; i += CL_NT) { const uint32_t e = Es[i]; Tu[i] = e; Td[i] = e; }
+    cluster.sync();
+    for (int d = 1; d < D; d <<= 1) {
+      uint32_t r[CL_WPT], tu[CL_WPT], td[CL_WPT];
+#pragma unroll
+      for (int k = 0; k < CL_WPT; ++k) {
+        const int i = tid + k * CL_NT;
+        if (i < words) {
+          const int zl = i / (H * NW);
+          const int rem = i - zl * (H * NW);
+          const int z = z0 + zl;
+          uint32_t rr = Rs[i], a = Tu[i], b = Td[i];
+          const uint32_t r0 = rr;
+          if (z >= d) {
+            const int zn = z - d, owner = zn / zs, off = (zn - owner * zs) * (H * NW) + rem;
+            const uint32_t* rR = cluster.map_shared_rank(Rs, owner);
+            const uint32_t* rT = cluster.map_shared_rank(Tu, owner);
+            rr |= a & rR[off]; a &= rT[off];
+          }
+          if (z + d < D) {
+            const int zn = z + d, owner = zn / zs, off = (zn - owner * zs) * (H * NW) + rem;
+            const uint32_t* rR = cluster.map_shared_rank(Rs, owner);
+            const uint32_t* rT = cluster.map_shared_rank(Td, owner);
+            rr |= b & rR[off]; b &= rT[off];
+          }
+          changed |= rr != r0;
+          r[k] = rr; tu[k] = a; td[k] = b;
+        }
+      }
+      cluster.sync();
+#pragma unroll
+      for (int k = 0; k < CL_WPT; ++k) {
+        const int i = tid + k * CL_NT;
+        if (i < words) { Rs[i] = r[k]; Tu[i] = tu[k]; Td[i] = td[k]; }
+      }
+      cluster.sync();
+    }
+    changed |= x_fill();
+    // ---- any bit changed anywhere in the cluster during this round?
+    const int any_local = __syncthreads_or(changed ? 1 : 0);
+    if (tid == 0) { flags[it & 1] = any_local; flags[(it + 1) & 1] = 0; }
+    cluster.sync();
+    int any = 0;
+    for (int c = 0; c < CS; ++c) any |= *cluster.map_shared_rank(&flags[it & 1], c);
+    if (!any) break;
+    changed = false;
+  }
+  cluster.sync();                                // no CTA may exit while its shared memory can still be read
+  for (int i = tid; i < words; i += CL_NT) R[gbase + (int64_t)z0 * H * NW + i] = Rs[i];
+}
+
+template <int NW>
+int launch_cluster_flood(const uint32_t* E, uint32_t* R, int N, int D, int H, cudaStream_t st) {
+  // smallest cluster whose slabs fit the per-thread register budget (CL_WPT words x CL_NT threads per array)
+  int cs = 1;
+  while (cs <= 8 && (int64_t)((D + cs - 1) / cs) * H * NW > (int64_t)CL_WPT * CL_NT) cs <<= 1;
+  if (cs > 8) return 1;                                    // does not fit: caller falls back
+  const int zs = (D + cs - 1) / cs;
+  const size_t smem = (size_t)4 * zs * H * NW * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(fill_flood_cluster_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * CL_WPT * CL_NT * 4);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(N * cs), 1, 1);
+  cfg.blockDim = dim3(CL_NT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fill_flood_cluster_kernel<NW>, E, R, D, H, zs);
+  return e == cudaSuccess ? 0 : -1;
+}
+
 inline unsigned grid_for(int64_t total) {
   int64_t b = crn_ceil_div(total, NT);
   if (b > 16LL * kNumSMs) b = 16LL * kNumSMs;
@@ -197,10 +435,6 @@ extern "C" int crn_fill_inside(const void* grid_in, void* grid_out, int32_t elem
   CRN_REQUIRE(dtype_kind >= 0 && dtype_kind <= 2 && !(dtype_kind == 1 && elem_size < 4),
               "crn_fill_inside: bad dtype kind");
   const int nw = (W + 31) / 32;
-  if (nw > MAXNW) {
-    crn_set_error("crn_fill_inside: W=%d > %d unsupported", W, MAXNW * 32);
-    return CRN_ERR_UNSUPPORTED;
-  }
   cudaStream_t st = crn_stream(stream);
   const int64_t rows = (int64_t)N * D * H;
   uint32_t* E = reinterpret_cast<uint32_t*>(workspace);
@@ -210,15 +444,32 @@ extern "C" int crn_fill_inside(const void* grid_in, void* grid_out, int32_t elem
   int threads = D > H ? D : H;
   threads = ((threads + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
-  switch (nw) {
-    case 1: fill_flood_kernel<1><<<N, threads, 0, st>>>(E, R, D, H); break;
-    case 2: fill_flood_kernel<2><<<N, threads, 0, st>>>(E, R, D, H); break;
-    case 3: fill_flood_kernel<3><<<N, threads, 0, st>>>(E, R, D, H); break;
-    case 4: fill_flood_kernel<4><<<N, threads, 0, st>>>(E, R, D, H); break;
-    case 5: fill_flood_kernel<5><<<N, threads, 0, st>>>(E, R, D, H); break;
-    case 6: fill_flood_kernel<6><<<N, threads, 0, st>>>(E, R, D, H); break;
-    case 7: fill_flood_kernel<7><<<N, threads, 0, st>>>(E, R, D, H); break;
-    default: fill_flood_kernel<8><<<N, threads, 0, st>>>(E, R, D, H); break;
+  int rc = 1;                                    // 1 = not handled by the cluster kernel
+  if (!(crn_get_flags() & 4096)) {               // bit 12 of crn_set_flags: force the line-sweep kernels (A/B)
+    switch (nw) {
+      case 1: rc = launch_cluster_flood<1>(E, R, N, D, H, st); break;
+      case 2: rc = launch_cluster_flood<2>(E, R, N, D, H, st); break;
+      case 3: rc = launch_cluster_flood<3>(E, R, N, D, H, st); break;
+      case 4: rc = launch_cluster_flood<4>(E, R, N, D, H, st); break;
+      default: break;
+    }
+  }
+  if (rc < 0) {
+    crn_set_error("crn_fill_inside: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return CRN_ERR_LAUNCH;
+  }
+  if (rc == 1) {
+    switch (nw) {
+      case 1: fill_flood_kernel<1><<<N, threads, 0, st>>>(E, R, D, H); break;
+      case 2: fill_flood_kernel<2><<<N, threads, 0, st>>>(E, R, D, H); break;
+      case 3: fill_flood_kernel<3><<<N, threads, 0, st>>>(E, R, D, H); break;
+      case 4: fill_flood_kernel<4><<<N, threads, 0, st>>>(E, R, D, H); break;
+      case 5: fill_flood_kernel<5><<<N, threads, 0, st>>>(E, R, D, H); break;
+      case 6: fill_flood_kernel<6><<<N, threads, 0, st>>>(E, R, D, H); break;
+      case 7: fill_flood_kernel<7><<<N, threads, 0, st>>>(E, R, D, H); break;
+      case 8: fill_flood_kernel<8><<<N, threads, 0, st>>>(E, R, D, H); break;
+      default: fill_flood_wide_kernel<<<N, threads, 0, st>>>(E, R, D, H, nw); break;
+    }
   }
   fill_unpack_kernel<<<grid_for(rows * W), NT, 0, st>>>(R, elem_size, dtype_kind, rows, W, nw, grid_out);
   crn_count_launches(2);

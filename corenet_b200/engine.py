@@ -54,6 +54,9 @@ def _call(name, *args, hbm=None):
   """C-ABI launch on the current stream.  Under PROFILE the HBM-bound kernels of the path are bracketed with CUDA
   events: entries ("hbm", family, algorithmic bytes, start, end) -- bench.py turns them into achieved GB/s.
   hbm = (label, bytes) overrides the per-function table."""
+  if NCU_PICK is not None and NCU_PICK("call", name):
+    _ncu_bracket(name, args)
+    return
   fam = (hbm and (lambda a: hbm)) or HBM_BYTES.get(name) if PROFILE is not None else None
   if fam is None:
     _lib.call(name, *args)
@@ -64,6 +67,20 @@ def _call(name, *args, hbm=None):
   e1.record()
   label, nbytes = fam(args)
   PROFILE.append(("hbm", label, nbytes, e0, e1))
+
+
+# scripts/ncu_capture.py sets this to a predicate (kind, name) -> bool: the chosen launches are bracketed with
+# cudaProfilerStart/Stop so that `ncu --profile-from-start off` captures exactly them (kind = "call" with the C-ABI
+# name for non-conv launches, else the conv tag fwd_tc / dgrad_gt / wgrad_tc ... with the layer name).
+NCU_PICK = None
+
+
+def _ncu_bracket(fn, args):
+  t.cuda.cudart().cudaProfilerStart()
+  try:
+    _lib.call(fn, *args)
+  finally:
+    t.cuda.cudart().cudaProfilerStop()
 
 
 def _b_skip_fwd(a):      # (cmap, B, h, w, Cs, cmap_cs, mat, offs, gd, gh, gw, out, out_cs, out_co, st)
@@ -199,6 +216,9 @@ def conv_call(kind, layer, d, *args):
     tag, fn, a = _conv_dispatch(kind, layer, d, args)
     calls = [(tag, fn, a, d)]
   for tag, fn, a, dd in calls:
+    if NCU_PICK is not None and NCU_PICK(tag, layer.name):
+      _ncu_bracket(fn, a)
+      continue
     if PROFILE is None:
       _lib.call(fn, *a)
       continue
@@ -231,6 +251,8 @@ DETERMINISTIC_SKIP_BWD = True
 
 def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
   """ConvTranspose3d k=7 s=2 forward through crn_convt7_tc."""
+  if NCU_PICK is not None and NCU_PICK("fwd_tc", layer.name):
+    return _ncu_bracket("crn_convt7_tc", (C.byref(d), inp, wtc, bias, out, status, st))
   if PROFILE is None:
     _lib.call("crn_convt7_tc", C.byref(d), inp, wtc, bias, out, status, st)
     return
@@ -243,6 +265,8 @@ def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
 
 def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st):
   """ConvTranspose3d k=7 s=2 dgrad through crn_convt7_tc_dgrad."""
+  if NCU_PICK is not None and NCU_PICK("dgrad_tc", layer.name):
+    return _ncu_bracket("crn_convt7_tc_dgrad", (C.byref(d), dy, wtc, dx, status, st))
   if PROFILE is None:
     _lib.call("crn_convt7_tc_dgrad", C.byref(d), dy, wtc, dx, status, st)
     return
@@ -256,6 +280,8 @@ def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st):
 def conv5_tcs_call(layer, d, inp, wtc, bias, out, status, st, kind=0):
   """Conv3d k=5 forward (kind 0) / dgrad (kind 1) with <= 32 output channels through crn_conv5_tcs2 (kz taps
   stacked into N)."""
+  if NCU_PICK is not None and NCU_PICK("fwd_tc" if kind == 0 else "dgrad_tc", layer.name):
+    return _ncu_bracket("crn_conv5_tcs2", (C.byref(d), kind, inp, wtc, bias, out, status, st))
   if PROFILE is None:
     _lib.call("crn_conv5_tcs2", C.byref(d), kind, inp, wtc, bias, out, status, st)
     return
@@ -269,6 +295,8 @@ def conv5_tcs_call(layer, d, inp, wtc, bias, out, status, st, kind=0):
 def conv5_tc_call(kind, layer, d, inp, wtc, bias, out, status, st):
   """kind: 'fwd' | 'dgrad' through crn_conv5_tc."""
   k = 0 if kind == "fwd" else 1
+  if NCU_PICK is not None and NCU_PICK(kind + "_tc", layer.name):
+    return _ncu_bracket("crn_conv5_tc", (C.byref(d), k, inp, wtc, bias, out, status, st))
   if PROFILE is None:
     _lib.call("crn_conv5_tc", C.byref(d), k, inp, wtc, bias, out, status, st)
     return
@@ -850,6 +878,7 @@ class Plan:
     self.logits = t.zeros(B, eng.model.config.decoder.num_output_channels, *res, dtype=t.float32, device=self.dev)
 
   # ------------------------------------------------------------------ forward
+  @t.no_grad()
   def forward(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, training: bool,
               want_features: bool = False, pack: bool = True, run_encoder: bool = True) -> t.Tensor:
     """Enqueues the forward pass on the current stream and returns the plan-owned logits buffer
@@ -988,6 +1017,7 @@ class Plan:
     return logits
 
   # ------------------------------------------------------------------ backward
+  @t.no_grad()
   def backward(self, grad_logits: t.Tensor, grads: Dict[str, t.Tensor], chunk_cb=None, comm_stream=None):
     """grads: name -> zero/empty tensor per parameter (filled here).
 

@@ -41,7 +41,8 @@ int64_t crn_launch_count(void);
 /* Debug / A-B switches: bit0 = disable the row-direct conv kernels, bit1 = disable the tap-row wgrad
  * kernel (both fall back to the generic implicit-GEMM kernels), bit4 = disable split-K in the generic and the
  * tcgen05 implicit-GEMM kernels, bit5 = disable the stem wgrad kernel, bit6 = 3 narrow MMAs instead of N doubling in
- * conv_tc5, bits 8-11 = gemm_tc_kernel debug (timeline stamps / skip stores / skip gathers / skip MMAs). */
+ * conv_tc5, bits 8-11 = gemm_tc_kernel debug (timeline stamps / skip stores / skip gathers / skip MMAs),
+ * bit12 = crn_fill_inside uses the global-memory line-sweep kernels instead of the shared-memory cluster kernel. */
 void crn_set_flags(int32_t flags);
 
 /* ------------------------------------------------------------------------

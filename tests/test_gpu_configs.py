@@ -176,8 +176,9 @@ def test_fgbg_labeled_confusion_matches_reference_rule():
   gts = gt.to(t.int64) * labels[:, None, None, None]
   exp = t.bincount((gts * k + pred).reshape(-1), minlength=k * k).reshape(k, k)
   cm = t.zeros(k, k, dtype=t.int64, device=dev)
-  _lib.call("crn_argmax_confusion_labeled", logits.to(dev).data_ptr(), gt.to(dev).data_ptr(), 0, b, c, s,
-            labels.to(dev).data_ptr(), k, cm.data_ptr(), _lib.stream_ptr())
+  d_logits, d_gt, d_labels = logits.to(dev), gt.to(dev), labels.to(dev)
+  _lib.call("crn_argmax_confusion_labeled", d_logits.data_ptr(), d_gt.data_ptr(), 0, b, c, s,
+            d_labels.data_ptr(), k, cm.data_ptr(), _lib.stream_ptr())
   assert t.equal(cm.cpu(), exp)
 
 

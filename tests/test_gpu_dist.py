@@ -13,6 +13,8 @@ ranks on one device), which exercises the same Trainer code with the collective 
     (pipeline.py:199-230) -- on the drop-in module, through the graph-replayed autograd path.
 """
 import os
+import queue
+import time
 
 import numpy as np
 import pytest
@@ -98,10 +100,23 @@ def _run(mode):
   procs = [ctx.Process(target=_worker, args=(r, 2, port, ngpu, mode, q)) for r in range(2)]
   for p in procs:
     p.start()
-  res = dict(q.get(timeout=600) for _ in range(2))
-  for p in procs:
-    p.join(timeout=120)
-    assert p.exitcode == 0
+  res, deadline = {}, time.time() + 420
+  try:
+    while len(res) < 2:
+      try:
+        rank, r = q.get(timeout=2)
+        res[rank] = r
+      except queue.Empty:
+        dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+        assert not dead, f"a rank died (exit codes {dead}); see its traceback above"
+        assert time.time() < deadline, "two-rank run timed out"
+    for p in procs:
+      p.join(timeout=120)
+      assert p.exitcode == 0
+  finally:
+    for p in procs:
+      if p.is_alive():
+        p.kill()
   return res
 
 

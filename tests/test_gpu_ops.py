@@ -769,13 +769,25 @@ def test_fill_known_answers(dtype):
 
 @pytest.mark.parametrize("shape,p", [((3, 16, 16, 16), 0.3), ((2, 9, 20, 45), 0.45), ((2, 7, 7, 7), 0.5),
                                      ((1, 40, 33, 70), 0.38), ((1, 1, 1, 1), 0.5), ((2, 1, 8, 3), 0.4),
-                                     ((2, 64, 64, 64), 0.34), ((1, 33, 65, 129), 0.36), ((1, 5, 5, 256), 0.3)])
+                                     ((2, 64, 64, 64), 0.34), ((1, 33, 65, 129), 0.36), ((1, 5, 5, 256), 0.3),
+                                     ((2, 17, 30, 128), 0.4), ((1, 130, 20, 40), 0.42), ((1, 6, 9, 300), 0.35),
+                                     ((1, 3, 4, 1000), 0.3), ((20, 24, 24, 24), 0.4)])
 def test_fill_random_bit_exact(shape, p):
+  """Random grids (percolating densities: long winding paths) through the shared-memory cluster kernel, the
+  register line-sweep kernel (W <= 256) and the wide kernel (any W; the reference has no size limit): bit-exact."""
+  from corenet_b200 import _lib
   from corenet_b200.cc import fill_voxels
   rng = np.random.default_rng(sum(shape))
   g = (rng.random(shape) < p).astype(np.float32)
+  exp = FO.fill_inside_voxels_oracle(g)
   out = fill_voxels.fill_inside_voxels_gpu(t.from_numpy(g).to(dev())).cpu().numpy()
-  np.testing.assert_array_equal(out, FO.fill_inside_voxels_oracle(g))
+  np.testing.assert_array_equal(out, exp)
+  _lib.lib().crn_set_flags(4096)             # A/B: global-memory line sweeps
+  try:
+    out2 = fill_voxels.fill_inside_voxels_gpu(t.from_numpy(g).to(dev())).cpu().numpy()
+  finally:
+    _lib.lib().crn_set_flags(0)
+  np.testing.assert_array_equal(out2, exp)
 
 
 def test_fill_maze_and_shells_128():
