@@ -36,9 +36,11 @@ __global__ void __launch_bounds__(NT) loss_sums_kernel(const float* __restrict__
   double dI = 0.0, dU = 0.0, dX = 0.0;
   float fI = 0.f, fU = 0.f, fX = 0.f;
   int cnt = 0;
+  bool bad = false;       // fminf/fmaxf drop NaN operands; torch.min/max (losses.py:80-81) propagate them: so do we
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < S; i += (int64_t)gridDim.x * NT) {
     float s[MAXC], mx, sum;
     softmax_c(base + i, C, S, s, mx, sum);
+    bad |= sum != sum;
     const int L = load_gt<GT>(gt, (int64_t)n * S + i, C);
     if (mode == 0) {
       float pfg = 0.f;
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(NT) loss_sums_kernel(const float* __restrict__
     if (++cnt == 64) { dI += fI; dU += fU; dX += fX; fI = fU = fX = 0.f; cnt = 0; }
   }
   dI += fI; dU += fU; dX += fX;
+  if (bad) dI = __longlong_as_double(0x7ff8000000000000LL);
   dI = warp_sum(dI); dU = warp_sum(dU); dX = warp_sum(dX);
   __shared__ double red[3][NT / 32];
   if ((threadIdx.x & 31) == 0) {

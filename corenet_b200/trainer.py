@@ -103,7 +103,9 @@ class Trainer:
     self.backend = t.distributed.get_backend(process_group) if dist_on else None
     # NCCL collectives are stream-ordered and capturable; gloo's are host-synchronous
     self.collective_in_graph = (self.backend == "nccl") if collective_in_graph is None else collective_in_graph
-    self.overlap_allreduce = overlap_allreduce and self.world > 1
+    # the chunked, overlapped exchange needs stream-ordered collectives whenever the step is graph-captured
+    self.overlap_allreduce = (overlap_allreduce and self.world > 1
+                              and (self.collective_in_graph or not use_graph))
     self.flat, self.views = flatten_parameters(model)
     eng = engine_lib.get_engine(model)
     eng.invalidate()
@@ -204,8 +206,16 @@ class Trainer:
     # replays run no Python): the engine's re-pack signature is keyed on this counter
     self.eng.weights_epoch += 1
 
+  def _update_in_body(self) -> bool:
+    """Whether all-reduce + Adam are enqueued by _step_body (and therefore captured with it) or follow it eagerly
+    (host-synchronous collectives, i.e. gloo, cannot be captured)."""
+    return self.world == 1 or self.collective_in_graph or not self.use_graph
+
   def _eager_step(self, image, v2s, offsets, gt):
-    loss = self._step_body(image, v2s, offsets, gt, True)
+    in_body = self._update_in_body()
+    loss = self._step_body(image, v2s, offsets, gt, in_body)
+    if not in_body:
+      self._update_all()
     self._weights_changed()
     return loss
 
@@ -283,7 +293,7 @@ class Trainer:
       if gs["calls"] < 2:                       # eager warm-up: lazy initialisation must not happen under capture
         gs["calls"] += 1
         return self._eager_step(*gs["in"])
-      in_graph = self.world == 1 or self.collective_in_graph
+      in_graph = self._update_in_body()
       n0 = _lib.lib().crn_launch_count()
       self.eng._ver_sig = None                  # the captured step re-packs the weights unconditionally
       g = t.cuda.CUDAGraph()

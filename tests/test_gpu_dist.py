@@ -86,7 +86,8 @@ def _worker(rank, world, port, ngpu, mode, out):
         opt.step()
         losses_.append(float(loss))
       res.update(losses=losses_, flat=t.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu())
-    out.put((rank, res))
+    # tensors by value (numpy): torch's fd-based tensor sharing needs the sender alive when the parent unpickles
+    out.put((rank, {k: (v.numpy() if isinstance(v, t.Tensor) else v) for k, v in res.items()}))
     dist.barrier()
   finally:
     dist.destroy_process_group()
@@ -105,7 +106,7 @@ def _run(mode):
     while len(res) < 2:
       try:
         rank, r = q.get(timeout=2)
-        res[rank] = r
+        res[rank] = {k: (t.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in r.items()}
       except queue.Empty:
         dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
         assert not dead, f"a rank died (exit codes {dead}); see its traceback above"
