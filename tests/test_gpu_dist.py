@@ -150,7 +150,7 @@ def test_two_rank_trainer_gradient_is_rank_mean(mode):
           f"losses {res[r]['losses']}")
     # eval-mode BN is well conditioned; train mode at random init amplifies the atomics-order noise of two separate
     # runs (same bound as test_trainer_cuda_graph_matches_eager)
-    assert err <= (1e-1 if train_mode else 1e-4)
+    assert err <= (1e-1 if train_mode else 3e-4)
     assert abs(res[r]["losses"][0] - ls[r]) <= (2e-3 if train_mode else 5e-6)
     assert res[r]["step"] == STEPS and res[r]["graph_launches"] > 100
     assert res[r]["nbt"] == (STEPS if train_mode else 0)
@@ -183,7 +183,7 @@ def test_ddp_wrapped_module_with_torch_adam():
   for r in (0, 1):
     err = ((res[r]["grad_step1"] - mean).double().norm() / mean.double().norm()).item()
     print(f"\n[ddp/{res[r]['backend']}] rank {r}: DDP-averaged gradient vs mean of single-rank gradients: {err:.2e}")
-    assert err <= 1e-4
+    assert err <= 3e-4                 # separate runs differ by the split-K atomics order (observed 3e-5 .. 8e-5)
     assert abs(res[r]["losses"][0] - ls[r]) <= 5e-6
   assert t.equal(res[0]["flat"], res[1]["flat"])
   # same trajectory as the fused Trainer path (same optimiser hyper-parameters)
