@@ -85,6 +85,11 @@ _SIGS = {
     "crn_softmax_planar": ([vp, i32, i32, i64, vp, vp], i32),
     "crn_argmax_confusion": ([vp, vp, i32, i32, i32, i64, vp, vp], i32),
     "crn_argmax_confusion_labeled": ([vp, vp, i32, i32, i32, i64, vp, i32, vp, vp], i32),
+    "crn_loss_sums_l": ([vp, i32, vp, i32, i32, i32, i64, i32, vp, vp], i32),
+    "crn_loss_bwd_l": ([vp, i32, vp, i32, i32, i32, i64, i32, vp, vp, vp, i32, vp], i32),
+    "crn_softmax_l": ([vp, i32, i32, i32, i64, vp, vp], i32),
+    "crn_argmax_confusion_l": ([vp, i32, vp, i32, i32, i32, i64, vp, i32, vp, vp], i32),
+    "crn_rows_to_planar": ([vp, i32, i32, i64, i32, vp, vp], i32),
     "crn_fill_workspace_bytes": ([i32, i32, i32, i32], i64),
     "crn_fill_inside": ([vp, vp, i32, i32, i32, i32, i32, i32, vp, vp], i32),
     "crn_voxelize_mesh": ([vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp], i32),

@@ -129,6 +129,30 @@ __global__ void planar_to_rows_kernel(const float* __restrict__ x, int N, int C,
   }
 }
 
+// rows [N*S][CP] -> planar [N][C][S]: a warp reads 32 consecutive rows (coalesced: CP floats each) through shared
+// memory and writes, per channel, 32 consecutive floats of a plane
+__global__ void __launch_bounds__(NT) rows_to_planar_kernel(const float* __restrict__ rows, int N, int C, int64_t S,
+                                                            int CP, float* __restrict__ out) {
+  __shared__ float tile[NT / 32][32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)N * S;
+  const int64_t nwarps = ((int64_t)gridDim.x * NT) >> 5;
+  for (int64_t base = (((int64_t)blockIdx.x * NT + threadIdx.x) >> 5) * 32; base < total; base += nwarps * 32) {
+    const int cnt = (int)((total - base) < 32 ? (total - base) : 32);
+    for (int k = lane; k < cnt * CP; k += 32) {
+      const int r = k / CP, c = k - r * CP;
+      tile[warp][r][c] = __ldg(rows + base * CP + k);
+    }
+    __syncwarp();
+    const int64_t i = base + lane;
+    if (lane < cnt) {
+      const int64_t n = i / S, sidx = i - n * S;
+      for (int c = 0; c < C; ++c) out[(n * C + c) * S + sidx] = tile[warp][lane][c];
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
                             float bc1, float bc2_sqrt, float gscale) {
@@ -276,6 +300,14 @@ extern "C" int crn_planar_to_rows(const float* x, int32_t N, int32_t C, int64_t 
   CRN_REQUIRE(x && out && N > 0 && C > 0 && S > 0 && CP >= C, "crn_planar_to_rows: bad args");
   planar_to_rows_kernel<<<grid_for((int64_t)N * S), NT, 0, crn_stream(stream)>>>(x, N, C, S, CP, out);
   CRN_LAUNCH_CHECK("planar_to_rows");
+  return CRN_OK;
+}
+
+extern "C" int crn_rows_to_planar(const float* rows, int32_t N, int32_t C, int64_t S, int32_t CP, float* out,
+                                  void* stream) {
+  CRN_REQUIRE(rows && out && N > 0 && C > 0 && S > 0 && CP >= C && CP <= 32, "crn_rows_to_planar: bad args (CP <= 32)");
+  rows_to_planar_kernel<<<grid_for((int64_t)N * S), NT, 0, crn_stream(stream)>>>(rows, N, C, S, CP, out);
+  CRN_LAUNCH_CHECK("rows_to_planar");
   return CRN_OK;
 }
 

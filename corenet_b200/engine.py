@@ -105,6 +105,11 @@ HBM_BYTES = {
     "crn_loss_sums": lambda a: ("loss_sums", (4 * a[4] + (8 if a[2] else 4)) * a[3] * a[5]),
     "crn_loss_bwd": lambda a: ("loss_bwd", (8 * a[4] + (8 if a[2] else 4)) * a[3] * a[5]),
     "crn_softmax_planar": lambda a: ("softmax", 8 * a[1] * a[2] * a[3]),
+    "crn_loss_sums_l": lambda a: ("loss_sums", (4 * (a[1] or a[5]) + (8 if a[3] else 4)) * a[4] * a[6]),
+    "crn_loss_bwd_l": lambda a: ("loss_bwd", (4 * (a[1] or a[5]) + 4 * (a[11] or a[5]) + (8 if a[3] else 4)) * a[4] * a[6]),
+    "crn_softmax_l": lambda a: ("softmax", 4 * ((a[1] or a[3]) + a[3]) * a[2] * a[4]),
+    "crn_argmax_confusion_l": lambda a: ("argmax_confusion", (4 * (a[1] or a[5]) + (8 if a[3] else 4)) * a[4] * a[6]),
+    "crn_rows_to_planar": lambda a: ("rows_to_planar", 4 * (a[4] + a[2]) * a[1] * a[3]),
     "crn_argmax_confusion_labeled": lambda a: ("argmax_confusion", (4 * a[4] + (8 if a[2] else 4)) * a[3] * a[5]),
     "crn_adam_step_guarded": lambda a: ("adam", 28 * a[4]),
     "crn_unpack_wgrads": lambda a: ("unpack_wgrads", 8 * a[3]),
@@ -247,10 +252,13 @@ WGRAD_SIDE_STREAM = True
 USE_TC5S = True
 # ray-traced skip backward as a sorted per-pixel gather (bit-reproducible) instead of float atomics
 DETERMINISTIC_SKIP_BWD = True
+# logits layer with > 4 classes through the padded channels-last rows path (see Engine._ensure_device)
+USE_ROWS_LOGITS = True
 
 
-def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
-  """ConvTranspose3d k=7 s=2 forward through crn_convt7_tc."""
+def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None):
+  """ConvTranspose3d k=7 s=2 forward through crn_convt7_tc.  acct: descriptor whose MACs are reported (the launch
+  descriptor may carry zero-padded output channels)."""
   if NCU_PICK is not None and NCU_PICK("fwd_tc", layer.name):
     return _ncu_bracket("crn_convt7_tc", (C.byref(d), inp, wtc, bias, out, status, st))
   if PROFILE is None:
@@ -260,10 +268,10 @@ def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st):
   e0.record()
   _lib.call("crn_convt7_tc", C.byref(d), inp, wtc, bias, out, status, st)
   e1.record()
-  PROFILE.append(("fwd_tc", layer.name, conv_macs(d), e0, e1))
+  PROFILE.append(("fwd_tc", layer.name, conv_macs(acct or d), e0, e1))
 
 
-def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st):
+def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st, acct=None):
   """ConvTranspose3d k=7 s=2 dgrad through crn_convt7_tc_dgrad."""
   if NCU_PICK is not None and NCU_PICK("dgrad_tc", layer.name):
     return _ncu_bracket("crn_convt7_tc_dgrad", (C.byref(d), dy, wtc, dx, status, st))
@@ -274,7 +282,7 @@ def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st):
   e0.record()
   _lib.call("crn_convt7_tc_dgrad", C.byref(d), dy, wtc, dx, status, st)
   e1.record()
-  PROFILE.append(("dgrad_tc", layer.name, conv_macs(d), e0, e1))
+  PROFILE.append(("dgrad_tc", layer.name, conv_macs(acct or d), e0, e1))
 
 
 def conv5_tcs_call(layer, d, inp, wtc, bias, out, status, st, kind=0):
@@ -481,6 +489,20 @@ class Engine:
           self.tct_slices[l.name] = [
               (t.zeros(lib.crn_tct_packed_floats(mid, 16, 0), dtype=t.float32, device=dev),
                t.zeros(mid, 16, 7, 7, 7, dtype=t.float32, device=dev), co0) for co0 in range(0, t_out, 16)]
+    # logits layer with more than 4 classes (SEMANTIC task, C = 15): the class-scatter kernels run on the channel count
+    # padded to a multiple of 4 (zero weights / bias in the pad channels) and write / read channels-last ROWS
+    # [B*128^3, cp]: float4 epilogues instead of per-channel planar scalars, tcgen05 dgrad (needs Cout % 4 == 0), and
+    # the training step never materialises planar logits or logit gradients (the loss kernels take rows)
+    self.rows_pad = {}
+    stage, cin, mid, t_out, skip_c, enc_c, g = self.dec_plan[-1]
+    l = self.L[f"stage_{stage}.t1"]
+    cp = _r4(t_out)
+    if USE_TC and USE_ROWS_LOGITS and l.k == (7, 7, 7) and 4 < t_out and cp <= 16 and g % 16 == 0 and mid % 4 == 0 and mid <= 64:
+      self.rows_pad[l.name] = dict(
+          cp=cp, w=t.zeros(mid, cp, 7, 7, 7, dtype=t.float32, device=dev), b=t.zeros(cp, dtype=t.float32, device=dev),
+          fwd=t.zeros(lib.crn_tct_packed_floats(mid, cp, 0), dtype=t.float32, device=dev),
+          dgrad=t.zeros(lib.crn_tct_packed_floats(mid, cp, 1), dtype=t.float32, device=dev))
+      self.tct_w.pop(l.name, None)
     # wide layers (>= 32 channels on both sides): implicit-GEMM forward / dgrad (csrc/conv_gemm_tc.cu) and weight
     # gradient (csrc/conv_wgrad_tc.cu) on tcgen05
     self.gt_w = {}
@@ -642,6 +664,12 @@ class Engine:
         for wt, wslice, co0 in self.tct_slices.get(l.name, ()):
           wslice.copy_(P[l.name + ".weight"][:, co0:co0 + 16])
           _call("crn_tct_pack", wslice.data_ptr(), l.cin, 16, 0, wt.data_ptr(), _lib.stream_ptr())
+        if l.name in self.rows_pad:
+          rp = self.rows_pad[l.name]
+          rp["w"][:, :l.cout].copy_(P[l.name + ".weight"])
+          rp["b"][:l.cout].copy_(P[l.name + ".bias"])
+          _call("crn_tct_pack", rp["w"].data_ptr(), l.cin, rp["cp"], 0, rp["fwd"].data_ptr(), _lib.stream_ptr())
+          _call("crn_tct_pack", rp["w"].data_ptr(), l.cin, rp["cp"], 1, rp["dgrad"].data_ptr(), _lib.stream_ptr())
         if l.name in self.tct_w:
           for dg, wt in enumerate(self.tct_w[l.name]):
             if wt is not None:
@@ -751,6 +779,7 @@ class Plan:
     self.dev = eng.dev
     self.busy = False
     self._n = {"fwd": 0, "bwd": 0}
+    self.rows_cp = 0       # > 0: the logits layer works on channels-last rows of this pitch (see Engine.rows_pad)
     self._build()
     self.arena_fwd = t.zeros(max(self._n["fwd"], 1), dtype=t.float64, device=self.dev)
     self.arena_bwd = t.zeros(max(self._n["bwd"], 1), dtype=t.float64, device=self.dev)
@@ -871,6 +900,13 @@ class Plan:
         st["glog"] = t.zeros(B * g2 ** 3, cp, dtype=t.float32, device=self.dev) if self.need_grad else None
         st["d_t"] = st["lt"].desc(z2.cs, (g, g, g), cp, (g2, g2, g2), B, planar=True)
         st["d_t_bwd"] = st["lt"].desc(z2.cs, (g, g, g), cp, (g2, g2, g2), B, planar=False)
+        st["rows"] = eng.rows_pad.get(st["lt"].name)
+        if st["rows"] is not None:
+          d16 = st["lt"].desc(z2.cs, (g, g, g), cp, (g2, g2, g2), B, planar=False)
+          d16.Cout = d16.CoutP = cp
+          st["d_t_rows"] = d16
+          st["logits_rows"] = t.zeros(B * g2 ** 3, cp, dtype=t.float32, device=self.dev)
+          self.rows_cp = cp
       self.stages.append(st)
     self.scratch64 = t.zeros(4096, dtype=t.float64, device=self.dev)
     self.offs = t.zeros(B, 3, dtype=t.float32, device=self.dev)
@@ -880,7 +916,8 @@ class Plan:
   # ------------------------------------------------------------------ forward
   @t.no_grad()
   def forward(self, image: t.Tensor, v2s: t.Tensor, offsets: t.Tensor, training: bool,
-              want_features: bool = False, pack: bool = True, run_encoder: bool = True) -> t.Tensor:
+              want_features: bool = False, pack: bool = True, run_encoder: bool = True,
+              rows_logits: bool = False) -> t.Tensor:
     """Enqueues the forward pass on the current stream and returns the plan-owned logits buffer
     float32[B,C,D,H,W] (overwritten by the next forward of this plan).  pack=False: the caller has already
     re-packed the weights (graph replays pack outside the captured region when the weights did not change);
@@ -904,7 +941,7 @@ class Plan:
       eng.join_packs()
     if want_features:
       return None
-    return self._forward_decoder(v2s, offsets, training, P, bias, st)
+    return self._forward_decoder(v2s, offsets, training, P, bias, st, rows_logits)
 
   def _forward_encoder(self, image, training, P, bias, st):
     eng, B = self.eng, self.B
@@ -930,7 +967,7 @@ class Plan:
       blk["bn_c"].fwd(training)
     _call("crn_spatial_mean_fwd", self.enc_out.p, B, 64, 2048, self.feat.p, st)
 
-  def _forward_decoder(self, v2s, offsets, training, P, bias, st):
+  def _forward_decoder(self, v2s, offsets, training, P, bias, st, rows_logits=False):
     eng, B = self.eng, self.B
     # ---- decoder
     L = eng.L
@@ -1002,6 +1039,16 @@ class Plan:
           g2 = 2 * g
           _call("crn_skip_sample_fwd", cmap.p, B, hw, hw, sd["skip_c"], cmap.cs, mat.data_ptr(),
                 self.offs.data_ptr(), g2, g2, g2, nxt.p, nxt.cs, sd["t_out"], st)
+      elif sd["rows"] is not None:
+        rp, rows = sd["rows"], sd["logits_rows"]
+        convt7_tc_call(sd["lt"], sd["d_t_rows"], sd["z2"].p, rp["fwd"].data_ptr(), rp["b"].data_ptr(), rows.data_ptr(),
+                       eng.tc_status.data_ptr(), st, acct=sd["d_t_bwd"])
+        _call("crn_status_poison", eng.tc_status.data_ptr(), rows.data_ptr(), rows.numel() // B, B, st)
+        if rows_logits:
+          logits = rows
+        else:
+          logits = self.logits
+          _call("crn_rows_to_planar", rows.data_ptr(), B, sd["t_out"], (2 * g) ** 3, rp["cp"], logits.data_ptr(), st)
       else:
         logits = self.logits
         if USE_TC and eng.tct_w.get(sd["lt"].name, (None, None))[0] is not None:
@@ -1013,13 +1060,16 @@ class Plan:
     if self.need_grad and DETERMINISTIC_SKIP_BWD:
       t.cuda.current_stream().wait_event(lists_ev)
     # a tcgen05 barrier timeout (status word != 0) must not go unnoticed: NaN in every scene's logits
-    _call("crn_status_poison", eng.tc_status.data_ptr(), logits.data_ptr(), logits[0].numel(), B, st)
+    if logits is self.logits:
+      _call("crn_status_poison", eng.tc_status.data_ptr(), logits.data_ptr(), logits[0].numel(), B, st)
     return logits
 
   # ------------------------------------------------------------------ backward
   @t.no_grad()
-  def backward(self, grad_logits: t.Tensor, grads: Dict[str, t.Tensor], chunk_cb=None, comm_stream=None):
-    """grads: name -> zero/empty tensor per parameter (filled here).
+  def backward(self, grad_logits: t.Tensor, grads: Dict[str, t.Tensor], chunk_cb=None, comm_stream=None,
+               grad_is_rows: bool = False):
+    """grads: name -> zero/empty tensor per parameter (filled here).  grad_is_rows: the caller has written the
+    logit gradient as channels-last rows straight into this plan's `glog_rows()` buffer (rows-mode plans only).
 
     chunk_cb(i): data-parallel hook.  The parameters are finished in three chunks in backward order -- GRAD_CHUNKS:
     0 = decoder, 1 = encoder stage4+5, 2 = the rest -- and as soon as every gradient of chunk i is final its
@@ -1100,9 +1150,14 @@ class Plan:
         g2 = 2 * g
         S = g2 ** 3
         cp = sd["glog"].shape[1]
-        _call("crn_planar_to_rows", grad_logits.data_ptr(), B, sd["t_out"], S, cp, sd["glog"].data_ptr(), st)
-        _call("crn_colsum_planar", grad_logits.data_ptr(), B, sd["t_out"], S,
-              grads[lt.name + ".bias"].data_ptr(), self.scratch64.data_ptr(), st)
+        if grad_is_rows:
+          assert sd["rows"] is not None and grad_logits.data_ptr() == sd["glog"].data_ptr()
+          _call("crn_colsum", sd["glog"].data_ptr(), B * S, sd["t_out"], cp, 0, grads[lt.name + ".bias"].data_ptr(),
+                self.scratch64.data_ptr(), st)
+        else:
+          _call("crn_planar_to_rows", grad_logits.data_ptr(), B, sd["t_out"], S, cp, sd["glog"].data_ptr(), st)
+          _call("crn_colsum_planar", grad_logits.data_ptr(), B, sd["t_out"], S,
+                grads[lt.name + ".bias"].data_ptr(), self.scratch64.data_ptr(), st)
         dy_ptr, d_t = sd["glog"].data_ptr(), sd["d_t_bwd"]
       else:
         nxt = sd["next"]
@@ -1125,7 +1180,10 @@ class Plan:
           _call("crn_spatial_mean_fwd", cmap.gp, B, hw * hw, cmap.cs, ssum.data_ptr(), st)
           ssum.mul_(float(hw * hw))
       wgrad(lt, d_t, sd["z2"].p, dy_ptr)
-      if USE_TC and eng.tct_w.get(lt.name, (None, None))[1] is not None:
+      if stage == 6 and sd["rows"] is not None:
+        convt7_tc_dgrad_call(lt, sd["d_t_rows"], dy_ptr, sd["rows"]["dgrad"].data_ptr(), sd["z2"].gp,
+                             eng.tc_status.data_ptr(), st, acct=d_t)
+      elif USE_TC and eng.tct_w.get(lt.name, (None, None))[1] is not None:
         convt7_tc_dgrad_call(lt, d_t, dy_ptr, eng.tct_w[lt.name][1].data_ptr(), sd["z2"].gp, eng.tc_status.data_ptr(), st)
       else:
         dgrad(lt, d_t, dy_ptr, sd["z2"].gp, 0)
@@ -1217,6 +1275,10 @@ class Plan:
       offs[len(jobs)] = tot
       ent = cache[key] = (jobs, eng._to_dev(items, self.dev), eng._to_dev(offs, self.dev), tot)
     _call("crn_gather_f64_to_f32", ent[1].data_ptr(), ent[2].data_ptr(), len(jobs), ent[3], _lib.stream_ptr())
+
+  def glog_rows(self) -> t.Tensor:
+    """The rows-layout logit-gradient buffer float32[B*128^3, rows_cp] the backward pass reads (rows-mode plans)."""
+    return self.stages[-1]["glog"]
 
   # ------------------------------------------------------------------ graph-replayed entry points (module path)
   def _sig(self):

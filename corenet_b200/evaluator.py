@@ -39,10 +39,11 @@ class Evaluator:
     st = _lib.stream_ptr()
     b = image.shape[0]
     plan = self.eng.get_plan(b, image.device, False)
-    logits = plan.forward(image, v2s, offsets, False, pack=pack)
-    s = logits[0, 0].numel()
-    _call("crn_softmax_planar", logits.data_ptr(), b, self.c, s, self.pmf.data_ptr(), st)
-    _call("crn_argmax_confusion_labeled", logits.data_ptr(), gt.data_ptr(), int(gt.dtype == t.int64), b, self.c, s,
+    logits = plan.forward(image, v2s, offsets, False, pack=pack, rows_logits=True)
+    rows = plan.rows_cp          # > 0: channels-last rows straight from the logits layer's epilogue (C > 4)
+    s = self.pmf[0, 0].numel()
+    _call("crn_softmax_l", logits.data_ptr(), rows, b, self.c, s, self.pmf.data_ptr(), st)
+    _call("crn_argmax_confusion_l", logits.data_ptr(), rows, gt.data_ptr(), int(gt.dtype == t.int64), b, self.c, s,
           labels.data_ptr() if labels is not None else None, self.k, self.confusion_matrix.data_ptr(), st)
 
   def _gstate(self, image, v2s, offsets, gt, labels):

@@ -151,13 +151,14 @@ class Trainer:
       self._status_ev.record()
 
   # ------------------------------------------------------------------ one step, enqueued on the current stream
-  def _bufs(self, b, c, dev):
+  def _bufs(self, b, c, dev, planar_grad=True):
     key = (b, c)
     if key not in self._loss_bufs:
       self._loss_bufs[key] = dict(
           sums=t.empty(4 * b, dtype=t.float64, device=dev), loss=t.empty(1, dtype=t.float32, device=dev),
           coef=t.empty(2 * b + 1, dtype=t.float32, device=dev),
-          dlogits=t.empty(b, c, 128, 128, 128, dtype=t.float32, device=dev))
+          dlogits=(t.empty((b, c) + tuple(self.model.config.decoder.resolution), dtype=t.float32, device=dev)
+                   if planar_grad else None))
     return self._loss_bufs[key]
 
   def _adam(self, lo, hi, bump, scale):
@@ -179,20 +180,27 @@ class Trainer:
     st = _lib.stream_ptr()
     b = image.shape[0]
     plan = eng.get_plan(b, image.device, True)
-    logits = plan.forward(image, v2s, offsets, model.training)
-    c = logits.shape[1]
-    s = logits[0, 0].numel()
-    lb = self._bufs(b, c, image.device)
+    # rows-mode plans (C > 4) hand over / take the logits and their gradient as channels-last rows
+    rows = plan.rows_cp
+    logits = plan.forward(image, v2s, offsets, model.training, rows_logits=True)
+    c = model.config.decoder.num_output_channels
+    s = 1
+    for r in model.config.decoder.resolution:
+      s *= r
+    lb = self._bufs(b, c, image.device, planar_grad=not rows)
+    dlogits = plan.glog_rows() if rows else lb["dlogits"]
     is64 = int(gt.dtype == t.int64)
-    _call("crn_loss_sums", logits.data_ptr(), gt.data_ptr(), is64, b, c, s, self.mode, lb["sums"].data_ptr(), st)
+    _call("crn_loss_sums_l", logits.data_ptr(), rows, gt.data_ptr(), is64, b, c, s, self.mode, lb["sums"].data_ptr(),
+          st)
     _call("crn_loss_finalize", lb["sums"].data_ptr(), b, c, s, self.mode, lb["loss"].data_ptr(),
           lb["coef"].data_ptr(), st)
-    _call("crn_loss_bwd", logits.data_ptr(), gt.data_ptr(), is64, b, c, s, self.mode, lb["coef"].data_ptr(),
-          None, lb["dlogits"].data_ptr(), st)
+    _call("crn_loss_bwd_l", logits.data_ptr(), rows, gt.data_ptr(), is64, b, c, s, self.mode, lb["coef"].data_ptr(),
+          None, dlogits.data_ptr(), rows, st)
+    bw = dict(grad_is_rows=bool(rows))
     if with_update and self.overlap_allreduce:
-      plan.backward(lb["dlogits"], self.grads, chunk_cb=self._chunk_cb, comm_stream=self._comm_stream)
+      plan.backward(dlogits, self.grads, chunk_cb=self._chunk_cb, comm_stream=self._comm_stream, **bw)
     else:
-      plan.backward(lb["dlogits"], self.grads)
+      plan.backward(dlogits, self.grads, **bw)
       if with_update:
         self._update_all()
     return lb["loss"]

@@ -239,6 +239,21 @@ int crn_argmax_confusion(const float* logits, const void* gt, int32_t gt_is_i64,
 int crn_argmax_confusion_labeled(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N, int32_t C,
                                  int64_t S, const int32_t* scene_label, int32_t K, int64_t* cm, void* stream);
 
+/* Layout-aware forms: rows_cp == 0 -> planar logits [N, C, S] (the reference's NCDHW); rows_cp > 0 -> channels-last
+ * rows [N*S, rows_cp] (rows_cp = C rounded up to a multiple of 4) as the tcgen05 epilogue of the last transposed
+ * convolution writes them for C > 4: the training step then never materialises planar logits / logit gradients.
+ * crn_loss_bwd_l writes dlogits in the layout d_rows_cp selects (pad channels written as 0). */
+int crn_loss_sums_l(const float* logits, int32_t rows_cp, const void* gt, int32_t gt_is_i64, int32_t N, int32_t C,
+                    int64_t S, int32_t mode, double* sums, void* stream);
+int crn_loss_bwd_l(const float* logits, int32_t rows_cp, const void* gt, int32_t gt_is_i64, int32_t N, int32_t C,
+                   int64_t S, int32_t mode, const float* coef, const float* gscale, float* dlogits,
+                   int32_t d_rows_cp, void* stream);
+int crn_softmax_l(const float* logits, int32_t rows_cp, int32_t N, int32_t C, int64_t S, float* pmf, void* stream);
+int crn_argmax_confusion_l(const float* logits, int32_t rows_cp, const void* gt, int32_t gt_is_i64, int32_t N,
+                           int32_t C, int64_t S, const int32_t* scene_label, int32_t K, int64_t* cm, void* stream);
+/* channels-last rows [N*S][CP] -> planar [N][C][S] (the boundary layout of CoreNet.forward). */
+int crn_rows_to_planar(const float* rows, int32_t N, int32_t C, int64_t S, int32_t CP, float* out, void* stream);
+
 /* ------------------------------------------------------------------------
  * fill_inside_voxels.  Replaces cc/fill_voxels_gpu.cu:136-171 (kernels
  * :96-132) / cc/fill_voxels_cpu.cc:158-183.  grid: [N, D, H, W] of `elem_size`

@@ -272,3 +272,81 @@ def test_trainer_rejects_bad_label_dtype_and_guards_failed_steps():
   tr.eng.tc_status.zero_()
   tr.step(*args, gt)
   assert int(tr.step_dev) == 2 and not t.equal(tr.flat, before)
+
+
+@pytest.mark.parametrize("c,mode", [(15, 1), (15, 0), (6, 1), (2, 0), (3, 1)])
+def test_loss_kernels_rows_layout_equals_planar(c, mode):
+  """The channels-last rows forms (crn_*_l with rows_cp > 0: what the padded logits layer writes for C > 4) against
+  the planar forms on the same values: sums / loss / gradient / softmax / confusion must agree."""
+  from corenet_b200 import _lib
+  dev = t.device("cuda", 0)
+  g = t.Generator().manual_seed(c * 7 + mode)
+  b, s = 2, 24 * 24 * 24
+  cp = (c + 3) // 4 * 4
+  logits = t.randn(b, c, s, generator=g) * 3
+  gt = t.randint(0, c, (b, s), generator=g, dtype=t.int32).to(dev)
+  planar = logits.to(dev).contiguous()
+  rows = t.full((b * s, cp), 7.0, device=dev)                    # pad channels hold garbage: must be ignored
+  rows[:, :c] = logits.permute(0, 2, 1).reshape(b * s, c).to(dev)
+  st = _lib.stream_ptr()
+  out = {}
+  for name, x, rc in (("planar", planar, 0), ("rows", rows, cp)):
+    sums = t.empty(4 * b, dtype=t.float64, device=dev)
+    loss = t.empty(1, device=dev)
+    coef = t.empty(2 * b + 1, device=dev)
+    _lib.call("crn_loss_sums_l", x.data_ptr(), rc, gt.data_ptr(), 0, b, c, s, mode, sums.data_ptr(), st)
+    _lib.call("crn_loss_finalize", sums.data_ptr(), b, c, s, mode, loss.data_ptr(), coef.data_ptr(), st)
+    d = t.full_like(x, 5.0)
+    _lib.call("crn_loss_bwd_l", x.data_ptr(), rc, gt.data_ptr(), 0, b, c, s, mode, coef.data_ptr(), None,
+              d.data_ptr(), rc, st)
+    pmf = t.empty(b, c, s, device=dev)
+    _lib.call("crn_softmax_l", x.data_ptr(), rc, b, c, s, pmf.data_ptr(), st)
+    cm = t.zeros(c, c, dtype=t.int64, device=dev)
+    _lib.call("crn_argmax_confusion_l", x.data_ptr(), rc, gt.data_ptr(), 0, b, c, s, None, c, cm.data_ptr(), st)
+    out[name] = (sums.cpu(), loss.cpu(), d.cpu(), pmf.cpu(), cm.cpu())
+  p, r = out["planar"], out["rows"]
+  assert t.allclose(p[0][:3 * b], r[0][:3 * b], rtol=1e-12) or t.allclose(p[0], r[0], rtol=1e-9, atol=1e-9)
+  assert t.allclose(p[1], r[1], rtol=1e-6)
+  d_rows = r[2].reshape(b, s, cp)
+  assert t.allclose(p[2], d_rows[..., :c].permute(0, 2, 1), rtol=1e-5, atol=1e-9)
+  assert (d_rows[..., c:] == 0).all()                              # pad channels of the gradient are written as 0
+  assert t.equal(p[3], r[3]) and t.equal(p[4], r[4])
+  # reference arithmetic (torch) on the planar values
+  from oracle import corenet_oracle as O
+  lg = logits.reshape(b, c, 24, 24, 24).clone().requires_grad_(True)
+  fn = O.iou_fgbg if mode == 0 else O.xent_times_iou_agnostic
+  lo = fn(gt.cpu().long().reshape(b, 24, 24, 24), lg)
+  lo.backward()
+  assert abs(float(p[1]) - float(lo)) <= 1e-5 * max(1.0, abs(float(lo)))
+  assert ((p[2].reshape(lg.shape) - lg.grad).abs().max() / lg.grad.abs().max()).item() <= 1e-4
+  # rows -> planar conversion
+  back = t.empty(b, c, s, device=dev)
+  _lib.call("crn_rows_to_planar", rows.data_ptr(), b, c, s, cp, back.data_ptr(), st)
+  assert t.equal(back, planar)
+
+
+def test_trainer_rows_path_matches_module_path_c15():
+  """C = 15: the Trainer keeps logits and their gradient as channels-last rows (padded tcgen05 logits layer, rows loss
+  kernels); the module path converts to / from the reference's planar layout.  Same step, same gradients."""
+  from corenet_b200.model import losses
+  from corenet_b200.trainer import Trainer
+  from corenet_b200 import engine
+  dev = t.device("cuda", 0)
+  inp = MGC.config_inputs("E")
+  args = [inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev)]
+  gt = inp["gt"].to(dev)
+  m = build_model(15).to(dev).eval()
+  logits = m(*args)
+  loss = losses.xent_times_iou_agnostic(gt, logits)
+  loss.backward()
+  g_mod = t.cat([p.grad.reshape(-1) for p in m.parameters()])
+  plan = engine.get_engine(m).plans[(2, True)][0]
+  assert plan.rows_cp == 16, "C = 15 must run the padded rows path"
+  m2 = build_model(15).to(dev).eval()
+  tr = Trainer(m2, loss="xent_times_iou_agnostic", use_graph=False, lr=0.0)
+  l2 = tr.step(*args, gt)
+  err = ((tr.grad - g_mod).double().norm() / g_mod.double().norm()).item()
+  print(f"\nC=15 Trainer(rows) vs module(planar): loss {float(l2):.7f} vs {float(loss):.7f}, grad rel-L2 {err:.2e}")
+  assert abs(float(l2) - float(loss)) <= 1e-5 * abs(float(loss))
+  assert err <= 3e-4
+  tr.check_status(wait=True)
