@@ -607,7 +607,13 @@ def run_native(args):
       line["cpu_baseline"] = cpu_baseline(wl)
     print(json.dumps(line))
   if world > 1:
-    dist.destroy_process_group()
+    # the captured step holds NCCL kernels: destroy_process_group() blocks while such graphs are alive (observed on
+    # torch 2.11 / NCCL 2.28), so every rank synchronises and leaves without tearing the communicator down
+    dist.barrier()
+    t.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def build_roofline(prof, steps, pk, pk_src, layers_path):
@@ -678,6 +684,9 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--layers", default=None, help="write a per-layer conv / HBM-kernel timing table to this file")
   args = ap.parse_args()
+  if os.environ.get("CRN_FAULT_TIMEOUT"):        # debugging aid: dump all Python stacks and exit if the run stalls
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ["CRN_FAULT_TIMEOUT"]), exit=True)
   if args.impl == "reference":
     run_reference(args)
   elif args.impl == "reference-gpu":

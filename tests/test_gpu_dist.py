@@ -89,8 +89,15 @@ def _worker(rank, world, port, ngpu, mode, out):
     # tensors by value (numpy): torch's fd-based tensor sharing needs the sender alive when the parent unpickles
     out.put((rank, {k: (v.numpy() if isinstance(v, t.Tensor) else v) for k, v in res.items()}))
     dist.barrier()
+    if backend == "nccl":
+      # CUDA graphs that captured NCCL kernels make destroy_process_group() block: flush the result queue and leave
+      out.close()
+      out.join_thread()
+      t.cuda.synchronize()
+      os._exit(0)
   finally:
-    dist.destroy_process_group()
+    if backend != "nccl":
+      dist.destroy_process_group()
 
 
 def _run(mode):
