@@ -96,6 +96,61 @@ __global__ void __launch_bounds__(NT) fill_unpack_kernel(const uint32_t* __restr
   }
 }
 
+// Fast paths for 4-byte elements and W % 128 == 0 (the pipeline's 128^3 float32 / int32 grids): a lane moves 16 B
+// (4 voxels), a warp one 128-voxel chunk = 4 mask words, UNR chunks in flight per warp.
+template <bool IS_FLOAT, int UNR>
+__global__ void __launch_bounds__(NT) fill_pack4_kernel(const uint4* __restrict__ grid, int64_t chunks /*rows*W/128*/,
+                                                        int D, int H, int cpr /*chunks per row*/,
+                                                        uint32_t* __restrict__ E, uint32_t* __restrict__ R) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * NT + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * NT) >> 5;
+  for (int64_t c0 = warp0 * UNR; c0 < chunks; c0 += nwarps * UNR) {
+    uint4 v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (c0 + u < chunks) v[u] = __ldg(grid + (c0 + u) * 32 + lane);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (c0 + u >= chunks) break;
+      uint32_t nib;
+      if (IS_FLOAT) {
+        nib = (!(__uint_as_float(v[u].x) > 0.f) ? 1u : 0u) | (!(__uint_as_float(v[u].y) > 0.f) ? 2u : 0u) |
+              (!(__uint_as_float(v[u].z) > 0.f) ? 4u : 0u) | (!(__uint_as_float(v[u].w) > 0.f) ? 8u : 0u);
+      } else {
+        nib = (!((int)v[u].x > 0) ? 1u : 0u) | (!((int)v[u].y > 0) ? 2u : 0u) | (!((int)v[u].z > 0) ? 4u : 0u) |
+              (!((int)v[u].w > 0) ? 8u : 0u);
+      }
+      uint32_t w = nib << (4 * (lane & 7));            // 8 lanes = 32 voxels = one word
+      w |= __shfl_xor_sync(0xffffffffu, w, 1);
+      w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      w |= __shfl_xor_sync(0xffffffffu, w, 4);
+      if ((lane & 7) == 0) {
+        const int64_t chunk = c0 + u;
+        const int64_t row = chunk / cpr;
+        const int wi = (int)(chunk - row * cpr) * 4 + (lane >> 3);
+        const int y = (int)(row % H);
+        const int z = (int)((row / H) % D);
+        const int64_t wd = row * (cpr * 4) + wi;
+        E[wd] = w;
+        R[wd] = (z == 0 || y == 0) ? w : (wi == 0 ? (w & 1u) : 0u);
+      }
+    }
+  }
+}
+
+template <bool IS_FLOAT>
+__global__ void __launch_bounds__(NT) fill_unpack4_kernel(const uint32_t* __restrict__ R, int64_t quads /*voxels/4*/,
+                                                          uint4* __restrict__ out) {
+  const uint32_t one = IS_FLOAT ? 0x3f800000u : 1u;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < quads; i += (int64_t)gridDim.x * NT) {
+    const uint32_t r = __ldg(R + (i >> 3)) >> (4 * (int)(i & 7));      // W % 128 == 0: words never straddle rows
+    uint4 o;
+    o.x = (r & 1u) ? 0u : one; o.y = (r & 2u) ? 0u : one; o.z = (r & 4u) ? 0u : one; o.w = (r & 8u) ? 0u : one;
+    out[i] = o;
+  }
+}
+
 // r <- all bits of E-runs that contain a bit of r  (r subset of E), multiword.
 template <int NW>
 __device__ __forceinline__ void row_fill(uint32_t (&r)[NW], const uint32_t (&e)[NW]) {
@@ -302,38 +357,43 @@ __global__ void __launch_bounds__(CL_NT) fill_flood_cluster_kernel(const uint32_
     return ch;
   };
 
-  bool changed = x_fill();
+  x_fill();
   __syncthreads();
   for (int it = 0;; ++it) {
-    // ---- y: CTA-local doubling
-    for (int i = tid; i < words; i += CL_NT) { const uint32_t e = Es[i]; Tu[i] = e; Td[i] = e; }
-    __syncthreads();
-    for (int d = 1; d < H; d <<= 1) {
-      uint32_t r[CL_WPT], tu[CL_WPT], td[CL_WPT];
+    // ---- in-plane closure (x carry chains + y doubling), CTA-local: every z-plane has its own seeds (the y = 0 row
+    // and the x = 0 column), so almost all of the outside region is reached here without touching the cluster
+    for (;;) {
+      bool ch = false;
+      for (int i = tid; i < words; i += CL_NT) { const uint32_t e = Es[i]; Tu[i] = e; Td[i] = e; }
+      __syncthreads();
+      for (int d = 1; d < H; d <<= 1) {
+        uint32_t r[CL_WPT], tu[CL_WPT], td[CL_WPT];
 #pragma unroll
-      for (int k = 0; k < CL_WPT; ++k) {
-        const int i = tid + k * CL_NT;
-        if (i < words) {
-          const int y = (i / NW) % H;
-          uint32_t rr = Rs[i], a = Tu[i], b = Td[i];
-          const uint32_t r0 = rr;
-          if (y >= d) { rr |= a & Rs[i - d * NW]; a &= Tu[i - d * NW]; }
-          if (y + d < H) { rr |= b & Rs[i + d * NW]; b &= Td[i + d * NW]; }
-          changed |= rr != r0;
-          r[k] = rr; tu[k] = a; td[k] = b;
+        for (int k = 0; k < CL_WPT; ++k) {
+          const int i = tid + k * CL_NT;
+          if (i < words) {
+            const int y = (i / NW) % H;
+            uint32_t rr = Rs[i], a = Tu[i], b = Td[i];
+            const uint32_t r0 = rr;
+            if (y >= d) { rr |= a & Rs[i - d * NW]; a &= Tu[i - d * NW]; }
+            if (y + d < H) { rr |= b & Rs[i + d * NW]; b &= Td[i + d * NW]; }
+            ch |= rr != r0;
+            r[k] = rr; tu[k] = a; td[k] = b;
+          }
         }
-      }
-      __syncthreads();
+        __syncthreads();
 #pragma unroll
-      for (int k = 0; k < CL_WPT; ++k) {
-        const int i = tid + k * CL_NT;
-        if (i < words) { Rs[i] = r[k]; Tu[i] = tu[k]; Td[i] = td[k]; }
+        for (int k = 0; k < CL_WPT; ++k) {
+          const int i = tid + k * CL_NT;
+          if (i < words) { Rs[i] = r[k]; Tu[i] = tu[k]; Td[i] = td[k]; }
+        }
+        __syncthreads();
       }
-      __syncthreads();
+      ch |= x_fill();
+      if (!__syncthreads_or(ch ? 1 : 0)) break;
     }
-    changed |= x_fill();
-    __syncthreads();
     // ---- z: doubling across the slabs of the cluster
+    bool changed = false;
     for (int i = tid; i < words; i += CL_NT) { const uint32_t e = Es[i]; Tu[i] = e; Td[i] = e; }
     cluster.sync();
     for (int d = 1; d < D; d <<= 1) {
@@ -371,15 +431,13 @@ __global__ void __launch_bounds__(CL_NT) fill_flood_cluster_kernel(const uint32_
       }
       cluster.sync();
     }
-    changed |= x_fill();
-    // ---- any bit changed anywhere in the cluster during this round?
+    // ---- did the z phase reach anything new anywhere in the cluster?  (the in-plane closure above had converged)
     const int any_local = __syncthreads_or(changed ? 1 : 0);
     if (tid == 0) { flags[it & 1] = any_local; flags[(it + 1) & 1] = 0; }
     cluster.sync();
     int any = 0;
     for (int c = 0; c < CS; ++c) any |= *cluster.map_shared_rank(&flags[it & 1], c);
     if (!any) break;
-    changed = false;
   }
   cluster.sync();                                // no CTA may exit while its shared memory can still be read
   for (int i = tid; i < words; i += CL_NT) R[gbase + (int64_t)z0 * H * NW + i] = Rs[i];
@@ -439,8 +497,19 @@ extern "C" int crn_fill_inside(const void* grid_in, void* grid_out, int32_t elem
   const int64_t rows = (int64_t)N * D * H;
   uint32_t* E = reinterpret_cast<uint32_t*>(workspace);
   uint32_t* R = E + rows * nw;
-  fill_pack_kernel<<<grid_for(rows * nw * 32), NT, 0, st>>>(grid_in, elem_size, dtype_kind, rows, D, H, W, nw,
-                                                           E, R);
+  const bool fast4 = elem_size == 4 && dtype_kind != 2 && W % 128 == 0 &&
+                     (reinterpret_cast<uintptr_t>(grid_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(grid_out) & 15) == 0;
+  if (fast4) {
+    const int64_t chunks = rows * (W / 128);
+    const unsigned g = grid_for(crn_ceil_div(chunks, 2) * 32);
+    if (dtype_kind == 1)
+      fill_pack4_kernel<true, 2><<<g, NT, 0, st>>>(reinterpret_cast<const uint4*>(grid_in), chunks, D, H, W / 128, E, R);
+    else
+      fill_pack4_kernel<false, 2><<<g, NT, 0, st>>>(reinterpret_cast<const uint4*>(grid_in), chunks, D, H, W / 128, E, R);
+  } else {
+    fill_pack_kernel<<<grid_for(rows * nw * 32), NT, 0, st>>>(grid_in, elem_size, dtype_kind, rows, D, H, W, nw,
+                                                             E, R);
+  }
   int threads = D > H ? D : H;
   threads = ((threads + 31) / 32) * 32;
   if (threads > 1024) threads = 1024;
@@ -471,7 +540,14 @@ extern "C" int crn_fill_inside(const void* grid_in, void* grid_out, int32_t elem
       default: fill_flood_wide_kernel<<<N, threads, 0, st>>>(E, R, D, H, nw); break;
     }
   }
-  fill_unpack_kernel<<<grid_for(rows * W), NT, 0, st>>>(R, elem_size, dtype_kind, rows, W, nw, grid_out);
+  if (fast4) {
+    if (dtype_kind == 1)
+      fill_unpack4_kernel<true><<<grid_for(rows * W / 4), NT, 0, st>>>(R, rows * W / 4, reinterpret_cast<uint4*>(grid_out));
+    else
+      fill_unpack4_kernel<false><<<grid_for(rows * W / 4), NT, 0, st>>>(R, rows * W / 4, reinterpret_cast<uint4*>(grid_out));
+  } else {
+    fill_unpack_kernel<<<grid_for(rows * W), NT, 0, st>>>(R, elem_size, dtype_kind, rows, W, nw, grid_out);
+  }
   crn_count_launches(2);
   CRN_LAUNCH_CHECK("fill_inside");
   return CRN_OK;
