@@ -159,6 +159,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
             o.x += v[qd * 4]; o.y += v[qd * 4 + 1]; o.z += v[qd * 4 + 2]; o.w += v[qd * 4 + 3];
             *reinterpret_cast<float4*>(dst[qd]) = o;
           }
+        } else if (first && p.planar && p.cout_cls == 2 && p.gN == 16 && c0 == 0) {
+          // FG_BG logits (2 planes): the px = 0 / px = 1 classes of a coarse voxel are neighbouring fine voxels of the
+          // same plane row -> one 8-byte store per (pz, py, channel); consecutive lanes (coarse x) write consecutive
+          // 8 bytes, so every 32-byte sector is written whole by one instruction
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                         // q = pz * 2 + py
+            const int oz = 2 * (z0 + zz) + (q >> 1), oy = 2 * y + (q & 1);
+            const long long sp = ((long long)oz * OH + oy) * OW + 2 * x;
+#pragma unroll
+            for (int co = 0; co < 2; ++co) {
+              const float b = p.bias ? __ldg(p.bias + co) : 0.f;
+              *reinterpret_cast<float2*>(p.out + ((long long)n * 2 + co) * oS + sp) =
+                  make_float2(v[q * 4 + co] + b, v[q * 4 + 2 + co] + b);
+            }
+          }
         } else if (first) {                                     // nothing to read: plain stores, no batching
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
