@@ -28,13 +28,21 @@ constexpr int XS = TX + 4, YS = TY + 4;
 constexpr int CHUNK_BYTES = YS * XS * 16;        // one 4-channel chunk of a plane  (3840)
 constexpr int PART_BYTES = 2 * CHUNK_BYTES;      // 8 channels                       (7680)
 constexpr int PLANE_BYTES = 2 * PART_BYTES;      // hi + lo                          (15360)
-constexpr int ZT = 4, NPLANE = ZT + 4, NSLOT = NPLANE;
+constexpr int ZT = 4;
+constexpr int MAXSLOT = 10;                      // plane ring capacity
 constexpr int NP = 16;                           // padded output channels
 constexpr int BLK = 2 * NP;                      // B rows / accumulator columns per output plane: [hi | lo]
-constexpr int SROWS = 5 * BLK;                   // rows of one stacked part (kz = 4..0)
-constexpr int KC_BYTES = 2 * SROWS * 16;         // one 4-channel K chunk of a tap: part 0 rows + part 1 rows (LBO)
-constexpr int TAP_BYTES = 2 * KC_BYTES;          // 10240
-constexpr int WROW_BYTES = 5 * TAP_BYTES;        // the 5 kx taps of one ky (all kz)   (51200)
+// KT = taps per axis: 5 (Conv3d k=5) or 4 (ConvTranspose3d k=7 s=2 seen from the coarse grid, see conv_tc5.cu)
+template <int KT>
+struct Geo {
+  // planes per K pass, and ring slots: KT = 4 has shared memory left for 3 extra slots, so the producers can stage the
+  // first planes of the next pass while the MMAs of this pass still run (KT = 5 fills the 227 KB with NPLANE slots)
+  static constexpr int NPLANE = ZT + KT - 1, NSLOT = KT == 4 ? NPLANE + 3 : NPLANE;
+  static constexpr int SROWS = KT * BLK;                 // rows of one stacked part (kz = KT-1..0)
+  static constexpr int KC_BYTES = 2 * SROWS * 16;        // one 4-channel K chunk of a tap: part 0 rows + part 1 rows (LBO)
+  static constexpr int TAP_BYTES = 2 * KC_BYTES;         // 10240 (KT = 5) / 8192 (KT = 4)
+  static constexpr int WROW_BYTES = KT * TAP_BYTES;      // the KT kx taps of one ky (all kz): 51200 / 32768
+};
 constexpr int WSTAGES = 2;
 constexpr int NTHREADS = 320;
 constexpr int ACOLS = BLK;                       // 32 accumulator columns per plane
@@ -44,10 +52,11 @@ struct TC5SParams {
   const float* in; const float* wtc; const float* bias; float* out; int* status;
   int N, D, H, W, gK, gN, in_cs, in_co, out_cs, out_co, P;
   int tiles_x, tiles_y, tiles_z, nitems;
+  int cout_cls;            // GATH: channels per parity class of the fine gradient (K = 8 * cout_cls)
 };
 
 struct __align__(8) Barriers {
-  uint64_t plane_full[NSLOT], plane_empty[NSLOT];
+  uint64_t plane_full[MAXSLOT], plane_empty[MAXSLOT];
   uint64_t w_full[WSTAGES], w_empty[WSTAGES];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
@@ -61,9 +70,14 @@ __device__ __forceinline__ void decode_item(const TC5SParams& p, int item, int& 
   z0 = (t % p.tiles_z) * ZT; n = t / p.tiles_z;
 }
 
-template <bool WIDE>
+// GATH: dgrad of ConvTranspose3d k=7 s=2 p=3 -- K = 8 * cout_cls class channels gathered from the fine gradient
+// (class channel (c, co) of coarse voxel i is dY[2i + c][co]), 4^3 taps at offsets -2..1, N = Cin (conv_tc5.cu GATH).
+template <bool WIDE, int KT, bool GATH>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams p) {
   constexpr int NOUT = WIDE ? 32 : 16;             // output channels held per plane
+  constexpr int HLO = (KT == 5 || GATH) ? 2 : 1;   // most negative tap offset
+  constexpr int NPLANE = Geo<KT>::NPLANE, NSLOT = Geo<KT>::NSLOT, SROWS = Geo<KT>::SROWS;
+  constexpr int KC_BYTES = Geo<KT>::KC_BYTES, TAP_BYTES = Geo<KT>::TAP_BYTES, WROW_BYTES = Geo<KT>::WROW_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;
   uint8_t* wring = smem + NSLOT * PLANE_BYTES;
@@ -100,13 +114,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
 #pragma unroll
         for (int e = 0; e < NOUT; ++e) sum[zz][e] = 0.f;
       for (int pass = 0; pass < p.P && !dead; ++pass) {
-        for (int ky = 0; ky < 5; ++ky, ++G) {
+        for (int ky = 0; ky < KT; ++ky, ++G) {
           const int st = (int)(G & 1);
           if (!tc::mbar_wait(&B->acc_full[st], (uint32_t)(G >> 1) & 1, ab)) { fail(); dead = true; break; }
           tc::fence_after_sync();
 #pragma unroll
           for (int zz = 0; zz < ZT; ++zz) {
-            // plane zz always receives at least its kz = 2 contribution (input plane z0 + zz is inside the volume)
+            // plane zz always receives at least its kz = HLO contribution (input plane z0 + zz is inside the volume)
             const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + st * (ZT * ACOLS) + zz * ACOLS;
             float v[16];
             tc::tmem_ld16(ta, v);
@@ -151,25 +165,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
           const int slot = (int)(L % NSLOT);
           const uint32_t use = (uint32_t)(L / NSLOT);
           if (use > 0 && !tc::mbar_wait(&B->plane_empty[slot], (use - 1) & 1, ab)) { fail(); dead = true; break; }
-          const int q = z0 - 2 + r;
+          const int q = z0 - HLO + r;
           if (q >= 0 && q < p.D) {
             uint8_t* dst = ring + slot * PLANE_BYTES;
-            for (int u = pt; u < YS * XS * 2; u += 128) {
-              const int kc = u & 1; const int v = u >> 1;
-              const int xs = v % XS, ys = v / XS;
-              const int y = y0 - 2 + ys, x = x0 - 2 + xs;
-              const int k = pass * 8 + kc * 4;
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
-                const long long off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
-                a = __ldg(reinterpret_cast<const float4*>(p.in + off));
+            // all gathers of this thread are issued before the first split / store: NU independent loads in flight
+            constexpr int NU = (YS * XS * 2 + 127) / 128;
+            float4 a[NU];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+              const int u = pt + i * 128;
+              a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (u < YS * XS * 2) {
+                const int kc = u & 1; const int v = u >> 1;
+                const int xs = v % XS, ys = v / XS;
+                const int y = y0 - HLO + ys, x = x0 - HLO + xs;
+                const int k = pass * 8 + kc * 4;
+                if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
+                  long long off;
+                  if constexpr (GATH) {              // class channel k = (cls, co) lives at fine voxel 2i + cls
+                    const int cls = k / p.cout_cls, co = k - cls * p.cout_cls;
+                    off = ((((long long)n * (2 * p.D) + 2 * q + (cls >> 2)) * (2 * p.H) + 2 * y + ((cls >> 1) & 1)) *
+                               (2 * p.W) + 2 * x + (cls & 1)) * p.in_cs + p.in_co + co;
+                  } else {
+                    off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
+                  }
+                  a[i] = __ldg(reinterpret_cast<const float4*>(p.in + off));
+                }
               }
-              float4 hi, lo;
-              tc::split_tf32(a.x, hi.x, lo.x); tc::split_tf32(a.y, hi.y, lo.y);
-              tc::split_tf32(a.z, hi.z, lo.z); tc::split_tf32(a.w, hi.w, lo.w);
-              const int o = kc * CHUNK_BYTES + v * 16;
-              *reinterpret_cast<float4*>(dst + o) = hi;
-              *reinterpret_cast<float4*>(dst + PART_BYTES + o) = lo;
+            }
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+              const int u = pt + i * 128;
+              if (u < YS * XS * 2) {
+                const int kc = u & 1; const int v = u >> 1;
+                float4 hi, lo;
+                tc::split_tf32(a[i].x, hi.x, lo.x); tc::split_tf32(a[i].y, hi.y, lo.y);
+                tc::split_tf32(a[i].z, hi.z, lo.z); tc::split_tf32(a[i].w, hi.w, lo.w);
+                const int o = kc * CHUNK_BYTES + v * 16;
+                *reinterpret_cast<float4*>(dst + o) = hi;
+                *reinterpret_cast<float4*>(dst + PART_BYTES + o) = lo;
+              }
             }
             tc::fence_async_smem();
           }
@@ -189,7 +224,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
         int n, z0, y0, x0;
         decode_item(p, item, n, z0, y0, x0);
         for (int pass = 0; pass < p.P && !dead; ++pass, L0 += NPLANE) {
-          for (int ky = 0; ky < 5 && !dead; ++ky, ++G, ++Wn) {
+          for (int ky = 0; ky < KT && !dead; ++ky, ++G, ++Wn) {
             const int st = (int)(G & 1);
             if (G >= 2 && !tc::mbar_wait(&B->acc_empty[st], (uint32_t)((G >> 1) - 1) & 1, ab)) { fail(); dead = true; break; }
             const int ws = (int)(Wn % WSTAGES);
@@ -206,15 +241,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
                 if (!tc::mbar_wait(&B->plane_full[slot], (uint32_t)(L / NSLOT) & 1, ab)) { fail(); dead = true; break; }
                 tc::fence_after_sync();
               }
-              const int zin = z0 - 2 + q;
+              const int zin = z0 - HLO + q;
               if (zin >= 0 && zin < p.D) {
-                // output planes zz = q - kz, kz = 0..4, clipped to the item: the stack [zlo, zhi]
-                const int zlo = q > 4 ? q - 4 : 0, zhi = q < ZT - 1 ? q : ZT - 1;
-                // B rows: block b holds kz = 4 - b; plane zlo needs kz = q - zlo -> first block 4 - (q - zlo)
-                const uint32_t boff = (uint32_t)(4 - (q - zlo)) * (BLK * 16);
+                // output planes zz = q - kz, kz = 0..KT-1, clipped to the item: the stack [zlo, zhi]
+                const int zlo = q > KT - 1 ? q - (KT - 1) : 0, zhi = q < ZT - 1 ? q : ZT - 1;
+                // B rows: block b holds kz = KT-1 - b; plane zlo needs kz = q - zlo -> first block KT-1 - (q - zlo)
+                const uint32_t boff = (uint32_t)(KT - 1 - (q - zlo)) * (BLK * 16);
                 const uint32_t alo0 = ((ring_u32 + (uint32_t)slot * PLANE_BYTES) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
 #pragma unroll
-                for (int kx = 0; kx < 5; ++kx) {
+                for (int kx = 0; kx < KT; ++kx) {
                   // ND16: (A_hi, [W_hi|W_lo]), (A_lo, [W_hi|0]);   WIDE: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
 #pragma unroll
                   for (int part = 0; part < (WIDE ? 3 : 2); ++part) {
@@ -243,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
                   }
                 }
               }
-              if (ky == 4) tc::commit(&B->plane_empty[slot]);      // last sweep of the pass: plane q is dead
+              if (ky == KT - 1) tc::commit(&B->plane_empty[slot]); // last sweep of the pass: plane q is dead
             }
             if (dead) break;
             tc::commit(&B->w_empty[ws]);
@@ -259,11 +294,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
       bool dead = false;
       for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
         for (int pass = 0; pass < p.P && !dead; ++pass) {
-          for (int ky = 0; ky < 5; ++ky, ++Wn) {
+          for (int ky = 0; ky < KT; ++ky, ++Wn) {
             const int ws = (int)(Wn % WSTAGES);
             const uint32_t use = (uint32_t)(Wn / WSTAGES);
             if (use > 0 && !tc::mbar_wait(&B->w_empty[ws], (use - 1) & 1, ab)) { fail(); dead = true; break; }
-            const float* src = p.wtc + ((size_t)pass * 5 + ky) * (WROW_BYTES / 4);
+            const float* src = p.wtc + ((size_t)pass * KT + ky) * (WROW_BYTES / 4);
             const uint32_t bar = tc::smem_u32(&B->w_full[ws]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)WROW_BYTES)
                          : "memory");
@@ -307,9 +342,10 @@ __global__ void tc5s_pack_kernel(const float* __restrict__ w, int Cout, int Cin,
     }
     float hi, lo;
     tc::split_tf32(v, hi, lo);
-    const long long kcb = (((long long)pass * 5 + ky) * 5 + kx) * (TAP_BYTES / 4) + (long long)kc * (KC_BYTES / 4);
+    const long long kcb = (((long long)pass * 5 + ky) * 5 + kx) * (Geo<5>::TAP_BYTES / 4) +
+                          (long long)kc * (Geo<5>::KC_BYTES / 4);
     const long long row0 = kcb + ((long long)(4 - kz) * BLK + n) * 4 + e;              // region 0
-    const long long row1 = row0 + (long long)SROWS * 4;                               // region 1
+    const long long row1 = row0 + (long long)Geo<5>::SROWS * 4;                       // region 1
     if (wide) {
       out[row0] = hi;
       out[row1] = lo;
@@ -320,19 +356,57 @@ __global__ void tc5s_pack_kernel(const float* __restrict__ w, int Cout, int Cin,
   }
 }
 
-template <bool WIDE>
+// class-gather dgrad weights (ConvTranspose3d [Cin][Cout][7][7][7]) in the stacked layout:
+//   wtc[P][jy][jx][kc][region][blk = 3 - jz][32 rows][4 floats], K index kk = (class, co), N = ci,
+//   tap j <-> offset j - 2 per axis, filter index k = c - 1 + 2*j (zero outside 0..6)   (conv_tc5.cu tct_pack, dgrad)
+__global__ void tcts_pack_kernel(const float* __restrict__ w, int Cin, int Cout, int wide, int P,
+                                 float* __restrict__ out) {
+  const long long total = (long long)P * 16 * 2 * 4 * 32 * 4;      // (pass, jy, jx, kc, jz, n, e)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 3); long long r = i >> 2;
+    const int n = (int)(r & 31); r >>= 5;
+    const int jz = (int)(r & 3); r >>= 2;
+    const int kc = (int)(r & 1); r >>= 1;
+    const int jx = (int)(r & 3); r >>= 2;
+    const int jy = (int)(r & 3); const int pass = (int)(r >> 2);
+    if (!wide && n >= 16) continue;
+    const int kk = pass * 8 + kc * 4 + e;
+    float v = 0.f;
+    if (n < Cin && kk < 8 * Cout) {
+      const int cls = kk / Cout, co = kk - cls * Cout;
+      const int kz = (cls >> 2) - 1 + 2 * jz, ky = ((cls >> 1) & 1) - 1 + 2 * jy, kx = (cls & 1) - 1 + 2 * jx;
+      if ((unsigned)kz < 7u && (unsigned)ky < 7u && (unsigned)kx < 7u)
+        v = w[(((long long)n * Cout + co) * 7 + kz) * 49 + ky * 7 + kx];
+    }
+    float hi, lo;
+    tc::split_tf32(v, hi, lo);
+    const long long kcb = (((long long)pass * 4 + jy) * 4 + jx) * (Geo<4>::TAP_BYTES / 4) +
+                          (long long)kc * (Geo<4>::KC_BYTES / 4);
+    const long long row0 = kcb + ((long long)(3 - jz) * BLK + n) * 4 + e;              // region 0
+    const long long row1 = row0 + (long long)Geo<4>::SROWS * 4;                       // region 1
+    if (wide) {
+      out[row0] = hi;
+      out[row1] = lo;
+    } else {
+      out[row0] = hi; out[row0 + NP * 4] = lo;
+      out[row1] = hi; out[row1 + NP * 4] = 0.f;
+    }
+  }
+}
+
+template <bool WIDE, int KT = 5, bool GATH = false>
 int launch_tc5s(const TC5SParams& p, cudaStream_t st) {
-  const size_t smem = (size_t)NSLOT * PLANE_BYTES + (size_t)WSTAGES * WROW_BYTES + sizeof(Barriers) + 64;
+  const size_t smem = (size_t)Geo<KT>::NSLOT * PLANE_BYTES + (size_t)WSTAGES * Geo<KT>::WROW_BYTES + sizeof(Barriers) + 64;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc5s_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc5s_kernel<WIDE, KT, GATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       crn_set_error("conv_tc5s: cannot set %zu bytes of dynamic shared memory", smem);
       return CRN_ERR_LAUNCH;
     }
     configured = true;
   }
   const int grid = p.nitems < kNumSMs ? p.nitems : kNumSMs;
-  conv_tc5s_kernel<WIDE><<<grid, NTHREADS, smem, st>>>(p);
+  conv_tc5s_kernel<WIDE, KT, GATH><<<grid, NTHREADS, smem, st>>>(p);
   CRN_LAUNCH_CHECK("conv_tc5s");
   return CRN_OK;
 }
@@ -340,7 +414,45 @@ int launch_tc5s(const TC5SParams& p, cudaStream_t st) {
 }  // namespace
 
 // K = reduction channels (Cin for the forward operator, Cout for dgrad)
-extern "C" int64_t crn_tc5s_packed_floats(int32_t K) { return (int64_t)((K + 7) / 8) * 5 * (WROW_BYTES / 4); }
+extern "C" int64_t crn_tc5s_packed_floats(int32_t K) { return (int64_t)((K + 7) / 8) * 5 * (Geo<5>::WROW_BYTES / 4); }
+
+// ---- dgrad of ConvTranspose3d k=7 s=2 p=3 with the 4 jz taps stacked into N (Cin <= 32, Cout % 4 == 0)
+extern "C" int64_t crn_tcts_packed_floats(int32_t Cout) { return (int64_t)(8 * Cout / 8) * 4 * (Geo<4>::WROW_BYTES / 4); }
+
+extern "C" int crn_tcts_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream) {
+  CRN_REQUIRE(w && out && Cout > 0 && Cin > 0 && Cin <= 32 && Cout % 4 == 0, "crn_tcts_pack: Cin <= 32, Cout % 4 == 0");
+  const int P = Cout;                                   // K = 8 * Cout class channels in passes of 8
+  const long long total = (long long)P * 16 * 2 * 4 * 32 * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  tcts_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cin, Cout, Cin > 16 ? 1 : 0, P, out);
+  CRN_LAUNCH_CHECK("tcts_pack");
+  return CRN_OK;
+}
+
+extern "C" int crn_convt7_tcs_dgrad(const crn_conv_desc* d, const float* dy, const float* wtc, float* dx,
+                                    int32_t* status, void* stream) {
+  CRN_REQUIRE(d && dy && wtc && dx && status, "crn_convt7_tcs_dgrad: null pointer");
+  CRN_REQUIRE(d->transposed && d->kD == 7 && d->kH == 7 && d->kW == 7 && d->stride == 2 && d->pad == 3,
+              "crn_convt7_tcs_dgrad: only ConvTranspose3d k=7 s=2 p=3");
+  CRN_REQUIRE(d->oD == 2 * d->iD && d->oH == 2 * d->iH && d->oW == 2 * d->iW, "crn_convt7_tcs_dgrad: output must be 2x input");
+  CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % ZT == 0 && d->iD >= 4,
+              "crn_convt7_tcs_dgrad: input grid must tile by 8x16x4");
+  CRN_REQUIRE(!d->y_planar && d->Cout % 4 == 0 && d->Cin % 4 == 0 && d->Cin <= 32,
+              "crn_convt7_tcs_dgrad: Cout % 4, Cin % 4, Cin <= 32, channels-last dy");
+  CRN_REQUIRE(d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
+              "crn_convt7_tcs_dgrad: channel strides/offsets must be multiples of 4");
+  TC5SParams p{};
+  p.in = dy; p.wtc = wtc; p.bias = nullptr; p.out = dx; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  p.gK = 8 * d->Cout; p.gN = d->Cin; p.cout_cls = d->Cout;
+  p.in_cs = d->y_cs; p.in_co = d->y_co; p.out_cs = d->x_cs; p.out_co = d->x_co;
+  p.P = (p.gK + 7) / 8;
+  p.tiles_x = p.W / TX; p.tiles_y = p.H / TY; p.tiles_z = p.D / ZT;
+  p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
+  cudaStream_t st = crn_stream(stream);
+  return p.gN <= 16 ? launch_tc5s<false, 4, true>(p, st) : launch_tc5s<true, 4, true>(p, st);
+}
 
 extern "C" int crn_tc5s_pack2(const float* w, int32_t Cout, int32_t Cin, int32_t dgrad, float* out, void* stream) {
   CRN_REQUIRE(w && out && Cout > 0 && Cin > 0, "crn_tc5s_pack2: bad args");

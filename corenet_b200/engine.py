@@ -254,6 +254,8 @@ USE_TC5S = True
 DETERMINISTIC_SKIP_BWD = True
 # logits layer with > 4 classes through the padded channels-last rows path (see Engine._ensure_device)
 USE_ROWS_LOGITS = True
+# ConvTranspose3d k=7 dgrad with Cin <= 32 through the jz-stacked kernel (crn_convt7_tcs_dgrad)
+USE_TCTS = True
 
 
 def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None):
@@ -271,16 +273,16 @@ def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None):
   PROFILE.append(("fwd_tc", layer.name, conv_macs(acct or d), e0, e1))
 
 
-def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st, acct=None):
-  """ConvTranspose3d k=7 s=2 dgrad through crn_convt7_tc_dgrad."""
+def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st, acct=None, fn="crn_convt7_tc_dgrad"):
+  """ConvTranspose3d k=7 s=2 dgrad through crn_convt7_tc_dgrad (or the jz-stacked crn_convt7_tcs_dgrad)."""
   if NCU_PICK is not None and NCU_PICK("dgrad_tc", layer.name):
-    return _ncu_bracket("crn_convt7_tc_dgrad", (C.byref(d), dy, wtc, dx, status, st))
+    return _ncu_bracket(fn, (C.byref(d), dy, wtc, dx, status, st))
   if PROFILE is None:
-    _lib.call("crn_convt7_tc_dgrad", C.byref(d), dy, wtc, dx, status, st)
+    _lib.call(fn, C.byref(d), dy, wtc, dx, status, st)
     return
   e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
   e0.record()
-  _lib.call("crn_convt7_tc_dgrad", C.byref(d), dy, wtc, dx, status, st)
+  _lib.call(fn, C.byref(d), dy, wtc, dx, status, st)
   e1.record()
   PROFILE.append(("dgrad_tc", layer.name, conv_macs(acct or d), e0, e1))
 
@@ -503,6 +505,15 @@ class Engine:
           fwd=t.zeros(lib.crn_tct_packed_floats(mid, cp, 0), dtype=t.float32, device=dev),
           dgrad=t.zeros(lib.crn_tct_packed_floats(mid, cp, 1), dtype=t.float32, device=dev))
       self.tct_w.pop(l.name, None)
+    # transposed-conv dgrad with the jz taps stacked into N (csrc/conv_tc5s.cu, KT = 4): Cin <= 32, Cout % 4 == 0
+    self.tcts_wd = {}
+    if USE_TC and USE_TCTS:
+      for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
+        l = self.L[f"stage_{stage}.t1"]
+        co = self.rows_pad[l.name]["cp"] if l.name in self.rows_pad else t_out
+        if l.k == (7, 7, 7) and g % 16 == 0 and mid % 4 == 0 and mid <= 32 and co % 4 == 0 and (
+            l.name in self.rows_pad or self.tct_w.get(l.name, (None, None))[1] is not None):
+          self.tcts_wd[l.name] = (t.zeros(lib.crn_tcts_packed_floats(co), dtype=t.float32, device=dev), co)
     # wide layers (>= 32 channels on both sides): implicit-GEMM forward / dgrad (csrc/conv_gemm_tc.cu) and weight
     # gradient (csrc/conv_wgrad_tc.cu) on tcgen05
     self.gt_w = {}
@@ -670,6 +681,10 @@ class Engine:
           rp["b"][:l.cout].copy_(P[l.name + ".bias"])
           _call("crn_tct_pack", rp["w"].data_ptr(), l.cin, rp["cp"], 0, rp["fwd"].data_ptr(), _lib.stream_ptr())
           _call("crn_tct_pack", rp["w"].data_ptr(), l.cin, rp["cp"], 1, rp["dgrad"].data_ptr(), _lib.stream_ptr())
+        if l.name in self.tcts_wd:
+          wsrc = self.rows_pad[l.name]["w"] if l.name in self.rows_pad else P[l.name + ".weight"]
+          buf, co = self.tcts_wd[l.name]
+          _call("crn_tcts_pack", wsrc.data_ptr(), l.cin, co, buf.data_ptr(), _lib.stream_ptr())
         if l.name in self.tct_w:
           for dg, wt in enumerate(self.tct_w[l.name]):
             if wt is not None:
@@ -1180,7 +1195,11 @@ class Plan:
           _call("crn_spatial_mean_fwd", cmap.gp, B, hw * hw, cmap.cs, ssum.data_ptr(), st)
           ssum.mul_(float(hw * hw))
       wgrad(lt, d_t, sd["z2"].p, dy_ptr)
-      if stage == 6 and sd["rows"] is not None:
+      if lt.name in eng.tcts_wd:
+        d_dg = sd["d_t_rows"] if (stage == 6 and sd["rows"] is not None) else d_t
+        convt7_tc_dgrad_call(lt, d_dg, dy_ptr, eng.tcts_wd[lt.name][0].data_ptr(), sd["z2"].gp,
+                             eng.tc_status.data_ptr(), st, acct=d_t, fn="crn_convt7_tcs_dgrad")
+      elif stage == 6 and sd["rows"] is not None:
         convt7_tc_dgrad_call(lt, sd["d_t_rows"], dy_ptr, sd["rows"]["dgrad"].data_ptr(), sd["z2"].gp,
                              eng.tc_status.data_ptr(), st, acct=d_t)
       elif USE_TC and eng.tct_w.get(lt.name, (None, None))[1] is not None:

@@ -385,6 +385,16 @@ int crn_convt7_wgrad_line_supported(const crn_conv_desc* d);
 int crn_convt7_wgrad_line(const crn_conv_desc* d, const float* x, const float* dy, float* dw_packed, int32_t* status,
                           void* stream);
 
+/* dgrad of ConvTranspose3d k=7 s=2 p=3 for Cin <= 32, Cout % 4 == 0 with the four jz taps STACKED INTO N (one staged
+ * plane of the class-channel view of dy feeds the accumulators of four coarse output planes: N = 4 x 32 per
+ * tcgen05.mma instead of 32; same idea as crn_conv5_tcs2).  Weights packed by crn_tcts_pack
+ * (crn_tcts_packed_floats(Cout) floats).  Coarse grid must tile by 8 (x) x 16 (y) x 4 (z).
+ * (model/reconstruction_decoder.py:85,93 backward.) */
+int64_t crn_tcts_packed_floats(int32_t Cout);
+int crn_tcts_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream);
+int crn_convt7_tcs_dgrad(const crn_conv_desc* d, const float* dy, const float* wtc, float* dx, int32_t* status,
+                         void* stream);
+
 /* Fused Adam step over a flat list (state.py:65-66) — next-row (f2) op. */
 int crn_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, float grad_scale, void* stream);

@@ -519,6 +519,36 @@ def test_conv_transpose7_dgrad_tcgen05(n, cin, cout, dhw):
   assert rel_err(got, ref) < 2e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw", [(1, 8, 4, (8, 16, 8)), (1, 32, 16, (8, 16, 16)), (2, 20, 8, (4, 16, 8)),
+                                              (1, 16, 16, (12, 32, 16)), (1, 12, 4, (4, 16, 8))])
+def test_conv_transpose7_dgrad_stacked_tcgen05(n, cin, cout, dhw):
+  """crn_convt7_tcs_dgrad (jz taps stacked into N, Cin <= 32) against torch fp64 and against the un-stacked kernel."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 11 + cout + 3)
+  wt = t.randn(cin, cout, 7, 7, 7, generator=g) * 0.05
+  dy = t.randn(n, cout, 2 * d, 2 * h, 2 * w, generator=g)
+  ref = F.conv3d(dy.double(), wt.double(), None, stride=2, padding=3)
+  r4 = lambda c: (c + 3) // 4 * 4
+  ycs = r4(cout) + 4
+  dyin = t.zeros(n * 8 * d * h * w, ycs, device=dev())
+  dyin[:, :cout] = dy.permute(0, 2, 3, 4, 1).reshape(-1, cout).to(dev())
+  out = t.full((n * d * h * w, r4(cin) + 4), float("nan"), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tcts_packed_floats(cout), device=dev())
+  st = _lib.stream_ptr()
+  wd = wt.to(dev()).contiguous()
+  _lib.call("crn_tcts_pack", wd.data_ptr(), cin, cout, wtc.data_ptr(), st)
+  desc = ops.make_desc(n, cin, cout, (d, h, w), (2 * d, 2 * h, 2 * w), (7, 7, 7), 2, 3, True, r4(cin) + 4, ycs)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  _lib.call("crn_convt7_tcs_dgrad", C.byref(desc), dyin.data_ptr(), wtc.data_ptr(), out.data_ptr(), status.data_ptr(), st)
+  t.cuda.synchronize()
+  assert int(status) == 0
+  assert bool(t.isnan(out[:, r4(cin):]).all()), "columns outside the layer's slice must stay untouched"
+  got = out[:, :cin].reshape(n, d, h, w, cin).permute(0, 4, 1, 2, 3)
+  assert rel_err(got, ref) < 2e-5
+
+
 def test_linear():
   from corenet_b200 import ops
   g = t.Generator().manual_seed(5)
