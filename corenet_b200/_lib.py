@@ -108,6 +108,9 @@ _SIGS = {
     "crn_tct_pack": ([vp, i32, i32, i32, vp, vp], i32),
     "crn_convt7_tc_dgrad": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_convt7_tc": ([_P(ConvDesc), vp, vp, vp, vp, vp, vp], i32),
+    "crn_tctsf_packed_floats": ([i32], i64),
+    "crn_tctsf_pack": ([vp, i32, i32, vp, vp], i32),
+    "crn_convt7_tcs_fwd": ([_P(ConvDesc), vp, vp, vp, vp, vp, vp], i32),
     "crn_tcts_packed_floats": ([i32], i64),
     "crn_tcts_pack": ([vp, i32, i32, vp, vp], i32),
     "crn_convt7_tcs_dgrad": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),

@@ -349,29 +349,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
           const int q = z0 - HLO + r;
           if (q >= 0 && q < p.D) {
             uint8_t* dst = ring + slot * PLANE_BYTES;
-            for (int u = pt; u < YS * XS * 2; u += 128) {
-              const int kc = u & 1; const int v = u >> 1;
-              const int xs = v % XS, ys = v / XS;
-              const int y = y0 - HLO + ys, x = x0 - HLO + xs;
-              const int k = pass * 8 + kc * 4;
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
-                long long off;
-                if constexpr (GATH) {                // class channel k = (cls, co) lives at fine voxel 2i + cls
-                  const int cls = k / p.cout_cls, co = k - cls * p.cout_cls;
-                  off = ((((long long)n * (2 * p.D) + 2 * q + (cls >> 2)) * (2 * p.H) + 2 * y + ((cls >> 1) & 1)) *
-                             (2 * p.W) + 2 * x + (cls & 1)) * p.in_cs + p.in_co + co;
-                } else {
-                  off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
+            // all gathers of this thread are issued before the first split / store: NU independent loads in flight
+            constexpr int NU = (YS * XS * 2 + 127) / 128;
+            float4 a[NU];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+              const int u = pt + i * 128;
+              a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (u < YS * XS * 2) {
+                const int kc = u & 1; const int v = u >> 1;
+                const int xs = v % XS, ys = v / XS;
+                const int y = y0 - HLO + ys, x = x0 - HLO + xs;
+                const int k = pass * 8 + kc * 4;
+                if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
+                  long long off;
+                  if constexpr (GATH) {              // class channel k = (cls, co) lives at fine voxel 2i + cls
+                    const int cls = k / p.cout_cls, co = k - cls * p.cout_cls;
+                    off = ((((long long)n * (2 * p.D) + 2 * q + (cls >> 2)) * (2 * p.H) + 2 * y + ((cls >> 1) & 1)) *
+                               (2 * p.W) + 2 * x + (cls & 1)) * p.in_cs + p.in_co + co;
+                  } else {
+                    off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
+                  }
+                  a[i] = __ldg(reinterpret_cast<const float4*>(p.in + off));
                 }
-                a = __ldg(reinterpret_cast<const float4*>(p.in + off));
               }
-              float4 hi, lo;
-              tc::split_tf32(a.x, hi.x, lo.x); tc::split_tf32(a.y, hi.y, lo.y);
-              tc::split_tf32(a.z, hi.z, lo.z); tc::split_tf32(a.w, hi.w, lo.w);
-              const int o = kc * CHUNK_BYTES + v * 16;
-              *reinterpret_cast<float4*>(dst + o) = hi;
-              *reinterpret_cast<float4*>(dst + PART_BYTES + o) = lo;
+            }
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+              const int u = pt + i * 128;
+              if (u < YS * XS * 2) {
+                const int kc = u & 1; const int v = u >> 1;
+                float4 hi, lo;
+                tc::split_tf32(a[i].x, hi.x, lo.x); tc::split_tf32(a[i].y, hi.y, lo.y);
+                tc::split_tf32(a[i].z, hi.z, lo.z); tc::split_tf32(a[i].w, hi.w, lo.w);
+                const int o = kc * CHUNK_BYTES + v * 16;
+                *reinterpret_cast<float4*>(dst + o) = hi;
+                *reinterpret_cast<float4*>(dst + PART_BYTES + o) = lo;
+              }
             }
             tc::fence_async_smem();
           }

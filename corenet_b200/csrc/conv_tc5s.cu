@@ -52,7 +52,8 @@ struct TC5SParams {
   const float* in; const float* wtc; const float* bias; float* out; int* status;
   int N, D, H, W, gK, gN, in_cs, in_co, out_cs, out_co, P;
   int tiles_x, tiles_y, tiles_z, nitems;
-  int cout_cls;            // GATH: channels per parity class of the fine gradient (K = 8 * cout_cls)
+  int cout_cls;            // GATH / SCAT: channels per parity class of the fine grid (K resp. N = 8 * cout_cls)
+  int planar;              // SCAT: out is [N, Cout, 2D, 2H, 2W] instead of channels-last rows
 };
 
 struct __align__(8) Barriers {
@@ -72,7 +73,9 @@ __device__ __forceinline__ void decode_item(const TC5SParams& p, int item, int& 
 
 // GATH: dgrad of ConvTranspose3d k=7 s=2 p=3 -- K = 8 * cout_cls class channels gathered from the fine gradient
 // (class channel (c, co) of coarse voxel i is dY[2i + c][co]), 4^3 taps at offsets -2..1, N = Cin (conv_tc5.cu GATH).
-template <bool WIDE, int KT, bool GATH>
+// SCAT: forward of that layer for 8 * Cout <= 16 class columns (the FG_BG logits layer, Cout = 2): 4^3 taps at offsets
+// -1..2 on the coarse input, the epilogue scatters column (class, co) of coarse voxel i to fine voxel 2i + class.
+template <bool WIDE, int KT, bool GATH, bool SCAT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams p) {
   constexpr int NOUT = WIDE ? 32 : 16;             // output channels held per plane
   constexpr int HLO = (KT == 5 || GATH) ? 2 : 1;   // most negative tap offset
@@ -135,6 +138,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
         }
       }
       if (dead) break;
+      if constexpr (SCAT) {
+        const int OH = 2 * p.H, OW = 2 * p.W;
+        const long long oS = (long long)(2 * p.D) * OH * OW;
+#pragma unroll
+        for (int zz = 0; zz < ZT; ++zz) {
+          if (p.planar && p.cout_cls == 2) {
+            // px = 0 / 1 classes of a coarse voxel are neighbouring fine voxels of a plane row: 8-byte stores
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {                      // qd = pz * 2 + py
+              const int oz = 2 * (z0 + zz) + (qd >> 1), oy = 2 * y + (qd & 1);
+              const long long sp = ((long long)oz * OH + oy) * OW + 2 * x;
+#pragma unroll
+              for (int co = 0; co < 2; ++co) {
+                const float b = p.bias ? __ldg(p.bias + co) : 0.f;
+                *reinterpret_cast<float2*>(p.out + ((long long)n * 2 + co) * oS + sp) =
+                    make_float2(sum[zz][qd * 4 + co] + b, sum[zz][qd * 4 + 2 + co] + b);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (e >= p.gN) continue;
+              const int cls = e / p.cout_cls, co = e - cls * p.cout_cls;
+              const int oz = 2 * (z0 + zz) + (cls >> 2), oy = 2 * y + ((cls >> 1) & 1), ox = 2 * x + (cls & 1);
+              const long long sp = ((long long)oz * OH + oy) * OW + ox;
+              float* dst = p.planar ? p.out + ((long long)n * p.cout_cls + co) * oS + sp
+                                    : p.out + ((long long)n * oS + sp) * p.out_cs + p.out_co + co;
+              *dst = sum[zz][e] + (p.bias ? __ldg(p.bias + co) : 0.f);
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int zz = 0; zz < ZT; ++zz) {
         const long long pos = (((long long)n * p.D + (z0 + zz)) * p.H + y) * p.W + x;
@@ -150,6 +185,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
             *reinterpret_cast<float4*>(dst + c) = o;
           }
         }
+      }
       }
     }
   } else if (warp < 8) {
@@ -394,19 +430,49 @@ __global__ void tcts_pack_kernel(const float* __restrict__ w, int Cin, int Cout,
   }
 }
 
-template <bool WIDE, int KT = 5, bool GATH = false>
+// forward class weights of ConvTranspose3d [Cin][Cout][7][7][7] with 8 * Cout <= 16 in the stacked ND16 layout:
+//   K = ci, N column n = class * Cout + co, tap j <-> input offset j - 1 per axis, filter index k = c + 5 - 2*j
+__global__ void tctsf_pack_kernel(const float* __restrict__ w, int Cin, int Cout, int P, float* __restrict__ out) {
+  const long long total = (long long)P * 16 * 2 * 4 * 16 * 4;      // (pass, jy, jx, kc, jz, n, e)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 3); long long r = i >> 2;
+    const int n = (int)(r & 15); r >>= 4;
+    const int jz = (int)(r & 3); r >>= 2;
+    const int kc = (int)(r & 1); r >>= 1;
+    const int jx = (int)(r & 3); r >>= 2;
+    const int jy = (int)(r & 3); const int pass = (int)(r >> 2);
+    const int ci = pass * 8 + kc * 4 + e;
+    float v = 0.f;
+    if (ci < Cin && n < 8 * Cout) {
+      const int cls = n / Cout, co = n - cls * Cout;
+      const int kz = (cls >> 2) + 5 - 2 * jz, ky = ((cls >> 1) & 1) + 5 - 2 * jy, kx = (cls & 1) + 5 - 2 * jx;
+      if ((unsigned)kz < 7u && (unsigned)ky < 7u && (unsigned)kx < 7u)
+        v = w[(((long long)ci * Cout + co) * 7 + kz) * 49 + ky * 7 + kx];
+    }
+    float hi, lo;
+    tc::split_tf32(v, hi, lo);
+    const long long kcb = (((long long)pass * 4 + jy) * 4 + jx) * (Geo<4>::TAP_BYTES / 4) +
+                          (long long)kc * (Geo<4>::KC_BYTES / 4);
+    const long long row0 = kcb + ((long long)(3 - jz) * BLK + n) * 4 + e;              // region 0
+    const long long row1 = row0 + (long long)Geo<4>::SROWS * 4;                       // region 1
+    out[row0] = hi; out[row0 + NP * 4] = lo;
+    out[row1] = hi; out[row1 + NP * 4] = 0.f;
+  }
+}
+
+template <bool WIDE, int KT = 5, bool GATH = false, bool SCAT = false>
 int launch_tc5s(const TC5SParams& p, cudaStream_t st) {
   const size_t smem = (size_t)Geo<KT>::NSLOT * PLANE_BYTES + (size_t)WSTAGES * Geo<KT>::WROW_BYTES + sizeof(Barriers) + 64;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc5s_kernel<WIDE, KT, GATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc5s_kernel<WIDE, KT, GATH, SCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       crn_set_error("conv_tc5s: cannot set %zu bytes of dynamic shared memory", smem);
       return CRN_ERR_LAUNCH;
     }
     configured = true;
   }
   const int grid = p.nitems < kNumSMs ? p.nitems : kNumSMs;
-  conv_tc5s_kernel<WIDE, KT, GATH><<<grid, NTHREADS, smem, st>>>(p);
+  conv_tc5s_kernel<WIDE, KT, GATH, SCAT><<<grid, NTHREADS, smem, st>>>(p);
   CRN_LAUNCH_CHECK("conv_tc5s");
   return CRN_OK;
 }
@@ -428,6 +494,42 @@ extern "C" int crn_tcts_pack(const float* w, int32_t Cin, int32_t Cout, float* o
   tcts_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cin, Cout, Cin > 16 ? 1 : 0, P, out);
   CRN_LAUNCH_CHECK("tcts_pack");
   return CRN_OK;
+}
+
+// ---- forward of ConvTranspose3d k=7 s=2 p=3 with 8 * Cout <= 16 (the FG_BG logits layer), jz taps stacked into N
+extern "C" int64_t crn_tctsf_packed_floats(int32_t Cin) { return (int64_t)((Cin + 7) / 8) * 4 * (Geo<4>::WROW_BYTES / 4); }
+
+extern "C" int crn_tctsf_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream) {
+  CRN_REQUIRE(w && out && Cout > 0 && Cin > 0 && 8 * Cout <= 16, "crn_tctsf_pack: Cout <= 2");
+  const int P = (Cin + 7) / 8;
+  cudaMemsetAsync(out, 0, (size_t)crn_tctsf_packed_floats(Cin) * 4, crn_stream(stream));   // rows 16..31 of WIDE slots unused
+  const long long total = (long long)P * 16 * 2 * 4 * 16 * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  tctsf_pack_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(w, Cin, Cout, P, out);
+  CRN_LAUNCH_CHECK("tctsf_pack");
+  return CRN_OK;
+}
+
+extern "C" int crn_convt7_tcs_fwd(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
+                                  int32_t* status, void* stream) {
+  CRN_REQUIRE(d && x && wtc && y && status, "crn_convt7_tcs_fwd: null pointer");
+  CRN_REQUIRE(d->transposed && d->kD == 7 && d->kH == 7 && d->kW == 7 && d->stride == 2 && d->pad == 3,
+              "crn_convt7_tcs_fwd: only ConvTranspose3d k=7 s=2 p=3");
+  CRN_REQUIRE(d->oD == 2 * d->iD && d->oH == 2 * d->iH && d->oW == 2 * d->iW, "crn_convt7_tcs_fwd: output must be 2x input");
+  CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % ZT == 0 && d->iD >= 4,
+              "crn_convt7_tcs_fwd: input grid must tile by 8x16x4");
+  CRN_REQUIRE(!d->bias_n_stride && d->Cin % 4 == 0 && d->x_cs % 4 == 0 && d->x_co % 4 == 0 && 8 * d->Cout <= 16,
+              "crn_convt7_tcs_fwd: Cin, x strides multiples of 4, Cout <= 2");
+  TC5SParams p{};
+  p.in = x; p.wtc = wtc; p.bias = bias; p.out = y; p.status = status;
+  p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
+  p.gK = d->Cin; p.gN = 8 * d->Cout; p.cout_cls = d->Cout; p.planar = d->y_planar;
+  p.in_cs = d->x_cs; p.in_co = d->x_co; p.out_cs = d->y_cs; p.out_co = d->y_co;
+  p.P = (p.gK + 7) / 8;
+  p.tiles_x = p.W / TX; p.tiles_y = p.H / TY; p.tiles_z = p.D / ZT;
+  p.nitems = p.N * p.tiles_x * p.tiles_y * p.tiles_z;
+  return launch_tc5s<false, 4, false, true>(p, crn_stream(stream));
 }
 
 extern "C" int crn_convt7_tcs_dgrad(const crn_conv_desc* d, const float* dy, const float* wtc, float* dx,

@@ -258,17 +258,17 @@ USE_ROWS_LOGITS = True
 USE_TCTS = True
 
 
-def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None):
-  """ConvTranspose3d k=7 s=2 forward through crn_convt7_tc.  acct: descriptor whose MACs are reported (the launch
-  descriptor may carry zero-padded output channels)."""
+def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None, fn="crn_convt7_tc"):
+  """ConvTranspose3d k=7 s=2 forward through crn_convt7_tc (or the jz-stacked crn_convt7_tcs_fwd).  acct: descriptor
+  whose MACs are reported (the launch descriptor may carry zero-padded output channels)."""
   if NCU_PICK is not None and NCU_PICK("fwd_tc", layer.name):
-    return _ncu_bracket("crn_convt7_tc", (C.byref(d), inp, wtc, bias, out, status, st))
+    return _ncu_bracket(fn, (C.byref(d), inp, wtc, bias, out, status, st))
   if PROFILE is None:
-    _lib.call("crn_convt7_tc", C.byref(d), inp, wtc, bias, out, status, st)
+    _lib.call(fn, C.byref(d), inp, wtc, bias, out, status, st)
     return
   e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
   e0.record()
-  _lib.call("crn_convt7_tc", C.byref(d), inp, wtc, bias, out, status, st)
+  _lib.call(fn, C.byref(d), inp, wtc, bias, out, status, st)
   e1.record()
   PROFILE.append(("fwd_tc", layer.name, conv_macs(acct or d), e0, e1))
 
@@ -514,6 +514,13 @@ class Engine:
         if l.k == (7, 7, 7) and g % 16 == 0 and mid % 4 == 0 and mid <= 32 and co % 4 == 0 and (
             l.name in self.rows_pad or self.tct_w.get(l.name, (None, None))[1] is not None):
           self.tcts_wd[l.name] = (t.zeros(lib.crn_tcts_packed_floats(co), dtype=t.float32, device=dev), co)
+    # forward of the FG_BG logits layer (Cout <= 2) with the jz taps stacked into N (crn_convt7_tcs_fwd)
+    self.tctsf_w = {}
+    if USE_TC and USE_TCTS:
+      stage, cin, mid, t_out, skip_c, enc_c, g = self.dec_plan[-1]
+      l = self.L[f"stage_{stage}.t1"]
+      if l.k == (7, 7, 7) and t_out <= 2 and g % 16 == 0 and mid % 4 == 0:
+        self.tctsf_w[l.name] = t.zeros(lib.crn_tctsf_packed_floats(mid), dtype=t.float32, device=dev)
     # wide layers (>= 32 channels on both sides): implicit-GEMM forward / dgrad (csrc/conv_gemm_tc.cu) and weight
     # gradient (csrc/conv_wgrad_tc.cu) on tcgen05
     self.gt_w = {}
@@ -681,6 +688,9 @@ class Engine:
           rp["b"][:l.cout].copy_(P[l.name + ".bias"])
           _call("crn_tct_pack", rp["w"].data_ptr(), l.cin, rp["cp"], 0, rp["fwd"].data_ptr(), _lib.stream_ptr())
           _call("crn_tct_pack", rp["w"].data_ptr(), l.cin, rp["cp"], 1, rp["dgrad"].data_ptr(), _lib.stream_ptr())
+        if l.name in self.tctsf_w:
+          _call("crn_tctsf_pack", P[l.name + ".weight"].data_ptr(), l.cin, l.cout, self.tctsf_w[l.name].data_ptr(),
+                _lib.stream_ptr())
         if l.name in self.tcts_wd:
           wsrc = self.rows_pad[l.name]["w"] if l.name in self.rows_pad else P[l.name + ".weight"]
           buf, co = self.tcts_wd[l.name]
@@ -1066,7 +1076,10 @@ class Plan:
           _call("crn_rows_to_planar", rows.data_ptr(), B, sd["t_out"], (2 * g) ** 3, rp["cp"], logits.data_ptr(), st)
       else:
         logits = self.logits
-        if USE_TC and eng.tct_w.get(sd["lt"].name, (None, None))[0] is not None:
+        if sd["lt"].name in eng.tctsf_w:
+          convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tctsf_w[sd["lt"].name].data_ptr(), bias(sd["lt"]),
+                         logits.data_ptr(), eng.tc_status.data_ptr(), st, fn="crn_convt7_tcs_fwd")
+        elif USE_TC and eng.tct_w.get(sd["lt"].name, (None, None))[0] is not None:
           convt7_tc_call(sd["lt"], sd["d_t"], sd["z2"].p, eng.tct_w[sd["lt"].name][0].data_ptr(), bias(sd["lt"]),
                          logits.data_ptr(), eng.tc_status.data_ptr(), st)
         else:

@@ -390,6 +390,12 @@ int crn_convt7_wgrad_line(const crn_conv_desc* d, const float* x, const float* d
  * tcgen05.mma instead of 32; same idea as crn_conv5_tcs2).  Weights packed by crn_tcts_pack
  * (crn_tcts_packed_floats(Cout) floats).  Coarse grid must tile by 8 (x) x 16 (y) x 4 (z).
  * (model/reconstruction_decoder.py:85,93 backward.) */
+/* ... and the FORWARD of that layer for Cout <= 2 (the FG_BG logits layer: 8 parity classes x 2 channels = 16
+ * accumulator columns per coarse plane, four planes stacked per tcgen05.mma); y planar [N, Cout, 2D, 2H, 2W] or rows. */
+int64_t crn_tctsf_packed_floats(int32_t Cin);
+int crn_tctsf_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream);
+int crn_convt7_tcs_fwd(const crn_conv_desc* d, const float* x, const float* wtc, const float* bias, float* y,
+                       int32_t* status, void* stream);
 int64_t crn_tcts_packed_floats(int32_t Cout);
 int crn_tcts_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream);
 int crn_convt7_tcs_dgrad(const crn_conv_desc* d, const float* dy, const float* wtc, float* dx, int32_t* status,

@@ -519,6 +519,43 @@ def test_conv_transpose7_dgrad_tcgen05(n, cin, cout, dhw):
   assert rel_err(got, ref) < 2e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw,planar", [(1, 16, 2, (8, 16, 8), True), (2, 16, 2, (4, 32, 16), True),
+                                                     (1, 12, 2, (8, 16, 8), False), (1, 20, 1, (4, 16, 8), True)])
+def test_conv_transpose7_fwd_stacked_tcgen05(n, cin, cout, dhw, planar):
+  """crn_convt7_tcs_fwd (the FG_BG logits layer: Cout <= 2, jz taps stacked into N) against torch fp64."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 5 + cout)
+  wt = t.randn(cin, cout, 7, 7, 7, generator=g) * 0.05
+  bias = t.randn(cout, generator=g)
+  x = t.randn(n, cin, d, h, w, generator=g)
+  ref = F.conv_transpose3d(x.double(), wt.double(), bias.double(), stride=2, padding=3, output_padding=1)
+  r4 = lambda c: (c + 3) // 4 * 4
+  xin = t.zeros(n * d * h * w, r4(cin), device=dev())
+  xin[:, :cin] = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).to(dev())
+  S = 8 * d * h * w
+  ycs = r4(cout) + 4
+  out = t.full((n * cout * S,) if planar else (n * S, ycs), float("nan"), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tctsf_packed_floats(cin), device=dev())
+  st = _lib.stream_ptr()
+  wd, b = wt.to(dev()).contiguous(), bias.to(dev())
+  _lib.call("crn_tctsf_pack", wd.data_ptr(), cin, cout, wtc.data_ptr(), st)
+  desc = ops.make_desc(n, cin, cout, (d, h, w), (2 * d, 2 * h, 2 * w), (7, 7, 7), 2, 3, True, r4(cin), ycs)
+  desc.y_planar = int(planar)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  _lib.call("crn_convt7_tcs_fwd", C.byref(desc), xin.data_ptr(), wtc.data_ptr(), b.data_ptr(), out.data_ptr(),
+            status.data_ptr(), st)
+  t.cuda.synchronize()
+  assert int(status) == 0
+  if planar:
+    got = out.reshape(n, cout, 2 * d, 2 * h, 2 * w)
+  else:
+    got = out[:, :cout].reshape(n, 2 * d, 2 * h, 2 * w, cout).permute(0, 4, 1, 2, 3)
+    assert bool(t.isnan(out[:, cout:]).all()), "columns outside the layer's slice must stay untouched"
+  assert rel_err(got, ref) < 2e-5
+
+
 @pytest.mark.parametrize("n,cin,cout,dhw", [(1, 8, 4, (8, 16, 8)), (1, 32, 16, (8, 16, 16)), (2, 20, 8, (4, 16, 8)),
                                               (1, 16, 16, (12, 32, 16)), (1, 12, 4, (4, 16, 8))])
 def test_conv_transpose7_dgrad_stacked_tcgen05(n, cin, cout, dhw):
