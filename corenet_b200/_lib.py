@@ -65,6 +65,12 @@ _SIGS = {
     "crn_brn_bwd_reduce": ([vp, i32, i32, vp, vp, vp, i32, i32, i64, i32, vp, i32, i32, vp, vp, vp], i32),
     "crn_brn_bwd_dx": ([vp, i32, i32, vp, i32, i32, i64, i32, vp, vp, vp, i32, i32, vp, i32, i32, i32,
                         vp, vp, vp, vp], i32),
+    "crn_brn_fused_supported": ([i64, i32], i32),
+    "crn_brn_nbt_snapshot": ([vp, i32, vp, vp], i32),
+    "crn_brn_fwd_fused": ([vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, i32, vp, i32, vp, i32, i32, vp, vp,
+                           vp], i32),
+    "crn_brn_bwd_fused": ([vp, i32, i32, vp, vp, vp, i32, i32, i64, i32, vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp,
+                           vp, vp], i32),
     "crn_preprocess_image": ([vp, i32, i32, i32, vp, vp], i32),
     "crn_maxpool_fwd": ([vp, i32, i32, i32, i32, vp, vp, vp], i32),
     "crn_maxpool_bwd": ([vp, vp, i32, i32, i32, i32, vp, vp], i32),

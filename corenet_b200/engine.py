@@ -256,6 +256,8 @@ DETERMINISTIC_SKIP_BWD = True
 USE_ROWS_LOGITS = True
 # ConvTranspose3d k=7 dgrad with Cin <= 32 through the jz-stacked kernel (crn_convt7_tcs_dgrad)
 USE_TCTS = True
+# BatchRenorm of small maps through the single-launch cluster kernels (csrc/brn_fused.cu)
+USE_FUSED_BRN = True
 
 
 def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None, fn="crn_convt7_tc"):
@@ -761,11 +763,24 @@ class BRNOp:
     self.acc = plan.slot("fwd", 3 * C_)
     self.bacc = plan.slot("bwd", 2 * C_)
     self.dxsum = plan.slot("bwd", C_)
+    # small maps: statistics + coefficients + apply (and reduce + dx) in ONE launch each (csrc/brn_fused.cu)
+    self.fused = bool(USE_FUSED_BRN and _lib.lib().crn_brn_fused_supported(x.rows, C_) and x.cs % 4 == 0
+                      and y.cs % 4 == 0)
+    self.snap_index = plan.register_fused_brn(self) if self.fused else -1
 
   def fwd(self, training):
     P, Bf = self.plan.eng.tensors()
     st = _lib.stream_ptr()
     n, x = self.name, self.x
+    if self.fused:
+      _call("crn_brn_fwd_fused", x.p, x.rows, self.C, x.cs, 0, int(self.relu_in), P[n + ".weight"].data_ptr(),
+            P[n + ".bias"].data_ptr(), Bf[n + ".running_mean"].data_ptr(), Bf[n + ".running_var"].data_ptr(),
+            self.plan.nbt_snapshot.data_ptr() + 8 * self.snap_index if training else None, BRN_EPS, BRN_MOMENTUM,
+            int(training), self.res.p if self.res is not None else None, int(self.relu_out), self.y.p, self.y.cs, 0,
+            self.y_pre.p if self.y_pre is not None else None, self.coef.data_ptr(), st,
+            hbm=("brn_fwd_fused", (12 + (4 if self.res is not None else 0) + (4 if self.y_pre is not None else 0))
+                 * x.rows * self.C))
+      return
     if training:
       _call("crn_brn_stats", x.p, x.rows, self.C, x.cs, 0, int(self.relu_in), self.acc.data_ptr(), st)
     _call("crn_brn_finalize", self.acc.data_ptr(), x.rows, self.C, P[n + ".weight"].data_ptr(),
@@ -786,6 +801,12 @@ class BRNOp:
     g_out = g_store_ptr
     if g_out is None and (self.relu_out or g_extra_ptr is not None):
       g_out = dy_ptr
+    if self.fused:
+      _call("crn_brn_bwd_fused", dy_ptr, dy_cs, 0, self.y.p if self.relu_out else None, g_extra_ptr, x.p, x.cs, 0,
+            x.rows, self.C, self.coef.data_ptr(), int(self.relu_in), int(self.relu_out), int(training), g_out, dx_ptr,
+            dx_cs, 0, 0, grads[n + ".weight"].data_ptr(), grads[n + ".bias"].data_ptr(), self.dxsum.data_ptr(), st,
+            hbm=("brn_bwd_fused", 28 * x.rows * self.C))
+      return self.dxsum
     _call("crn_brn_bwd_reduce", dy_ptr, dy_cs, 0, self.y.p if self.relu_out else None, g_extra_ptr, x.p,
           x.cs, 0, x.rows, self.C, self.coef.data_ptr(), int(self.relu_in), int(self.relu_out), g_out,
           self.bacc.data_ptr(), st)
@@ -804,6 +825,7 @@ class Plan:
     self.dev = eng.dev
     self.busy = False
     self._n = {"fwd": 0, "bwd": 0}
+    self.fused_brn = []    # BRNOp instances on the single-launch path, in construction order (encoder first)
     self.rows_cp = 0       # > 0: the logits layer works on channels-last rows of this pitch (see Engine.rows_pad)
     self._build()
     self.arena_fwd = t.zeros(max(self._n["fwd"], 1), dtype=t.float64, device=self.dev)
@@ -822,6 +844,24 @@ class Plan:
 
   def f32(self, n):
     return t.zeros(n, dtype=t.float32, device=self.dev)
+
+  def register_fused_brn(self, op) -> int:
+    self.fused_brn.append(op)
+    return len(self.fused_brn) - 1
+
+  def _snapshot_nbt(self, lo, hi):
+    """ONE launch: copies num_batches_tracked of the fused BatchRenorm instances [lo, hi) into the plan's snapshot
+    array and increments the originals (batch_renorm.py:58); the pointer list is cached per buffer set."""
+    if hi <= lo:
+      return
+    _, Bf = self.eng.tensors()
+    ptrs = tuple(Bf[op.name + ".num_batches_tracked"].data_ptr() for op in self.fused_brn[lo:hi])
+    cache = self.__dict__.setdefault("_nbt_cache", {})
+    ent = cache.get((lo, hi))
+    if ent is None or ent[0] != ptrs:
+      arr = (C.c_int64 * len(ptrs))(*ptrs)
+      ent = cache[(lo, hi)] = (ptrs, self.eng._to_dev(arr, self.dev))
+    _call("crn_brn_nbt_snapshot", ent[1].data_ptr(), hi - lo, self.nbt_snapshot.data_ptr() + 8 * lo, _lib.stream_ptr())
 
   def slot(self, which, n):
     s = Slot(self, which, self._n[which], n)
@@ -934,6 +974,8 @@ class Plan:
           self.rows_cp = cp
       self.stages.append(st)
     self.scratch64 = t.zeros(4096, dtype=t.float64, device=self.dev)
+    self.nbt_snapshot = t.zeros(max(len(self.fused_brn), 1), dtype=t.int64, device=self.dev)
+    self.n_fused_enc = sum(1 for op in self.fused_brn if op.name.startswith("encoder."))
     self.offs = t.zeros(B, 3, dtype=t.float32, device=self.dev)
     res = eng.model.config.decoder.resolution
     self.logits = t.zeros(B, eng.model.config.decoder.num_output_channels, *res, dtype=t.float32, device=self.dev)
@@ -971,6 +1013,8 @@ class Plan:
   def _forward_encoder(self, image, training, P, bias, st):
     eng, B = self.eng, self.B
     # ---- encoder
+    if training:
+      self._snapshot_nbt(0, self.n_fused_enc)
     _call("crn_preprocess_image", image.data_ptr(), B, 256, 256, self.img4.p, st)
     conv_call("fwd", eng.L["stem"], self.d_stem, self.img4.p, eng.wf(eng.L["stem"]), bias(eng.L["stem"]),
               self.s1.p, 0, st)
@@ -995,6 +1039,8 @@ class Plan:
   def _forward_decoder(self, v2s, offsets, training, P, bias, st, rows_logits=False):
     eng, B = self.eng, self.B
     # ---- decoder
+    if training:
+      self._snapshot_nbt(self.n_fused_enc, len(self.fused_brn))
     L = eng.L
     lat = eng.lat
     conv_call("fwd", L["stage_0"], self.d_s0, self.feat.p, eng.wf(L["stage_0"]), bias(L["stage_0"]),

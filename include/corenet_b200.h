@@ -151,6 +151,25 @@ int crn_brn_bwd_dx(const float* g, int32_t g_cs, int32_t g_co, const float* x, i
                    int32_t dx_cs, int32_t dx_co, int32_t dx_accumulate, float* dweight,
                    float* dbias, double* dxsum, void* stream);
 
+/* Single-launch forms for SMALL activations (rows * C <= 5 Mi elements, C % 8 == 0: the 53 encoder instances and
+ * the coarse decoder stages at the training batch size): a thread-block cluster owns 8 channels, reduces in a fixed
+ * order through distributed shared memory (no atomics: bit-reproducible statistics), derives the coefficients and
+ * applies them in the same launch; backward = reduce + dx in one launch.  Same arithmetic and the same coef[6*C] as
+ * crn_brn_finalize.  Because blocks of a launch may start after others finished, num_batches_tracked is not touched
+ * here: crn_brn_nbt_snapshot(counters[n] (device array of pointers), n, snapshot[n]) copies the counters of all fused
+ * instances of a forward pass and increments the originals in ONE launch; crn_brn_fwd_fused reads its snapshot entry.
+ * dxsum (double[C]) is WRITTEN (not accumulated). */
+int crn_brn_fused_supported(int64_t rows, int32_t C);
+int crn_brn_nbt_snapshot(int64_t* const* counters, int32_t n, int64_t* snapshot, void* stream);
+int crn_brn_fwd_fused(const float* x, int64_t rows, int32_t C, int32_t x_cs, int32_t x_co, int32_t relu_in,
+                      const float* weight, const float* bias, float* running_mean, float* running_var,
+                      const int64_t* nt_snapshot, float eps, float momentum, int32_t training, const float* res,
+                      int32_t relu_out, float* y, int32_t y_cs, int32_t y_co, float* y_pre, float* coef, void* stream);
+int crn_brn_bwd_fused(const float* dy, int32_t dy_cs, int32_t dy_co, const float* y_act, const float* g_extra,
+                      const float* x, int32_t x_cs, int32_t x_co, int64_t rows, int32_t C, const float* coef,
+                      int32_t relu_in, int32_t relu_out, int32_t training, float* g_out, float* dx, int32_t dx_cs,
+                      int32_t dx_co, int32_t dx_accumulate, float* dweight, float* dbias, double* dxsum, void* stream);
+
 /* ------------------------------------------------------------------------
  * Small encoder ops (model/resnet50.py:134-140,176-204).
  * ---------------------------------------------------------------------- */

@@ -632,6 +632,88 @@ def test_batch_renorm(shape, training, nbt):
 
 
 # ---------------------------------------------------------------------------- small encoder ops
+@pytest.mark.parametrize("rows,c,relu_in,relu_out,res,training,nbt", [
+    (4 * 64 * 64, 64, 0, 1, 0, 1, 0), (4 * 16 * 16, 1024, 0, 1, 1, 1, 50000), (256, 2048, 0, 0, 0, 1, 12000),
+    (2048, 224, 1, 0, 0, 1, 0), (1000, 8, 1, 1, 1, 1, 7000), (4 * 32 * 32, 512, 0, 1, 1, 0, 0), (77, 16, 0, 0, 0, 1, 3)])
+def test_batch_renorm_fused_matches_three_kernel_path(rows, c, relu_in, relu_out, res, training, nbt):
+  """csrc/brn_fused.cu (one launch per direction, cluster-owned channels, no atomics) against the stats / finalize /
+  apply and reduce / dx kernels of csrc/brn.cu on the same inputs, plus run-to-run bit reproducibility."""
+  from corenet_b200 import _lib
+  lib = _lib.lib()
+  assert lib.crn_brn_fused_supported(rows, c)
+  d = dev()
+  g = t.Generator().manual_seed(rows + c)
+  cs = c + 8                                     # rows wider than the channel slice
+  x = (t.randn(rows, cs, generator=g) * 2 + 0.5).to(d)
+  resid = t.randn(rows, cs, generator=g).to(d) if res else None
+  w, b = (t.rand(c, generator=g) + 0.5).to(d), t.randn(c, generator=g).to(d)
+  rm0, rv0 = t.randn(c, generator=g).to(d) * 0.1, (t.rand(c, generator=g) + 0.5).to(d)
+  dy = t.randn(rows, cs, generator=g).to(d)
+  gex = t.randn(rows, cs, generator=g).to(d) if res else None
+  st = _lib.stream_ptr()
+  eps, mom = 1e-3, 0.01
+
+  def ptr(v):
+    return v.data_ptr() if v is not None else None
+
+  def run(fused):
+    rm, rv = rm0.clone(), rv0.clone()
+    cnt = t.tensor(nbt, dtype=t.int64, device=d)
+    coef = t.zeros(6 * c, device=d)
+    y = t.full((rows, cs), float("nan"), device=d)
+    ypre = t.full((rows, cs), float("nan"), device=d) if res else None
+    acc = t.zeros(3 * c, dtype=t.float64, device=d)
+    if fused:
+      snap = t.zeros(1, dtype=t.int64, device=d)
+      if training:
+        plist = t.tensor([cnt.data_ptr()], dtype=t.int64, device=d)
+        _lib.call("crn_brn_nbt_snapshot", plist.data_ptr(), 1, snap.data_ptr(), st)
+      _lib.call("crn_brn_fwd_fused", x.data_ptr(), rows, c, cs, 0, relu_in, w.data_ptr(), b.data_ptr(), rm.data_ptr(),
+                rv.data_ptr(), snap.data_ptr() if training else None, eps, mom, training, ptr(resid), relu_out,
+                y.data_ptr(), cs, 0, ptr(ypre), coef.data_ptr(), st)
+    else:
+      if training:
+        _lib.call("crn_brn_stats", x.data_ptr(), rows, c, cs, 0, relu_in, acc.data_ptr(), st)
+      _lib.call("crn_brn_finalize", acc.data_ptr(), rows, c, w.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                cnt.data_ptr(), eps, mom, training, coef.data_ptr(), st)
+      _lib.call("crn_brn_apply", x.data_ptr(), rows, c, cs, 0, coef.data_ptr(), ptr(resid), relu_in, relu_out,
+                y.data_ptr(), cs, 0, ptr(ypre), st)
+    # backward
+    gout = t.full((rows, cs), float("nan"), device=d) if (relu_out or res) else None
+    dx = t.full((rows, cs), float("nan"), device=d)
+    dw, db = t.zeros(c, device=d), t.zeros(c, device=d)
+    dxsum = t.zeros(c, dtype=t.float64, device=d)
+    bacc = t.zeros(2 * c, dtype=t.float64, device=d)
+    if fused:
+      _lib.call("crn_brn_bwd_fused", dy.data_ptr(), cs, 0, y.data_ptr() if relu_out else None, ptr(gex), x.data_ptr(),
+                cs, 0, rows, c, coef.data_ptr(), relu_in, relu_out, training, ptr(gout), dx.data_ptr(), cs, 0, 0,
+                dw.data_ptr(), db.data_ptr(), dxsum.data_ptr(), st)
+    else:
+      _lib.call("crn_brn_bwd_reduce", dy.data_ptr(), cs, 0, y.data_ptr() if relu_out else None, ptr(gex), x.data_ptr(),
+                cs, 0, rows, c, coef.data_ptr(), relu_in, relu_out, ptr(gout), bacc.data_ptr(), st)
+      gsrc = gout if gout is not None else dy
+      _lib.call("crn_brn_bwd_dx", gsrc.data_ptr(), cs, 0, x.data_ptr(), cs, 0, rows, c, coef.data_ptr(), bacc.data_ptr(),
+                None, relu_in, training, dx.data_ptr(), cs, 0, 0, dw.data_ptr(), db.data_ptr(), dxsum.data_ptr(), st)
+    t.cuda.synchronize()
+    return dict(y=y[:, :c], ypre=None if ypre is None else ypre[:, :c], coef=coef, rm=rm, rv=rv, cnt=int(cnt),
+                gout=None if gout is None else gout[:, :c], dx=dx[:, :c], dw=dw, db=db, dxsum=dxsum,
+                pad=(y[:, c:], dx[:, c:]))
+
+  a, b1, b2 = run(False), run(True), run(True)
+  assert a["cnt"] == b1["cnt"] == nbt + (1 if training else 0)
+  for k in ("y", "ypre", "coef", "rm", "rv", "gout", "dx", "dw", "db", "dxsum"):
+    if a[k] is None:
+      continue
+    tol = 2e-5 if k in ("dx", "dw", "db") else 5e-6
+    if k == "dxsum":      # column sums of dx cancel to ~0 in training mode: compare against the scale of the summands
+      scale = a["dx"].double().abs().sum(0)
+      assert bool(((b1[k] - a[k]).abs() <= 1e-5 * scale + 1e-12).all()), k
+    else:
+      assert rel_err(b1[k], a[k]) <= tol, (k, rel_err(b1[k], a[k]))
+    assert t.equal(b1[k], b2[k]), f"{k}: the fused path must be bit-reproducible"
+  assert bool(t.isnan(b1["pad"][0]).all()) and bool(t.isnan(b1["pad"][1]).all()), "pad columns must stay untouched"
+
+
 def test_preprocess_and_maxpool_and_mean():
   from corenet_b200 import _lib
   g = t.Generator().manual_seed(0)
