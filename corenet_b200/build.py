@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + ([] if os.environ.get("CRN_NO_DIAG") == "1" else ["-DCRN_DIAG"])   # diagnostics: include/corenet_b200_diag.h
 
 
 def sources():
@@ -29,7 +29,7 @@ def sources():
 
 def _digest():
   h = hashlib.sha256()
-  for f in sorted(os.listdir(CSRC)) + ["../../include/corenet_b200.h"]:
+  for f in sorted(os.listdir(CSRC)) + ["../../include/corenet_b200.h", "../../include/corenet_b200_diag.h"]:
     p = os.path.join(CSRC, f)
     if os.path.isfile(p):
       h.update(f.encode())

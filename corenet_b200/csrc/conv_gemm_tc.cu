@@ -502,7 +502,10 @@ extern "C" int crn_conv_gemm_tc(const crn_conv_desc* d, int32_t kind, const floa
   return BN == 64 ? launch_gt<64>(p, grid, st) : launch_gt<128>(p, grid, st);
 }
 
+#ifdef CRN_DIAG
+extern "C" int crn_gemm_tc_debug_read(long long* host_dst, int32_t n);
 extern "C" int crn_gemm_tc_debug_read(long long* host_dst, int32_t n) {
   return cudaMemcpyFromSymbol(host_dst, g_gt_dbg, sizeof(long long) * (n > 4096 ? 4096 : n)) == cudaSuccess ? CRN_OK
                                                                                                              : CRN_ERR_LAUNCH;
 }
+#endif  // CRN_DIAG

@@ -2,7 +2,9 @@
 // accumulator.  mode 0: single-pass TF32 (operands truncated by the tensor core), mode 1: 3xTF32 split.
 // Exercises exactly the pieces the conv kernel relies on: no-swizzle K-major smem descriptors, the
 // instruction descriptor, TMEM alloc/ld, tcgen05.commit -> mbarrier.
+#ifdef CRN_DIAG
 #include "common.cuh"
+#include "corenet_b200_diag.h"
 #include "tc_common.cuh"
 
 namespace {
@@ -188,3 +190,4 @@ extern "C" int crn_tc_probe_mn(const float* A, const float* B, float* D, int32_t
   CRN_LAUNCH_CHECK("tc_probe_mn");
   return CRN_OK;
 }
+#endif  // CRN_DIAG

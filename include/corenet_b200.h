@@ -302,16 +302,6 @@ int crn_voxelize_mesh(const float* triangles, const int32_t* tri_mesh, int32_t T
 int crn_merge_mesh_grids(const float* mesh_grids, const int32_t* mesh_scene, const float* labels,
                          int32_t M, int64_t voxels, int32_t* out, void* stream);
 
-/* Bring-up / self-test of the tcgen05 (5th-gen tensor core) path: D[128,N] = A[128,K] * B[N,K]^T with
- * tf32 operands and an fp32 TMEM accumulator; mode 0 = single-pass TF32, 1 = 3xTF32 split.
- * status (device int) is set to 1 if the mbarrier wait timed out. */
-int crn_tc_probe(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode,
-                 int32_t* status, void* stream);
-/* Same for MN-major operands (reduction index slow in memory, the weight-gradient case):
- * D[128,N] = sum_k A[k+shift][m] * B[k][n], A [K+4][128], B [K+4][N]; shift moves the A descriptor by whole rows. */
-int crn_tc_probe_mn(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode, int32_t shift,
-                    int32_t* status, void* stream);
-
 /* Conv3d k=5 s=1 p=2 forward / dgrad on tcgen05 tensor cores (3xTF32, fp32 TMEM accumulators):
  * replaces the cuDNN call behind nn.Conv3d(k=5) at model/reconstruction_decoder.py:66,74,82,91.
  * Weights are pre-split (hi/lo) and packed per 8-channel pass by crn_tc5_pack (w is the PyTorch
@@ -373,9 +363,6 @@ int crn_gemm_tc_pack(const crn_gemm_tc_pack_item* items, const int64_t* offsets,
                      void* stream);
 int crn_conv_gemm_tc(const crn_conv_desc* d, int32_t kind, const float* in, const float* wtc, const float* bias,
                      float* out, int32_t accumulate, int32_t* status, void* stream);
-
-/* Debug: with crn_set_flags bit 8 the kernel stamps a per-CTA clock64 timeline; copies n (<= 4096) int64 to host. */
-int crn_gemm_tc_debug_read(long long* host_dst, int32_t n);
 
 /* Weight gradient of the wide layers on tcgen05 (3xTF32; both operands are MN-major tf32 UMMA operands in the
  * 128B-swizzle / 32B-base layout).  Same contract as crn_conv_wgrad: dWf[tap][ci][co] += sum_rows x * dy, dw zeroed

@@ -6,10 +6,14 @@ import re
 from tests.conftest import ROOT
 
 
-def header_symbols():
-  src = open(os.path.join(ROOT, "include", "corenet_b200.h")).read()
-  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-  return sorted(set(re.findall(r"\b(crn_[a-z0-9_]+)\s*\(", src)))
+def header_symbols(names=("corenet_b200.h", "corenet_b200_diag.h")):
+  """Entry points declared by the boundary header and by the diagnostics header (built with -DCRN_DIAG)."""
+  out = set()
+  for name in names:
+    src = open(os.path.join(ROOT, "include", name)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out |= set(re.findall(r"\b(crn_[a-z0-9_]+)\s*\(", src))
+  return sorted(out)
 
 
 def test_library_exports_every_declared_symbol():
@@ -37,3 +41,9 @@ def test_sass_is_sm100a():
   from corenet_b200 import build
   out = subprocess.run(["cuobjdump", "-lelf", build.LIB_PATH], capture_output=True, text=True).stdout
   assert "sm_100a" in out
+
+
+def test_diagnostics_are_not_in_the_boundary_header():
+  boundary = header_symbols(("corenet_b200.h",))
+  assert not [s for s in boundary if "probe" in s or "debug" in s]
+  assert {"crn_tc_probe", "crn_tc_probe_mn", "crn_gemm_tc_debug_read"} <= set(header_symbols(("corenet_b200_diag.h",)))
