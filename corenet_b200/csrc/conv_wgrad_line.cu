@@ -1078,7 +1078,9 @@ extern "C" int crn_convt7_wgrad_line_supported(const crn_conv_desc* d) {
   if (d->oD != 2 * d->iD || d->oH != 2 * d->iH || d->oW != 2 * d->iW || d->y_planar) return 0;
   if (d->Cin % 4 || d->x_cs % 4 || d->x_co % 4 || d->y_cs % 4 || d->y_co % 4 || d->CoutP % 4) return 0;
   if (d->iD < 3) return 0;
-  if (d->Cin <= 16 && d->Cout <= 4 && d->y_cs == 4 && d->y_co == 0 && d->CoutP == 4 && (d->iW == 64 || d->iW == 32)) return 2;
+  // narrow variant: <= 4 output channels, possibly a 4-channel slice (y_co) of wider gradient rows (y_cs) whose dW
+  // columns land at the same offset of a wider packed row (CoutP): the 15-class logits layer runs as 4 such slices
+  if (d->Cin <= 16 && d->Cout <= 4 && (d->iW == 64 || d->iW == 32)) return 2;
   if (d->Cin > 32 || d->Cout != 16) return 0;
   return d->iW == 32 || d->iW == 16;
 }

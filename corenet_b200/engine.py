@@ -194,7 +194,19 @@ def _wgrad_t7_slices(eng, layer, d, args):
   calls = eng.wl_split.get(key)
   if calls is None:
     calls = []
-    if d.Cin % 32 == 0 and d.Cout % 16 == 0 and d.Cin <= 64 and d.Cout <= 32 and (d.Cin > 32 or d.Cout > 16):
+    if d.Cin <= 16 and 4 < d.Cout <= 16 and d.y_cs % 4 == 0 and d.CoutP % 4 == 0:
+      # the C > 4 logits layer (channels-last gradient rows of pitch y_cs): 4-output-channel slices through the narrow
+      # tap-stacked kernel; pad channels of the last slice carry zero gradient
+      for co0 in range(0, _r4(d.Cout), 4):
+        ds = ConvDesc.from_buffer_copy(bytes(d))
+        ds.Cout, ds.y_co = 4, d.y_co + co0
+        if _lib.lib().crn_convt7_wgrad_line_supported(C.byref(ds)) != 2:
+          calls = []
+          break
+        da = ConvDesc.from_buffer_copy(bytes(ds))       # accounting: the real channels of the slice
+        da.Cout = min(4, d.Cout - co0)
+        calls.append((ds, 4 * co0, da))
+    elif d.Cin % 32 == 0 and d.Cout % 16 == 0 and d.Cin <= 64 and d.Cout <= 32 and (d.Cin > 32 or d.Cout > 16):
       for ci0 in range(0, d.Cin, 32):
         for co0 in range(0, d.Cout, 16):
           ds = ConvDesc.from_buffer_copy(bytes(d))
@@ -202,7 +214,7 @@ def _wgrad_t7_slices(eng, layer, d, args):
           if not _lib.lib().crn_convt7_wgrad_line_supported(C.byref(ds)):
             calls = []
             break
-          calls.append((ds, 4 * (ci0 * d.CoutP + co0)))
+          calls.append((ds, 4 * (ci0 * d.CoutP + co0), ds))
         if not calls:
           break
     eng.wl_split[key] = calls
@@ -210,7 +222,7 @@ def _wgrad_t7_slices(eng, layer, d, args):
     return None
   x, dy, dw, st = args
   status = eng.tc_status.data_ptr()
-  return [("wgrad_tc", "crn_convt7_wgrad_line", (C.byref(ds), x, dy, dw + off, status, st), ds) for ds, off in calls]
+  return [("wgrad_tc", "crn_convt7_wgrad_line", (C.byref(ds), x, dy, dw + off, status, st), da) for ds, off, da in calls]
 
 
 def conv_call(kind, layer, d, *args):

@@ -385,6 +385,39 @@ def test_convt7_wgrad_line_tcgen05(n, cin, cout, dhw, ycs):
   assert rel_err(dw[:, :, :cout], ref) < 5e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,dhw", [(1, 16, 15, (4, 5, 64)), (2, 12, 7, (3, 6, 32))])
+def test_convt7_wgrad_line_channel_slices(n, cin, cout, dhw):
+  """The C > 4 logits layer's weight gradient as 4-output-channel slices of the narrow tap-stacked kernel: dy rows of
+  pitch 16 (pad channels zero), dW columns land in a packed row of CoutP = r4(Cout)."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  g = t.Generator().manual_seed(cin + cout)
+  x = t.randn((n, cin) + dhw, generator=g)
+  wt = (t.randn(cin, cout, 7, 7, 7, generator=g) * 0.05).double().requires_grad_(True)
+  y = F.conv_transpose3d(x.double(), wt, None, stride=2, padding=3, output_padding=1)
+  gy = t.randn(y.shape, generator=g)
+  y.backward(gy.double())
+  fine = tuple(y.shape[2:])
+  xr = x.permute(0, 2, 3, 4, 1).reshape(-1, cin).contiguous().to(dev())
+  cp = (cout + 3) // 4 * 4
+  gr = t.zeros(gy.numel() // cout, cp)
+  gr[:, :cout] = gy.permute(0, 2, 3, 4, 1).reshape(-1, cout)
+  gr = gr.to(dev())
+  dw = t.zeros(343, cin, cp, device=dev())
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  for co0 in range(0, cp, 4):
+    desc = ops.make_desc(n, cin, 4, dhw, fine, (7, 7, 7), 2, 3, True, cin, cp)
+    desc.y_co, desc.CoutP = co0, cp
+    assert _lib.lib().crn_convt7_wgrad_line_supported(C.byref(desc)) == 2
+    _lib.call("crn_convt7_wgrad_line", C.byref(desc), xr.data_ptr(), gr.data_ptr(), dw.data_ptr() + 4 * co0,
+              status.data_ptr(), _lib.stream_ptr())
+  t.cuda.synchronize()
+  assert int(status) == 0
+  ref = wt.grad.reshape(cin, cout, 343).permute(2, 0, 1)
+  assert rel_err(dw[:, :, :cout], ref) < 5e-5
+  assert float(dw[:, :, cout:].abs().max()) == 0.0 if cp > cout else True
+
+
 @pytest.mark.parametrize("n,cin,cout,dhw", [(1, 8, 16, (8, 16, 8)), (2, 28, 16, (12, 32, 16)), (1, 12, 8, (8, 16, 24)),
                                               (1, 28, 16, (20, 16, 8))])
 def test_conv5_kz_stacked_tcgen05(n, cin, cout, dhw):
