@@ -624,9 +624,13 @@ def build_roofline(prof, steps, pk, pk_src, layers_path):
       f = hbm.setdefault(name, [0.0, 0.0, 0])
       f[0] += e0.elapsed_time(e1); f[1] += work; f[2] += 1
       continue
-    k = {"wgrad": "wgrad_kernels(ffma)", "wgrad_tc": "wgrad_tc_kernel(tcgen05)", "fwd_gt": "gemm_tc_kernel(tcgen05)",
-         "dgrad_gt": "gemm_tc_kernel(tcgen05)", "fwd_tc": "conv_tc5_kernel(tcgen05)",
-         "dgrad_tc": "conv_tc5_kernel(tcgen05)"}.get(kind, "conv_fwd_dgrad_kernels(ffma)")
+    # one family per kernel function (source file in csrc/)
+    k = {"wgrad": "wgrad_kernels(ffma)", "wgrad_tc": "wgrad_tc_kernel(tcgen05, per-tap: conv_wgrad_tc.cu)",
+         "wgrad_line": "wgrad_line/tline/xline_kernel(tcgen05, tap-stacked: conv_wgrad_line.cu)",
+         "fwd_gt": "gemm_tc_kernel(tcgen05: conv_gemm_tc.cu)", "dgrad_gt": "gemm_tc_kernel(tcgen05: conv_gemm_tc.cu)",
+         "fwd_tc": "conv_tc5_kernel(tcgen05: conv_tc5.cu)", "dgrad_tc": "conv_tc5_kernel(tcgen05: conv_tc5.cu)",
+         "fwd_tcs": "conv_tc5s_kernel(tcgen05, z-taps stacked: conv_tc5s.cu)",
+         "dgrad_tcs": "conv_tc5s_kernel(tcgen05, z-taps stacked: conv_tc5s.cu)"}.get(kind, "conv_fwd_dgrad_kernels(ffma)")
     f = fam.setdefault(k, [0.0, 0.0, 0])
     f[0] += e0.elapsed_time(e1); f[1] += 2.0 * work; f[2] += 1
   if layers_path:
@@ -656,11 +660,14 @@ def build_roofline(prof, steps, pk, pk_src, layers_path):
   except Exception:
     pass
   hbm_peak = pk["hbm_gbs"]
+  all_flops = sum(v[1] for v in fam.values())
   return {"bound": "tensor", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
           "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
           "peak_source": f"{pk_src} bf16 sustained",
           "launches": dom[1][2], "kernel_ms_per_step": dom[1][0] / steps,
           "all_conv_ms_per_step": conv_ms / steps,
+          "all_conv_tflops": all_flops / (conv_ms * 1e-3) / 1e12, "all_conv_frac": all_flops / (conv_ms * 1e-3) / 1e12 / peak,
+          "conv_gflop_per_step": all_flops / steps / 1e9,
           "families": {k: {"ms_per_step": v[0] / steps, "tflops": v[1] / (v[0] * 1e-3) / 1e12}
                        for k, v in fam.items()},
           "hbm": {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[2] // steps,

@@ -165,7 +165,7 @@ def _conv_dispatch(kind, layer, d, args):
         ok = eng.wl_ok[layer.name] = bool(_lib.lib().crn_conv_wgrad_xline_supported(C.byref(d)))
       if ok:
         x, dy, dw, st = args
-        return "wgrad_tc", "crn_conv_wgrad_xline", (C.byref(d), x, dy, dw, status, st)
+        return "wgrad_line", "crn_conv_wgrad_xline", (C.byref(d), x, dy, dw, status, st)
     if kind == "wgrad" and layer.name in eng.gt_wgrad:
       x, dy, dw, st = args
       return "wgrad_tc", "crn_conv_wgrad_tc", (C.byref(d), x, dy, dw, status, st)
@@ -175,14 +175,14 @@ def _conv_dispatch(kind, layer, d, args):
         ok = eng.wl_ok[layer.name] = bool(_lib.lib().crn_convt7_wgrad_line_supported(C.byref(d)))
       if ok:
         x, dy, dw, st = args
-        return "wgrad_tc", "crn_convt7_wgrad_line", (C.byref(d), x, dy, dw, status, st)
+        return "wgrad_line", "crn_convt7_wgrad_line", (C.byref(d), x, dy, dw, status, st)
     if kind == "wgrad" and layer.k == (5, 5, 5) and not layer.transposed:
       ok = eng.wl_ok.get(layer.name)
       if ok is None:                        # narrow Conv3d k=5 layers: tap-stacked tcgen05 kernel (csrc/conv_wgrad_line.cu)
         ok = eng.wl_ok[layer.name] = bool(_lib.lib().crn_conv_wgrad_line_supported(C.byref(d)))
       if ok:
         x, dy, dw, st = args
-        return "wgrad_tc", "crn_conv_wgrad_line", (C.byref(d), x, dy, dw, status, st)
+        return "wgrad_line", "crn_conv_wgrad_line", (C.byref(d), x, dy, dw, status, st)
   return kind, _CONV_FN[kind], (C.byref(d),) + tuple(args)
 
 
@@ -222,7 +222,7 @@ def _wgrad_t7_slices(eng, layer, d, args):
     return None
   x, dy, dw, st = args
   status = eng.tc_status.data_ptr()
-  return [("wgrad_tc", "crn_convt7_wgrad_line", (C.byref(ds), x, dy, dw + off, status, st), da) for ds, off, da in calls]
+  return [("wgrad_line", "crn_convt7_wgrad_line", (C.byref(ds), x, dy, dw + off, status, st), da) for ds, off, da in calls]
 
 
 def conv_call(kind, layer, d, *args):
@@ -275,7 +275,8 @@ USE_FUSED_BRN = True
 def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None, fn="crn_convt7_tc"):
   """ConvTranspose3d k=7 s=2 forward through crn_convt7_tc (or the jz-stacked crn_convt7_tcs_fwd).  acct: descriptor
   whose MACs are reported (the launch descriptor may carry zero-padded output channels)."""
-  if NCU_PICK is not None and NCU_PICK("fwd_tc", layer.name):
+  tag = "fwd_tcs" if fn == "crn_convt7_tcs_fwd" else "fwd_tc"
+  if NCU_PICK is not None and NCU_PICK(tag, layer.name):
     return _ncu_bracket(fn, (C.byref(d), inp, wtc, bias, out, status, st))
   if PROFILE is None:
     _lib.call(fn, C.byref(d), inp, wtc, bias, out, status, st)
@@ -284,12 +285,13 @@ def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None, fn="crn
   e0.record()
   _lib.call(fn, C.byref(d), inp, wtc, bias, out, status, st)
   e1.record()
-  PROFILE.append(("fwd_tc", layer.name, conv_macs(acct or d), e0, e1))
+  PROFILE.append((tag, layer.name, conv_macs(acct or d), e0, e1))
 
 
 def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st, acct=None, fn="crn_convt7_tc_dgrad"):
   """ConvTranspose3d k=7 s=2 dgrad through crn_convt7_tc_dgrad (or the jz-stacked crn_convt7_tcs_dgrad)."""
-  if NCU_PICK is not None and NCU_PICK("dgrad_tc", layer.name):
+  tag = "dgrad_tcs" if fn == "crn_convt7_tcs_dgrad" else "dgrad_tc"
+  if NCU_PICK is not None and NCU_PICK(tag, layer.name):
     return _ncu_bracket(fn, (C.byref(d), dy, wtc, dx, status, st))
   if PROFILE is None:
     _lib.call(fn, C.byref(d), dy, wtc, dx, status, st)
@@ -298,13 +300,13 @@ def convt7_tc_dgrad_call(layer, d, dy, wtc, dx, status, st, acct=None, fn="crn_c
   e0.record()
   _lib.call(fn, C.byref(d), dy, wtc, dx, status, st)
   e1.record()
-  PROFILE.append(("dgrad_tc", layer.name, conv_macs(acct or d), e0, e1))
+  PROFILE.append((tag, layer.name, conv_macs(acct or d), e0, e1))
 
 
 def conv5_tcs_call(layer, d, inp, wtc, bias, out, status, st, kind=0):
   """Conv3d k=5 forward (kind 0) / dgrad (kind 1) with <= 32 output channels through crn_conv5_tcs2 (kz taps
   stacked into N)."""
-  if NCU_PICK is not None and NCU_PICK("fwd_tc" if kind == 0 else "dgrad_tc", layer.name):
+  if NCU_PICK is not None and NCU_PICK("fwd_tcs" if kind == 0 else "dgrad_tcs", layer.name):
     return _ncu_bracket("crn_conv5_tcs2", (C.byref(d), kind, inp, wtc, bias, out, status, st))
   if PROFILE is None:
     _lib.call("crn_conv5_tcs2", C.byref(d), kind, inp, wtc, bias, out, status, st)
@@ -313,7 +315,7 @@ def conv5_tcs_call(layer, d, inp, wtc, bias, out, status, st, kind=0):
   e0.record()
   _lib.call("crn_conv5_tcs2", C.byref(d), kind, inp, wtc, bias, out, status, st)
   e1.record()
-  PROFILE.append(("fwd_tc" if kind == 0 else "dgrad_tc", layer.name, conv_macs(d), e0, e1))
+  PROFILE.append(("fwd_tcs" if kind == 0 else "dgrad_tcs", layer.name, conv_macs(d), e0, e1))
 
 
 def conv5_tc_call(kind, layer, d, inp, wtc, bias, out, status, st):

@@ -22,11 +22,11 @@ from corenet_b200 import configuration, engine  # noqa: E402
 from corenet_b200.model.core_net import CoreNet  # noqa: E402
 from corenet_b200.trainer import Trainer  # noqa: E402
 
-CONV = {("fwd_tc", "decoder.stage_6.c1"), ("dgrad_tc", "decoder.stage_6.c1"), ("wgrad_tc", "decoder.stage_6.c1"),
-        ("fwd_tc", "decoder.stage_5.t1"), ("dgrad_tc", "decoder.stage_5.t1"), ("fwd_tc", "decoder.stage_6.t1"),
+CONV = {("fwd_tcs", "decoder.stage_6.c1"), ("dgrad_tcs", "decoder.stage_6.c1"), ("wgrad_line", "decoder.stage_6.c1"),
+        ("fwd_tc", "decoder.stage_5.t1"), ("dgrad_tcs", "decoder.stage_5.t1"), ("fwd_tcs", "decoder.stage_6.t1"),
         ("fwd_gt", "decoder.stage_4.c1"), ("fwd_gt", "encoder.stage3.b.op_b.conv"),
         ("dgrad_gt", "encoder.stage4.b.op_c.conv"), ("wgrad_tc", "encoder.stage4.b.op_b.conv"),
-        ("wgrad_tc", "decoder.stage_4.c1"), ("dgrad", "decoder.stage_6.t1"), ("fwd", "encoder.stage1.conv")}
+        ("wgrad_line", "decoder.stage_4.c1"), ("dgrad", "decoder.stage_6.t1"), ("fwd", "encoder.stage1.conv")}
 CALLS_ONCE = {"crn_loss_sums", "crn_loss_bwd", "crn_adam_step_guarded", "crn_unpack_wgrads",
               "crn_softmax_planar", "crn_argmax_confusion_labeled"}
 CALLS_ALL = {"crn_skip_sample_fwd", "crn_skip_sample_bwd_sorted", "crn_skip_build_lists"}
