@@ -668,6 +668,13 @@ def build_roofline(prof, steps, pk, pk_src, layers_path):
           "all_conv_ms_per_step": conv_ms / steps,
           "all_conv_tflops": all_flops / (conv_ms * 1e-3) / 1e12, "all_conv_frac": all_flops / (conv_ms * 1e-3) / 1e12 / peak,
           "conv_gflop_per_step": all_flops / steps / 1e9,
+          # continuity with round 1, whose dominant family was the k5 / transposed-k7 forward+dgrad kernels
+          # (conv_tc5.cu + conv_tc5s.cu together; 6.84 ms at 75.1 TFLOP/s then)
+          "tracked_conv_tc5_family": (lambda a, b: {"ms_per_step": (a[0] + b[0]) / steps,
+                                                   "tflops": (a[1] + b[1]) / ((a[0] + b[0]) * 1e-3) / 1e12,
+                                                   "frac": (a[1] + b[1]) / ((a[0] + b[0]) * 1e-3) / 1e12 / peak})(
+              fam.get("conv_tc5_kernel(tcgen05: conv_tc5.cu)", [1e-9, 0.0, 0]),
+              fam.get("conv_tc5s_kernel(tcgen05, z-taps stacked: conv_tc5s.cu)", [1e-9, 0.0, 0])),
           "families": {k: {"ms_per_step": v[0] / steps, "tflops": v[1] / (v[0] * 1e-3) / 1e12}
                        for k, v in fam.items()},
           "hbm": {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[2] // steps,
