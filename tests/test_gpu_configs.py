@@ -350,3 +350,76 @@ def test_trainer_rows_path_matches_module_path_c15():
   assert abs(float(l2) - float(loss)) <= 1e-5 * abs(float(loss))
   assert err <= 3e-4
   tr.check_status(wait=True)
+
+
+def test_trainer_prefetch_with_device_resident_gt_pipeline():
+  """m9-style loop: the ground truth of step k+1 (rasterise + fill + label merge on the GPU) is produced by a callable
+  on the copy stream while step k runs; the losses must equal those of the same steps fed with precomputed grids."""
+  from corenet_b200.data import batched_example as be
+  from corenet_b200.trainer import Trainer
+  from tests.conftest import cube_mesh
+  dev = t.device("cuda", 0)
+  inp = MGC.config_inputs("E")
+  b = inp["image"].shape[0]
+  meshes = [cube_mesh(0.99) / 3.0 * 0.5 + 0.1, cube_mesh(0.99) / 3.0 * 0.35 + 0.5, cube_mesh(0.99) / 3.0 * 0.3 + 0.3]
+  verts = t.from_numpy(np.concatenate(meshes)).pin_memory()
+  ntri = [t.tensor([12], dtype=t.int32), t.tensor([12, 12], dtype=t.int32)]
+  labels = [[3], [7, 12]]
+  offs = inp["offsets"]
+
+  def gt_fn():
+    return be.voxelize(verts, ntri, offs, (128, 128, 128), be.VoxelContentSemanticLabel(labels),
+                       image_resolution_multiplier=8, conservative_rasterization=False)[1]
+  grid = gt_fn()
+  assert grid.dtype == t.int32 and tuple(grid.shape) == (b, 128, 128, 128) and int(grid.max()) == 12
+  host = [x.pin_memory() for x in (inp["image"], inp["v2s"], inp["offsets"])]
+  runs = []
+  for use_fn in (False, True):
+    tr = Trainer(build_model(15).to(dev).eval(), loss="xent_times_iou_agnostic")
+    tr.prefetch(*host, gt_fn if use_fn else grid)
+    ls = []
+    for _ in range(4):
+      loss = tr.step()
+      tr.prefetch(*host, gt_fn if use_fn else grid)
+      ls.append(float(loss))
+    tr.step()
+    tr.check_status(wait=True)
+    runs.append(ls)
+  print("\nprecomputed GT:", runs[0], "\nGT callable   :", runs[1])
+  assert np.isfinite(runs[0]).all() and abs(runs[0][0] - runs[1][0]) <= 1e-6 * abs(runs[0][0])
+  assert max(abs(x - y) for x, y in zip(*runs)) <= 2e-3 * abs(runs[0][0])
+
+
+def test_evaluator_fgbg_labels_and_semantic_rows():
+  """Evaluator end to end: FG_BG task (C=2, predictions / GT scaled by the scene's class id into a K x K matrix,
+  evaluation_results.py:40-51) and SEMANTIC task (C=15: the rows-layout logits path) against torch on the logits the
+  module itself returns."""
+  from corenet_b200.evaluator import Evaluator
+  dev = t.device("cuda", 0)
+  inp = MGC.config_inputs("E")
+  args = [inp["image"].to(dev), inp["v2s"].to(dev), inp["offsets"].to(dev)]
+  # SEMANTIC
+  m = build_model(15).to(dev).eval()
+  gt = inp["gt"].to(dev).to(t.int32)
+  ev = Evaluator(m)
+  for _ in range(4):
+    pmf = ev.add_batch(*args, gt)
+  with t.no_grad():
+    logits = m(*args)
+  assert t.allclose(pmf, logits.softmax(1), atol=1e-5)
+  pred = logits.argmax(1)
+  exp = t.bincount((gt.long() * 15 + pred).reshape(-1), minlength=225).reshape(15, 15)
+  assert (ev.confusion_matrix.cpu() - 4 * exp.cpu()).abs().sum().item() <= 4e-5 * gt.numel()
+  assert ev.graph_launches > 100
+  # FG_BG with dataset classes
+  m2 = build_model(2).to(dev).eval()
+  gt2 = (inp["gt"] > 0).to(t.int32).to(dev)
+  labels = t.tensor([4, 9], dtype=t.int32, device=dev)
+  ev2 = Evaluator(m2, num_classes=14)
+  ev2.add_batch(*args, gt2, labels)
+  with t.no_grad():
+    pred2 = m2(*args).argmax(1).long() * labels.long()[:, None, None, None]
+  exp2 = t.bincount(((gt2.long() * labels.long()[:, None, None, None]) * 14 + pred2).reshape(-1), minlength=196).reshape(14, 14)
+  assert (ev2.confusion_matrix.cpu() - exp2.cpu()).abs().sum().item() <= 1e-5 * gt2.numel()
+  with pytest.raises(ValueError):
+    ev2.add_batch(*args, gt2)          # FG_BG needs the scene labels

@@ -169,3 +169,26 @@ def test_transformations_match_oracle():
   a = tt.look_at_rh([.5, .5, -.87], [.5, .5, .5], [0, -1, 0])
   assert t.allclose(a, O.look_at_rh([.5, .5, -.87], [.5, .5, .5], [0, -1, 0]), atol=0, rtol=0)
   assert t.equal(tt.ortho_lh(0, 4, 3, 0, 0, 5), O.ortho_lh(0, 4, 3, 0, 0, 5))
+
+
+def test_compat_overlay_without_a_reference_checkout():
+  """compat.install() in a process that has no reference on its path: `corenet.*` resolves to this package (the
+  overlaid hot-path modules plus the fallbacks for configuration / super_resolution / batched_example)."""
+  import subprocess
+  import sys
+  from tests.conftest import ROOT
+  code = (
+      "import sys; sys.path.insert(0, %r)\n"
+      "import corenet_b200.compat as compat; compat.install()\n"
+      "import corenet.model.core_net as cn, corenet.configuration as cfg, corenet.cc.fill_voxels as fv\n"
+      "import corenet.super_resolution as sr, corenet.geometry.voxelization as vz\n"
+      "from corenet.model import losses\n"
+      "from corenet.data import batched_example\n"
+      "m = cn.CoreNet(cfg.default_config(2))\n"
+      "assert type(m).__module__ == 'corenet_b200.model.core_net' and len(m.state_dict()) == 458\n"
+      "assert sr.super_resolution_from_state.__module__ == 'corenet_b200.super_resolution'\n"
+      "assert vz.voxelize_mesh.__module__ == 'corenet_b200.geometry.voxelization'\n"
+      "assert losses.iou_fgbg and batched_example.voxelize and fv.get_module\n"
+      "print('ok')\n") % ROOT
+  r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/")
+  assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-800:]
