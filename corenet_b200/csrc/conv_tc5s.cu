@@ -189,64 +189,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
       }
     }
   } else if (warp < 8) {
-    // ============================ PRODUCERS: halo gather + hi/lo split; plane r of every pass goes to slot r
+    // ============================ PRODUCERS: halo gather + hi/lo split into the plane ring.
+    // Software-pipelined: the gathers of plane L+1 are issued (into registers) right after plane L has been handed over,
+    // i.e. BEFORE the wait for slot L+1 to become free, so the global-memory latency overlaps that wait and the
+    // turnaround of a slot (freed -> full again) is only split + shared stores.
     const int pt = tid - 128;
-    long long L = 0;                               // running plane-load index (slot = L % NSLOT = r)
-    bool dead = false;
-    for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
-      int n, z0, y0, x0;
-      decode_item(p, item, n, z0, y0, x0);
-      for (int pass = 0; pass < p.P && !dead; ++pass) {
-        for (int r = 0; r < NPLANE; ++r, ++L) {
-          const int slot = (int)(L % NSLOT);
-          const uint32_t use = (uint32_t)(L / NSLOT);
-          if (use > 0 && !tc::mbar_wait(&B->plane_empty[slot], (use - 1) & 1, ab)) { fail(); dead = true; break; }
-          const int q = z0 - HLO + r;
-          if (q >= 0 && q < p.D) {
-            uint8_t* dst = ring + slot * PLANE_BYTES;
-            // all gathers of this thread are issued before the first split / store: NU independent loads in flight
-            constexpr int NU = (YS * XS * 2 + 127) / 128;
-            float4 a[NU];
+    constexpr int NU = (YS * XS * 2 + 127) / 128;
+    int item = blockIdx.x, pass = 0, r = 0;
+    int n = 0, z0 = 0, y0 = 0, x0 = 0;
+    if (item < p.nitems) decode_item(p, item, n, z0, y0, x0);
+    float4 a[NU];
+    bool inside = false;                           // plane inside the volume (else: nothing to stage, MMAs skip it)
+    auto gather = [&]() {
+      const int q = z0 - HLO + r;
+      inside = q >= 0 && q < p.D;
 #pragma unroll
-            for (int i = 0; i < NU; ++i) {
-              const int u = pt + i * 128;
-              a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (u < YS * XS * 2) {
-                const int kc = u & 1; const int v = u >> 1;
-                const int xs = v % XS, ys = v / XS;
-                const int y = y0 - HLO + ys, x = x0 - HLO + xs;
-                const int k = pass * 8 + kc * 4;
-                if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
-                  long long off;
-                  if constexpr (GATH) {              // class channel k = (cls, co) lives at fine voxel 2i + cls
-                    const int cls = k / p.cout_cls, co = k - cls * p.cout_cls;
-                    off = ((((long long)n * (2 * p.D) + 2 * q + (cls >> 2)) * (2 * p.H) + 2 * y + ((cls >> 1) & 1)) *
-                               (2 * p.W) + 2 * x + (cls & 1)) * p.in_cs + p.in_co + co;
-                  } else {
-                    off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
-                  }
-                  a[i] = __ldg(reinterpret_cast<const float4*>(p.in + off));
-                }
-              }
+      for (int i = 0; i < NU; ++i) {
+        const int u = pt + i * 128;
+        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inside && u < YS * XS * 2) {
+          const int kc = u & 1; const int v = u >> 1;
+          const int xs = v % XS, ys = v / XS;
+          const int y = y0 - HLO + ys, x = x0 - HLO + xs;
+          const int k = pass * 8 + kc * 4;
+          if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
+            long long off;
+            if constexpr (GATH) {                  // class channel k = (cls, co) lives at fine voxel 2i + cls
+              const int cls = k / p.cout_cls, co = k - cls * p.cout_cls;
+              off = ((((long long)n * (2 * p.D) + 2 * q + (cls >> 2)) * (2 * p.H) + 2 * y + ((cls >> 1) & 1)) *
+                         (2 * p.W) + 2 * x + (cls & 1)) * p.in_cs + p.in_co + co;
+            } else {
+              off = ((((long long)n * p.D + q) * p.H + y) * p.W + x) * p.in_cs + p.in_co + k;
             }
-#pragma unroll
-            for (int i = 0; i < NU; ++i) {
-              const int u = pt + i * 128;
-              if (u < YS * XS * 2) {
-                const int kc = u & 1; const int v = u >> 1;
-                float4 hi, lo;
-                tc::split_tf32(a[i].x, hi.x, lo.x); tc::split_tf32(a[i].y, hi.y, lo.y);
-                tc::split_tf32(a[i].z, hi.z, lo.z); tc::split_tf32(a[i].w, hi.w, lo.w);
-                const int o = kc * CHUNK_BYTES + v * 16;
-                *reinterpret_cast<float4*>(dst + o) = hi;
-                *reinterpret_cast<float4*>(dst + PART_BYTES + o) = lo;
-              }
-            }
-            tc::fence_async_smem();
+            a[i] = __ldg(reinterpret_cast<const float4*>(p.in + off));
           }
-          tc::mbar_arrive(&B->plane_full[slot]);
         }
       }
+    };
+    if (item < p.nitems) gather();
+    for (long long L = 0; item < p.nitems; ++L) {
+      const int slot = (int)(L % NSLOT);
+      const uint32_t use = (uint32_t)(L / NSLOT);
+      if (use > 0 && !tc::mbar_wait(&B->plane_empty[slot], (use - 1) & 1, ab)) { fail(); break; }
+      if (inside) {
+        uint8_t* dst = ring + slot * PLANE_BYTES;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          const int u = pt + i * 128;
+          if (u < YS * XS * 2) {
+            const int kc = u & 1; const int v = u >> 1;
+            float4 hi, lo;
+            tc::split_tf32(a[i].x, hi.x, lo.x); tc::split_tf32(a[i].y, hi.y, lo.y);
+            tc::split_tf32(a[i].z, hi.z, lo.z); tc::split_tf32(a[i].w, hi.w, lo.w);
+            const int o = kc * CHUNK_BYTES + v * 16;
+            *reinterpret_cast<float4*>(dst + o) = hi;
+            *reinterpret_cast<float4*>(dst + PART_BYTES + o) = lo;
+          }
+        }
+        tc::fence_async_smem();
+      }
+      tc::mbar_arrive(&B->plane_full[slot]);
+      // next (item, pass, plane)
+      if (++r == NPLANE) {
+        r = 0;
+        if (++pass == p.P) {
+          pass = 0;
+          item += gridDim.x;
+          if (item < p.nitems) decode_item(p, item, n, z0, y0, x0);
+        }
+      }
+      if (item < p.nitems) gather();
     }
   } else if (warp == 8) {
     // ============================ MMA ISSUER (one elected thread)
