@@ -364,8 +364,12 @@ __global__ void brn_nbt_snapshot_kernel(long long* const* ptrs, int n, long long
 
 template <typename P>
 cudaError_t launch_fused(void (*kern)(const P), const P& p, long long rows, int C, cudaStream_t st) {
+  // blocks per cluster (row split): as many as keep every block at >= 128 rows AND the whole grid within one wave of
+  // two blocks per SM -- these blocks are latency-bound (a handful of dependent round trips each), so a second wave
+  // of tiny blocks doubles the kernel time (wide layers: C/8 clusters already fill the machine)
+  const int groups = C / CG;
   int cs = 1;
-  while (cs < 8 && rows / (2 * cs) >= RPS) cs <<= 1;        // >= 128 rows per block, at most 8 blocks per cluster
+  while (cs < 8 && rows / (2 * cs) >= RPS && 2 * cs * groups <= 2 * kNumSMs) cs <<= 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)cs, (unsigned)(C / CG), 1);
   cfg.blockDim = dim3(NT, 1, 1);

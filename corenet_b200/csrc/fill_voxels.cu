@@ -8,13 +8,12 @@
 //              x=0 / y=0 / z=0 faces (near-face rule)      [HBM read]
 //   B. flood:  R <- fixpoint of "R spreads through E", so the result is the exact
 //              connected component.  Grids whose bit planes fit the shared memory
-//              of a thread-block cluster (up to 8 CTAs x 128 KB: 128^3 and smaller)
-//              run fill_flood_cluster_kernel: each CTA keeps a z-slab of E, R and
-//              two pass-through masks in shared memory; x spreads by carry chains
-//              (128 voxels per add), y and z by log2(extent) doubling steps
-//              (segmented OR-scan on whole bit rows; z steps read the neighbour
-//              slabs through distributed shared memory).  Larger grids fall back to
-//              register-/global-memory line sweeps (fill_flood_kernel, any W).
+//              of a thread-block cluster (up to 8 CTAs x 192 KB: 128^3 .. 160^3)
+//              run fill_flood_cluster_kernel: each CTA keeps a z-slab of E and R in
+//              shared memory; x spreads by carry chains (128 voxels per add), y and z
+//              by register-carried line sweeps over whole bit rows (the z lines cross
+//              the cluster slab by slab through distributed shared memory).  Larger
+//              grids fall back to the same sweeps from global memory (any W).
 //   C. unpack: out = R ? 0 : 1 in the element type                   [HBM write]
 // Algorithmic bytes: read T + write T per voxel; scratch is 0.25 B/voxel.
 #include "common.cuh"
@@ -300,16 +299,18 @@ __global__ void __launch_bounds__(1024) fill_flood_wide_kernel(const uint32_t* _
 }
 
 // ---- shared-memory / cluster flood ---------------------------------------------------------------------------
-// One cluster of CS CTAs per grid; CTA `rank` owns the z-slab [rank*zs, rank*zs + zs).  Shared memory per CTA:
-// E, R and the two pass-through masks Tu, Td of the slab ([zs][H][NW] words each, <= CL_WPT * CL_NT words).
-//   doubling step d along an axis (a segmented OR-scan of whole 128-bit rows):
-//     R[i]  |= Tu[i] & R[i-d]  |  Td[i] & R[i+d]
-//     Tu[i] &= Tu[i-d]           (Tu[i] = "the d rows ending at i are all empty")      Td likewise upwards
-//   after ceil(log2(extent)) steps every bit reachable from a reached bit along that axis through empty voxels is set.
-// y steps are CTA-local; z steps read rows of other slabs through distributed shared memory (cluster.sync between the
-// read and the write half of a step).  Iterated with the x carry chains until no bit changes in a whole round.
-constexpr int CL_NT = 512;
-constexpr int CL_WPT = 16;                       // words per thread kept in registers during a doubling step
+// One cluster of CS CTAs per grid; CTA `rank` owns the z-slab [rank*zs, rank*zs + zs) and keeps its E (empty) and R
+// (reached) bit planes in shared memory ([zs][H][NW] words each).  All propagation is by register-carried LINE SWEEPS
+// over whole 32*NW-bit rows: a sweep walks a line of rows, ORs `E & previous row` into the row and, if the row grew,
+// re-closes it along x with the carry chains (row_fill), so one sweep carries the flood around corners in its plane.
+//   * in-plane closure (CTA-local): one thread per z-plane sweeps +y then -y until nothing changes -- every plane has
+//     its own seeds (the y = 0 row and the x = 0 column), so nearly all of the outside region is reached here;
+//   * z sweeps: one thread per (y) row line walks the planes; the line crosses the cluster slab by slab: stage s of
+//     the +z sweep runs in CTA s and takes its incoming row from the last plane of CTA s-1 through distributed shared
+//     memory (cluster.sync between stages), then the same downwards;
+//   * repeated until a z phase reaches nothing new in any CTA.
+constexpr int CL_NT = 256;
+constexpr int CL_MAXW = 24576;                   // words per slab array: 2 arrays x 96 KB
 namespace cg = cooperative_groups;
 
 template <int NW>
@@ -323,8 +324,6 @@ __global__ void __launch_bounds__(CL_NT) fill_flood_cluster_kernel(const uint32_
   const int cap = zs * H * NW;                   // words per slab array (same in every CTA)
   uint32_t* Es = sm;
   uint32_t* Rs = Es + cap;
-  uint32_t* Tu = Rs + cap;
-  uint32_t* Td = Tu + cap;
   __shared__ int flags[2];
   const int z0 = rank * zs;
   const int nz = max(0, min(zs, D - z0));
@@ -338,100 +337,85 @@ __global__ void __launch_bounds__(CL_NT) fill_flood_cluster_kernel(const uint32_
   if (tid < 2) flags[tid] = 0;
   __syncthreads();
 
-  auto x_fill = [&]() -> bool {                  // carry chains along x, one row per thread iteration
+  // walks `count` rows starting at row index `row` with stride `step` (in rows); prev = reached bits of the row before
+  auto sweep = [&](int row, int count, int step, uint32_t (&prev)[NW]) -> bool {
     bool ch = false;
-    for (int row = tid; row < rows; row += CL_NT) {
-      uint32_t e[NW], r[NW], r0[NW];
+    for (int k = 0; k < count; ++k, row += step) {
+      uint32_t e[NW], r[NW];
+      bool grew = false;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) { e[w] = Es[row * NW + w]; r0[w] = r[w] = Rs[row * NW + w]; }
-      row_fill<NW>(r, e);
-      bool c = false;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) c |= r[w] != r0[w];
-      if (c) {
+      for (int w = 0; w < NW; ++w) {
+        e[w] = Es[row * NW + w];
+        const uint32_t r0 = Rs[row * NW + w];
+        r[w] = r0 | (e[w] & prev[w]);
+        grew |= r[w] != r0;
+      }
+      if (grew) {
+        row_fill<NW>(r, e);
 #pragma unroll
         for (int w = 0; w < NW; ++w) Rs[row * NW + w] = r[w];
         ch = true;
       }
+#pragma unroll
+      for (int w = 0; w < NW; ++w) prev[w] = r[w];
     }
     return ch;
   };
 
-  x_fill();
+  // seeds spread along their rows
+  for (int row = tid; row < rows; row += CL_NT) {
+    uint32_t e[NW], r[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { e[w] = Es[row * NW + w]; r[w] = Rs[row * NW + w]; }
+    row_fill<NW>(r, e);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) Rs[row * NW + w] = r[w];
+  }
   __syncthreads();
   for (int it = 0;; ++it) {
-    // ---- in-plane closure (x carry chains + y doubling), CTA-local: every z-plane has its own seeds (the y = 0 row
-    // and the x = 0 column), so almost all of the outside region is reached here without touching the cluster
+    // ---- in-plane closure: thread zl sweeps plane zl along +y, then -y, until no plane changes
     for (;;) {
       bool ch = false;
-      for (int i = tid; i < words; i += CL_NT) { const uint32_t e = Es[i]; Tu[i] = e; Td[i] = e; }
-      __syncthreads();
-      for (int d = 1; d < H; d <<= 1) {
-        uint32_t r[CL_WPT], tu[CL_WPT], td[CL_WPT];
+      for (int zl = tid; zl < nz; zl += CL_NT) {
+        uint32_t prev[NW];
 #pragma unroll
-        for (int k = 0; k < CL_WPT; ++k) {
-          const int i = tid + k * CL_NT;
-          if (i < words) {
-            const int y = (i / NW) % H;
-            uint32_t rr = Rs[i], a = Tu[i], b = Td[i];
-            const uint32_t r0 = rr;
-            if (y >= d) { rr |= a & Rs[i - d * NW]; a &= Tu[i - d * NW]; }
-            if (y + d < H) { rr |= b & Rs[i + d * NW]; b &= Td[i + d * NW]; }
-            ch |= rr != r0;
-            r[k] = rr; tu[k] = a; td[k] = b;
-          }
-        }
-        __syncthreads();
+        for (int w = 0; w < NW; ++w) prev[w] = 0u;
+        ch |= sweep(zl * H, H, 1, prev);
 #pragma unroll
-        for (int k = 0; k < CL_WPT; ++k) {
-          const int i = tid + k * CL_NT;
-          if (i < words) { Rs[i] = r[k]; Tu[i] = tu[k]; Td[i] = td[k]; }
-        }
-        __syncthreads();
+        for (int w = 0; w < NW; ++w) prev[w] = 0u;
+        ch |= sweep(zl * H + H - 1, H, -1, prev);
       }
-      ch |= x_fill();
       if (!__syncthreads_or(ch ? 1 : 0)) break;
     }
-    // ---- z: doubling across the slabs of the cluster
+    // ---- z sweeps across the cluster, slab by slab
     bool changed = false;
-    for (int i = tid; i < words; i += CL_NT) { const uint32_t e = Es[i]; Tu[i] = e; Td[i] = e; }
-    cluster.sync();
-    for (int d = 1; d < D; d <<= 1) {
-      uint32_t r[CL_WPT], tu[CL_WPT], td[CL_WPT];
+    cluster.sync();                              // every slab's in-plane closure is visible to its neighbours
+    for (int s = 0; s < CS; ++s) {               // +z
+      if (rank == s && nz > 0) {
+        const uint32_t* below = rank > 0 ? cluster.map_shared_rank(Rs, rank - 1) + (size_t)(zs - 1) * H * NW : nullptr;
+        for (int y = tid; y < H; y += CL_NT) {
+          uint32_t prev[NW];
 #pragma unroll
-      for (int k = 0; k < CL_WPT; ++k) {
-        const int i = tid + k * CL_NT;
-        if (i < words) {
-          const int zl = i / (H * NW);
-          const int rem = i - zl * (H * NW);
-          const int z = z0 + zl;
-          uint32_t rr = Rs[i], a = Tu[i], b = Td[i];
-          const uint32_t r0 = rr;
-          if (z >= d) {
-            const int zn = z - d, owner = zn / zs, off = (zn - owner * zs) * (H * NW) + rem;
-            const uint32_t* rR = cluster.map_shared_rank(Rs, owner);
-            const uint32_t* rT = cluster.map_shared_rank(Tu, owner);
-            rr |= a & rR[off]; a &= rT[off];
-          }
-          if (z + d < D) {
-            const int zn = z + d, owner = zn / zs, off = (zn - owner * zs) * (H * NW) + rem;
-            const uint32_t* rR = cluster.map_shared_rank(Rs, owner);
-            const uint32_t* rT = cluster.map_shared_rank(Td, owner);
-            rr |= b & rR[off]; b &= rT[off];
-          }
-          changed |= rr != r0;
-          r[k] = rr; tu[k] = a; td[k] = b;
+          for (int w = 0; w < NW; ++w) prev[w] = below ? below[y * NW + w] : 0u;
+          changed |= sweep(y, nz, H, prev);
         }
       }
       cluster.sync();
+    }
+    for (int s = CS - 1; s >= 0; --s) {          // -z
+      if (rank == s && nz > 0) {
+        const bool has_above = rank + 1 < CS && z0 + zs < D;
+        const uint32_t* above = has_above ? cluster.map_shared_rank(Rs, rank + 1) : nullptr;
+        for (int y = tid; y < H; y += CL_NT) {
+          uint32_t prev[NW];
 #pragma unroll
-      for (int k = 0; k < CL_WPT; ++k) {
-        const int i = tid + k * CL_NT;
-        if (i < words) { Rs[i] = r[k]; Tu[i] = tu[k]; Td[i] = td[k]; }
+          for (int w = 0; w < NW; ++w) prev[w] = above ? above[y * NW + w] : 0u;
+          changed |= sweep((nz - 1) * H + y, nz, -H, prev);
+        }
       }
       cluster.sync();
     }
-    // ---- did the z phase reach anything new anywhere in the cluster?  (the in-plane closure above had converged)
+    // ---- did the z phase reach anything new anywhere in the cluster?  (the in-plane closure had converged)
     const int any_local = __syncthreads_or(changed ? 1 : 0);
     if (tid == 0) { flags[it & 1] = any_local; flags[(it + 1) & 1] = 0; }
     cluster.sync();
@@ -445,15 +429,16 @@ __global__ void __launch_bounds__(CL_NT) fill_flood_cluster_kernel(const uint32_
 
 template <int NW>
 int launch_cluster_flood(const uint32_t* E, uint32_t* R, int N, int D, int H, cudaStream_t st) {
-  // smallest cluster whose slabs fit the per-thread register budget (CL_WPT words x CL_NT threads per array)
+  // the smallest cluster whose slabs fit the shared memory (2 arrays of <= CL_MAXW words per CTA); at least 8 CTAs per
+  // grid when the grid is deep enough: the in-plane sweeps run one thread per plane, so more slabs = more parallel lines
   int cs = 1;
-  while (cs <= 8 && (int64_t)((D + cs - 1) / cs) * H * NW > (int64_t)CL_WPT * CL_NT) cs <<= 1;
-  if (cs > 8) return 1;                                    // does not fit: caller falls back
+  while (cs < 8 && ((int64_t)((D + cs - 1) / cs) * H * NW > CL_MAXW || (D + cs - 1) / cs > 16)) cs <<= 1;
+  if ((int64_t)((D + cs - 1) / cs) * H * NW > CL_MAXW) return 1;      // does not fit: caller falls back
   const int zs = (D + cs - 1) / cs;
-  const size_t smem = (size_t)4 * zs * H * NW * sizeof(uint32_t);
+  const size_t smem = (size_t)2 * zs * H * NW * sizeof(uint32_t);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(fill_flood_cluster_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * CL_WPT * CL_NT * 4);
+    cudaFuncSetAttribute(fill_flood_cluster_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CL_MAXW * 4);
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -520,6 +505,10 @@ extern "C" int crn_fill_inside(const void* grid_in, void* grid_out, int32_t elem
       case 2: rc = launch_cluster_flood<2>(E, R, N, D, H, st); break;
       case 3: rc = launch_cluster_flood<3>(E, R, N, D, H, st); break;
       case 4: rc = launch_cluster_flood<4>(E, R, N, D, H, st); break;
+      case 5: rc = launch_cluster_flood<5>(E, R, N, D, H, st); break;
+      case 6: rc = launch_cluster_flood<6>(E, R, N, D, H, st); break;
+      case 7: rc = launch_cluster_flood<7>(E, R, N, D, H, st); break;
+      case 8: rc = launch_cluster_flood<8>(E, R, N, D, H, st); break;
       default: break;
     }
   }
