@@ -23,7 +23,7 @@ constexpr int NT = 256;
 constexpr int CG = 8;      // channels per cluster: 2 float4 per row
 constexpr int RPS = NT / 2;  // rows per sweep of a block
 constexpr int UNR = 4;      // forward: row loads in flight per thread
-constexpr int UNB = 1;      // backward: 3-4 streams per row already; more rows in flight cost occupancy (184 registers)
+constexpr int UNB = 2;      // backward: 3-4 streams per row already; more rows in flight cost occupancy (184 registers)
 
 struct BrnFwd {
   const float* x; long long rows; int C, x_cs, x_co, relu_in;
@@ -391,7 +391,9 @@ inline bool aligned4(int a, int b) { return a % 4 == 0 && b % 4 == 0; }
 // 1 when the fused single-launch kernels take this instance: channels in groups of 8, small enough that the second
 // read of a pass is served by L2 and that C/8 clusters of <= 8 blocks fill the machine.
 extern "C" int crn_brn_fused_supported(int64_t rows, int32_t C) {
-  return rows >= 1 && C >= CG && C % CG == 0 && rows * (int64_t)C <= (int64_t)5 * 1024 * 1024;
+  // at most 16384 rows: a cluster splits the rows over <= 8 blocks, and beyond ~2048 rows per block the three-kernel
+  // path of brn.cu (row-parallel grids) is faster (measured: 65536 x 64 took 32 / 93 us fused vs ~20 / 25 us)
+  return rows >= 1 && rows <= 16384 && C >= CG && C % CG == 0 && rows * (int64_t)C <= (int64_t)5 * 1024 * 1024;
 }
 
 extern "C" int crn_brn_nbt_snapshot(int64_t* const* counters, int32_t n, int64_t* snapshot, void* stream) {

@@ -667,7 +667,7 @@ def test_batch_renorm(shape, training, nbt):
 # ---------------------------------------------------------------------------- small encoder ops
 @pytest.mark.parametrize("rows,c,relu_in,relu_out,res,training,nbt", [
     (4 * 64 * 64, 64, 0, 1, 0, 1, 0), (4 * 16 * 16, 1024, 0, 1, 1, 1, 50000), (256, 2048, 0, 0, 0, 1, 12000),
-    (2048, 224, 1, 0, 0, 1, 0), (1000, 8, 1, 1, 1, 1, 7000), (4 * 32 * 32, 512, 0, 1, 1, 0, 0), (77, 16, 0, 0, 0, 1, 3)])
+    (2048, 224, 1, 0, 0, 1, 0), (1000, 8, 1, 1, 1, 1, 7000), (16384, 256, 0, 1, 1, 1, 100), (4 * 32 * 32, 512, 0, 1, 1, 0, 0), (77, 16, 0, 0, 0, 1, 3)])
 def test_batch_renorm_fused_matches_three_kernel_path(rows, c, relu_in, relu_out, res, training, nbt):
   """csrc/brn_fused.cu (one launch per direction, cluster-owned channels, no atomics) against the stats / finalize /
   apply and reduce / dx kernels of csrc/brn.cu on the same inputs, plus run-to-run bit reproducibility."""
