@@ -139,35 +139,44 @@ __device__ __forceinline__ void shade_fragment(const TriSetup& s, int i, int j, 
 }
 
 // one warp per triangle; lanes stride over the pixels of its bounding box
+// Triangles are staged in SHARED MEMORY: a warp owns one triangle at a time; its lane 0 runs the fixed-point edge /
+// snapping set-up (fp64-heavy) ONCE into the warp's shared TriSetup record, all 32 lanes then load that record (one
+// broadcast read) and cover a strided share of the pixel range. (Round 1 ran the set-up redundantly in all 32 lanes and
+// kept the record in registers; staging 32 triangles per block was measured too: 10x slower on the m9 meshes, the
+// rasterisation needs one warp per triangle in flight.)
 __global__ void __launch_bounds__(NT) voxelize_kernel(const float* __restrict__ tris,
                                                       const int32_t* __restrict__ tri_mesh, int T,
                                                       const float* __restrict__ v2x, int W, int H, int D,
                                                       int R, int pdm, int side, int conservative,
                                                       float* __restrict__ grid) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = NT / 32;
-  for (int t = blockIdx.x * warps_per_block + (threadIdx.x >> 5); t < T; t += gridDim.x * warps_per_block) {
+  __shared__ TriSetup staged[NT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = blockIdx.x * (NT / 32) + warp; t < T; t += gridDim.x * (NT / 32)) {
     const int mesh = tri_mesh[t];
-    TriSetup s;
-    setup_triangle(tris + (int64_t)t * 9, v2x + (int64_t)mesh * 16, W, H, D, R, pdm, conservative != 0, s);
-    if (!s.valid) continue;
-    const int nx = s.i1 - s.i0 + 1;
-    const long long npix = (long long)nx * (s.j1 - s.j0 + 1);
-    for (long long q = lane; q < npix; q += 32) {
-      const int j = s.j0 + (int)(q / nx), i = s.i0 + (int)(q % nx);
-      const long long px = (long long)i * 256 + 128, py = (long long)j * 256 + 128;
-      bool in = true;
+    if (lane == 0)
+      setup_triangle(tris + (int64_t)t * 9, v2x + (int64_t)mesh * 16, W, H, D, R, pdm, conservative != 0, staged[warp]);
+    __syncwarp();
+    const TriSetup s = staged[warp];  // broadcast read into registers: the pixel loop re-reads the edge terms per pixel
+    __syncwarp();
+    if (s.valid) {
+      const int nx = s.i1 - s.i0 + 1;
+      const long long npix = (long long)nx * (s.j1 - s.j0 + 1);
+      for (long long q = lane; q < npix; q += 32) {
+        const int j = s.j0 + (int)(q / nx), i = s.i0 + (int)(q % nx);
+        const long long px = (long long)i * 256 + 128, py = (long long)j * 256 + 128;
+        bool in = true;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const long long e = s.A[k] * px + s.B[k] * py + s.C[k];
-        if (conservative) {
-          const long long slack = 128 * (llabs(s.A[k]) + llabs(s.B[k]));
-          in = in && (e + slack >= 0);
-        } else {
-          in = in && (e > 0 || (e == 0 && s.tl[k]));
+        for (int e3 = 0; e3 < 3; ++e3) {
+          const long long e = s.A[e3] * px + s.B[e3] * py + s.C[e3];
+          if (conservative) {
+            const long long slack = 128 * (llabs(s.A[e3]) + llabs(s.B[e3]));
+            in = in && (e + slack >= 0);
+          } else {
+            in = in && (e > 0 || (e == 0 && s.tl[e3]));
+          }
         }
+        if (in) shade_fragment(s, i, j, mesh, W, H, D, side, grid);
       }
-      if (in) shade_fragment(s, i, j, mesh, W, H, D, side, grid);
     }
   }
 }
