@@ -54,6 +54,7 @@ struct TC5SParams {
   int tiles_x, tiles_y, tiles_z, nitems;
   int cout_cls;            // GATH / SCAT: channels per parity class of the fine grid (K resp. N = 8 * cout_cls)
   int planar;              // SCAT: out is [N, Cout, 2D, 2H, 2W] instead of channels-last rows
+  int in_planar;           // GATH: the fine gradient is planar [N, 2, 2D, 2H, 2W] (cout_cls == 2, the FG_BG logits)
 };
 
 struct __align__(8) Barriers {
@@ -215,6 +216,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
           if ((unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W && k < p.gK) {
             long long off;
             if constexpr (GATH) {                  // class channel k = (cls, co) lives at fine voxel 2i + cls
+              if (p.in_planar) {
+                // cout_cls == 2: chunk k..k+3 = classes (cls, cls + 1), i.e. px = 0 / 1, x channels (0, 1): the two
+                // fine voxels are neighbours of a plane row -> one float2 per channel plane
+                const int cls = k >> 1;
+                const long long fS = (long long)(2 * p.D) * (2 * p.H) * (2 * p.W);
+                const long long sp = ((long long)(2 * q + (cls >> 2)) * (2 * p.H) + 2 * y + ((cls >> 1) & 1)) * (2 * p.W) + 2 * x;
+                const float2 c0 = __ldg(reinterpret_cast<const float2*>(p.in + ((long long)n * 2) * fS + sp));
+                const float2 c1 = __ldg(reinterpret_cast<const float2*>(p.in + ((long long)n * 2 + 1) * fS + sp));
+                a[i] = make_float4(c0.x, c1.x, c0.y, c1.y);
+                continue;
+              }
               const int cls = k / p.cout_cls, co = k - cls * p.cout_cls;
               off = ((((long long)n * (2 * p.D) + 2 * q + (cls >> 2)) * (2 * p.H) + 2 * y + ((cls >> 1) & 1)) *
                          (2 * p.W) + 2 * x + (cls & 1)) * p.in_cs + p.in_co + co;
@@ -494,11 +506,13 @@ int launch_tc5s(const TC5SParams& p, cudaStream_t st) {
 // K = reduction channels (Cin for the forward operator, Cout for dgrad)
 extern "C" int64_t crn_tc5s_packed_floats(int32_t K) { return (int64_t)((K + 7) / 8) * 5 * (Geo<5>::WROW_BYTES / 4); }
 
-// ---- dgrad of ConvTranspose3d k=7 s=2 p=3 with the 4 jz taps stacked into N (Cin <= 32, Cout % 4 == 0)
+// ---- dgrad of ConvTranspose3d k=7 s=2 p=3 with the 4 jz taps stacked into N (Cin <= 32; Cout % 4 == 0 with a
+// channels-last dy, or Cout == 2 with the planar FG_BG logit gradient)
 extern "C" int64_t crn_tcts_packed_floats(int32_t Cout) { return (int64_t)(8 * Cout / 8) * 4 * (Geo<4>::WROW_BYTES / 4); }
 
 extern "C" int crn_tcts_pack(const float* w, int32_t Cin, int32_t Cout, float* out, void* stream) {
-  CRN_REQUIRE(w && out && Cout > 0 && Cin > 0 && Cin <= 32 && Cout % 4 == 0, "crn_tcts_pack: Cin <= 32, Cout % 4 == 0");
+  CRN_REQUIRE(w && out && Cout > 0 && Cin > 0 && Cin <= 32 && (Cout % 4 == 0 || Cout == 2),
+              "crn_tcts_pack: Cin <= 32, Cout % 4 == 0 or Cout == 2");
   const int P = Cout;                                   // K = 8 * Cout class channels in passes of 8
   const long long total = (long long)P * 16 * 2 * 4 * 32 * 4;
   int blocks = (int)((total + 255) / 256);
@@ -552,14 +566,18 @@ extern "C" int crn_convt7_tcs_dgrad(const crn_conv_desc* d, const float* dy, con
   CRN_REQUIRE(d->oD == 2 * d->iD && d->oH == 2 * d->iH && d->oW == 2 * d->iW, "crn_convt7_tcs_dgrad: output must be 2x input");
   CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % ZT == 0 && d->iD >= 4,
               "crn_convt7_tcs_dgrad: input grid must tile by 8x16x4");
-  CRN_REQUIRE(!d->y_planar && d->Cout % 4 == 0 && d->Cin % 4 == 0 && d->Cin <= 32,
-              "crn_convt7_tcs_dgrad: Cout % 4, Cin % 4, Cin <= 32, channels-last dy");
-  CRN_REQUIRE(d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
-              "crn_convt7_tcs_dgrad: channel strides/offsets must be multiples of 4");
+  CRN_REQUIRE(d->Cin % 4 == 0 && d->Cin <= 32 && d->x_cs % 4 == 0 && d->x_co % 4 == 0,
+              "crn_convt7_tcs_dgrad: Cin % 4, Cin <= 32, dx channel stride/offset multiples of 4");
+  if (d->y_planar) {
+    CRN_REQUIRE(d->Cout == 2, "crn_convt7_tcs_dgrad: a planar dy must have 2 channels");
+  } else {
+    CRN_REQUIRE(d->Cout % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
+                "crn_convt7_tcs_dgrad: channels-last dy needs Cout, stride, offset multiples of 4");
+  }
   TC5SParams p{};
   p.in = dy; p.wtc = wtc; p.bias = nullptr; p.out = dx; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
-  p.gK = 8 * d->Cout; p.gN = d->Cin; p.cout_cls = d->Cout;
+  p.gK = 8 * d->Cout; p.gN = d->Cin; p.cout_cls = d->Cout; p.in_planar = d->y_planar;
   p.in_cs = d->y_cs; p.in_co = d->y_co; p.out_cs = d->x_cs; p.out_co = d->x_co;
   p.P = (p.gK + 7) / 8;
   p.tiles_x = p.W / TX; p.tiles_y = p.H / TY; p.tiles_z = p.D / ZT;

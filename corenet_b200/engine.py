@@ -530,6 +530,10 @@ class Engine:
         if l.k == (7, 7, 7) and g % 16 == 0 and mid % 4 == 0 and mid <= 32 and co % 4 == 0 and (
             l.name in self.rows_pad or self.tct_w.get(l.name, (None, None))[1] is not None):
           self.tcts_wd[l.name] = (t.zeros(lib.crn_tcts_packed_floats(co), dtype=t.float32, device=dev), co)
+        elif (l.k == (7, 7, 7) and g % 16 == 0 and mid % 4 == 0 and mid <= 32 and t_out == 2 and stage == 6
+              and l.name not in self.rows_pad):
+          # FG_BG logits layer: the class-channel gather reads the PLANAR logit gradient (float2 per channel plane)
+          self.tcts_wd[l.name] = (t.zeros(lib.crn_tcts_packed_floats(2), dtype=t.float32, device=dev), 2)
     # forward of the FG_BG logits layer (Cout <= 2) with the jz taps stacked into N (crn_convt7_tcs_fwd)
     self.tctsf_w = {}
     if USE_TC and USE_TCTS:
@@ -1269,8 +1273,10 @@ class Plan:
           ssum.mul_(float(hw * hw))
       wgrad(lt, d_t, sd["z2"].p, dy_ptr)
       if lt.name in eng.tcts_wd:
-        d_dg = sd["d_t_rows"] if (stage == 6 and sd["rows"] is not None) else d_t
-        convt7_tc_dgrad_call(lt, d_dg, dy_ptr, eng.tcts_wd[lt.name][0].data_ptr(), sd["z2"].gp,
+        d_dg, dy_dg = (sd["d_t_rows"] if (stage == 6 and sd["rows"] is not None) else d_t), dy_ptr
+        if stage == 6 and sd["rows"] is None:
+          d_dg, dy_dg = sd["d_t"], grad_logits.data_ptr()      # planar gradient of the two FG_BG logits
+        convt7_tc_dgrad_call(lt, d_dg, dy_dg, eng.tcts_wd[lt.name][0].data_ptr(), sd["z2"].gp,
                              eng.tc_status.data_ptr(), st, acct=d_t, fn="crn_convt7_tcs_dgrad")
       elif stage == 6 and sd["rows"] is not None:
         convt7_tc_dgrad_call(lt, sd["d_t_rows"], dy_ptr, sd["rows"]["dgrad"].data_ptr(), sd["z2"].gp,

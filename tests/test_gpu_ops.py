@@ -619,6 +619,32 @@ def test_conv_transpose7_dgrad_stacked_tcgen05(n, cin, cout, dhw):
   assert rel_err(got, ref) < 2e-5
 
 
+@pytest.mark.parametrize("n,cin,dhw", [(1, 16, (8, 16, 8)), (2, 12, (4, 16, 16)), (1, 32, (4, 32, 8))])
+def test_conv_transpose7_dgrad_stacked_planar_logits(n, cin, dhw):
+  """crn_convt7_tcs_dgrad on the PLANAR gradient of the two FG_BG logits (float2 class gathers) against torch fp64."""
+  import ctypes as C
+  from corenet_b200 import _lib, ops
+  d, h, w = dhw
+  g = t.Generator().manual_seed(cin * 7 + d)
+  wt = t.randn(cin, 2, 7, 7, 7, generator=g) * 0.05
+  dy = t.randn(n, 2, 2 * d, 2 * h, 2 * w, generator=g)
+  ref = F.conv3d(dy.double(), wt.double(), None, stride=2, padding=3)
+  dyd = dy.to(dev()).contiguous()
+  out = t.full((n * d * h * w, cin + 4), float("nan"), device=dev())
+  wtc = t.zeros(_lib.lib().crn_tcts_packed_floats(2), device=dev())
+  st = _lib.stream_ptr()
+  wd = wt.to(dev()).contiguous()
+  _lib.call("crn_tcts_pack", wd.data_ptr(), cin, 2, wtc.data_ptr(), st)
+  desc = ops.make_desc(n, cin, 2, (d, h, w), (2 * d, 2 * h, 2 * w), (7, 7, 7), 2, 3, True, cin + 4, 4, planar=True)
+  status = t.zeros(1, dtype=t.int32, device=dev())
+  _lib.call("crn_convt7_tcs_dgrad", C.byref(desc), dyd.data_ptr(), wtc.data_ptr(), out.data_ptr(), status.data_ptr(), st)
+  t.cuda.synchronize()
+  assert int(status) == 0
+  assert bool(t.isnan(out[:, cin:]).all()), "columns outside the layer's slice must stay untouched"
+  got = out[:, :cin].reshape(n, d, h, w, cin).permute(0, 4, 1, 2, 3)
+  assert rel_err(got, ref) < 2e-5
+
+
 def test_linear():
   from corenet_b200 import ops
   g = t.Generator().manual_seed(5)
