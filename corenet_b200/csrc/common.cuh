@@ -7,6 +7,8 @@
 
 void crn_set_error(const char* fmt, ...);
 void crn_count_launches(int n);
+// bit 13 of crn_set_flags: single-pass TF32 (only the hi x hi product of the 3xTF32 split is issued)
+static inline int crn_single_pass();
 int crn_get_flags();              // debug switches, see crn_set_flags   // bumps the process-wide kernel launch counter
 
 #define CRN_REQUIRE(cond, ...)            \
@@ -26,6 +28,8 @@ int crn_get_flags();              // debug switches, see crn_set_flags   // bump
     }                                                                       \
     crn_count_launches(1);                                                  \
   } while (0)
+
+static inline int crn_single_pass() { return (crn_get_flags() >> 13) & 1; }
 
 static inline cudaStream_t crn_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -45,6 +45,7 @@ struct GTParams {
   int kchunks;                      // ceil(gK / 16)
   int nstages;                      // taps * kchunks
   int ksplit, accumulate;
+  int single;                       // 1: single-pass TF32 (hi x hi only)
   int dbg;                          // debug bits: 1 timeline stamps, 2 skip epilogue stores, 4 skip gathers, 8 skip MMAs
   // transposed-gather mode (tmode = 1): out[o] = sum_k in[(o + pad - k) / ts] W[k] over the taps with an exact
   // quotient (ConvTranspose forward = dgrad of a strided convolution).  Output positions are ordered by parity
@@ -288,8 +289,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
           const uint64_t dbl = tc::make_desc(b_base + B_PART_BYTES + ks * 2 * B_KQ_BYTES, B_KQ_BYTES, 128);
           const uint32_t d = tmem + st * BN;
           tc::mma_tf32(d, dah, dbh, idesc, (i % FL == 0 && ks == 0) ? 0u : 1u);
-          tc::mma_tf32(d, dal, dbh, idesc, 1u);
-          tc::mma_tf32(d, dah, dbl, idesc, 1u);
+          if (!p.single) {
+            tc::mma_tf32(d, dal, dbh, idesc, 1u);
+            tc::mma_tf32(d, dah, dbl, idesc, 1u);
+          }
         }
         tc::commit(&B->empty[slot]);
         if (i % FL == FL - 1 || i == nst - 1) tc::commit(&B->acc_full[st]);
@@ -436,6 +439,7 @@ extern "C" int crn_conv_gemm_tc(const crn_conv_desc* d, int32_t kind, const floa
   GTParams p{};
   p.in = in; p.wtc = wtc; p.out = out; p.status = status; p.accumulate = accumulate;
   p.dbg = (crn_get_flags() >> 8) & 15;
+  p.single = crn_single_pass();
   p.N = d->N; p.kD = d->kD; p.kH = d->kH; p.kW = d->kW;
   const int K3[3] = {d->kD, d->kH, d->kW}, I3[3] = {d->iD, d->iH, d->iW}, O3[3] = {d->oD, d->oH, d->oW};
   int s3[3], p3[3];

@@ -47,6 +47,7 @@ struct TC5Params {
   int planar;           // scatter mode: out is [N, Cout, 2D, 2H, 2W] instead of channels-last
   int tiles_x, tiles_y, tiles_z;
   int nitems;
+  int single;           // 1: single-pass TF32 (the A_lo / W_lo products are not issued)
 };
 
 struct __align__(8) Barriers {
@@ -448,6 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
                   const uint64_t db = tc::make_desc(wbase + kx * WTAP_BYTES, 2 * NPAD * 16, 128);
 #pragma unroll
                   for (int part = 0; part < 2; ++part) {
+                    if (part && p.single) break;
 #pragma unroll
                     for (int zz = 0; zz < ZT; ++zz) {
                       if (!((valid >> zz) & 1u)) continue;
@@ -463,6 +465,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
                   const uint64_t dbl = tc::make_desc(b_lo, NPAD * 16, 128);
 #pragma unroll
                   for (int part = 0; part < 3; ++part) {
+                    if (part && p.single) break;
 #pragma unroll
                     for (int zz = 0; zz < ZT; ++zz) {
                       if (!((valid >> zz) & 1u)) continue;
@@ -665,6 +668,7 @@ extern "C" int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* i
   CRN_REQUIRE(d->iW % TX == 0 && d->iH % TY == 0 && d->iD % 8 == 0, "crn_conv5_tc: grid must tile by 8x16x8");
   CRN_REQUIRE(!d->y_planar && !d->bias_n_stride, "crn_conv5_tc: planar / per-scene bias unsupported");
   TC5Params p{};
+  p.single = crn_single_pass();
   p.in = in; p.wtc = wtc; p.bias = kind == 0 ? bias : nullptr; p.out = out; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   if (kind == 0) {
@@ -732,6 +736,7 @@ extern "C" int crn_convt7_tc(const crn_conv_desc* d, const float* x, const float
   CRN_REQUIRE(d->Cin % 4 == 0 && d->x_cs % 4 == 0 && d->x_co % 4 == 0 && 8 * d->Cout <= 128,
               "crn_convt7_tc: Cin, x strides must be multiples of 4 and Cout <= 16");
   TC5Params p{};
+  p.single = crn_single_pass();
   p.in = x; p.wtc = wtc; p.bias = bias; p.out = y; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   p.gK = d->Cin; p.gN = 8 * d->Cout; p.cout_cls = d->Cout; p.planar = d->y_planar;
@@ -768,6 +773,7 @@ extern "C" int crn_convt7_tc_dgrad(const crn_conv_desc* d, const float* dy, cons
   CRN_REQUIRE(d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
               "crn_convt7_tc_dgrad: channel strides/offsets must be multiples of 4");
   TC5Params p{};
+  p.single = crn_single_pass();
   p.in = dy; p.wtc = wtc; p.bias = nullptr; p.out = dx; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   p.gK = 8 * d->Cout; p.gN = d->Cin; p.cout_cls = d->Cout;

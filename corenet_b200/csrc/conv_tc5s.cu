@@ -54,6 +54,8 @@ struct TC5SParams {
   int tiles_x, tiles_y, tiles_z, nitems;
   int cout_cls;            // GATH / SCAT: channels per parity class of the fine grid (K resp. N = 8 * cout_cls)
   int planar;              // SCAT: out is [N, Cout, 2D, 2H, 2W] instead of channels-last rows
+  int single;              // 1: single-pass TF32 (the A_lo / W_lo products are not issued)
+  int dbg;                 // crn_set_flags bit 8: per-CTA wait-time accounting (crn_tc5s_debug_read)
   int in_planar;           // GATH: the fine gradient is planar [N, 2, 2D, 2H, 2W] (cout_cls == 2, the FG_BG logits)
 };
 
@@ -64,6 +66,17 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
   int abort_flag;
 };
+
+// debug (crn_set_flags bit 8): per CTA [mma total, mma wait acc_empty, w_full, plane_full, producer total, producer wait
+// plane_empty, epilogue total, epilogue wait acc_full] in clock64 cycles
+__device__ long long g_tc5s_dbg[kNumSMs * 8];
+#define TC5S_TIMED(accum, call)                         \
+  ([&]() -> bool {                                      \
+    const long long t0__ = p.dbg ? clock64() : 0;       \
+    const bool ok__ = (call);                           \
+    if (p.dbg) accum += clock64() - t0__;               \
+    return ok__;                                        \
+  }())
 
 __device__ __forceinline__ void decode_item(const TC5SParams& p, int item, int& n, int& z0, int& y0, int& x0) {
   int t = item;
@@ -86,7 +99,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
   uint8_t* ring = smem;
   uint8_t* wring = smem + NSLOT * PLANE_BYTES;
   Barriers* B = reinterpret_cast<Barriers*>(wring + WSTAGES * WROW_BYTES);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)tc::uniform_u32((uint32_t)tid >> 5);   // warp-uniform for the compiler (role branches)
   if (tid == 0) {
     for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&B->plane_full[i], 128); tc::mbar_init(&B->plane_empty[i], 1); }
     for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&B->w_full[i], 1); tc::mbar_init(&B->w_empty[i], 1); }
@@ -98,7 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = B->tmem_base;
+  const uint32_t tmem = tc::uniform_u32(B->tmem_base);
   const uint32_t ring_u32 = tc::smem_u32(ring), wring_u32 = tc::smem_u32(wring);
   auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
   volatile int* ab = &B->abort_flag;
@@ -107,6 +121,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
     // ============================ EPILOGUE: one flush per (pass, ky) group into register sums, one store per item
     long long G = 0;
     bool dead = false;
+    long long tw_acc = 0;
+    const long long t_begin = p.dbg ? clock64() : 0;
     for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
       int n, z0, y0, x0;
       decode_item(p, item, n, z0, y0, x0);
@@ -120,7 +136,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
       for (int pass = 0; pass < p.P && !dead; ++pass) {
         for (int ky = 0; ky < KT; ++ky, ++G) {
           const int st = (int)(G & 1);
-          if (!tc::mbar_wait(&B->acc_full[st], (uint32_t)(G >> 1) & 1, ab)) { fail(); dead = true; break; }
+          if (!TC5S_TIMED(tw_acc, tc::mbar_wait(&B->acc_full[st], (uint32_t)(G >> 1) & 1, ab))) { fail(); dead = true; break; }
           tc::fence_after_sync();
 #pragma unroll
           for (int zz = 0; zz < ZT; ++zz) {
@@ -189,6 +205,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
       }
       }
     }
+    if (p.dbg && tid == 0) {
+      g_tc5s_dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
+      g_tc5s_dbg[blockIdx.x * 8 + 7] = tw_acc;
+    }
   } else if (warp < 8) {
     // ============================ PRODUCERS: halo gather + hi/lo split into the plane ring.
     // Software-pipelined: the gathers of plane L+1 are issued (into registers) right after plane L has been handed over,
@@ -239,10 +259,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
       }
     };
     if (item < p.nitems) gather();
+    long long tw_slot = 0;
+    const long long t_begin = p.dbg ? clock64() : 0;
     for (long long L = 0; item < p.nitems; ++L) {
       const int slot = (int)(L % NSLOT);
       const uint32_t use = (uint32_t)(L / NSLOT);
-      if (use > 0 && !tc::mbar_wait(&B->plane_empty[slot], (use - 1) & 1, ab)) { fail(); break; }
+      if (use > 0 && !TC5S_TIMED(tw_slot, tc::mbar_wait(&B->plane_empty[slot], (use - 1) & 1, ab))) { fail(); break; }
       if (inside) {
         uint8_t* dst = ring + slot * PLANE_BYTES;
 #pragma unroll
@@ -272,23 +294,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
       }
       if (item < p.nitems) gather();
     }
+    if (p.dbg && pt == 0) {
+      g_tc5s_dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      g_tc5s_dbg[blockIdx.x * 8 + 5] = tw_slot;
+    }
   } else if (warp == 8) {
-    // ============================ MMA ISSUER (one elected thread)
-    if (lane == 0) {
+    // ============================ MMA ISSUER: the whole warp runs the loop converged, one elected lane issues
+    {
       constexpr uint32_t A_DESC_HI = (uint32_t)((XS * 16) >> 4) | (1u << 14);   // SBO field | version 1 (bit 46)
       long long L0 = 0;                             // plane-load index of r = 0 of the current pass
       long long Wn = 0;                             // running weight-row (ky) index
       long long G = 0;                              // running (pass, ky) group index -> accumulator stage
       bool dead = false;
+      long long tw_acc = 0, tw_w = 0, tw_plane = 0;
+      const long long t_begin = p.dbg ? clock64() : 0;
+      const int p_single = p.single, p_dbg = p.dbg;
       for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
         int n, z0, y0, x0;
         decode_item(p, item, n, z0, y0, x0);
         for (int pass = 0; pass < p.P && !dead; ++pass, L0 += NPLANE) {
           for (int ky = 0; ky < KT && !dead; ++ky, ++G, ++Wn) {
             const int st = (int)(G & 1);
-            if (G >= 2 && !tc::mbar_wait(&B->acc_empty[st], (uint32_t)((G >> 1) - 1) & 1, ab)) { fail(); dead = true; break; }
+            if (G >= 2 && !TC5S_TIMED(tw_acc, tc::mbar_wait(&B->acc_empty[st], (uint32_t)((G >> 1) - 1) & 1, ab))) { fail(); dead = true; break; }
             const int ws = (int)(Wn % WSTAGES);
-            if (!tc::mbar_wait(&B->w_full[ws], (uint32_t)(Wn / WSTAGES) & 1, ab)) { fail(); dead = true; break; }
+            if (!TC5S_TIMED(tw_w, tc::mbar_wait(&B->w_full[ws], (uint32_t)(Wn / WSTAGES) & 1, ab))) { fail(); dead = true; break; }
             tc::fence_after_sync();
             const uint32_t wbase = wring_u32 + ws * WROW_BYTES;
             const uint32_t acc0 = tmem + st * (ZT * ACOLS);
@@ -298,7 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
               const long long L = L0 + q;
               const int slot = (int)(L % NSLOT);
               if (ky == 0) {                        // planes arrive during the first sweep of a pass
-                if (!tc::mbar_wait(&B->plane_full[slot], (uint32_t)(L / NSLOT) & 1, ab)) { fail(); dead = true; break; }
+                if (!TC5S_TIMED(tw_plane, tc::mbar_wait(&B->plane_full[slot], (uint32_t)(L / NSLOT) & 1, ab))) { fail(); dead = true; break; }
                 tc::fence_after_sync();
               }
               const int zin = z0 - HLO + q;
@@ -307,44 +336,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
                 const int zlo = q > KT - 1 ? q - (KT - 1) : 0, zhi = q < ZT - 1 ? q : ZT - 1;
                 // B rows: block b holds kz = KT-1 - b; plane zlo needs kz = q - zlo -> first block KT-1 - (q - zlo)
                 const uint32_t boff = (uint32_t)(KT - 1 - (q - zlo)) * (BLK * 16);
-                const uint32_t alo0 = ((ring_u32 + (uint32_t)slot * PLANE_BYTES) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16);
+                // descriptor words: everything that does not depend on (kx, part) is folded into a_q / b_q here, so one
+                // MMA costs two uniform adds (smem addresses >> 4 stay below 2^14: the adds never carry into LBO)
+                const uint32_t a_q = (((ring_u32 + (uint32_t)slot * PLANE_BYTES) >> 4) | ((uint32_t)(CHUNK_BYTES >> 4) << 16)) +
+                                     (uint32_t)(ky * XS);
+                const uint32_t b_q = (((wbase + boff) >> 4) & 0x3FFFu) | ((uint32_t)(KC_BYTES >> 4) << 16);
+                constexpr uint32_t B_DESC_HI = (uint32_t)(128 >> 4) | (1u << 14);     // SBO | version 1
+                const int cnt = zhi - zlo + 1;
+                const uint32_t idesc_q = tc::make_idesc_tf32(128, BLK * cnt, 0, 0);
+                const uint32_t acc_q = acc0 + zlo * ACOLS;
+                const bool fresh = ns <= zhi;          // some planes of the stack get their first contribution now
+                const int zs = ns > zlo ? ns : zlo;
+                if (fresh) ns = zhi + 1;
+                const bool skip = (p_dbg & 2) != 0;
 #pragma unroll
                 for (int kx = 0; kx < KT; ++kx) {
                   // ND16: (A_hi, [W_hi|W_lo]), (A_lo, [W_hi|0]);   WIDE: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
 #pragma unroll
                   for (int part = 0; part < (WIDE ? 3 : 2); ++part) {
+                    if ((part && p_single) || skip) break;
                     const bool a_lo = part == 1;
                     const bool b_r1 = WIDE ? part == 2 : part == 1;
-                    const uint32_t alo = alo0 + (ky * XS + kx) + (a_lo ? (PART_BYTES >> 4) : 0);
-                    const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
-                    const uint32_t bb = wbase + kx * TAP_BYTES + (b_r1 ? SROWS * 16 : 0) + boff;
-                    if (kx == 0 && part == 0 && ns <= zhi) {
-                      // planes [max(zlo, ns), zhi] get their first contribution of the group: overwrite them
-                      const int zs = ns > zlo ? ns : zlo;
-                      if (zs > zlo) {
-                        const int cnt = zs - zlo;
-                        tc::mma_tf32(acc0 + zlo * ACOLS, da, tc::make_desc(bb, KC_BYTES, 128),
-                                     tc::make_idesc_tf32(128, BLK * cnt, 0, 0), 1u);
-                      }
-                      const int cnt2 = zhi - zs + 1;
-                      tc::mma_tf32(acc0 + zs * ACOLS, da, tc::make_desc(bb + (uint32_t)(zs - zlo) * (BLK * 16), KC_BYTES, 128),
-                                   tc::make_idesc_tf32(128, BLK * cnt2, 0, 0), 0u);
-                      ns = zhi + 1;
+                    const uint64_t da = ((uint64_t)A_DESC_HI << 32) | (a_q + (uint32_t)(kx + (a_lo ? (PART_BYTES >> 4) : 0)));
+                    const uint32_t blo = b_q + (uint32_t)((kx * TAP_BYTES + (b_r1 ? SROWS * 16 : 0)) >> 4);
+                    const uint64_t db = ((uint64_t)B_DESC_HI << 32) | blo;
+                    if (kx == 0 && part == 0 && fresh) {
+                      // planes [zs, zhi] are overwritten (first MMA of the group on them), [zlo, zs) accumulate
+                      if (zs > zlo)
+                        tc::mma_tf32_e(acc_q, da, db, tc::make_idesc_tf32(128, BLK * (zs - zlo), 0, 0), 1u);
+                      tc::mma_tf32_e(acc0 + zs * ACOLS, da, db + (uint64_t)((uint32_t)(zs - zlo) * (BLK * 16 >> 4)),
+                                     tc::make_idesc_tf32(128, BLK * (zhi - zs + 1), 0, 0), 0u);
                     } else {
-                      const int cnt = zhi - zlo + 1;
-                      tc::mma_tf32(acc0 + zlo * ACOLS, da, tc::make_desc(bb, KC_BYTES, 128),
-                                   tc::make_idesc_tf32(128, BLK * cnt, 0, 0), 1u);
+                      tc::mma_tf32_e(acc_q, da, db, idesc_q, 1u);
                     }
                   }
                 }
               }
-              if (ky == KT - 1) tc::commit(&B->plane_empty[slot]); // last sweep of the pass: plane q is dead
+              if (ky == KT - 1) tc::commit_e(&B->plane_empty[slot]); // last sweep of the pass: plane q is dead
             }
             if (dead) break;
-            tc::commit(&B->w_empty[ws]);
-            tc::commit(&B->acc_full[st]);
+            tc::commit_e(&B->w_empty[ws]);
+            tc::commit_e(&B->acc_full[st]);
           }
         }
+      }
+      if (p.dbg && lane == 0) {
+        g_tc5s_dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+        g_tc5s_dbg[blockIdx.x * 8 + 1] = tw_acc;
+        g_tc5s_dbg[blockIdx.x * 8 + 2] = tw_w;
+        g_tc5s_dbg[blockIdx.x * 8 + 3] = tw_plane;
       }
     }
   } else {
@@ -548,6 +588,8 @@ extern "C" int crn_convt7_tcs_fwd(const crn_conv_desc* d, const float* x, const 
   CRN_REQUIRE(!d->bias_n_stride && d->Cin % 4 == 0 && d->x_cs % 4 == 0 && d->x_co % 4 == 0 && 8 * d->Cout <= 16,
               "crn_convt7_tcs_fwd: Cin, x strides multiples of 4, Cout <= 2");
   TC5SParams p{};
+  p.single = crn_single_pass();
+  p.dbg = (crn_get_flags() >> 8) & 3;    // bit 0: wait accounting, bit 1: skip the MMAs (issue-overhead probe)
   p.in = x; p.wtc = wtc; p.bias = bias; p.out = y; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   p.gK = d->Cin; p.gN = 8 * d->Cout; p.cout_cls = d->Cout; p.planar = d->y_planar;
@@ -575,6 +617,8 @@ extern "C" int crn_convt7_tcs_dgrad(const crn_conv_desc* d, const float* dy, con
                 "crn_convt7_tcs_dgrad: channels-last dy needs Cout, stride, offset multiples of 4");
   }
   TC5SParams p{};
+  p.single = crn_single_pass();
+  p.dbg = (crn_get_flags() >> 8) & 3;    // bit 0: wait accounting, bit 1: skip the MMAs (issue-overhead probe)
   p.in = dy; p.wtc = wtc; p.bias = nullptr; p.out = dx; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   p.gK = 8 * d->Cout; p.gN = d->Cin; p.cout_cls = d->Cout; p.in_planar = d->y_planar;
@@ -599,6 +643,14 @@ extern "C" int crn_tc5s_pack2(const float* w, int32_t Cout, int32_t Cin, int32_t
   return CRN_OK;
 }
 
+#ifdef CRN_DIAG
+extern "C" int crn_tc5s_debug_read(long long* host_dst, int32_t n);
+extern "C" int crn_tc5s_debug_read(long long* host_dst, int32_t n) {
+  return cudaMemcpyFromSymbol(host_dst, g_tc5s_dbg, sizeof(long long) * (n > kNumSMs * 8 ? kNumSMs * 8 : n)) == cudaSuccess
+             ? CRN_OK : CRN_ERR_LAUNCH;
+}
+#endif  // CRN_DIAG
+
 extern "C" int crn_tc5s_pack(const float* w, int32_t Cout, int32_t Cin, float* out, void* stream) {
   CRN_REQUIRE(Cout <= 16, "crn_tc5s_pack: Cout <= 16 (use crn_tc5s_pack2)");
   return crn_tc5s_pack2(w, Cout, Cin, 0, out, stream);
@@ -618,6 +670,8 @@ extern "C" int crn_conv5_tcs2(const crn_conv_desc* d, int32_t kind, const float*
   CRN_REQUIRE(d->x_cs % 4 == 0 && d->x_co % 4 == 0 && d->y_cs % 4 == 0 && d->y_co % 4 == 0,
               "crn_conv5_tcs: channel strides/offsets must be multiples of 4");
   TC5SParams p{};
+  p.single = crn_single_pass();
+  p.dbg = (crn_get_flags() >> 8) & 3;    // bit 0: wait accounting, bit 1: skip the MMAs (issue-overhead probe)
   p.in = in; p.wtc = wtc; p.bias = kind == 0 ? bias : nullptr; p.out = out; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   if (kind == 0) {

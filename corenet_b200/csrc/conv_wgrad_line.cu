@@ -40,6 +40,7 @@ struct WLParams {
   int npass;
   int pass_begin[12];  // prefix sums of line-steps per pass (npass + 1 entries)
   int flush_every;
+  int single;          // 1: single-pass TF32 (the lo products are not issued)
 };
 
 struct __align__(8) WLBarriers {
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
               tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbh + ro, idesc, acc);
             } else if (a < nk) {
               tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbh + ro, idesc, acc);
-              tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbl + ro, idesc, 1u);
+              if (!p.single) tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbl + ro, idesc, 1u);
             }
           }
         }
@@ -432,6 +433,7 @@ extern "C" int crn_conv_wgrad_line(const crn_conv_desc* d, const float* x, const
   CRN_REQUIRE(d && x && dy && dw_packed && status, "crn_conv_wgrad_line: null pointer");
   CRN_REQUIRE(crn_conv_wgrad_line_supported(d), "crn_conv_wgrad_line: unsupported layer shape");
   WLParams p{};
+  p.single = crn_single_pass();
   p.x = x; p.dy = dy; p.dw = dw_packed; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   p.Cin = d->Cin; p.Cout = d->Cout;
@@ -710,7 +712,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tline_kernel(const WLParams
           for (int a = 0; a < 4; ++a) {
             const uint64_t bo = (uint64_t)((r * 8 + a) * 8);    // (r*8 + a) rows of 128 bytes, >> 4
             tc::mma_tf32(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbh0 + bo, idesc, acc);
-            tc::mma_tf32(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbl0 + bo, idesc, 1u);
+            if (!p.single) tc::mma_tf32(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbl0 + bo, idesc, 1u);
           }
         }
         first = false;
@@ -1013,7 +1015,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_t2line_kernel(const WLParam
 #pragma unroll
         for (int r = 0; r < RUNS; ++r) {
           tc::mma_tf32(tmem, da0 + (uint64_t)(r * 64), dbh0 + (uint64_t)(r * 64), idesc, (first && r == 0) ? 0u : 1u);
-          tc::mma_tf32(tmem, da0 + (uint64_t)(r * 64), dbl0 + (uint64_t)(r * 64), idesc, 1u);
+          if (!p.single) tc::mma_tf32(tmem, da0 + (uint64_t)(r * 64), dbl0 + (uint64_t)(r * 64), idesc, 1u);
         }
         first = false;
         tc::commit(&B->empty_y[yslot]);
@@ -1092,6 +1094,7 @@ extern "C" int crn_convt7_wgrad_line(const crn_conv_desc* d, const float* x, con
   CRN_REQUIRE(d && x && dy && dw_packed && status, "crn_convt7_wgrad_line: null pointer");
   CRN_REQUIRE(crn_convt7_wgrad_line_supported(d), "crn_convt7_wgrad_line: unsupported layer shape");
   WLParams p{};
+  p.single = crn_single_pass();
   p.x = x; p.dy = dy; p.dw = dw_packed; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   p.Cin = d->Cin; p.Cout = d->Cout;
@@ -1117,6 +1120,7 @@ struct WXParams {
   int mtiles, ntiles;      // 128-channel Cin tiles, BN-channel Cout tiles
   int lines;               // N * D * H image rows per (kz, ky) pass
   int flush_every;
+  int single;          // 1: single-pass TF32 (the lo products are not issued)
 };
 
 template <int W, int BN>
@@ -1297,8 +1301,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_xline_kernel(const WXParams
           for (int a = 0; a < 5; ++a) {                    // kx = a: x rows shifted by a
             const uint64_t xo = (uint64_t)((r * 8 + a) * 8), yo = (uint64_t)(r * 64);
             tc::mma_tf32(tmem + a * BN, dxh + xo, dyh + yo, idesc, (first && r == 0) ? 0u : 1u);
-            tc::mma_tf32(tmem + a * BN, dxl + xo, dyh + yo, idesc, 1u);
-            tc::mma_tf32(tmem + a * BN, dxh + xo, dyl + yo, idesc, 1u);
+            if (!p.single) {
+              tc::mma_tf32(tmem + a * BN, dxl + xo, dyh + yo, idesc, 1u);
+              tc::mma_tf32(tmem + a * BN, dxh + xo, dyl + yo, idesc, 1u);
+            }
           }
         }
         first = false;
@@ -1358,6 +1364,7 @@ extern "C" int crn_conv_wgrad_xline(const crn_conv_desc* d, const float* x, cons
   CRN_REQUIRE(d && x && dy && dw_packed && status, "crn_conv_wgrad_xline: null pointer");
   CRN_REQUIRE(crn_conv_wgrad_xline_supported(d), "crn_conv_wgrad_xline: unsupported layer shape");
   WXParams p{};
+  p.single = crn_single_pass();
   p.x = x; p.dy = dy; p.dw = dw_packed; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   p.Cin = d->Cin; p.Cout = d->Cout;

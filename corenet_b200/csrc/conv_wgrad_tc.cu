@@ -41,6 +41,7 @@ struct WTParams {
   float* dw;           // [tap][CinP][CoutP]
   int* status;
   int CinP, CoutP;
+  int single;          // 1: single-pass TF32 (hi x hi only)
   int m_is_cin;        // D[m][n]: m = ci, n = co (1) or m = co, n = ci (0)
   int N, bD, bH, bW;   // base grid
   int kD, kH, kW, sD, sH, sW, pD, pH, pW;
@@ -261,8 +262,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const WTParams p)
           const uint64_t dql = tc::make_desc_mn32(q_base + Q_PART_BYTES + ks * 1024, CB_BYTES, 512);
           const uint32_t d = tmem + st * BN;
           tc::mma_tf32(d, dph, dqh, idesc, (i % FLW == 0 && ks == 0) ? 0u : 1u);
-          tc::mma_tf32(d, dpl, dqh, idesc, 1u);
-          tc::mma_tf32(d, dph, dql, idesc, 1u);
+          if (!p.single) {
+            tc::mma_tf32(d, dpl, dqh, idesc, 1u);
+            tc::mma_tf32(d, dph, dql, idesc, 1u);
+          }
         }
         tc::commit(&B->empty[slot]);
         if (i % FLW == FLW - 1 || i == nst - 1) tc::commit(&B->acc_full[st]);
@@ -306,7 +309,7 @@ extern "C" int crn_conv_wgrad_tc(const crn_conv_desc* d, const float* x, const f
                   d->y_co % 4 == 0 && d->CoutP % 4 == 0,
               "crn_conv_wgrad_tc: channels, strides and offsets must be multiples of 4");
   WTParams p{};
-  p.dw = dw_packed; p.status = status; p.CinP = d->CinP; p.CoutP = d->CoutP;
+  p.dw = dw_packed; p.status = status; p.CinP = d->CinP; p.CoutP = d->CoutP; p.single = crn_single_pass();
   p.N = d->N; p.kD = d->kD; p.kH = d->kH; p.kW = d->kW;
   const int K3[3] = {d->kD, d->kH, d->kW}, I3[3] = {d->iD, d->iH, d->iW}, O3[3] = {d->oD, d->oH, d->oW};
   int s3[3], p3[3];

@@ -54,10 +54,38 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// One lane of a CONVERGED warp (always the same one for the full mask).  The MMA-issuing warp runs its whole loop with
+// all 32 lanes and warp-uniform values (warp index / TMEM base made uniform with uniform_u32) and only the tcgen05.mma /
+// tcgen05.commit instructions sit under elect_one(): the compiler then keeps descriptors in uniform registers.  Issuing
+// from an `if (lane == 0)` region instead makes every UTCHMMA a vote loop (ELECT / R2UR / BRA.U.ANY, ~30 SASS instructions
+// per MMA), which made the issuing thread -- not the tensor pipe -- the critical path (profiles/r02g_tc5s_waits.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// value of lane 0, known to the compiler as warp-uniform
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // all previously issued tcgen05.mma of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// elected-lane forms for a converged issuing warp
+__device__ __forceinline__ void mma_tf32_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if (elect_one()) mma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void commit_e(uint64_t* bar) {
+  if (elect_one()) commit(bar);
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {   // warp-collective

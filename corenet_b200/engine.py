@@ -271,6 +271,24 @@ USE_TCTS = True
 # BatchRenorm of small maps through the single-launch cluster kernels (csrc/brn_fused.cu)
 USE_FUSED_BRN = True
 
+# Arithmetic of the tcgen05 convolution kernels.  "3xtf32" (default, fp32-class: every product is the three-term
+# hi/lo TF32 split, see DESIGN.md "Precision") or "tf32" (single pass: only hi x hi is issued -- what cuDNN does with
+# torch.backends.cudnn.allow_tf32 = True; measured in profiles/r02_precision_study.md).  The non-default mode is an
+# opt-in: the reference's default arithmetic for Conv3d on CUDA is TF32 too, but the parity bar of this repo (logits
+# <= 1e-3 against the fp64 oracle) is only met by "3xtf32".
+PRECISION = "3xtf32"
+_PRECISION_FLAG = 1 << 13
+
+
+def set_precision(mode: str) -> None:
+  """Selects the MMA arithmetic of every tcgen05 kernel (bit 13 of crn_set_flags).  Captured CUDA graphs bake the
+  choice in; Plan / Trainer / Evaluator key their graphs on it, so a change re-captures on the next call."""
+  global PRECISION
+  if mode not in ("3xtf32", "tf32"):
+    raise ValueError(f"precision must be '3xtf32' or 'tf32', got {mode!r}")
+  PRECISION = mode
+  _lib.lib().crn_set_flags(_PRECISION_FLAG if mode == "tf32" else 0)
+
 
 def convt7_tc_call(layer, d, inp, wtc, bias, out, status, st, acct=None, fn="crn_convt7_tc"):
   """ConvTranspose3d k=7 s=2 forward through crn_convt7_tc (or the jz-stacked crn_convt7_tcs_fwd).  acct: descriptor
@@ -1383,7 +1401,7 @@ class Plan:
     """Everything a captured graph bakes in: parameter / buffer addresses and the kernel routing switches."""
     P, Bf = self.eng.tensors()
     return (tuple(p.data_ptr() for p in P.values()), tuple(b.data_ptr() for b in Bf.values()), USE_TC, USE_TC5S,
-            WGRAD_SIDE_STREAM)
+            WGRAD_SIDE_STREAM, PRECISION)
 
   def _graph_state(self, key):
     sig = self._sig()

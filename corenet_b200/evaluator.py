@@ -54,7 +54,7 @@ class Evaluator:
     if (labels is None) != (self.k == self.c):
       raise ValueError("scene labels are needed exactly when num_classes != num_output_channels (FG_BG task)")
     dev = next(self.model.parameters()).device
-    key = (tuple(image.shape), tuple(gt.shape), gt.dtype, labels is not None)
+    key = (tuple(image.shape), tuple(gt.shape), gt.dtype, labels is not None, engine_lib.PRECISION)
     gs = self._graphs.get(key)
     if gs is None:
       xs = [(image, None), (v2s, t.float32), (offsets, t.float32), (gt, None)]

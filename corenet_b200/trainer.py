@@ -237,7 +237,8 @@ class Trainer:
 
   def _gstate(self, image, v2s, offsets, gt):
     self._check_inputs(image, v2s, offsets, gt)
-    key = (tuple(image.shape), tuple(gt.shape), gt.dtype, self.flat.device, self.model.training)
+    key = (tuple(image.shape), tuple(gt.shape), gt.dtype, self.flat.device, self.model.training,
+           engine_lib.PRECISION)
     gs = self._graphs.get(key)
     if gs is None:
       mk = lambda: [t.empty(x.shape, dtype=d or x.dtype, device=self.flat.device)

@@ -42,7 +42,9 @@ int64_t crn_launch_count(void);
  * kernel (both fall back to the generic implicit-GEMM kernels), bit4 = disable split-K in the generic and the
  * tcgen05 implicit-GEMM kernels, bit5 = disable the stem wgrad kernel, bit6 = 3 narrow MMAs instead of N doubling in
  * conv_tc5, bits 8-11 = gemm_tc_kernel debug (timeline stamps / skip stores / skip gathers / skip MMAs),
- * bit12 = crn_fill_inside uses the global-memory line-sweep kernels instead of the shared-memory cluster kernel. */
+ * bit12 = crn_fill_inside uses the global-memory line-sweep kernels instead of the shared-memory cluster kernel,
+ * bit13 = single-pass TF32: every tcgen05 kernel issues only the hi x hi product of its 3xTF32 operand split (an
+ *         opt-in precision mode, engine.set_precision("tf32"); the default three-term split is fp32-class). */
 void crn_set_flags(int32_t flags);
 
 /* ------------------------------------------------------------------------

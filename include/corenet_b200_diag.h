@@ -25,6 +25,9 @@ int crn_tc_probe_mn(const float* A, const float* B, float* D, int32_t N, int32_t
 
 /* Debug: with crn_set_flags bit 8 the kernel stamps a per-CTA clock64 timeline; copies n (<= 4096) int64 to host. */
 int crn_gemm_tc_debug_read(long long* host_dst, int32_t n);
+/* Same switch for conv_tc5s_kernel: per CTA 8 int64 = cycles of [MMA thread total, its waits on acc_empty / w_full /
+ * plane_full, producer total, its wait on plane_empty, epilogue total, its wait on acc_full]; n <= 148 * 8. */
+int crn_tc5s_debug_read(long long* host_dst, int32_t n);
 
 #ifdef __cplusplus
 }
