@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
   uint8_t* bbuf = smem + NSTAGE * A_STAGE_BYTES;
   GTBarriers* B = reinterpret_cast<GTBarriers*>(bbuf + NSTAGE * B_STAGE_BYTES);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)tc::uniform_u32((uint32_t)tid >> 5);   // warp-uniform for the compiler (role branches)
   const int mt = blockIdx.x, nt = blockIdx.y, z = blockIdx.z;
   if (tid == 0) GT_STAMP(0);
   // transposed-gather mode: parity class of this tile, its taps per axis (k = r + ts*j, j < K_c) and the input
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = B->tmem_base;
+  const uint32_t tmem = tc::uniform_u32(B->tmem_base);
   const uint32_t abuf_u32 = tc::smem_u32(abuf), bbuf_u32 = tc::smem_u32(bbuf);
   if (tid == 0) GT_STAMP(1);
   auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
     }
   } else if (warp == 8) {
     // ============================ MMA ISSUER (one elected thread)
-    if (lane == 0) {
+    {  // converged warp, elected lane issues (tc_common.cuh elect_one)
+      const int p_single = p.single;
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, BN, 0, 0);
       int st = 0;
       bool dead = false;
@@ -288,14 +290,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
           const uint64_t dbh = tc::make_desc(b_base + ks * 2 * B_KQ_BYTES, B_KQ_BYTES, 128);
           const uint64_t dbl = tc::make_desc(b_base + B_PART_BYTES + ks * 2 * B_KQ_BYTES, B_KQ_BYTES, 128);
           const uint32_t d = tmem + st * BN;
-          tc::mma_tf32(d, dah, dbh, idesc, (i % FL == 0 && ks == 0) ? 0u : 1u);
-          if (!p.single) {
-            tc::mma_tf32(d, dal, dbh, idesc, 1u);
-            tc::mma_tf32(d, dah, dbl, idesc, 1u);
+          tc::mma_tf32_e(d, dah, dbh, idesc, (i % FL == 0 && ks == 0) ? 0u : 1u);
+          if (!p_single) {
+            tc::mma_tf32_e(d, dal, dbh, idesc, 1u);
+            tc::mma_tf32_e(d, dah, dbl, idesc, 1u);
           }
         }
-        tc::commit(&B->empty[slot]);
-        if (i % FL == FL - 1 || i == nst - 1) tc::commit(&B->acc_full[st]);
+        tc::commit_e(&B->empty[slot]);
+        if (i % FL == FL - 1 || i == nst - 1) tc::commit_e(&B->acc_full[st]);
       }
       GT_STAMP(3);
     }

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
   uint8_t* wring = smem + NSLOT * PLANE_BYTES;
   Barriers* B = reinterpret_cast<Barriers*>(wring + WSTAGES * WROW_BYTES);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)tc::uniform_u32((uint32_t)tid >> 5);   // warp-uniform for the compiler (role branches)
   if (tid == 0) {
     for (int i = 0; i < NSLOT; ++i) { tc::mbar_init(&B->plane_full[i], 128); tc::mbar_init(&B->plane_empty[i], 1); }
     for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&B->w_full[i], 1); tc::mbar_init(&B->w_empty[i], 1); }
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = B->tmem_base;
+  const uint32_t tmem = tc::uniform_u32(B->tmem_base);
   const uint32_t ring_u32 = tc::smem_u32(ring), wring_u32 = tc::smem_u32(wring);
 
   auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
@@ -395,8 +396,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
       }
     }
   } else if (warp == 8) {
-    // ============================ MMA ISSUER (one elected thread)
-    if (lane == 0) {
+    // ============================ MMA ISSUER: the whole warp runs the loop converged, one elected lane issues
+    // (tc_common.cuh elect_one: an `if (lane == 0)` region turns every UTCHMMA into a vote loop)
+    {
+      const int p_single = p.single;
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, NPAD, 0, 0);
       constexpr uint32_t idesc2 = tc::make_idesc_tf32(128, 2 * NPAD, 0, 0);
       constexpr uint32_t A_DESC_HI = (uint32_t)((XS * 16) >> 4) | (1u << 14);   // SBO field | version 1 (bit 46)
@@ -440,55 +443,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5_kernel(const TC5Params p
               if (!tc::mbar_wait(&B->w_full[ws], (uint32_t)(Wn / WSTAGES) & 1, ab)) { fail(); dead = true; break; }
               tc::fence_after_sync();
               const uint32_t wbase = wring_u32 + ws * WROW_BYTES;
+              // low descriptor words of the weight row (smem addresses >> 4 stay below 2^14: adding tap offsets never
+              // carries into the LBO field)
+              constexpr uint32_t B_DESC_HI = (uint32_t)(128 >> 4) | (1u << 14);       // SBO | version 1
+              const uint32_t wlo_nd = ((wbase >> 4) & 0x3FFFu) | ((uint32_t)((2 * NPAD * 16) >> 4) << 16);
+              const uint32_t wlo_w = ((wbase >> 4) & 0x3FFFu) | ((uint32_t)((NPAD * 16) >> 4) << 16);
               // Interleave the 8 output planes: consecutive tcgen05.mma go to DIFFERENT accumulators, so the
               // tensor pipe never waits on a read-after-write of the same TMEM tile.
 #pragma unroll
               for (int kx = 0; kx < KT; ++kx) {
                 if constexpr (ND) {
                   // tap layout [kc][hi rows | lo rows][16 B]: one descriptor, N = 2*NPAD or the first NPAD rows
-                  const uint64_t db = tc::make_desc(wbase + kx * WTAP_BYTES, 2 * NPAD * 16, 128);
+                  const uint64_t db = ((uint64_t)B_DESC_HI << 32) |
+                                      (wlo_nd + (uint32_t)((kx * WTAP_BYTES) >> 4));
 #pragma unroll
                   for (int part = 0; part < 2; ++part) {
-                    if (part && p.single) break;
+                    if (part && p_single) break;
 #pragma unroll
                     for (int zz = 0; zz < ZT; ++zz) {
                       if (!((valid >> zz) & 1u)) continue;
                       const uint32_t alo = abase[zz] + (ky * XS + kx) + (part == 1 ? (PART_BYTES >> 4) : 0);
                       const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
                       const uint32_t acc = (kx | part) ? 1u : ((started >> zz) & 1u);
-                      tc::mma_tf32(tmem + st * (ZT * ACOLS) + zz * ACOLS, da, db, part == 0 ? idesc2 : idesc, acc);
+                      tc::mma_tf32_e(tmem + st * (ZT * ACOLS) + zz * ACOLS, da, db, part == 0 ? idesc2 : idesc, acc);
                     }
                   }
                 } else {
-                  const uint32_t b_hi = wbase + kx * WTAP_BYTES, b_lo = b_hi + 2 * NPAD * 16;
-                  const uint64_t dbh = tc::make_desc(b_hi, NPAD * 16, 128);
-                  const uint64_t dbl = tc::make_desc(b_lo, NPAD * 16, 128);
+                  const uint64_t dbh = ((uint64_t)B_DESC_HI << 32) | (wlo_w + (uint32_t)((kx * WTAP_BYTES) >> 4));
+                  const uint64_t dbl = dbh + (uint64_t)((2 * NPAD * 16) >> 4);
 #pragma unroll
                   for (int part = 0; part < 3; ++part) {
-                    if (part && p.single) break;
+                    if (part && p_single) break;
 #pragma unroll
                     for (int zz = 0; zz < ZT; ++zz) {
                       if (!((valid >> zz) & 1u)) continue;
                       const uint32_t alo = abase[zz] + (ky * XS + kx) + (part == 1 ? (PART_BYTES >> 4) : 0);
                       const uint64_t da = ((uint64_t)A_DESC_HI << 32) | alo;
                       const uint32_t acc = (kx | part) ? 1u : ((started >> zz) & 1u);
-                      tc::mma_tf32(tmem + st * (ZT * ACOLS) + zz * ACOLS, da, part == 2 ? dbl : dbh, idesc, acc);
+                      tc::mma_tf32_e(tmem + st * (ZT * ACOLS) + zz * ACOLS, da, part == 2 ? dbl : dbh, idesc, acc);
                     }
                   }
                 }
               }
               started |= valid;
-              tc::commit(&B->w_empty[ws]);          // weight row free once these MMAs have completed
+              tc::commit_e(&B->w_empty[ws]);          // weight row free once these MMAs have completed
             }
             if (dead) break;
-            tc::commit(&B->plane_empty[(L0 + kz) % NSLOT]);      // plane r = kz is done
+            tc::commit_e(&B->plane_empty[(L0 + kz) % NSLOT]);      // plane r = kz is done
             if (kz % KZG == KZG - 1 || kz == KT - 1) {
-              tc::commit(&B->acc_full[st]);                      // this group's partial sums are complete
+              tc::commit_e(&B->acc_full[st]);                      // this group's partial sums are complete
               ++G;
             }
           }
           if (dead) break;
-          for (int r = KT; r < NPLANE; ++r) tc::commit(&B->plane_empty[(L0 + r) % NSLOT]);
+          for (int r = KT; r < NPLANE; ++r) tc::commit_e(&B->plane_empty[(L0 + r) % NSLOT]);
         }
       }
     }

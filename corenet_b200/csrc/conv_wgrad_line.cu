@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
   uint8_t* yring = smem + XALL * XL;
   WLBarriers* B = reinterpret_cast<WLBarriers*>(yring + YSLOTS * YL);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)tc::uniform_u32((uint32_t)tid >> 5);   // warp-uniform for the compiler (role branches)
   const int T = p.pass_begin[p.npass];
   const int t0 = (int)((long long)T * blockIdx.x / gridDim.x), t1 = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
 
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = B->tmem_base;
+  const uint32_t tmem = tc::uniform_u32(B->tmem_base);
   const uint32_t xring_u32 = tc::smem_u32(xring), yring_u32 = tc::smem_u32(yring);
   auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
   volatile int* ab = &B->abort_flag;
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
     // This single thread is the critical path (its instruction latency, not the tensor pipe, bounded the first
     // version): no divisions, no per-step decode -- the step state is carried incrementally, descriptors are built
     // once per step and advanced by adding the run offset to the 14-bit start-address field.
-    if (lane == 0) {
+    {  // converged warp, elected lane issues (tc_common.cuh elect_one)
+      const int p_single = p.single;
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, ACOLS, 1, 1);
       uint32_t q = 0;               // x line loads consumed so far (mirrors the producers' counter)
       uint32_t nflush = 0;
@@ -346,15 +348,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
 #pragma unroll
           for (int a = 0; a < NACC; ++a) {
             if (CB == 1) {
-              tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbh + ro, idesc, acc);
+              tc::mma_tf32_e(tmem + a * ACOLS, da[a] + ro, dbh + ro, idesc, acc);
             } else if (a < nk) {
-              tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbh + ro, idesc, acc);
-              if (!p.single) tc::mma_tf32(tmem + a * ACOLS, da[a] + ro, dbl + ro, idesc, 1u);
+              tc::mma_tf32_e(tmem + a * ACOLS, da[a] + ro, dbh + ro, idesc, acc);
+              if (!p_single) tc::mma_tf32_e(tmem + a * ACOLS, da[a] + ro, dbl + ro, idesc, 1u);
             }
           }
         }
         first = false;
-        tc::commit(&B->empty_y[yslot]);
+        tc::commit_e(&B->empty_y[yslot]);
         if (++yslot == YSLOTS) { yslot = 0; yphase ^= 1; }
         // release the x lines the next step drops from the window
         const bool next_fresh = (y + 1 == p.H);
@@ -362,13 +364,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
           const int ndrop = next_fresh ? nk : 1;
           uint32_t sl = w0slot;
           for (int j = 0; j < ndrop; ++j) {
-            tc::commit(&B->empty_x[sl]);
+            tc::commit_e(&B->empty_x[sl]);
             if (++sl == XS) sl = 0;
           }
         }
         if (++mod_ctr == p.flush_every) mod_ctr = 0;
         if (t == t1 - 1 || t + 1 >= pass_end || mod_ctr == 0) {
-          tc::commit(&B->acc_full);
+          tc::commit_e(&B->acc_full);
           ++nflush;
           first = true;
         }
@@ -495,7 +497,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tline_kernel(const WLParams
   uint8_t* yring = smem + XALL * XL;
   WLBarriers* B = reinterpret_cast<WLBarriers*>(yring + YS * YL);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)tc::uniform_u32((uint32_t)tid >> 5);   // warp-uniform for the compiler (role branches)
   const int T = p.pass_begin[p.npass];
   const int t0 = (int)((long long)T * blockIdx.x / gridDim.x), t1 = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
 
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tline_kernel(const WLParams
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = B->tmem_base;
+  const uint32_t tmem = tc::uniform_u32(B->tmem_base);
   const uint32_t xring_u32 = tc::smem_u32(xring), yring_u32 = tc::smem_u32(yring);
   auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
   volatile int* ab = &B->abort_flag;
@@ -678,7 +681,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tline_kernel(const WLParams
     }
   } else {
     // ============================ MMA ISSUER (incremental step state, see wgrad_line_kernel)
-    if (lane == 0) {
+    {  // converged warp, elected lane issues (tc_common.cuh elect_one)
+      const int p_single = p.single;
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, 128, 1, 1);
       uint32_t nflush = 0;
       bool first = true;            // next MMA of every accumulator overwrites (start of a flush interval)
@@ -711,25 +715,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tline_kernel(const WLParams
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             const uint64_t bo = (uint64_t)((r * 8 + a) * 8);    // (r*8 + a) rows of 128 bytes, >> 4
-            tc::mma_tf32(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbh0 + bo, idesc, acc);
-            if (!p.single) tc::mma_tf32(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbl0 + bo, idesc, 1u);
+            tc::mma_tf32_e(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbh0 + bo, idesc, acc);
+            if (!p_single) tc::mma_tf32_e(tmem + a * TCOLS, da0 + (uint64_t)(r * 64), dbl0 + bo, idesc, 1u);
           }
         }
         first = false;
-        tc::commit(&B->empty_y[yslot]);
+        tc::commit_e(&B->empty_y[yslot]);
         if (++yslot == YS) { yslot = 0; yphase ^= 1; }
         const bool next_fresh = (y + 1 == p.H);
         if (t + 1 < t1) {
           const int ndrop = next_fresh ? 2 : 1;
           uint32_t sl = w0slot;
           for (int j = 0; j < ndrop; ++j) {
-            tc::commit(&B->empty_x[sl]);
+            tc::commit_e(&B->empty_x[sl]);
             if (++sl == XS) sl = 0;
           }
         }
         if (++mod_ctr == p.flush_every) mod_ctr = 0;
         if (t == t1 - 1 || t + 1 >= pass_end || mod_ctr == 0) {
-          tc::commit(&B->acc_full);
+          tc::commit_e(&B->acc_full);
           ++nflush;
           first = true;
         }
@@ -799,7 +803,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_t2line_kernel(const WLParam
   uint8_t* yring = smem + XALL * XL;
   WLBarriers* B = reinterpret_cast<WLBarriers*>(yring + YS * YL);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)tc::uniform_u32((uint32_t)tid >> 5);   // warp-uniform for the compiler (role branches)
   const int T = p.pass_begin[p.npass];
   const int t0 = (int)((long long)T * blockIdx.x / gridDim.x), t1 = (int)((long long)T * (blockIdx.x + 1) / gridDim.x);
 
@@ -817,7 +822,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_t2line_kernel(const WLParam
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = B->tmem_base;
+  const uint32_t tmem = tc::uniform_u32(B->tmem_base);
   const uint32_t xring_u32 = tc::smem_u32(xring), yring_u32 = tc::smem_u32(yring);
   auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
   volatile int* ab = &B->abort_flag;
@@ -985,7 +990,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_t2line_kernel(const WLParam
     }
   } else {
     // ============================ MMA ISSUER (incremental step state, see wgrad_line_kernel)
-    if (lane == 0) {
+    {  // converged warp, elected lane issues (tc_common.cuh elect_one)
+      const int p_single = p.single;
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, 128, 1, 1);
       uint32_t nflush = 0;
       bool first = true;
@@ -1014,24 +1020,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_t2line_kernel(const WLParam
         const uint64_t dbl0 = tc::make_desc_mn32(ybase + YH, 128, 512);
 #pragma unroll
         for (int r = 0; r < RUNS; ++r) {
-          tc::mma_tf32(tmem, da0 + (uint64_t)(r * 64), dbh0 + (uint64_t)(r * 64), idesc, (first && r == 0) ? 0u : 1u);
-          if (!p.single) tc::mma_tf32(tmem, da0 + (uint64_t)(r * 64), dbl0 + (uint64_t)(r * 64), idesc, 1u);
+          tc::mma_tf32_e(tmem, da0 + (uint64_t)(r * 64), dbh0 + (uint64_t)(r * 64), idesc, (first && r == 0) ? 0u : 1u);
+          if (!p_single) tc::mma_tf32_e(tmem, da0 + (uint64_t)(r * 64), dbl0 + (uint64_t)(r * 64), idesc, 1u);
         }
         first = false;
-        tc::commit(&B->empty_y[yslot]);
+        tc::commit_e(&B->empty_y[yslot]);
         if (++yslot == YS) { yslot = 0; yphase ^= 1; }
         const bool next_fresh = (y + 1 == p.H);
         if (t + 1 < t1) {
           const int ndrop = next_fresh ? 4 : 1;
           uint32_t sl = w0slot;
           for (int j = 0; j < ndrop; ++j) {
-            tc::commit(&B->empty_x[sl]);
+            tc::commit_e(&B->empty_x[sl]);
             if (++sl == XS) sl = 0;
           }
         }
         if (++mod_ctr == p.flush_every) mod_ctr = 0;
         if (t == t1 - 1 || t + 1 >= pass_end || mod_ctr == 0) {
-          tc::commit(&B->acc_full);
+          tc::commit_e(&B->acc_full);
           ++nflush;
           first = true;
         }
@@ -1138,7 +1144,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_xline_kernel(const WXParams
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   WLBarriers* B = reinterpret_cast<WLBarriers*>(smem + NS * STAGE);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)tc::uniform_u32((uint32_t)tid >> 5);   // warp-uniform for the compiler (role branches)
   // blockIdx.y = (m tile, n tile); blockIdx.x splits the 25 * lines steps
   const int mt = blockIdx.y / p.ntiles, nt = blockIdx.y % p.ntiles;
   const long long T = 25LL * p.lines;
@@ -1157,7 +1164,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_xline_kernel(const WXParams
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = B->tmem_base;
+  const uint32_t tmem = tc::uniform_u32(B->tmem_base);
   const uint32_t smem_u32 = tc::smem_u32(smem);
   auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
   volatile int* ab = &B->abort_flag;
@@ -1280,7 +1287,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_xline_kernel(const WXParams
     }
   } else {
     // ============================ MMA ISSUER
-    if (lane == 0) {
+    {  // converged warp, elected lane issues (tc_common.cuh elect_one)
+      const int p_single = p.single;
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, BN, 1, 1);
       uint32_t nflush = 0, slot = 0, phase = 0;
       bool first = true, dead = false;
@@ -1300,20 +1308,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_xline_kernel(const WXParams
 #pragma unroll
           for (int a = 0; a < 5; ++a) {                    // kx = a: x rows shifted by a
             const uint64_t xo = (uint64_t)((r * 8 + a) * 8), yo = (uint64_t)(r * 64);
-            tc::mma_tf32(tmem + a * BN, dxh + xo, dyh + yo, idesc, (first && r == 0) ? 0u : 1u);
-            if (!p.single) {
-              tc::mma_tf32(tmem + a * BN, dxl + xo, dyh + yo, idesc, 1u);
-              tc::mma_tf32(tmem + a * BN, dxh + xo, dyl + yo, idesc, 1u);
+            tc::mma_tf32_e(tmem + a * BN, dxh + xo, dyh + yo, idesc, (first && r == 0) ? 0u : 1u);
+            if (!p_single) {
+              tc::mma_tf32_e(tmem + a * BN, dxl + xo, dyh + yo, idesc, 1u);
+              tc::mma_tf32_e(tmem + a * BN, dxh + xo, dyl + yo, idesc, 1u);
             }
           }
         }
         first = false;
-        tc::commit(&B->empty_x[slot]);
+        tc::commit_e(&B->empty_x[slot]);
         if (++slot == NS) { slot = 0; phase ^= 1; }
         if (++mod_ctr == p.flush_every) mod_ctr = 0;
         if (++line == p.lines) line = 0;
         if (t == t1 - 1 || line == 0 || mod_ctr == 0) {
-          tc::commit(&B->acc_full);
+          tc::commit_e(&B->acc_full);
           ++nflush;
           first = true;
         }

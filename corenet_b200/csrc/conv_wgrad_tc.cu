@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const WTParams p)
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 512 B alignment
   WTBarriers* B = reinterpret_cast<WTBarriers*>(smem + NSTAGE * STAGE_BYTES);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)tc::uniform_u32((uint32_t)tid >> 5);   // warp-uniform for the compiler (role branches)
   int bx = blockIdx.x;
   const int nt = bx % p.ntiles; bx /= p.ntiles;
   const int mt = bx % p.mtiles; const int tap = bx / p.mtiles;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const WTParams p)
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = B->tmem_base;
+  const uint32_t tmem = tc::uniform_u32(B->tmem_base);
   const uint32_t smem_u32 = tc::smem_u32(smem);
   auto fail = [&]() { B->abort_flag = 1; *p.status = 1; };
   volatile int* ab = &B->abort_flag;
@@ -238,7 +239,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const WTParams p)
     }
   } else {
     // ============================ MMA ISSUER (one elected thread)
-    if (lane == 0) {
+    {  // converged warp, elected lane issues (tc_common.cuh elect_one)
+      const int p_single = p.single;
       constexpr uint32_t idesc = tc::make_idesc_tf32(128, BN, 1, 1);
       int st = 0;
       bool dead = false;
@@ -261,14 +263,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_tc_kernel(const WTParams p)
           const uint64_t dqh = tc::make_desc_mn32(q_base + ks * 1024, CB_BYTES, 512);
           const uint64_t dql = tc::make_desc_mn32(q_base + Q_PART_BYTES + ks * 1024, CB_BYTES, 512);
           const uint32_t d = tmem + st * BN;
-          tc::mma_tf32(d, dph, dqh, idesc, (i % FLW == 0 && ks == 0) ? 0u : 1u);
-          if (!p.single) {
-            tc::mma_tf32(d, dpl, dqh, idesc, 1u);
-            tc::mma_tf32(d, dph, dql, idesc, 1u);
+          tc::mma_tf32_e(d, dph, dqh, idesc, (i % FLW == 0 && ks == 0) ? 0u : 1u);
+          if (!p_single) {
+            tc::mma_tf32_e(d, dpl, dqh, idesc, 1u);
+            tc::mma_tf32_e(d, dph, dql, idesc, 1u);
           }
         }
-        tc::commit(&B->empty[slot]);
-        if (i % FLW == FLW - 1 || i == nst - 1) tc::commit(&B->acc_full[st]);
+        tc::commit_e(&B->empty[slot]);
+        if (i % FLW == FLW - 1 || i == nst - 1) tc::commit_e(&B->acc_full[st]);
       }
     }
   }
