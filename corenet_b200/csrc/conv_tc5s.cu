@@ -302,9 +302,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
     // ============================ MMA ISSUER: the whole warp runs the loop converged, one elected lane issues
     {
       constexpr uint32_t A_DESC_HI = (uint32_t)((XS * 16) >> 4) | (1u << 14);   // SBO field | version 1 (bit 46)
-      long long L0 = 0;                             // plane-load index of r = 0 of the current pass
-      long long Wn = 0;                             // running weight-row (ky) index
-      long long G = 0;                              // running (pass, ky) group index -> accumulator stage
+      // ring slot / phase parity of plane r = 0 of the current pass and the weight-row / group counters are carried
+      // incrementally in 32-bit registers (no 64-bit modulo on the issue path)
+      int slot0 = 0;
+      uint32_t par0 = 0;
+      uint32_t Wn = 0;                              // running weight-row (ky) index
+      uint32_t G = 0;                               // running (pass, ky) group index -> accumulator stage
       bool dead = false;
       long long tw_acc = 0, tw_w = 0, tw_plane = 0;
       const long long t_begin = p.dbg ? clock64() : 0;
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
       for (int item = blockIdx.x; item < p.nitems && !dead; item += gridDim.x) {
         int n, z0, y0, x0;
         decode_item(p, item, n, z0, y0, x0);
-        for (int pass = 0; pass < p.P && !dead; ++pass, L0 += NPLANE) {
+        for (int pass = 0; pass < p.P && !dead; ++pass) {
           for (int ky = 0; ky < KT && !dead; ++ky, ++G, ++Wn) {
             const int st = (int)(G & 1);
             if (G >= 2 && !TC5S_TIMED(tw_acc, tc::mbar_wait(&B->acc_empty[st], (uint32_t)((G >> 1) - 1) & 1, ab))) { fail(); dead = true; break; }
@@ -324,10 +327,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
             int ns = 0;                             // accumulators [0, ns) of this group have been written
 #pragma unroll 1
             for (int q = 0; q < NPLANE; ++q) {
-              const long long L = L0 + q;
-              const int slot = (int)(L % NSLOT);
+              int slot = slot0 + q;
+              uint32_t par = par0;
+              if (slot >= NSLOT) { slot -= NSLOT; par ^= 1u; }
               if (ky == 0) {                        // planes arrive during the first sweep of a pass
-                if (!TC5S_TIMED(tw_plane, tc::mbar_wait(&B->plane_full[slot], (uint32_t)(L / NSLOT) & 1, ab))) { fail(); dead = true; break; }
+                if (!TC5S_TIMED(tw_plane, tc::mbar_wait(&B->plane_full[slot], par, ab))) { fail(); dead = true; break; }
                 tc::fence_after_sync();
               }
               const int zin = z0 - HLO + q;
@@ -378,6 +382,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc5s_kernel(const TC5SParams
             tc::commit_e(&B->w_empty[ws]);
             tc::commit_e(&B->acc_full[st]);
           }
+          slot0 += NPLANE;
+          if (slot0 >= NSLOT) { slot0 -= NSLOT; par0 ^= 1u; }
         }
       }
       if (p.dbg && lane == 0) {

@@ -146,6 +146,12 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
   return false;
 }
 
+// for a converged warp: every lane waits, the result is a warp vote (warp-uniform for the compiler, so that the error
+// exits of the issue loop do not make its control flow look divergent)
+__device__ __forceinline__ bool mbar_wait_all(uint64_t* bar, uint32_t parity, volatile int* abort_flag = nullptr) {
+  return __all_sync(0xffffffffu, mbar_wait(bar, parity, abort_flag)) != 0;
+}
+
 // fp32 -> (hi, lo) with hi = round-to-nearest tf32 and lo = a - hi (exact in fp32).
 // a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b with ~2^-21 relative error (3xTF32).
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
