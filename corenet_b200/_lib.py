@@ -124,6 +124,8 @@ _SIGS = {
     "crn_gemm_tc_pack": ([vp, vp, i32, i64, vp], i32),
     "crn_conv_gemm_tc": ([_P(ConvDesc), i32, vp, vp, vp, vp, i32, vp, vp], i32),
     "crn_gemm_tc_debug_read": ([vp, i32], i32),
+    "crn_tc5s_debug_read": ([vp, i32], i32),
+    "crn_wgrad_line_debug_read": ([vp, i32], i32),
     "crn_conv_wgrad_tc": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),
     "crn_conv_wgrad_line_supported": ([_P(ConvDesc)], i32),
     "crn_conv_wgrad_line": ([_P(ConvDesc), vp, vp, vp, vp, vp], i32),

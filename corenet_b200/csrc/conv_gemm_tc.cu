@@ -103,8 +103,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
     qz = (cls_z + p.pD - rz) / p.tsD; qy = (cls_y + p.pH - ry) / p.tsH; qx = (cls_x + p.pW - rx) / p.tsW;
     nstages = Kz * Ky * Kx * p.kchunks;
   }
-  const int s0 = (int)((long long)nstages * z / p.ksplit);
-  const int s1 = (int)((long long)nstages * (z + 1) / p.ksplit);
+  // (the 64-bit divisions go through a subroutine and lose the compiler's "warp-uniform" tag: restore it, the MMA
+  // warp's loop bounds must be uniform for its descriptors to stay in uniform registers)
+  const int s0 = (int)tc::uniform_u32((uint32_t)((long long)nstages * z / p.ksplit));
+  const int s1 = (int)tc::uniform_u32((uint32_t)((long long)nstages * (z + 1) / p.ksplit));
   const int nst = s1 - s0;
   // stage -> (filter tap, 16-channel chunk); tmode: tap of the class list -> real filter tap
   auto stage_tap = [&](int s, int& kz, int& ky, int& kx, int& kc) {
@@ -275,10 +277,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GTParams p) 
         if (i % FL == 0) {
           const int g = i / FL;
           st = g & 1;
-          if (g >= 2 && !tc::mbar_wait(&B->acc_empty[st], (uint32_t)((g >> 1) - 1) & 1, ab)) { fail(); dead = true; break; }
+          if (g >= 2 && !tc::mbar_wait_all(&B->acc_empty[st], (uint32_t)((g >> 1) - 1) & 1, ab)) { fail(); dead = true; break; }
           tc::fence_after_sync();
         }
-        if (!tc::mbar_wait(&B->full_a[slot], ph, ab) || !tc::mbar_wait(&B->full_b[slot], ph, ab)) { fail(); dead = true; break; }
+        if (!tc::mbar_wait_all(&B->full_a[slot], ph, ab) || !tc::mbar_wait_all(&B->full_b[slot], ph, ab)) { fail(); dead = true; break; }
         tc::fence_after_sync();
         if (i == 0) GT_STAMP(2);
         const uint32_t a_base = abuf_u32 + slot * A_STAGE_BYTES, b_base = bbuf_u32 + slot * B_STAGE_BYTES;

@@ -41,7 +41,19 @@ struct WLParams {
   int pass_begin[12];  // prefix sums of line-steps per pass (npass + 1 entries)
   int flush_every;
   int single;          // 1: single-pass TF32 (the lo products are not issued)
+  int dbg;             // crn_set_flags bit 8: wait-time accounting of wgrad_line_kernel (crn_wgrad_line_debug_read)
 };
+
+// debug: per CTA [mma total, mma wait full_x, full_y, acc_empty, producer total, producer wait empty_x + empty_y,
+// epilogue total, epilogue wait acc_full] in clock64 cycles
+__device__ long long g_wl_dbg[kNumSMs * 8];
+#define WL_TIMED(accum, call)                           \
+  ([&]() -> bool {                                      \
+    const long long t0__ = p.dbg ? clock64() : 0;       \
+    const bool ok__ = (call);                           \
+    if (p.dbg) accum += clock64() - t0__;               \
+    return ok__;                                        \
+  }())
 
 struct __align__(8) WLBarriers {
   uint64_t full_x[MAXX], empty_x[MAXX];
@@ -131,11 +143,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
     // ============================ EPILOGUE: TMEM -> atomic adds into dW at every flush point
     uint32_t nflush = 0;
     bool dead = false;
+    long long tw_e = 0;
+    const long long t_begin = p.dbg ? clock64() : 0;
     const int blk = warp;                                     // 32-lane block of the M operand this warp owns
     for (int t = t0; t < t1 && !dead; ++t) {
       const Step s = decode_step<CB>(p, t, t0);
       if (!flush_after(t, s)) continue;
-      if (!tc::mbar_wait(&B->acc_full, nflush & 1, ab)) { fail(); dead = true; break; }
+      if (!WL_TIMED(tw_e, tc::mbar_wait(&B->acc_full, nflush & 1, ab))) { fail(); dead = true; break; }
       tc::fence_after_sync();
       int ci, kyoff;
       if (CB == 1) { ci = lane; kyoff = blk >> 1; }           // blocks: (hi, y), (lo, y), (hi, y+1), (lo, y+1)
@@ -174,6 +188,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
       tc::fence_before_sync();
       tc::mbar_arrive(&B->acc_empty);
       ++nflush;
+    }
+    if (p.dbg && tid == 0) {
+      g_wl_dbg[blockIdx.x * 8 + 6] = clock64() - t_begin;
+      g_wl_dbg[blockIdx.x * 8 + 7] = tw_e;
     }
   } else if (warp < 8) {
     // ============================ PRODUCERS
@@ -222,11 +240,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
     };
     uint32_t q = 0, yq = 0;         // x / dy line loads so far
     bool dead = false;
+    long long tw_p = 0;
+    const long long t_begin = p.dbg ? clock64() : 0;
     auto store = [&](const Job& jb, const float4 (&buf)[4]) {
       if (jb.kind == 0) {
         const int slot = (int)(q % XS);
         const uint32_t use = q / XS;
-        if (use > 0 && !tc::mbar_wait(&B->empty_x[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+        if (use > 0 && !WL_TIMED(tw_p, tc::mbar_wait(&B->empty_x[slot], (use - 1) & 1, ab))) { fail(); dead = true; return; }
         uint8_t* base = xring + slot * XL;
 #pragma unroll
         for (int u = 0; u < XIT; ++u) {
@@ -252,7 +272,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
       } else {
         const int slot = (int)(yq % YSLOTS);
         const uint32_t use = yq / YSLOTS;
-        if (use > 0 && !tc::mbar_wait(&B->empty_y[slot], (use - 1) & 1, ab)) { fail(); dead = true; return; }
+        if (use > 0 && !WL_TIMED(tw_p, tc::mbar_wait(&B->empty_y[slot], (use - 1) & 1, ab))) { fail(); dead = true; return; }
         uint8_t* base = yring + slot * YL;
 #pragma unroll
         for (int u = 0; u < YIT; ++u) {
@@ -295,6 +315,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
         if (have[k]) issue(jobs[k], bufs[k]);
       }
     }
+    if (p.dbg && pt == 0) {
+      g_wl_dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
+      g_wl_dbg[blockIdx.x * 8 + 5] = tw_p;
+    }
   } else {
     // ============================ MMA ISSUER (one elected thread)
     // This single thread is the critical path (its instruction latency, not the tensor pipe, bounded the first
@@ -313,19 +337,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
       int mod_ctr = 0;                           // (t - t0 + 1) % flush_every, the epilogue's periodic flush rule
       uint32_t xslot = 0, xphase = 0;            // ring position / phase of the next x line load to consume
       uint32_t yslot = 0, yphase = 0;
+      long long tw_x = 0, tw_y = 0, tw_a = 0;
+      const long long t_begin = p.dbg ? clock64() : 0;
       for (int t = t0; t < t1 && !dead; ++t) {
         const int nk = CB == 1 ? 5 : ((pass & 1) ? 2 : 3);
         const bool fresh = (t == t0) || y == 0;
         const int nload = fresh ? nk : 1;
         for (int j = 0; j < nload; ++j) {
-          if (!tc::mbar_wait(&B->full_x[xslot], xphase, ab)) { fail(); dead = true; break; }
+          if (!WL_TIMED(tw_x, tc::mbar_wait(&B->full_x[xslot], xphase, ab))) { fail(); dead = true; break; }
           if (++xslot == XS) { xslot = 0; xphase ^= 1; }
         }
         if (dead) break;
         q += nload;
-        if (!tc::mbar_wait(&B->full_y[yslot], yphase, ab)) { fail(); dead = true; break; }
+        if (!WL_TIMED(tw_y, tc::mbar_wait(&B->full_y[yslot], yphase, ab))) { fail(); dead = true; break; }
         if (first && nflush > 0) {              // accumulators were handed to the epilogue: wait until it has read them
-          if (!tc::mbar_wait(&B->acc_empty, (nflush - 1) & 1, ab)) { fail(); dead = true; break; }
+          if (!WL_TIMED(tw_a, tc::mbar_wait(&B->acc_empty, (nflush - 1) & 1, ab))) { fail(); dead = true; break; }
         }
         tc::fence_after_sync();
         const uint32_t ybase = yring_u32 + yslot * YL;
@@ -376,6 +402,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_line_kernel(const WLParams 
         }
         if (++y == p.H) y = 0;
         if (t + 1 >= pass_end && t + 1 < t1) { ++pass; pass_end = p.pass_begin[pass + 1]; }
+      }
+      if (p.dbg && lane == 0) {
+        g_wl_dbg[blockIdx.x * 8 + 0] = clock64() - t_begin;
+        g_wl_dbg[blockIdx.x * 8 + 1] = tw_x;
+        g_wl_dbg[blockIdx.x * 8 + 2] = tw_y;
+        g_wl_dbg[blockIdx.x * 8 + 3] = tw_a;
       }
     }
   }
@@ -436,6 +468,7 @@ extern "C" int crn_conv_wgrad_line(const crn_conv_desc* d, const float* x, const
   CRN_REQUIRE(crn_conv_wgrad_line_supported(d), "crn_conv_wgrad_line: unsupported layer shape");
   WLParams p{};
   p.single = crn_single_pass();
+  p.dbg = (crn_get_flags() >> 8) & 1;
   p.x = x; p.dy = dy; p.dw = dw_packed; p.status = status;
   p.N = d->N; p.D = d->iD; p.H = d->iH; p.W = d->iW;
   p.Cin = d->Cin; p.Cout = d->Cout;
@@ -1383,3 +1416,11 @@ extern "C" int crn_conv_wgrad_xline(const crn_conv_desc* d, const float* x, cons
   cudaStream_t st = crn_stream(stream);
   return d->iW == 16 ? launch_wx<16, 64>(p, st) : launch_wx<8, 64>(p, st);
 }
+
+#ifdef CRN_DIAG
+extern "C" int crn_wgrad_line_debug_read(long long* host_dst, int32_t n);
+extern "C" int crn_wgrad_line_debug_read(long long* host_dst, int32_t n) {
+  return cudaMemcpyFromSymbol(host_dst, g_wl_dbg, sizeof(long long) * (n > kNumSMs * 8 ? kNumSMs * 8 : n)) == cudaSuccess
+             ? CRN_OK : CRN_ERR_LAUNCH;
+}
+#endif  // CRN_DIAG

@@ -28,6 +28,9 @@ int crn_gemm_tc_debug_read(long long* host_dst, int32_t n);
 /* Same switch for conv_tc5s_kernel: per CTA 8 int64 = cycles of [MMA thread total, its waits on acc_empty / w_full /
  * plane_full, producer total, its wait on plane_empty, epilogue total, its wait on acc_full]; n <= 148 * 8. */
 int crn_tc5s_debug_read(long long* host_dst, int32_t n);
+/* ... and for wgrad_line_kernel (Conv3d k=5 weight gradient): [MMA thread total, its waits on full_x / full_y /
+ * acc_empty, producer total, its waits on empty_x + empty_y, epilogue total, its wait on acc_full]. */
+int crn_wgrad_line_debug_read(long long* host_dst, int32_t n);
 
 #ifdef __cplusplus
 }

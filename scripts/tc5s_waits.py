@@ -14,8 +14,6 @@ from corenet_b200 import _lib, ops
 
 dev = t.device("cuda", 0)
 lib = _lib.lib()
-lib.crn_tc5s_debug_read.argtypes = [C.c_void_p, C.c_int32]
-lib.crn_tc5s_debug_read.restype = C.c_int
 
 SHAPES = [("stage_6.c1 fwd   28->16 @64^3", 4, 28, 16, 64, 0),
           ("stage_6.c1 dgrad 16->28 @64^3", 4, 28, 16, 64, 1),
