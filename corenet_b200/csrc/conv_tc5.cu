@@ -763,6 +763,8 @@ extern "C" int crn_convt7_tc(const crn_conv_desc* d, const float* x, const float
   if (p.gN <= 64) return launch_tc5<64, 4, false, 4, true>(p, st);
   // two planes per item keep two accumulator stages in TMEM (2*2*128 columns): 0.55 ms vs 0.74 ms with ZT = 4
   // on the stage-5 layer (scripts/tct_test.py)
+  // small grids (stage_4.t1 at 16^3, B = 4: 64 two-plane items on 148 SMs): one plane per item fills the machine
+  if ((long long)p.N * p.tiles_x * p.tiles_y * (p.D / 2) <= kNumSMs / 2) return launch_tc5<128, 1, false, 4, true>(p, st);
   return launch_tc5<128, 2, false, 4, true>(p, st);
 }
 

@@ -485,7 +485,8 @@ def test_conv5_kz_stacked_general_tcgen05(n, cin, cout, dhw, kind):
 @pytest.mark.parametrize("n,cin,cout,dhw,planar", [(1, 8, 2, (8, 16, 8), True), (2, 16, 2, (8, 32, 16), True),
                                                      (1, 12, 3, (8, 16, 8), True), (1, 8, 2, (8, 16, 8), False),
                                                      (1, 32, 16, (8, 16, 16), False), (1, 16, 8, (8, 16, 8), False),
-                                                     (1, 20, 4, (16, 16, 8), False)])
+                                                     (1, 20, 4, (16, 16, 8), False),
+                                                     (2, 8, 16, (16, 32, 32), False)])   # 128 items: two planes per item
 def test_conv_transpose7_tcgen05(n, cin, cout, dhw, planar):
   """ConvTranspose3d k=7 s=2 p=3 op=1 forward on the tcgen05 kernel (8 parity classes as one 4^3-tap conv with a
   scatter epilogue) against torch fp64; channels-last output inside a wider (concat) row, or planar logits.
