@@ -698,6 +698,8 @@ extern "C" int crn_conv5_tc(const crn_conv_desc* d, int32_t kind, const float* i
   }
   if (p.gN <= 16) return launch_tc5<16, 8, false>(p, st);
   if (p.gN <= 32) return launch_tc5<32, 8, false>(p, st);
+  // small grids (stage_4.c1 at 16^3, B = 4: 32 four-plane items): one output plane per item fills the machine
+  if ((long long)p.N * p.tiles_x * p.tiles_y * (p.D / 4) <= kNumSMs / 2) return launch_tc5<64, 1, false>(p, st);
   return launch_tc5<64, 4, false>(p, st);
 }
 

@@ -496,6 +496,15 @@ class Engine:
       if l.k == (5, 5, 5) and g >= 32 and g % 16 == 0 and cin <= 64 and mid <= 64:
         self.tc_w[l.name] = (t.zeros(lib.crn_tc5_packed_floats(cin, mid), dtype=t.float32, device=dev),
                              t.zeros(lib.crn_tc5_packed_floats(mid, cin), dtype=t.float32, device=dev))
+    # forward only (Cout <= 64, any Cin) on 16^3 grids: stage_4.c1 (112 -> 64).  The plane kernel stages an input plane
+    # once per kz and reads its 25 (ky, kx) taps from shared memory; the implicit-GEMM kernel re-gathers every tap from L2
+    # (0.64 ms at 46 TFLOP/s).  One output plane per work item fills the machine at this size (crn_conv5_tc).
+    self.tc_wf = {}
+    for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
+      l = self.L[f"stage_{stage}.c1"]
+      if (USE_TC and l.name not in self.tc_w and l.k == (5, 5, 5) and g == 16 and mid <= 64 and mid % 4 == 0
+          and cin % 4 == 0):
+        self.tc_wf[l.name] = t.zeros(lib.crn_tc5_packed_floats(cin, mid), dtype=t.float32, device=dev)
     # forward of the <= 16-output-channel layers: kz taps stacked into N (csrc/conv_tc5s.cu)
     # (<= 32 output channels; the dgrad of a layer is the same kernel with N = Cin)
     self.tcs_w = {}
@@ -706,6 +715,9 @@ class Engine:
     """tcgen05 weight re-packs (conv_tc5 / class-scatter / implicit-GEMM layouts) on the current stream."""
     if self.layers:
       for l in self.layers:
+        if l.name in self.tc_wf:
+          _call("crn_tc5_pack", P[l.name + ".weight"].data_ptr(), l.cout, l.cin, 0, self.tc_wf[l.name].data_ptr(),
+                _lib.stream_ptr())
         if l.name in self.tc_w:
           w = P[l.name + ".weight"]
           wf, wd = self.tc_w[l.name]
@@ -1115,6 +1127,9 @@ class Plan:
                        eng.tc_status.data_ptr(), st)
       elif USE_TC and sd["lc"].name in eng.tc_w:
         conv5_tc_call("fwd", sd["lc"], sd["d_c"], sd["z"].p, eng.tc_w[sd["lc"].name][0].data_ptr(), bias(sd["lc"]),
+                      sd["c"].p, eng.tc_status.data_ptr(), st)
+      elif USE_TC and sd["lc"].name in eng.tc_wf:
+        conv5_tc_call("fwd", sd["lc"], sd["d_c"], sd["z"].p, eng.tc_wf[sd["lc"].name].data_ptr(), bias(sd["lc"]),
                       sd["c"].p, eng.tc_status.data_ptr(), st)
       else:
         conv_call("fwd", sd["lc"], sd["d_c"], sd["z"].p, eng.wf(sd["lc"]), bias(sd["lc"]), sd["c"].p, 0, st)

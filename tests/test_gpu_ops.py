@@ -92,7 +92,9 @@ def test_conv_fwd_bwd(case):
 
 
 @pytest.mark.parametrize("n,cin,cout,dhw", [(1, 8, 16, (8, 16, 8)), (2, 28, 16, (16, 32, 16)), (1, 56, 32, (8, 16, 16)),
-                                              (1, 16, 12, (8, 16, 24))])
+                                              (1, 16, 12, (8, 16, 24)),
+                                              (3, 8, 40, (16, 32, 32)),      # 96 four-plane items (N <= 64 kernel)
+                                              (1, 112, 64, (16, 16, 16))])   # stage_4.c1: one plane per item, fwd only
 @pytest.mark.parametrize("kind", [0, 1], ids=["fwd", "dgrad"])
 def test_conv5_tcgen05(n, cin, cout, dhw, kind):
   """Conv3d k=5 on the tcgen05 tensor cores (3xTF32 + fp32 TMEM accumulation) against the fp64 oracle.
@@ -100,6 +102,8 @@ def test_conv5_tcgen05(n, cin, cout, dhw, kind):
   accumulations), operands are exact to ~2^-21."""
   import ctypes as C
   from corenet_b200 import _lib, ops
+  if kind == 1 and cin > 64:
+    pytest.skip("the plane kernel holds at most 64 output channels (dgrad: N = Cin)")
   d, h, w = dhw
   g = t.Generator().manual_seed(cin * 7 + cout + kind)
   wt = t.randn(cout, cin, 5, 5, 5, generator=g) * 0.05
