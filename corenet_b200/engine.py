@@ -509,6 +509,7 @@ class Engine:
     # (<= 32 output channels; the dgrad of a layer is the same kernel with N = Cin)
     self.tcs_w = {}
     self.tcs_wd = {}
+    self.tcs_wd_slices = {}
     if USE_TC5S:
       for stage, cin, mid, t_out, skip_c, enc_c, g in self.dec_plan:
         l = self.L[f"stage_{stage}.c1"]
@@ -517,6 +518,13 @@ class Engine:
             self.tcs_w[l.name] = t.zeros(lib.crn_tc5s_packed_floats(cin), dtype=t.float32, device=dev)
           if cin <= 32:
             self.tcs_wd[l.name] = t.zeros(lib.crn_tc5s_packed_floats(mid), dtype=t.float32, device=dev)
+          elif cin <= 64 and cin % 8 == 0:
+            # dgrad with 32 < Cin <= 64 input channels (stage_5.c1: 56): two launches of the stacked kernel, each on one
+            # half of the input channels (weight slice packed per half, dx written at the half's channel offset)
+            h = cin // 2
+            self.tcs_wd_slices[l.name] = [
+                (t.zeros(lib.crn_tc5s_packed_floats(mid), dtype=t.float32, device=dev),
+                 t.zeros(mid, h, 5, 5, 5, dtype=t.float32, device=dev), c0, h) for c0 in (0, h)]
     # ... and per eligible ConvTranspose3d(k=7, s=2) layer a packed copy for the forward (csrc/conv_tc5.cu, KT=4)
     self.tct_w = {}
     self.tct_slices = {}
@@ -727,6 +735,10 @@ class Engine:
             _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 0, wf.data_ptr(), _lib.stream_ptr())
           if l.name in self.tcs_wd:
             _call("crn_tc5s_pack2", w.data_ptr(), l.cout, l.cin, 1, self.tcs_wd[l.name].data_ptr(), _lib.stream_ptr())
+          elif l.name in self.tcs_wd_slices:
+            for buf, wslice, c0, h in self.tcs_wd_slices[l.name]:
+              wslice.copy_(w[:, c0:c0 + h])
+              _call("crn_tc5s_pack2", wslice.data_ptr(), l.cout, h, 1, buf.data_ptr(), _lib.stream_ptr())
           else:
             _call("crn_tc5_pack", w.data_ptr(), l.cout, l.cin, 1, wd.data_ptr(), _lib.stream_ptr())
         for wt, wslice, co0 in self.tct_slices.get(l.name, ()):
@@ -1324,6 +1336,16 @@ class Plan:
       if USE_TC and lc.name in eng.tcs_wd:
         conv5_tcs_call(lc, sd["d_c"], sd["c"].gp, eng.tcs_wd[lc.name].data_ptr(), None, sd["z"].gp,
                        eng.tc_status.data_ptr(), st, kind=1)
+      elif USE_TC and lc.name in eng.tcs_wd_slices:
+        if "d_c_slices" not in sd:
+          sd["d_c_slices"] = []
+          for buf, wslice, c0, h in eng.tcs_wd_slices[lc.name]:
+            dsl = type(sd["d_c"]).from_buffer_copy(sd["d_c"])
+            dsl.Cin = dsl.CinP = h
+            dsl.x_co = sd["d_c"].x_co + c0
+            sd["d_c_slices"].append(dsl)
+        for (buf, wslice, c0, h), dsl in zip(eng.tcs_wd_slices[lc.name], sd["d_c_slices"]):
+          conv5_tcs_call(lc, dsl, sd["c"].gp, buf.data_ptr(), None, sd["z"].gp, eng.tc_status.data_ptr(), st, kind=1)
       elif USE_TC and lc.name in eng.tc_w:
         conv5_tc_call("dgrad", lc, sd["d_c"], sd["c"].gp, eng.tc_w[lc.name][1].data_ptr(), None, sd["z"].gp,
                       eng.tc_status.data_ptr(), st)
