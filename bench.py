@@ -585,7 +585,7 @@ def run_native(args):
       # the GT pipeline alone (not overlapped), for the record
       ms_gt = timed(lambda: d_args[3](), steps)
       extra["gt_pipeline_ms"] = ms_gt / steps
-    if world == 1 and wl in ("h5", "m7", "h7") and base_mode == "3xtf32":
+    if world == 1 and wl in ("h5", "m7", "h7") and base_mode == "3xtf32" and not args.no_modes:
       # opt-in single-pass TF32 arithmetic (engine.set_precision("tf32"), one MMA per product instead of three):
       # reported beside the headline, never as the headline -- the parity bar (logits <= 1e-3) needs "3xtf32"
       engine.set_precision("tf32")
@@ -715,6 +715,7 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32"],
                   help="diagnostic: run the WHOLE bench in the opt-in single-pass TF32 mode (labelled in dtype/config)")
+  ap.add_argument("--no-modes", action="store_true", help="skip the extra single-pass-TF32 measurement (precision_modes)")
   ap.add_argument("--layers", default=None, help="write a per-layer conv / HBM-kernel timing table to this file")
   args = ap.parse_args()
   if os.environ.get("CRN_FAULT_TIMEOUT"):        # debugging aid: dump all Python stacks and exit if the run stalls

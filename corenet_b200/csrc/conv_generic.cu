@@ -463,19 +463,82 @@ __global__ void pack_weights_kernel(const crn_pack_item* items, const int64_t* o
   }
 }
 
-__global__ void unpack_wgrads_kernel(const crn_unpack_item* items, const int64_t* offsets, int n,
-                                     int64_t total) {
-  // iterate over the DESTINATION (PyTorch layout) for coalesced writes
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const int li = find_item(offsets, n, e);
-    const crn_unpack_item it = items[li];
-    const int64_t l = e - offsets[li];
-    const int tap = (int)(l % it.taps); const int64_t q = l / it.taps;
-    int ci, co;
-    if (it.dst_is_transposed) { co = (int)(q % it.Cout); ci = (int)(q / it.Cout); }
-    else { ci = (int)(q % it.Cin); co = (int)(q / it.Cin); }
-    it.dst[l] = it.src_packed[((int64_t)tap * it.CinP + ci) * it.CoutP + co];
+// Packed gradient [tap][CinP][CoutP] -> PyTorch layout ([Cout][Cin][taps], ConvTranspose: [Cin][Cout][taps]) as a
+// shared-memory tiled transpose: both sides move whole 128-byte lines.  (The first version iterated over the
+// destination and read the packed side 4 bytes at a time: 824 GB/s, 0.35 ms per step for the 94 MB of parameters.)
+//   tile = 32 co x CI ci x all taps; reads: per (tap, ci) 32 consecutive co; writes: per co (ci, tap) is one contiguous
+//   run of CI * taps >= 64 floats (CI = 64 for 1x1, 8 for 3x3, ..., 1 for >= 64 taps); transposed: per ci one run of 32 * taps.
+constexpr int UNPACK_TILE_FLOATS = 32 * 345;           // 32 co x 343 taps (+ padding)
+__device__ __forceinline__ int unpack_ci_per_tile(const crn_unpack_item& it) {
+  return it.dst_is_transposed ? 1 : (it.taps >= 64 ? 1 : (64 + it.taps - 1) / it.taps);
+}
+__device__ __forceinline__ int unpack_tiles(const crn_unpack_item& it) {
+  if (it.taps > 343) return 64;                         // generic element-wise path, 64 strided blocks
+  const int CI = unpack_ci_per_tile(it);
+  return ((it.Cout + 31) / 32) * ((it.Cin + CI - 1) / CI);
+}
+// The tiles of all items form one flat list that the blocks stride over (the items differ by 4 orders of magnitude
+// in size); a block walks the item list once, its tile index only grows.
+__global__ void __launch_bounds__(256) unpack_wgrads_kernel(const crn_unpack_item* items, int n) {
+  __shared__ float tile[UNPACK_TILE_FLOATS];
+  int li = 0;
+  long long base = 0;                                   // flat index of tile 0 of item li
+  crn_unpack_item it = items[0];
+  int nt = unpack_tiles(it);
+  for (long long tg = blockIdx.x;; tg += gridDim.x) {
+    while (li < n && tg >= base + nt) {
+      base += nt;
+      if (++li < n) { it = items[li]; nt = unpack_tiles(it); }
+    }
+    if (li >= n) break;
+    const int tl = (int)(tg - base);
+    const int taps = it.taps;
+    if (taps > 343) {                                   // no layer of the model; generic element-wise path
+      const int64_t total = (int64_t)it.Cin * it.Cout * taps;
+      for (int64_t l = (int64_t)tl * blockDim.x + threadIdx.x; l < total; l += (int64_t)64 * blockDim.x) {
+        const int tap = (int)(l % taps); const int64_t q = l / taps;
+        int ci, co;
+        if (it.dst_is_transposed) { co = (int)(q % it.Cout); ci = (int)(q / it.Cout); }
+        else { ci = (int)(q % it.Cin); co = (int)(q / it.Cin); }
+        it.dst[l] = it.src_packed[((int64_t)tap * it.CinP + ci) * it.CoutP + co];
+      }
+      continue;
+    }
+    const int CI = unpack_ci_per_tile(it);
+    const int run = CI * taps;                          // floats per co in the tile
+    const int ld = run | 1;                             // odd row stride: conflict-free transposed stores
+    const int tiles_co = (it.Cout + 31) / 32;
+    const int co0 = (tl % tiles_co) * 32, ci0 = (tl / tiles_co) * CI;
+    __syncthreads();
+    // 16-byte loads (CoutP is a multiple of 4, co0 of 32), several in flight per thread: with 4-byte loads the kernel
+    // was latency-bound at 1.2 TB/s
+#pragma unroll 4
+    for (int i = threadIdx.x; i < run * 8; i += blockDim.x) {
+      const int c4 = (i & 7) * 4, r = i >> 3;           // r = tap * CI + ci_l
+      const int tap = r / CI, ci_l = r - tap * CI;
+      const int co = co0 + c4, ci = ci0 + ci_l;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (co < it.CoutP && ci < it.Cin)
+        v = __ldg(reinterpret_cast<const float4*>(it.src_packed + ((int64_t)tap * it.CinP + ci) * it.CoutP + co));
+      float* dst = tile + c4 * ld + ci_l * taps + tap;
+      dst[0] = v.x; dst[ld] = v.y; dst[2 * ld] = v.z; dst[3 * ld] = v.w;
+    }
+    __syncthreads();
+    if (it.dst_is_transposed) {                         // [ci][co][tap]: one run of 32 * taps floats per ci
+      float* dst = it.dst + ((int64_t)ci0 * it.Cout + co0) * taps;
+      const int lim = (it.Cout - co0 < 32 ? it.Cout - co0 : 32) * taps;
+      for (int i = threadIdx.x; i < lim; i += blockDim.x) {
+        const int co_l = i / taps, tap = i - co_l * taps;
+        dst[i] = tile[co_l * ld + tap];
+      }
+    } else {                                            // [co][ci][tap]: per co one run of CI * taps floats
+      const int lim = (it.Cin - ci0 < CI ? it.Cin - ci0 : CI) * taps;
+      for (int i = threadIdx.x; i < run * 32; i += blockDim.x) {
+        const int co_l = i / run, j = i - co_l * run;
+        const int co = co0 + co_l;
+        if (co < it.Cout && j < lim) it.dst[((int64_t)co * it.Cin + ci0) * taps + j] = tile[co_l * ld + j];
+      }
+    }
   }
 }
 
@@ -668,8 +731,8 @@ extern "C" int crn_pack_weights(const crn_pack_item* items, const int64_t* offse
 extern "C" int crn_unpack_wgrads(const crn_unpack_item* items, const int64_t* offsets, int32_t n,
                                  int64_t total, void* stream) {
   CRN_REQUIRE(items && offsets && n > 0 && total > 0, "crn_unpack_wgrads: bad args");
-  const int blocks = (int)(crn_ceil_div(total, 256) < 8 * kNumSMs ? crn_ceil_div(total, 256) : 8 * kNumSMs);
-  unpack_wgrads_kernel<<<blocks, 256, 0, crn_stream(stream)>>>(items, offsets, n, total);
+  (void)offsets; (void)total;                           // kept in the signature: element prefix sums of the items
+  unpack_wgrads_kernel<<<4 * kNumSMs, 256, 0, crn_stream(stream)>>>(items, n);
   CRN_LAUNCH_CHECK("unpack_wgrads");
   return CRN_OK;
 }

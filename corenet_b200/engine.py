@@ -607,44 +607,50 @@ class Engine:
     self._gt_sig = None
     self._pack_stream = None
     self._pack_ev = None
+    self._pack_ev_bwd = None
     self.plans = {}
     self._ptr_sig = None
     self._ver_sig = None
 
-  def _pack_gemm_tc(self, P):
-    """ONE launch re-packs every tcgen05 implicit-GEMM weight (item list cached per parameter pointer set)."""
+  def _pack_gemm_tc(self, P, part):
+    """Re-packs the tcgen05 implicit-GEMM weights with one launch per part: "fwd" = the buffers the forward pass reads
+    (joined before the encoder blocks), "bwd" = the dgrad buffers (first read by the backward pass: their pack overlaps
+    the forward pass).  Item lists are cached per parameter pointer set."""
     if not self.gt_w and not self.gt_td and not self.gt_tf:
       return
     names = sorted(self.gt_w)
     sig = tuple(P[n + ".weight"].data_ptr() for n in names + sorted(self.gt_td) + sorted(self.gt_tf))
     if sig != self._gt_sig:
       lay = {l.name: l for l in self.layers}
-      entries = []
+      entries = {"fwd": [], "bwd": []}
       for n in names:
         for dg, buf in enumerate(self.gt_w[n]):
           if buf is not None:
-            entries.append((lay[n], P[n + ".weight"], dg, buf, False))
+            entries["bwd" if dg else "fwd"].append((lay[n], P[n + ".weight"], dg, buf, False))
       for n in sorted(self.gt_td):      # (layer, weight, dgrad flag, buffer, swap): convT weight read as [Cout'=Cin][Cin'=Cout]
-        entries.append((lay[n], P[n + ".weight"], 0, self.gt_td[n], True))
+        entries["bwd"].append((lay[n], P[n + ".weight"], 0, self.gt_td[n], True))
       for n in sorted(self.gt_tf):      # convT forward: K = Cin, N = Cout, flipped taps (transposed-gather mode)
-        entries.append((lay[n], P[n + ".weight"], 1, self.gt_tf[n], True))
-      items = (_lib.GemmTcPackItem * len(entries))()
-      offs = (C.c_int64 * (len(entries) + 1))()
-      tot = 0
-      for i, (l, w, dg, buf, swap) in enumerate(entries):
-        assert w.is_contiguous() and w.dtype == t.float32 and w.device == self.dev
-        it = items[i]
-        co, ci = (l.cin, l.cout) if swap else (l.cout, l.cin)
-        it.src, it.dst, it.Cout, it.Cin, it.taps, it.dgrad = w.data_ptr(), buf.data_ptr(), co, ci, l.taps, dg
-        offs[i] = tot
-        tot += buf.numel() // 2
-      offs[len(entries)] = tot
-      self._gt_items = self._to_dev(items, self.dev)
-      self._gt_offs = self._to_dev(offs, self.dev)
-      self._gt_n, self._gt_tot = len(entries), tot
+        entries["fwd"].append((lay[n], P[n + ".weight"], 1, self.gt_tf[n], True))
+      self._gt_parts = {}
+      for key, ent in entries.items():
+        if not ent:
+          continue
+        items = (_lib.GemmTcPackItem * len(ent))()
+        offs = (C.c_int64 * (len(ent) + 1))()
+        tot = 0
+        for i, (l, w, dg, buf, swap) in enumerate(ent):
+          assert w.is_contiguous() and w.dtype == t.float32 and w.device == self.dev
+          it = items[i]
+          co, ci = (l.cin, l.cout) if swap else (l.cout, l.cin)
+          it.src, it.dst, it.Cout, it.Cin, it.taps, it.dgrad = w.data_ptr(), buf.data_ptr(), co, ci, l.taps, dg
+          offs[i] = tot
+          tot += buf.numel() // 2
+        offs[len(ent)] = tot
+        self._gt_parts[key] = (self._to_dev(items, self.dev), self._to_dev(offs, self.dev), len(ent), tot)
       self._gt_sig = sig
-    _call("crn_gemm_tc_pack", self._gt_items.data_ptr(), self._gt_offs.data_ptr(), self._gt_n, self._gt_tot,
-          _lib.stream_ptr())
+    if part in self._gt_parts:
+      items, offs, n, tot = self._gt_parts[part]
+      _call("crn_gemm_tc_pack", items.data_ptr(), offs.data_ptr(), n, tot, _lib.stream_ptr())
 
   def tensors(self):
     """(name -> parameter, name -> buffer), cached."""
@@ -711,13 +717,21 @@ class Engine:
         self._pack_tc(P)
         self._pack_ev = t.cuda.Event()
         self._pack_ev.record(self._pack_stream)
+        if USE_TC and self.layers:
+          self._pack_gemm_tc(P, "bwd")
+          self._pack_ev_bwd = t.cuda.Event()
+          self._pack_ev_bwd.record(self._pack_stream)
       self._ver_sig = ver_sig
 
-  def join_packs(self):
-    """Main stream waits for the side-stream weight re-packs of this forward (no-op if none were launched)."""
+  def join_packs(self, fwd_only=False):
+    """Main stream waits for the side-stream weight re-packs of this forward (no-op if none were launched).
+    fwd_only: only for the buffers the forward pass reads; Plan.forward joins the dgrad packs when it ends."""
     if self._pack_ev is not None:
       t.cuda.current_stream().wait_event(self._pack_ev)
       self._pack_ev = None
+    if not fwd_only and self._pack_ev_bwd is not None:
+      t.cuda.current_stream().wait_event(self._pack_ev_bwd)
+      self._pack_ev_bwd = None
 
   def _pack_tc(self, P):
     """tcgen05 weight re-packs (conv_tc5 / class-scatter / implicit-GEMM layouts) on the current stream."""
@@ -762,7 +776,7 @@ class Engine:
             if wt is not None:
               _call("crn_tct_pack", P[l.name + ".weight"].data_ptr(), l.cin, l.cout, dg, wt.data_ptr(),
                     _lib.stream_ptr())
-      self._pack_gemm_tc(P)
+      self._pack_gemm_tc(P, "fwd")
 
   def chunk_layers(self, ci: int):
     """Conv layers of gradient chunk ci (GRAD_CHUNKS order)."""
@@ -1067,8 +1081,11 @@ class Plan:
       assert not training, "run_encoder=False is an inference-only path"
       eng.join_packs()
     if want_features:
+      eng.join_packs()
       return None
-    return self._forward_decoder(v2s, offsets, training, P, bias, st, rows_logits)
+    out = self._forward_decoder(v2s, offsets, training, P, bias, st, rows_logits)
+    eng.join_packs()                 # the dgrad re-packs ran beside the forward pass
+    return out
 
   def _forward_encoder(self, image, training, P, bias, st):
     eng, B = self.eng, self.B
@@ -1080,7 +1097,7 @@ class Plan:
               self.s1.p, 0, st)
     self.brn_stem.fwd(training)
     _call("crn_maxpool_fwd", self.s1a.p, B, 128, 128, 64, self.p1.p, self.p1_idx.data_ptr(), st)
-    eng.join_packs()
+    eng.join_packs(fwd_only=True)
     for blk in self.blocks:
       x = blk["x"]
       if blk["down"]:

@@ -12,7 +12,7 @@ with open(sys.argv[1], newline="") as f:
 for r in csv.DictReader(lines):
   if r.get("Metric Name") == "gpu__time_duration.sum":
     rows.append((r["Kernel Name"], float(r["Metric Value"]) * (1e-6 if r["Metric Unit"] == "ns" else 1e-3)))
-adam = [i for i, (k, _) in enumerate(rows) if "adam_kernel" in k or "adam_dev_kernel" in k]
+adam = [i for i, (k, _) in enumerate(rows) if "adam_kernel" in k or "adam_dev_kernel" in k or "adam_guarded_kernel" in k]
 if len(adam) >= 2:
   rows = rows[adam[-2] + 1:adam[-1] + 1]
 tot = sum(ms for _, ms in rows)

@@ -406,7 +406,9 @@ def test_evaluator_fgbg_labels_and_semantic_rows():
     pmf = ev.add_batch(*args, gt)
   with t.no_grad():
     logits = m(*args)
-  assert t.allclose(pmf, logits.softmax(1), atol=1e-5)
+  # two forwards of the same weights differ by split-K atomics order (~1e-5 of the logit range, |logit| ~ 5): 1e-4 on
+  # the probabilities; a layout / channel mix-up would be O(1)
+  assert t.allclose(pmf, logits.softmax(1), atol=1e-4)
   pred = logits.argmax(1)
   exp = t.bincount((gt.long() * 15 + pred).reshape(-1), minlength=225).reshape(15, 15)
   assert (ev.confusion_matrix.cpu() - 4 * exp.cpu()).abs().sum().item() <= 4e-5 * gt.numel()
