@@ -245,7 +245,8 @@ def test_eval_forward_between_trainer_steps_sees_new_weights():
     eng._ver_sig = None            # force a fresh pack: the reference answer for the current weights
     with t.no_grad():
       b = m(*args).clone()
-    assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item(), f"stale weights after step {i + 1}"
+    # (atomics-order noise between two forwards is ~1e-6; one stale Adam step at lr = 1e-2 moves the logits by percents)
+    assert (a - b).abs().max().item() <= 1e-5 * b.abs().max().item(), f"stale weights after step {i + 1}"
   assert tr.graph_launches > 100
   tr.check_status(wait=True)
 
@@ -386,7 +387,7 @@ def test_trainer_prefetch_with_device_resident_gt_pipeline():
     tr.check_status(wait=True)
     runs.append(ls)
   print("\nprecomputed GT:", runs[0], "\nGT callable   :", runs[1])
-  assert np.isfinite(runs[0]).all() and abs(runs[0][0] - runs[1][0]) <= 1e-6 * abs(runs[0][0])
+  assert np.isfinite(runs[0]).all() and abs(runs[0][0] - runs[1][0]) <= 1e-5 * abs(runs[0][0])
   assert max(abs(x - y) for x, y in zip(*runs)) <= 2e-3 * abs(runs[0][0])
 
 
@@ -468,4 +469,5 @@ def test_precision_mode_tf32_is_an_opt_in_with_its_own_bound(cfg_golden):
   m2 = build_model(2).to(dev).eval()
   with t.no_grad():
     again = m2(*args)
-  assert (again - full).abs().max().item() <= 2e-6 * full.abs().max().item(), "the default arithmetic is back"
+  # (two runs differ by split-K atomics order at the 1e-6 level; single-pass TF32 would be 1e-3)
+  assert (again - full).abs().max().item() <= 2e-5 * full.abs().max().item(), "the default arithmetic is back"

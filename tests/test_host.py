@@ -192,3 +192,18 @@ def test_compat_overlay_without_a_reference_checkout():
       "print('ok')\n") % ROOT
   r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/")
   assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-800:]
+
+
+def test_precision_mode_switch_is_host_side_state():
+  """engine.set_precision validates its argument and flips bit 13 of crn_set_flags (host-only call: no GPU needed);
+  the default is the fp32-class 3xTF32 split."""
+  from corenet_b200 import engine
+  assert engine.PRECISION == "3xtf32"
+  with pytest.raises(ValueError):
+    engine.set_precision("bf16")
+  try:
+    engine.set_precision("tf32")
+    assert engine.PRECISION == "tf32"
+  finally:
+    engine.set_precision("3xtf32")
+  assert engine.PRECISION == "3xtf32"
