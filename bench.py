@@ -199,11 +199,32 @@ def _oracle_state(classes):
   return params, state
 
 
-def cpu_reference(workload, steps, warmup):
+def _reference_cpu_model(classes):
+  """(CoreNet, losses module, voxel_metrics module) of the UNMODIFIED reference from the staged copy
+  baseline/_ref/src (baseline/stage_ref.py; git-ignored, travels to the GPU box), seeded like the oracle state, or
+  None when no copy is staged (the oracle port, pinned bit-exact to the reference, is timed instead)."""
+  import torch as t
+  try:
+    from baseline import ref_import
+    if ref_import.import_reference() is None:
+      return None
+    from corenet import configuration as rc, voxel_metrics as rm
+    from corenet.model import core_net, losses as rl
+    cfg = rc.CoreNetConfig(decoder=rc.DecoderConfig(resolution=(128, 128, 128), num_output_channels=classes,
+                                                    last_upscale_factor=2, latent_channels=64, skip_fraction=0.75))
+    t.manual_seed(0)
+    return core_net.CoreNet(cfg), rl, rm
+  except Exception as e:                         # a broken staging must not take the arm down: fall back to the port
+    print(f"bench: reference modules unavailable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+    return None
+
+
+def _cpu_reference(workload, steps, warmup, use_staged_reference=True):
   """The reference's own CPU implementation of the workload, all host threads, on a bounded sample (see `sample`).
-  Model / losses / metrics: oracle port of the reference's PyTorch modules (kind "port", pinned bit-exact to the
-  reference by oracle/make_golden.py); fill: the reference's fill_voxels_cpu.cc compiled in place (oracle/_ref,
-  kind "reference") when present.  Returns (units/s, seconds/step, kind, sample text)."""
+  Model / losses / metrics: the UNMODIFIED reference modules from the staged copy baseline/_ref/src (kind
+  "reference") when present, else the oracle port of them (kind "port", pinned bit-exact to the reference by
+  oracle/make_golden.py); fill: the reference's fill_voxels_cpu.cc compiled in place (oracle/_ref, kind "reference")
+  when present.  Returns (units/s, seconds/step, kind, sample text, host threads)."""
   import numpy as np
   import torch as t
   from oracle import corenet_oracle as O
@@ -229,19 +250,33 @@ def cpu_reference(workload, steps, warmup):
     units = 2 * VOX
     sample = "2 x 128^3 float32 grids per step (bounded sample of the 12-grid batch)"
   else:
-    params, state = _oracle_state(classes)
     image, v2s, offsets, gt = synthetic_batch(1, 0, classes)
     gt = gt.to(t.int64)
     units = VOX
+    ref_model = _reference_cpu_model(classes) if use_staged_reference else None
+    if ref_model is not None:
+      # the UNMODIFIED reference modules (staged copy baseline/_ref/src) on the host cores
+      kind = "reference"
+      model, ref_losses, ref_metrics = ref_model
+    else:
+      params, state = _oracle_state(classes)
     if workload == "h7":
-      def fn():
-        with t.no_grad():
-          logits = O.corenet_forward(state, image, v2s, offsets, False)
-          pmf = logits.softmax(1)
-          return O.confusion_matrix(pmf.argmax(1), gt, classes)
+      if ref_model is not None:
+        model.eval()
+
+        def fn():
+          with t.no_grad():
+            pmf = model(image, v2s, offsets).softmax(1)
+            return ref_metrics.confusion_matrix(pmf.argmax(1), gt, classes)
+      else:
+        def fn():
+          with t.no_grad():
+            logits = O.corenet_forward(state, image, v2s, offsets, False)
+            pmf = logits.softmax(1)
+            return O.confusion_matrix(pmf.argmax(1), gt, classes)
       sample = "1 scene per step: eval forward + softmax + argmax + confusion (bounded sample of the 8-scene batch)"
     else:
-      opt = t.optim.Adam(list(params.values()), lr=4e-4, eps=1e-4)
+      opt = t.optim.Adam(list(model.parameters() if ref_model is not None else params.values()), lr=4e-4, eps=1e-4)
       ref_fill = None
       if workload == "m9":
         from oracle import build_ref
@@ -252,10 +287,19 @@ def cpu_reference(workload, steps, warmup):
                            for i in range(3)]).astype(np.float32)
         shells_t = t.from_numpy(shells)
 
+      if ref_model is not None:
+        model.train()
+        ref_loss = getattr(ref_losses, loss_name)
+
       def fn():
         if ref_fill is not None:                 # GT: the reference's CPU fill on the scene's 3 mesh grids
           ref_fill.fill_inside_voxels_cpu(shells_t)
         opt.zero_grad()
+        if ref_model is not None:                # pipeline.py:224-230 of the reference
+          loss = ref_loss(gt, model(image, v2s, offsets))
+          loss.backward()
+          opt.step()
+          return
         nb = {}
         logits = O.corenet_forward(state, image, v2s, offsets, True, nb)
         loss = getattr(O, loss_name)(gt, logits)
@@ -273,6 +317,15 @@ def cpu_reference(workload, steps, warmup):
     fn()
   dt = (time.perf_counter() - t0) / steps
   return units / dt, dt, kind, f"{steps} steps x " + sample, cores
+
+
+def cpu_reference(workload, steps, warmup):
+  """_cpu_reference with the staged reference modules, falling back to the oracle port if they fail under this torch."""
+  try:
+    return _cpu_reference(workload, steps, warmup, True)
+  except Exception as e:
+    print(f"bench: staged reference failed ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+    return _cpu_reference(workload, steps, warmup, False)
 
 
 def run_reference(args):
