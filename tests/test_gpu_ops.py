@@ -1101,6 +1101,29 @@ def test_voxelize_random_meshes_bit_exact(cons, sub, mult, pdm):
   np.testing.assert_array_equal(got, exp)
 
 
+@pytest.mark.parametrize("cons", [False, True])
+def test_voxelize_large_triangles_and_translated_lattice_bit_exact(cons):
+  """The inputs of the oracle's property tests (tests/test_oracle_voxelize.py): triangles spanning the whole 12^3 grid
+  and beyond, a dyadic-lattice mesh moved by whole voxels through view2voxel, and a closed box -- vs the oracle."""
+  from corenet_b200.geometry import voxelization
+  from tests.conftest import cube_mesh
+  rng = np.random.default_rng(7)
+  c = rng.uniform(1.0, 11.0, size=(40, 1, 3))
+  soup = (c + rng.normal(0, 2.0, size=(40, 3, 3))).astype(np.float32)
+  lattice = (rng.integers(16, 48, size=(25, 3, 3)) / 8.0).astype(np.float32)
+  box = (cube_mesh(0.0) / 3.0 * (9.6 - 2.3) + 2.3).astype(np.float32)
+  tris = np.concatenate([soup, lattice, box])
+  ntri = [40, 25, 12]
+  v2x = np.stack([np.eye(4, dtype=np.float32)] * 3)
+  v2x[1, :3, 3] = [3, 1, 2]
+  res = (12, 12, 12)
+  exp = VO.voxelize_mesh_oracle(tris, ntri, res, v2x, image_resolution_multiplier=5, conservative_rasterization=cons)
+  got = voxelization.voxelize_mesh(t.from_numpy(tris), ntri, res, t.from_numpy(v2x), image_resolution_multiplier=5,
+                                   conservative_rasterization=cons).cpu().numpy()
+  assert exp[0].sum() > 100 and exp[1].sum() > 30 and exp[2].sum() > 200
+  np.testing.assert_array_equal(got, exp)
+
+
 def test_voxelize_fill_roundtrip_128():
   """Full size (128^3, mult 8): a closed icosphere-ish mesh voxelised + filled must be solid:
   every voxel whose centre is well inside the sphere is 1, everything well outside is 0."""
