@@ -55,7 +55,15 @@ def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--classes", type=int, default=2)
   ap.add_argument("--batch", type=int, default=4)
+  ap.add_argument("--top", action="store_true", help="only the dominant tcgen05 launches of the training step")
   args = ap.parse_args()
+  if args.top:
+    global CONV, CALLS_ONCE, CALLS_ALL, BRN_ONCE
+    CONV = {("fwd_tcs", "decoder.stage_6.c1"), ("dgrad_tcs", "decoder.stage_6.c1"), ("wgrad_line", "decoder.stage_6.c1"),
+            ("fwd_tcs", "decoder.stage_5.c1"), ("wgrad_line", "decoder.stage_5.c1"), ("dgrad_tcs", "decoder.stage_5.t1"),
+            ("wgrad_line", "decoder.stage_5.t1"), ("fwd_gt", "encoder.stage3.b.op_b.conv"),
+            ("wgrad_tc", "encoder.stage4.b.op_b.conv")}
+    CALLS_ONCE, CALLS_ALL, BRN_ONCE = set(), set(), set()
   dev = t.device("cuda", 0)
   t.manual_seed(0)
   model = CoreNet(configuration.default_config(args.classes)).to(dev).train()
@@ -90,6 +98,9 @@ def main():
   state["armed"] = True
   tr.step(*d_in)
   t.cuda.synchronize()
+  if args.top:
+    print("captured:", sorted(seen), "not seen:", [c for c in CONV if c not in seen])
+    return
   # evaluation kernels (softmax, argmax/confusion)
   from corenet_b200.evaluator import Evaluator
   model.eval()
