@@ -314,52 +314,9 @@ def skip_indices(b, hw, res3d, matrix, offsets):
 
 
 # ----------------------------------------------------------------------------
-# Losses (model/losses.py)
+# Losses: corenet_b200/model/losses.py (the reference's module name); re-exported as part of the operator surface
 # ----------------------------------------------------------------------------
-class _LossFn(t.autograd.Function):
-  @staticmethod
-  def forward(ctx, gt, logits, mode):
-    _need_cuda(gt, logits)
-    assert logits.dtype == t.float32 and logits.dim() == 5
-    b, c, d, h, w = logits.shape
-    assert gt.shape == (b, d, h, w) and gt.dtype in (t.int64, t.int32)
-    st = _lib.stream_ptr()
-    logits = logits.contiguous()
-    gt = gt.contiguous()
-    s = d * h * w
-    sums = t.empty(4 * b, dtype=t.float64, device=logits.device)
-    loss = t.empty(1, dtype=t.float32, device=logits.device)
-    coef = t.empty(2 * b + 1, dtype=t.float32, device=logits.device)
-    is64 = int(gt.dtype == t.int64)
-    _call("crn_loss_sums", logits.data_ptr(), gt.data_ptr(), is64, b, c, s, mode, sums.data_ptr(), st)
-    _call("crn_loss_finalize", sums.data_ptr(), b, c, s, mode, loss.data_ptr(), coef.data_ptr(), st)
-    ctx.save_for_backward(logits, gt, coef)
-    ctx.mode = mode
-    return loss[0]
-
-  @staticmethod
-  def backward(ctx, g):
-    logits, gt, coef = ctx.saved_tensors
-    b, c, d, h, w = logits.shape
-    st = _lib.stream_ptr()
-    gs = g.reshape(1).to(t.float32).contiguous()
-    dl = t.empty_like(logits)
-    _call("crn_loss_bwd", logits.data_ptr(), gt.data_ptr(), int(gt.dtype == t.int64), b, c, d * h * w,
-          ctx.mode, coef.data_ptr(), gs.data_ptr(), dl.data_ptr(), st)
-    return None, dl, None
-
-
-def iou_fgbg(gt_volume, logits, weights=None):
-  if weights is not None:
-    raise NotImplementedError("per-voxel loss weights are not used by the training pipeline "
-                              "(pipeline.py:228) and are not implemented")
-  return _LossFn.apply(gt_volume, logits, 0)
-
-
-def xent_times_iou_agnostic(gt_volume, logits, weights=None):
-  if weights is not None:
-    raise NotImplementedError("per-voxel loss weights are not implemented")
-  return _LossFn.apply(gt_volume, logits, 1)
+from corenet_b200.model.losses import _LossFn, iou_fgbg, xent_times_iou_agnostic  # noqa: E402,F401
 
 
 def softmax_channels(logits):
