@@ -147,14 +147,21 @@ __global__ void loss_finalize_kernel(const double* __restrict__ sums, int N, int
   }
   mean_iou /= (float)N;
   const float A = 1.f - mean_iou;
+  // mode 0: iou_fgbg, 1: (1 + iou_agnostic)(1 + xent), 2: iou_agnostic alone (losses.py:19-61), 3: xent alone (:117-141)
   float X = 0.f, fA = 1.f, fX = 0.f;
-  if (mode == 1) {
+  if (mode == 1 || mode == 3) {
     double xs = 0.0;
     for (int n = 0; n < N; ++n) xs += sums[n * 4 + 2];
     X = (float)(xs / ((double)N * (double)S));
+  }
+  if (mode == 1) {
     loss[0] = (1.f + A) * (1.f + X);
     fA = 1.f + X;          // d loss / dA
     fX = 1.f + A;          // d loss / dX
+  } else if (mode == 3) {
+    loss[0] = X;
+    fA = 0.f;
+    fX = 1.f;
   } else {
     loss[0] = A;
   }

@@ -64,3 +64,22 @@ def xent_times_iou_agnostic(gt_volume, logits, weights=None):
   if weights is not None:
     raise NotImplementedError("per-voxel loss weights are not implemented")
   return _LossFn.apply(gt_volume, logits, 1)
+
+
+def iou_agnostic(gt_volume, logits, weights=None):
+  """losses.py:19-61 of the reference: class-agnostic soft IoU loss (the first factor of xent_times_iou_agnostic)."""
+  if weights is not None:
+    raise NotImplementedError("per-voxel loss weights are not implemented")
+  return _LossFn.apply(gt_volume, logits, 2)
+
+
+def xent(gt_volume, logits, weights=None):
+  """losses.py:117-141 of the reference: mean cross entropy (the second factor of xent_times_iou_agnostic)."""
+  if weights is not None:
+    raise NotImplementedError("per-voxel loss weights are not implemented")
+  return _LossFn.apply(gt_volume, logits, 3)
+
+
+def xent_times_iou_fgbg(gt_volume, logits, weights=None):
+  """losses.py:163-178 of the reference (not selected by any shipped config): two fused passes, combined by autograd."""
+  return (1 + iou_fgbg(gt_volume, logits, weights)) * (1 + xent(gt_volume, logits, weights))

@@ -235,12 +235,14 @@ int crn_skip_indices(int32_t N, int32_t h, int32_t w, const float* m, const floa
 
 /* ------------------------------------------------------------------------
  * Losses on planar logits [N, C, S].  Replaces model/losses.py:64-114
- * (iou_fgbg) and :144-160 (xent_times_iou_agnostic).  gt: int32 or int64 [N,S].
+ * (iou_fgbg) and :144-160 (xent_times_iou_agnostic), and its two factors on their own (:19-61 iou_agnostic,
+ * :117-141 xent; modes 2 and 3 share the sums / backward passes of mode 1).  gt: int32 or int64 [N,S].
  * Pass 1 accumulates per-scene sums (double[N*4]: inter, union, xent, -);
  * the scalar combination is done by the host wrapper; pass 2 writes dlogits.
  * ---------------------------------------------------------------------- */
 int crn_loss_sums(const float* logits, const void* gt, int32_t gt_is_i64, int32_t N, int32_t C,
-                  int64_t S, int32_t mode /*0 fgbg, 1 agnostic+xent*/, double* sums, void* stream);
+                  int64_t S, int32_t mode /*0 iou_fgbg, 1 (1+iou_agnostic)(1+xent), 2 iou_agnostic, 3 xent*/, double* sums,
+                  void* stream);
 /* loss[0] and coef float[2N+1] = (dL/dI_n, dL/dU_n)..., dL/d(sum xent) from the per-scene sums. */
 int crn_loss_finalize(const double* sums, int32_t N, int32_t C, int64_t S, int32_t mode, float* loss,
                       float* coef, void* stream);

@@ -931,10 +931,13 @@ def test_losses_known_answers():
   np.testing.assert_allclose(losses.iou_fgbg(gt, lg).item(), 0.3579613, rtol=1e-5, atol=1e-6)
   want = (1 + 0.8060565) * (1 + 1.4547757)
   np.testing.assert_allclose(losses.xent_times_iou_agnostic(gt, lg).item(), want, rtol=1e-5, atol=1e-6)
+  np.testing.assert_allclose(losses.iou_agnostic(gt, lg).item(), 0.8060565, rtol=1e-5, atol=1e-6)     # :73
+  np.testing.assert_allclose(losses.xent(gt, lg).item(), 1.4547757, rtol=1e-5, atol=1e-6)             # :85
+  np.testing.assert_allclose(losses.xent_times_iou_fgbg(gt, lg).item(), (1 + 0.3579613) * (1 + 1.4547757), rtol=1e-5)
 
 
 @pytest.mark.parametrize("c,loss", [(2, "iou_fgbg"), (5, "iou_fgbg"), (5, "xent_times_iou_agnostic"),
-                                    (15, "xent_times_iou_agnostic")])
+                                    (15, "xent_times_iou_agnostic"), (5, "iou_agnostic"), (15, "xent"), (2, "xent")])
 def test_losses_random(c, loss):
   from corenet_b200.model import losses
   g = t.Generator().manual_seed(c)
