@@ -1,5 +1,6 @@
-"""Imports the UNMODIFIED reference package `corenet` (from /root/reference/src in the build container, from the
-staged copy baseline/_ref/src on the GPU box) under torch 2.11.  TEST / BASELINE INFRASTRUCTURE ONLY.
+"""Imports the UNMODIFIED reference package `corenet` (from the staged copy baseline/_ref/src -- written by
+baseline/stage_ref.py in the build container, travels to the GPU box -- else from /root/reference/src) under torch 2.11.
+TEST / BASELINE INFRASTRUCTURE ONLY.
 
 The reference pins packages that are absent from this image (json5, jq, google-cloud-storage, moderngl, tensorboard,
 dataclasses_jsonschema ...): none of them is on the model path, so they are replaced by inert stub modules created on
@@ -42,7 +43,9 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 
 
 def reference_src():
-  for p in ("/root/reference/src", os.path.join(HERE, "_ref", "src")):
+  # the staged copy first: bench.py and the GPU tests must not depend on /root/reference (absent on the GPU box);
+  # the checkout itself only serves the CPU tests of a build container in which nothing has been staged yet
+  for p in (os.path.join(HERE, "_ref", "src"), "/root/reference/src"):
     if os.path.isdir(os.path.join(p, "corenet")):
       return p
   return None
