@@ -49,3 +49,28 @@ def test_confusion_and_miou():
   cm = O.confusion_matrix(pred, gt, 3)
   assert cm.tolist() == [[1, 0, 1], [0, 1, 0], [0, 1, 2]]
   np.testing.assert_allclose(O.mean_iou(cm), (1 / 2 + 2 / 4) / 2)
+
+
+# src/corenet/test/voxel_metrics_test.py:25-80: the reference's own confusion-matrix / IoU known answers
+VM_GT = t.tensor([[[3, 2, 2, 4], [4, 3, 2, 2], [3, 1, 3, 0]], [[3, 0, 1, 3], [2, 3, 1, 1], [2, 3, 0, 4]]], dtype=t.int32)
+VM_PRED = t.tensor([[[0, 2, 3, 1], [1, 1, 1, 3], [4, 0, 2, 3]], [[1, 0, 1, 4], [2, 4, 4, 0], [4, 2, 4, 2]]], dtype=t.int32)
+VM_CM = [[1, 0, 0, 1, 1], [2, 1, 0, 0, 1], [0, 1, 2, 2, 1], [1, 2, 2, 0, 3], [0, 2, 1, 0, 0]]
+VM_IOU = [0.16666667, 0.11111111, 0.22222222, 0., 0.]
+
+
+def test_reference_confusion_matrix_known_answer():
+  cm = O.confusion_matrix(VM_PRED, VM_GT, 5)
+  assert cm.tolist() == VM_CM
+  np.testing.assert_allclose(O.mean_iou(cm), np.mean(VM_IOU[1:]), rtol=1e-6)
+
+
+def test_evaluator_iou_follows_the_reference_metrics():
+  """Evaluator.iou_per_class / mean_iou (host logic over the device confusion matrix) against
+  voxel_metrics_test.py:68-80 (iou = tp / (tp + fp + fn)) and evaluation_results.py:262-266 (mean over non-void)."""
+  from corenet_b200.evaluator import Evaluator
+  ev = Evaluator.__new__(Evaluator)
+  ev.confusion_matrix = t.tensor(VM_CM, dtype=t.int64)
+  np.testing.assert_allclose(ev.iou_per_class().numpy(), VM_IOU, rtol=1e-6)
+  np.testing.assert_allclose(ev.mean_iou(), np.mean(VM_IOU[1:]), rtol=1e-6)
+  ev.confusion_matrix = t.tensor([[5, 0, 0], [0, 3, 0], [0, 0, 0]], dtype=t.int64)     # class 2 absent everywhere
+  np.testing.assert_allclose(ev.mean_iou(), 1.0)
