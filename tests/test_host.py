@@ -207,3 +207,77 @@ def test_precision_mode_switch_is_host_side_state():
   finally:
     engine.set_precision("3xtf32")
   assert engine.PRECISION == "3xtf32"
+
+
+def test_transformations_reference_known_answers():
+  """src/corenet/test/transformations_test.py:26-115 on this package's helpers."""
+  import math
+  from corenet_b200.geometry import transformations as tt
+  assert t.equal(tt.scale((1, 2, 3)), t.tensor(((1, 0, 0, 0), (0, 2, 0, 0), (0, 0, 3, 0), (0, 0, 0, 1)), dtype=t.float32))
+  assert t.equal(tt.translate((1, 2, 3)),
+                 t.tensor(((1, 0, 0, 1), (0, 1, 0, 2), (0, 0, 1, 3), (0, 0, 0, 1)), dtype=t.float32))
+  two = tt.translate([[[1, 2, 3], [4, 5, 6]]])
+  assert two.shape == (1, 2, 4, 4) and two[0, 1, :3, 3].tolist() == [4, 5, 6] and two[0, 0, :3, 3].tolist() == [1, 2, 3]
+  assert t.allclose(tt.rotate(math.pi / 2, (0, 0, 1)),
+                    t.tensor(((0, -1, 0, 0), (1, 0, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1)), dtype=t.float32),
+                    rtol=1e-5, atol=1e-5)
+  m1 = ((1, 0, 0, 0), (0, 2, 0, 0), (0, 0, 3, 0), (0, 0, 0, 1))
+  m2 = ((1, 0, 0, 1), (0, 1, 0, 2), (0, 0, 1, 3), (0, 0, 0, 1))
+  p1 = ((12, 34, 56), (34, 32, 30), (11, 11, 18), (5, 6, 7))
+  p2 = ((1, 2, 3), (4, 5, 6), (6, 5, 4), (3, 2, 1))
+  want = t.tensor((((12, 68, 168), (34, 64, 90), (11, 22, 54), (5, 12, 21)),
+                   ((2, 4, 6), (5, 7, 9), (7, 7, 7), (4, 4, 4))), dtype=t.float32)
+  h = tt.transform_points_homogeneous((p1, p2), (m1, m2), w=1)
+  assert t.equal(h[..., :3] / h[..., 3:4], want) and t.equal(tt.transform_points((p1, p2), (m1, m2)), want)
+  mesh = (((12, 34, 56), (34, 32, 30), (11, 11, 18)), ((1, 2, 3), (4, 5, 6), (6, 5, 4)))
+  want = t.tensor((((12, 68, 168), (34, 64, 90), (11, 22, 54)), ((1, 4, 9), (4, 10, 18), (6, 10, 12))), dtype=t.float32)
+  assert t.equal(tt.transform_mesh(mesh, m1), want)
+
+
+def _reference_or_skip():
+  from baseline import ref_import
+  if ref_import.import_reference() is None:
+    pytest.skip("no reference checkout / staged copy")
+
+
+def test_transformations_and_batching_match_the_reference_functions():
+  """rotate / look_at / perspective / transform_* / chain against the reference module on random inputs, and
+  data.batched_example.batch (one batched product over all triangles) against the reference's per-mesh loop
+  (batched_example.py:67-97)."""
+  import types
+  import warnings
+  _reference_or_skip()
+  from corenet.data import batched_example as rb
+  from corenet.geometry import transformations as rt
+  from corenet_b200.data import batched_example as mb
+  from corenet_b200.geometry import transformations as tt
+  g = t.Generator().manual_seed(0)
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    for _ in range(4):
+      ang, ax = float(t.rand(1, generator=g) * 6 - 3), t.randn(3, generator=g)
+      assert t.allclose(tt.rotate(ang, ax), rt.rotate(ang, ax), atol=1e-6)
+      e, c, u = t.randn(3, generator=g), t.randn(3, generator=g), t.randn(3, generator=g)
+      assert t.allclose(tt.look_at_lh(e, c, u), rt.look_at_lh(e, c, u), atol=1e-6)
+      assert t.allclose(tt.look_at_rh(e, c, u), rt.look_at_rh(e, c, u), atol=1e-6)
+      assert t.equal(tt.perspective_lh(1.0, 1.3, 0.01, 9.0), rt.perspective_lh(1.0, 1.3, 0.01, 9.0))
+      mesh, mat = t.randn(2, 7, 3, 3, generator=g), t.randn(2, 4, 4, generator=g)
+      assert t.allclose(tt.transform_mesh(mesh, mat), rt.transform_mesh(mesh, mat), rtol=1e-5, atol=1e-6)
+      assert t.allclose(tt.transform_mesh(mesh, mat, False), rt.transform_mesh(mesh, mat, False), rtol=1e-5, atol=1e-6)
+      ms = [t.randn(4, 4, generator=g) for _ in range(3)]
+      assert t.equal(tt.chain(ms), rt.chain(ms))
+
+    def elem(nm, seed):
+      gg = t.Generator().manual_seed(seed)
+      ntri = t.randint(3, 9, (nm,), generator=gg).to(t.int32)
+      return types.SimpleNamespace(
+          view_transform=t.randn(4, 4, generator=gg), camera_transform=t.randn(4, 4, generator=gg), mesh_num_tri=ntri,
+          o2w_transforms=t.randn(nm, 4, 4, generator=gg), mesh_vertices=t.randn(int(ntri.sum()), 3, 3, generator=gg),
+          mesh_labels=t.arange(nm, dtype=t.int32), input_image=t.zeros(3, 8, 8, dtype=t.uint8), scene_id=f"s{seed}")
+    exs = [elem(2, 1), elem(3, 2), elem(1, 3)]
+    a, b = rb.batch(exs), mb.batch(exs)
+  assert t.allclose(a.vertices, b.vertices, rtol=1e-5, atol=1e-5)
+  for f in ("view_transform", "camera_transform", "input_image", "grid_sampling_offset"):
+    assert t.equal(getattr(a, f), getattr(b, f)), f
+  assert a.scene_id == b.scene_id and all(t.equal(x, y) for x, y in zip(a.mesh_num_tri, b.mesh_num_tri))
+  assert b.to("cpu").vertices.shape == a.vertices.shape and b.grid is None
