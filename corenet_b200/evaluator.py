@@ -133,16 +133,47 @@ class Evaluator:
       t.distributed.all_reduce(self.confusion_matrix, op=t.distributed.ReduceOp.SUM, group=self.pg)
     return self.confusion_matrix
 
-  def iou_per_class(self) -> t.Tensor:
-    """TP / (TP + FP + FN) per class (voxel_metrics.py:61-107), float64[K]."""
+  def tfpn(self):
+    """(tp, tn, fp, fn) float64[K] per class from the confusion matrix (voxel_metrics.py:61-97: rows = ground truth,
+    columns = prediction)."""
     cm = self.confusion_matrix.to(t.float64)
     tp = cm.diag()
-    return tp / (cm.sum(0) + cm.sum(1) - tp)
+    fp = cm.sum(0) - tp
+    fn = cm.sum(1) - tp
+    return tp, cm.sum() - tp - fp - fn, fp, fn
+
+  def tfpn_fg(self):
+    """Class-agnostic foreground / background counts (voxel_metrics.py:100-107): scalars tp, tn, fp, fn."""
+    cm = self.confusion_matrix.to(t.float64)
+    return cm[1:, 1:].sum(), cm[0, 0], cm[0, 1:].sum(), cm[1:, 0].sum()
+
+  @staticmethod
+  def _nan_tp_div(tp, y):
+    # voxel_metrics.py:118-120: a class without a single true positive gets NaN (and drops out of the mean below),
+    # not 0 -- the shipped behaviour of the reference (its own test expects 0 and fails, SURVEY F10)
+    return t.where(tp == 0, t.full_like(tp, float("nan")), tp / y)
+
+  def metrics(self) -> dict:
+    """iou / precision / recall, float64[K + 1]: one entry per class plus the class-agnostic "__global__" entry last
+    (evaluation_results.py:188-210 builds the same table as a DataFrame)."""
+    out = {}
+    (tp, _, fp, fn), (gtp, _, gfp, gfn) = self.tfpn(), self.tfpn_fg()
+    tp, fp, fn = t.cat([tp, gtp[None]]), t.cat([fp, gfp[None]]), t.cat([fn, gfn[None]])
+    out["iou"] = self._nan_tp_div(tp, tp + fp + fn)
+    out["precision"] = self._nan_tp_div(tp, tp + fp)
+    out["recall"] = self._nan_tp_div(tp, tp + fn)
+    return out
+
+  def iou_per_class(self) -> t.Tensor:
+    """TP / (TP + FP + FN) per class, NaN where TP == 0 (voxel_metrics.py:118-135), float64[K]."""
+    return self.metrics()["iou"][:-1]
 
   def mean_iou(self) -> float:
-    """Mean IoU over the non-void classes (evaluation_results.py:262-266)."""
+    """Mean IoU over the non-void classes (evaluation_results.py:262-266: a pandas mean, which skips the NaN classes;
+    NaN when no class has a true positive)."""
     iou = self.iou_per_class()[1:]
-    return float(iou[~iou.isnan()].mean())       # classes absent from both GT and prediction are skipped (pandas mean)
+    ok = ~iou.isnan()
+    return float(iou[ok].mean()) if bool(ok.any()) else float("nan")
 
   def check_status(self) -> None:
     if int(self.eng.tc_status) != 0:

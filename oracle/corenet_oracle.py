@@ -373,12 +373,20 @@ def confusion_matrix(pred: t.Tensor, gt: t.Tensor, num_classes: int) -> t.Tensor
   return t.bincount(idx, minlength=num_classes * num_classes).reshape(num_classes, num_classes)
 
 
-def mean_iou(cm: t.Tensor) -> float:
-  """IoU per non-void class = TP / (TP + FP + FN); mean over classes 1.. ."""
+def iou_per_class(cm: t.Tensor) -> t.Tensor:
+  """voxel_metrics.py:61-97,118-135: IoU = TP / (TP + FP + FN), NaN for a class without a true positive
+  (nan_tp_div; the reference's own test expects 0 there and fails as shipped -- SURVEY F10)."""
   cm = cm.to(t.float64)
   tp = cm.diag()
   iou = tp / (cm.sum(0) + cm.sum(1) - tp)
-  return float(iou[1:].mean())
+  return t.where(tp == 0, t.full_like(iou, math.nan), iou)
+
+
+def mean_iou(cm: t.Tensor) -> float:
+  """evaluation_results.py:262-266: mean over the non-void classes of a pandas frame, i.e. NaN classes are skipped."""
+  iou = iou_per_class(cm)[1:]
+  ok = ~iou.isnan()
+  return float(iou[ok].mean()) if bool(ok.any()) else math.nan
 
 
 # --------------------------------------------------------------------------

@@ -1,4 +1,6 @@
 """Pins the loss restatements with the reference's known answers (src/corenet/test/losses_test.py:25-88)."""
+import math
+
 import numpy as np
 import torch as t
 
@@ -55,22 +57,57 @@ def test_confusion_and_miou():
 VM_GT = t.tensor([[[3, 2, 2, 4], [4, 3, 2, 2], [3, 1, 3, 0]], [[3, 0, 1, 3], [2, 3, 1, 1], [2, 3, 0, 4]]], dtype=t.int32)
 VM_PRED = t.tensor([[[0, 2, 3, 1], [1, 1, 1, 3], [4, 0, 2, 3]], [[1, 0, 1, 4], [2, 4, 4, 0], [4, 2, 4, 2]]], dtype=t.int32)
 VM_CM = [[1, 0, 0, 1, 1], [2, 1, 0, 0, 1], [0, 1, 2, 2, 1], [1, 2, 2, 0, 3], [0, 2, 1, 0, 0]]
-VM_IOU = [0.16666667, 0.11111111, 0.22222222, 0., 0.]
+VM_IOU = [0.16666667, 0.11111111, 0.22222222, math.nan, math.nan]     # the test file says 0., the shipped code NaN (F10)
+VM_PRECISION = [0.25, 0.16666667, 0.4, math.nan, math.nan]
+VM_RECALL = [0.33333333, 0.25, 0.33333333, math.nan, math.nan]
 
 
 def test_reference_confusion_matrix_known_answer():
   cm = O.confusion_matrix(VM_PRED, VM_GT, 5)
   assert cm.tolist() == VM_CM
-  np.testing.assert_allclose(O.mean_iou(cm), np.mean(VM_IOU[1:]), rtol=1e-6)
+  np.testing.assert_allclose(O.iou_per_class(cm).numpy(), VM_IOU, rtol=1e-6)
+  # evaluation_results.py:262-266 is a pandas mean: the NaN classes drop out
+  np.testing.assert_allclose(O.mean_iou(cm), np.mean(VM_IOU[1:3]), rtol=1e-6)
 
 
-def test_evaluator_iou_follows_the_reference_metrics():
-  """Evaluator.iou_per_class / mean_iou (host logic over the device confusion matrix) against
-  voxel_metrics_test.py:68-80 (iou = tp / (tp + fp + fn)) and evaluation_results.py:262-266 (mean over non-void)."""
+def test_evaluator_metrics_follow_the_reference():
+  """Evaluator.tfpn / metrics / iou_per_class / mean_iou (host logic over the device confusion matrix) against
+  voxel_metrics_test.py:47-80 and, when a copy of the reference is present, against its own
+  compute_tfpn / compute_tfpn_fg / compute_voxel_metrics and the pandas mean of evaluation_results.py:188-266."""
   from corenet_b200.evaluator import Evaluator
   ev = Evaluator.__new__(Evaluator)
   ev.confusion_matrix = t.tensor(VM_CM, dtype=t.int64)
-  np.testing.assert_allclose(ev.iou_per_class().numpy(), VM_IOU, rtol=1e-6)
-  np.testing.assert_allclose(ev.mean_iou(), np.mean(VM_IOU[1:]), rtol=1e-6)
+  tp, tn, fp, fn = ev.tfpn()
+  assert tp.tolist() == [1, 1, 2, 0, 0] and tn.tolist() == [18, 15, 15, 13, 15]
+  assert fp.tolist() == [3, 5, 3, 3, 6] and fn.tolist() == [2, 3, 4, 8, 3]
+  mm = ev.metrics()
+  np.testing.assert_allclose(mm["iou"][:-1].numpy(), VM_IOU, rtol=1e-6)
+  np.testing.assert_allclose(mm["precision"][:-1].numpy(), VM_PRECISION, rtol=1e-6)
+  np.testing.assert_allclose(mm["recall"][:-1].numpy(), VM_RECALL, rtol=1e-6)
+  np.testing.assert_allclose(ev.mean_iou(), np.mean(VM_IOU[1:3]), rtol=1e-6)
   ev.confusion_matrix = t.tensor([[5, 0, 0], [0, 3, 0], [0, 0, 0]], dtype=t.int64)     # class 2 absent everywhere
   np.testing.assert_allclose(ev.mean_iou(), 1.0)
+  ev.confusion_matrix = t.tensor([[5, 1], [2, 0]], dtype=t.int64)                       # no true positive at all
+  assert math.isnan(ev.mean_iou()) and math.isnan(O.mean_iou(ev.confusion_matrix))
+  from baseline import ref_import
+  if ref_import.import_reference() is None:
+    return
+  import dataclasses
+  import pandas
+  from corenet import voxel_metrics as vm
+  g = t.Generator().manual_seed(0)
+  for k in (2, 5, 15):
+    cm = t.randint(0, 50, (k, k), generator=g)
+    cm[t.rand(k, generator=g) < 0.3, :] = 0           # classes without ground truth
+    cm.fill_diagonal_(0) if k == 5 else None          # ... and a matrix without any true positive
+    ev.confusion_matrix = cm.to(t.int64)
+    ref = vm.compute_voxel_metrics(vm.compute_tfpn(cm))
+    ref_fg = vm.compute_voxel_metrics(vm.compute_tfpn_fg(cm))
+    mine = ev.metrics()
+    for name in ("iou", "precision", "recall"):
+      np.testing.assert_allclose(mine[name][:-1].numpy(), getattr(ref, name).numpy(), rtol=1e-12, equal_nan=True)
+      np.testing.assert_allclose(mine[name][-1].numpy(), getattr(ref_fg, name).numpy(), rtol=1e-12, equal_nan=True)
+    df = pandas.DataFrame(dataclasses.asdict(ref.cpu().numpy()), index=[f"c{i}" for i in range(k)]).T
+    want = float(df.iloc[:, 1:].T.mean().iou)          # get_mean_iou without the trailing __global__ column
+    np.testing.assert_allclose(ev.mean_iou(), want, rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(O.mean_iou(cm), want, rtol=1e-12, equal_nan=True)
