@@ -126,3 +126,17 @@ def voxelize_example(ex: BatchedExample, resolution: Tuple[int, int, int], **kwa
   (batched_example.py:121-197), on top of `voxelize` above."""
   v2x, grid = voxelize(ex.vertices, ex.mesh_num_tri, ex.grid_sampling_offset, resolution, **kwargs)
   return dataclasses.replace(ex, v2x_transform=v2x, grid=grid)
+
+
+def voxelize_batch(b: BatchedExample, voxelization_config) -> BatchedExample:
+  """pipeline.voxelize_batch (pipeline.py:126-150 of the reference): the voxel content and the rasteriser settings of a
+  `configuration.VoxelizationConfig` (SEMANTIC: the mesh's class, FG_BG: 1) applied to a batch."""
+  from corenet_b200 import configuration
+  content = {configuration.TaskType.SEMANTIC: VoxelContentSemanticLabel(b.mesh_labels),
+             configuration.TaskType.FG_BG: voxel_content_1}[voxelization_config.task_type]
+  return voxelize_example(
+      b, dataclasses.astuple(voxelization_config.resolution), voxel_content_fn=content,
+      sub_grid_sampling=voxelization_config.sub_grid_sampling,
+      image_resolution_multiplier=voxelization_config.voxelization_image_resolution_multiplier,
+      conservative_rasterization=voxelization_config.conservative_rasterization,
+      projection_depth_multiplier=voxelization_config.voxelization_projection_depth_multiplier)

@@ -1,4 +1,6 @@
 """Host-side logic that needs no GPU: module surface, state_dict compatibility, config, sharding, errors."""
+import dataclasses
+
 import numpy as np
 import pytest
 import torch as t
@@ -281,3 +283,31 @@ def test_transformations_and_batching_match_the_reference_functions():
     assert t.equal(getattr(a, f), getattr(b, f)), f
   assert a.scene_id == b.scene_id and all(t.equal(x, y) for x, y in zip(a.mesh_num_tri, b.mesh_num_tri))
   assert b.to("cpu").vertices.shape == a.vertices.shape and b.grid is None
+
+
+def test_voxelize_batch_passes_the_config_through(monkeypatch):
+  """data.batched_example.voxelize_batch = pipeline.voxelize_batch (pipeline.py:126-150): task type -> voxel content,
+  VoxelizationConfig fields -> rasteriser settings (the CUDA step itself is stubbed: host logic only)."""
+  from corenet_b200 import configuration as C
+  from corenet_b200.data import batched_example as be
+  seen = {}
+
+  def fake(vertices, mesh_num_tri, offsets, resolution, **kw):
+    seen.update(kw, resolution=resolution, n=len(mesh_num_tri))
+    return "v2x", "grid"
+  monkeypatch.setattr(be, "voxelize", fake)
+  ex = be.BatchedExample(vertices=t.zeros(5, 3, 3), view_transform=t.eye(4)[None], camera_transform=t.eye(4)[None],
+                         mesh_num_tri=[t.tensor([2, 3], dtype=t.int32)], mesh_labels=[t.tensor([7, 9], dtype=t.int32)],
+                         input_image=t.zeros(1, 3, 8, 8, dtype=t.uint8), scene_id=["s"],
+                         grid_sampling_offset=t.full((1, 3), 0.5))
+  cfg = C.VoxelizationConfig(task_type=C.TaskType.SEMANTIC, resolution=C.Resolution(depth=128, height=64, width=32),
+                             sub_grid_sampling=False, conservative_rasterization=True,
+                             voxelization_image_resolution_multiplier=7, voxelization_projection_depth_multiplier=2)
+  out = be.voxelize_batch(ex, cfg)
+  assert out.grid == "grid" and out.v2x_transform == "v2x" and out.vertices is ex.vertices
+  assert seen["resolution"] == (128, 64, 32) and seen["image_resolution_multiplier"] == 7
+  assert seen["conservative_rasterization"] is True and seen["projection_depth_multiplier"] == 2
+  assert seen["sub_grid_sampling"] is False and seen["voxel_content_fn"](0, 1) == 9
+  cfg = dataclasses.replace(cfg, task_type=C.TaskType.FG_BG)
+  be.voxelize_batch(ex, cfg)
+  assert seen["voxel_content_fn"](0, 1) == 1
