@@ -166,7 +166,10 @@ def hot_path_settings(cfg) -> dict:
   vox = VoxelizationConfig.from_dict(data["voxelization_config"])
   out = {"voxelization_config": vox, "batch_size": data["data_loader"]["batch_size"],
          "loss": "iou_fgbg" if vox.task_type == TaskType.FG_BG else "xent_times_iou_agnostic",
-         "resolution": dataclasses.astuple(vox.resolution)}
+         "resolution": dataclasses.astuple(vox.resolution),
+         # state.create_initial_state hands the decoder the REVERSED tuple (state.py:58; identical for the cubic grids
+         # the decoder supports)
+         "model_resolution": dataclasses.astuple(vox.resolution)[::-1]}
   if "train" in cfg:
     tr = cfg["train"]
     out.update(initial_learning_rate=tr.get("initial_learning_rate", 0.0004), adam_epsilon=tr.get("adam_epsilon", 1e-4),
