@@ -311,3 +311,32 @@ def test_voxelize_batch_passes_the_config_through(monkeypatch):
   cfg = dataclasses.replace(cfg, task_type=C.TaskType.FG_BG)
   be.voxelize_batch(ex, cfg)
   assert seen["voxel_content_fn"](0, 1) == 1
+
+
+def test_super_resolution_interleave_equals_the_reference_class():
+  """SuperResolutionInference (offsets, v2x rescale, pmf interleave) against the reference's own class
+  (super_resolution.py:45-112) around the same stub model with spatially varying output, multipliers 2 and 4."""
+  import warnings
+  _reference_or_skip()
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    from corenet import super_resolution as rs
+    from corenet_b200.super_resolution import SuperResolutionInference
+    calls = []
+
+    def stub(image, cam, v2x, grid_offsets):
+      calls.append((cam.clone(), v2x.clone(), grid_offsets.clone()))
+      n_off, b = grid_offsets.shape[:2]
+      g = t.Generator().manual_seed(n_off)
+      return t.rand(n_off, b, 3, 8, 8, 8, generator=g) + grid_offsets.sum(-1)[:, :, None, None, None, None]
+    go = t.tensor([[0.5, 0.25, 0.75], [0.1, 0.2, 0.3]])
+    g = t.Generator().manual_seed(1)
+    cam, v2x = t.randn(2, 4, 4, generator=g), t.randn(2, 4, 4, generator=g)
+    img = t.zeros(2, 3, 8, 8, dtype=t.uint8)
+    for mult in (2, 4):
+      out_res = (8 * mult,) * 3
+      a = rs.SuperResolutionInference(stub, (8, 8, 8))(img, cam, v2x, go, out_res)
+      b = SuperResolutionInference(stub, (8, 8, 8))(img, cam, v2x, go, out_res)
+      assert t.equal(a, b) and tuple(b.shape) == (2, 3) + out_res
+      (c1, x1, o1), (c2, x2, o2) = calls[-2], calls[-1]
+      assert t.equal(c1, c2) and t.equal(x1, x2) and t.equal(o1, o2)
