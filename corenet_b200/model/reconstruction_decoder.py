@@ -7,7 +7,6 @@ The arithmetic runs in the CUDA engine (corenet_b200/engine.py).
 """
 import collections
 
-import torch as t
 from torch import nn
 
 from corenet_b200 import configuration

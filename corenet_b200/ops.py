@@ -6,7 +6,7 @@ needed, and launches the kernels on the current stream.  They raise on CPU
 tensors: there is no CPU fallback.
 """
 import ctypes as C
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import torch as t
 
